@@ -1,0 +1,138 @@
+/*
+ * insr_b200.h -- C ABI of the B200-native INSR-PDE hot path (libinsr_b200.so).
+ *
+ * Plain C: pointers and sizes only, no torch types.  All tensors are FP32, row-major,
+ * contiguous DEVICE memory owned by the caller (PyTorch's caching allocator in the
+ * shipped host side); the library allocates nothing persistent, keeps no pointers between
+ * calls, enqueues all work on the cudaStream_t passed as `stream` and never synchronises.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference root):
+ *
+ *   insr_siren_forward   base/networks.py:67-71  MLP.forward  (nn.Sequential of nn.Linear +
+ *                        Sine, base/networks.py:21-27,50-60), and -- for order >= 1 -- the
+ *                        torch.autograd.grad(create_graph=True) sweeps of
+ *                        base/diff_ops.py:53-58 (gradient), :44-50 (divergence),
+ *                        :33-41 (laplace), :61-82 (jacobian), :6-30 (hessian).
+ *   insr_siren_backward  the autograd backward the reference triggers with
+ *                        loss.backward() at base/baseModel.py:77 (first-, second- and
+ *                        third-order chains through the graphs built by diff_ops).
+ *   insr_siren_lsq_step  the fused loss closures: residual + mean-square loss + backward in
+ *                        one pass, covering advection/model.py:43-52,68-91 and
+ *                        fluid/model.py:43-52,72-151 (see INTEGRATION.md for the mapping).
+ *
+ * Parameter vector `theta` (flat, the order of nn.Module.parameters()):
+ *   W1 (H x D), b1 (H), W2 (H x H), b2 (H), ..., W_{L+1} (H x H), b_{L+1} (H),
+ *   Wout (O x H), bout (O);  each W is (out, in) row-major exactly as nn.Linear stores it.
+ *
+ * Error behaviour: 0 on success; negative insr_status for argument errors; positive values
+ * are cudaError_t codes.  insr_last_error() returns a thread-local message.  There is no
+ * CPU fallback and no silent degradation: an unsupported shape is an error.
+ */
+#ifndef INSR_B200_H
+#define INSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INSR_ABI_VERSION 1
+#define INSR_MAX_IN 3       /* D: spatial dimension of the collocation points   */
+#define INSR_MAX_OUT 3      /* O: field components                              */
+#define INSR_MAX_HIDDEN 512 /* H: hidden_features (config.py:99)                */
+#define INSR_MAX_LAYERS 16  /* L: num_hidden_layers (config.py:98)              */
+
+typedef enum insr_status {
+    INSR_OK = 0,
+    INSR_ERR_NULL = -1,        /* a required pointer is NULL                        */
+    INSR_ERR_SHAPE = -2,       /* D/O/H/L/N outside the supported range             */
+    INSR_ERR_ORDER = -3,       /* unknown derivative order                          */
+    INSR_ERR_ALIGN = -4,       /* a buffer is not 16-byte aligned                   */
+    INSR_ERR_WORKSPACE = -5,   /* workspace missing or too small                    */
+    INSR_ERR_UNSUPPORTED = -6, /* valid request that this build cannot serve        */
+    INSR_ERR_NO_DEVICE = -7    /* no CUDA device / wrong architecture               */
+} insr_status;
+
+/* which derivative streams are propagated forward-mode through the layers */
+typedef enum insr_order {
+    INSR_ORDER_VALUE = 0, /* y                                            S = 1           */
+    INSR_ORDER_JAC = 1,   /* y, J[n,o,d] = dy_o/dx_d                      S = 1 + D       */
+    INSR_ORDER_LAP = 2,   /* y, J, lap[n,o] = sum_d d2y_o/dx_d^2          S = 2 + D       */
+    INSR_ORDER_HESS = 3   /* y, J, hess[n,o,d,e]                          S = 1+D+D(D+1)/2 */
+} insr_order;
+
+/* one SIREN field: MLP(in, out, num_hidden_layers, hidden, nonlinearity='sine') */
+typedef struct insr_siren_desc {
+    int32_t in_features;       /* D */
+    int32_t out_features;      /* O */
+    int32_t hidden_features;   /* H */
+    int32_t num_hidden_layers; /* L  (=> L+1 sine layers, L+2 Linear layers) */
+    float omega;               /* 30.0f in the reference (base/networks.py:27) */
+    int32_t flags;             /* INSR_FLAG_* */
+} insr_siren_desc;
+
+#define INSR_FLAG_NONE 0
+#define INSR_FLAG_FORCE_GENERIC 1 /* use the generic (any-H) kernels even where a fused one exists */
+
+int insr_version(void);
+const char *insr_last_error(void);
+
+/* number of floats in theta for this descriptor (0 if the descriptor is invalid) */
+int64_t insr_siren_theta_size(const insr_siren_desc *desc);
+
+/* bytes of scratch the caller must pass to forward (backward=0) / backward (backward=1) */
+size_t insr_siren_workspace_bytes(const insr_siren_desc *desc, int64_t n_points, int order,
+                                  int backward);
+
+/*
+ * Evaluate the field and its spatial derivatives at n_points collocation points.
+ *   x     (N, D)            y    (N, O)
+ *   jac   (N, O, D)         required for order >= 1, ignored otherwise
+ *   h2    (N, O)            per-output Laplacian for order == INSR_ORDER_LAP
+ *         (N, O, D, D)      full symmetric Hessian for order == INSR_ORDER_HESS
+ */
+int insr_siren_forward(const insr_siren_desc *desc, const float *theta, const float *x,
+                       int64_t n_points, int order, float *y, float *jac, float *h2,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Reverse sweep: given the cotangents of the outputs of insr_siren_forward (any of them may
+ * be NULL = zero), ACCUMULATE (+=) the parameter gradient into gtheta (flat, same layout as
+ * theta) and, if gx != NULL, WRITE the gradient w.r.t. the points into gx (N, D).
+ * The forward activations are recomputed inside the kernel; nothing is saved between calls.
+ */
+int insr_siren_backward(const insr_siren_desc *desc, const float *theta, const float *x,
+                        int64_t n_points, int order, const float *gy, const float *gjac,
+                        const float *gh2, float *gtheta, float *gx, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/*
+ * Fused least-squares step (one pass: forward streams -> residual -> loss partial -> reverse
+ * sweep -> parameter gradient; no activation recompute, no output round trip through HBM).
+ *
+ *   r[n,c] = sum_o ( cy[c,o] * y[n,o] + sum_d cj[c,o,d] * J[n,o,d] + cl[c,o] * lap[n,o] )
+ *            - target[n,c]                                   c = 0 .. n_res-1  (<= 4)
+ *   loss   = scale * sum_{n,c} r[n,c]^2          (scale = 1/(N*n_res) gives torch.mean)
+ *
+ * loss_out[0] += loss (device scalar, accumulated), gtheta += d loss / d theta.
+ * coef = { cy (n_res x O), cj (n_res x O x D), cl (n_res x O) } packed host floats.
+ */
+int insr_siren_lsq_step(const insr_siren_desc *desc, const float *theta, const float *x,
+                        int64_t n_points, int order, int n_res, const float *coef_host,
+                        const float *target, float scale, float *loss_out, float *gtheta,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* introspection used by bench.py / tests: which kernel family a call would dispatch to.
+ * returns 0 = generic, 1 = fused resident-weights kernel; negative = error. */
+int insr_siren_kernel_family(const insr_siren_desc *desc, int order, int backward);
+
+/* number of kernel launches issued by this library on the calling thread since the last
+ * call with reset != 0 (bench.py's gpu_launches counter) */
+int64_t insr_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSR_B200_H */

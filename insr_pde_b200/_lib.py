@@ -1,0 +1,120 @@
+"""ctypes binding of libinsr_b200.so (the C ABI declared in include/insr_b200.h).
+
+There is exactly one backend: the sm_100a CUDA library built in-tree by ``build.py``.  If it
+is missing and cannot be built, importing the operators fails loudly -- there is no CPU or
+PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libinsr_b200.so")
+
+ORDER_VALUE, ORDER_JAC, ORDER_LAP, ORDER_HESS = 0, 1, 2, 3
+FLAG_FORCE_GENERIC = 1
+
+EXPORTS = [
+    "insr_version", "insr_last_error", "insr_siren_theta_size", "insr_siren_workspace_bytes",
+    "insr_siren_forward", "insr_siren_backward", "insr_siren_lsq_step", "insr_siren_kernel_family",
+    "insr_launch_count",
+]
+
+
+class SirenDesc(ctypes.Structure):
+    _fields_ = [("in_features", ctypes.c_int32), ("out_features", ctypes.c_int32),
+                ("hidden_features", ctypes.c_int32), ("num_hidden_layers", ctypes.c_int32),
+                ("omega", ctypes.c_float), ("flags", ctypes.c_int32)]
+
+
+class InsrError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libinsr_b200 error {code}: {message}")
+        self.code = code
+
+
+_vp, _i64, _i32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t
+_dp = ctypes.POINTER(SirenDesc)
+
+
+class Library:
+    """thin typed wrapper over the shared object"""
+
+    def __init__(self, path):
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
+        c = self.cdll
+        c.insr_version.restype = _i32
+        c.insr_last_error.restype = ctypes.c_char_p
+        c.insr_siren_theta_size.restype = _i64
+        c.insr_siren_theta_size.argtypes = [_dp]
+        c.insr_siren_workspace_bytes.restype = _sz
+        c.insr_siren_workspace_bytes.argtypes = [_dp, _i64, _i32, _i32]
+        c.insr_siren_forward.restype = _i32
+        c.insr_siren_forward.argtypes = [_dp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]
+        c.insr_siren_backward.restype = _i32
+        c.insr_siren_backward.argtypes = [_dp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
+        c.insr_siren_lsq_step.restype = _i32
+        c.insr_siren_lsq_step.argtypes = [_dp, _vp, _vp, _i64, _i32, _i32, ctypes.POINTER(ctypes.c_float),
+                                          _vp, ctypes.c_float, _vp, _vp, _vp, _sz, _vp]
+        c.insr_siren_kernel_family.restype = _i32
+        c.insr_siren_kernel_family.argtypes = [_dp, _i32, _i32]
+        c.insr_launch_count.restype = _i64
+        c.insr_launch_count.argtypes = [_i32]
+
+    def check(self, rc):
+        if rc != 0:
+            raise InsrError(rc, (self.cdll.insr_last_error() or b"").decode())
+
+    def version(self):
+        return self.cdll.insr_version()
+
+    def theta_size(self, desc):
+        return int(self.cdll.insr_siren_theta_size(ctypes.byref(desc)))
+
+    def workspace_bytes(self, desc, n, order, backward):
+        return int(self.cdll.insr_siren_workspace_bytes(ctypes.byref(desc), n, order, int(backward)))
+
+    def kernel_family(self, desc, order, backward):
+        return int(self.cdll.insr_siren_kernel_family(ctypes.byref(desc), order, int(backward)))
+
+    def launch_count(self, reset=False):
+        return int(self.cdll.insr_launch_count(int(reset)))
+
+    def forward(self, desc, theta, x, n, order, y, jac, h2, ws, ws_bytes, stream):
+        self.check(self.cdll.insr_siren_forward(ctypes.byref(desc), theta, x, n, order, y, jac, h2,
+                                                ws, ws_bytes, stream))
+
+    def backward(self, desc, theta, x, n, order, gy, gjac, gh2, gtheta, gx, ws, ws_bytes, stream):
+        self.check(self.cdll.insr_siren_backward(ctypes.byref(desc), theta, x, n, order, gy, gjac, gh2,
+                                                 gtheta, gx, ws, ws_bytes, stream))
+
+    def lsq_step(self, desc, theta, x, n, order, n_res, coef, target, scale, loss_out, gtheta, ws,
+                 ws_bytes, stream):
+        arr = (ctypes.c_float * len(coef))(*coef)
+        self.check(self.cdll.insr_siren_lsq_step(ctypes.byref(desc), theta, x, n, order, n_res, arr, target,
+                                                 scale, loss_out, gtheta, ws, ws_bytes, stream))
+
+
+_LIB = None
+_LOCK = threading.Lock()
+
+
+def get_lib() -> Library:
+    """the one and only backend; builds it in-tree on first use if nvcc is available."""
+    global _LIB
+    if _LIB is None:
+        with _LOCK:
+            if _LIB is None:
+                if not os.path.exists(LIB_PATH):
+                    from . import build
+                    build.build_library()
+                _LIB = Library(LIB_PATH)
+    return _LIB
+
+
+def make_desc(in_features, out_features, hidden_features, num_hidden_layers, omega=30.0, flags=0):
+    return SirenDesc(int(in_features), int(out_features), int(hidden_features), int(num_hidden_layers),
+                     float(omega), int(flags))

@@ -1,0 +1,265 @@
+// insr_abi.cu -- the extern "C" boundary of libinsr_b200.so (see include/insr_b200.h).
+//
+// Argument validation, kernel-family dispatch and launch bookkeeping.  No allocation, no
+// synchronisation, no state kept between calls except thread-local error text / counters.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "insr_b200.h"
+#include "siren_generic.cuh"
+#include "siren_fused.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int64_t g_launches = 0;
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_cuda(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+int validate(const insr_siren_desc *d, int64_t N, int order, SirenDims *dm) {
+    if (!d) return fail(INSR_ERR_NULL, "desc is NULL");
+    if (d->in_features < 1 || d->in_features > INSR_MAX_IN)
+        return fail(INSR_ERR_SHAPE, "in_features=%d outside [1,%d]", d->in_features, INSR_MAX_IN);
+    if (d->out_features < 1 || d->out_features > INSR_MAX_OUT)
+        return fail(INSR_ERR_SHAPE, "out_features=%d outside [1,%d]", d->out_features, INSR_MAX_OUT);
+    if (d->hidden_features < 1 || d->hidden_features > INSR_MAX_HIDDEN)
+        return fail(INSR_ERR_SHAPE, "hidden_features=%d outside [1,%d]", d->hidden_features, INSR_MAX_HIDDEN);
+    if (d->num_hidden_layers < 0 || d->num_hidden_layers > INSR_MAX_LAYERS)
+        return fail(INSR_ERR_SHAPE, "num_hidden_layers=%d outside [0,%d]", d->num_hidden_layers, INSR_MAX_LAYERS);
+    if (N < 0 || N > ((int64_t)1 << 31) - 1024)
+        return fail(INSR_ERR_SHAPE, "n_points=%lld outside [0, 2^31)", (long long)N);
+    if (order < INSR_ORDER_VALUE || order > INSR_ORDER_HESS)
+        return fail(INSR_ERR_ORDER, "order=%d is not one of 0,1,2,3", order);
+    dm->D = d->in_features; dm->O = d->out_features; dm->H = d->hidden_features;
+    dm->L = d->num_hidden_layers; dm->omega = d->omega;
+    return 0;
+}
+
+int check_device() {
+    static thread_local int cached = -1;
+    if (cached == 1) return 0;
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(INSR_ERR_NO_DEVICE, "no CUDA device");
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10)
+        return fail(INSR_ERR_NO_DEVICE, "libinsr_b200 is built for sm_100a only (device is sm_%d x)", major);
+    cached = 1;
+    return 0;
+}
+
+// number of workspace slots (= resident threads) of the generic kernels
+int generic_slots(int64_t N, size_t bytes_per_slot) {
+    const size_t budget = (size_t)768 << 20;
+    int64_t tmax = (int64_t)(budget / (bytes_per_slot ? bytes_per_slot : 1));
+    if (tmax > 148 * 512) tmax = 148 * 512;
+    if (tmax < 1024) tmax = 1024;
+    int64_t t = ((N + INSR_GEN_THREADS - 1) / INSR_GEN_THREADS) * INSR_GEN_THREADS;
+    if (t > tmax) t = (tmax / INSR_GEN_THREADS) * INSR_GEN_THREADS;
+    if (t < INSR_GEN_THREADS) t = INSR_GEN_THREADS;
+    return (int)t;
+}
+
+size_t generic_ws_bytes(const SirenDims &dm, int64_t N, int order, int backward) {
+    const int S = insr_nstreams(dm.D, order);
+    if (!backward) {
+        const size_t per = (size_t)2 * S * dm.H * sizeof(float);
+        return per * generic_slots(N, per);
+    }
+    const size_t per = insr_gen_bwd_ws_floats(S, dm.H, dm.L, dm.O, 1) * sizeof(float);
+    return per * generic_slots(N, per);
+}
+
+// ---------------------------------------------------------------- generic launches
+template <int D, int O, int ORDER>
+int launch_generic_fwd(const SirenDims &dm, const float *theta, const float *x, int64_t N, float *y,
+                       float *jac, float *h2, float *ws, void *stream) {
+    const int S = StreamCfg<D, ORDER>::S;
+    const int T = generic_slots(N, (size_t)2 * S * dm.H * sizeof(float));
+    auto kfn = k_generic_fwd<D, O, ORDER>;
+    INSR_LAUNCH(kfn, dim3(T / INSR_GEN_THREADS), dim3(INSR_GEN_THREADS), 0, stream, dm, theta, x, N, y,
+                jac, h2, ws, T);
+    ++g_launches;
+    return check_cuda("k_generic_fwd");
+}
+
+template <int D, int O, int ORDER>
+int launch_generic_bwd(const SirenDims &dm, const float *theta, const float *x, int64_t N,
+                       const float *gy, const float *gjac, const float *gh2, float *gtheta, float *gx,
+                       float *ws, void *stream) {
+    typedef StreamCfg<D, ORDER> C;
+    const int S = C::S;
+    const int T = generic_slots(N, insr_gen_bwd_ws_floats(S, dm.H, dm.L, dm.O, 1) * sizeof(float));
+    for (int64_t n0 = 0; n0 < N; n0 += T) {
+        const int nv = (int)((N - n0 < T) ? (N - n0) : T);
+        auto ksweep = k_generic_bwd_sweep<D, O, ORDER>;
+        INSR_LAUNCH(ksweep, dim3((nv + INSR_GEN_THREADS - 1) / INSR_GEN_THREADS), dim3(INSR_GEN_THREADS), 0,
+                    stream, dm, theta, x, N, n0, gy, gjac, gh2, gx, ws, T);
+        ++g_launches;
+        if (dm.L > 0) {
+            const int tiles = (dm.H + 31) / 32;
+            int zsplit = (2 * 148 + tiles * tiles * dm.L - 1) / (tiles * tiles * dm.L);
+            const int zmax = (nv + 255) / 256;
+            if (zsplit > zmax) zsplit = zmax;
+            if (zsplit < 1) zsplit = 1;
+            auto kw = k_generic_wgrad_hidden;
+            INSR_LAUNCH(kw, dim3(tiles, tiles, dm.L * zsplit), dim3(256), 0, stream, dm, S, ws, T, nv,
+                        zsplit, gtheta);
+            ++g_launches;
+        }
+        const int n_elem = dm.H * dm.D + dm.H + dm.O * dm.H + dm.O;
+        auto ke = k_generic_wgrad_edge;
+        INSR_LAUNCH(ke, dim3((n_elem + 7) / 8), dim3(256), 0, stream, dm, S, C::ND, ws, T, nv, x, n0,
+                    gtheta);
+        ++g_launches;
+        int rc = check_cuda("generic backward");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+#define INSR_DISPATCH_DO(D_, O_, ORD_, CALL)                                                     \
+    if (dm.D == D_ && dm.O == O_ && order == ORD_) { constexpr int D = D_, O = O_, ORDER = ORD_;  \
+        (void)D; (void)O; (void)ORDER; return CALL; }
+#define INSR_DISPATCH_O(D_, ORD_, CALL) \
+    INSR_DISPATCH_DO(D_, 1, ORD_, CALL) INSR_DISPATCH_DO(D_, 2, ORD_, CALL) INSR_DISPATCH_DO(D_, 3, ORD_, CALL)
+#define INSR_DISPATCH_ORD(D_, CALL) \
+    INSR_DISPATCH_O(D_, 0, CALL) INSR_DISPATCH_O(D_, 1, CALL) INSR_DISPATCH_O(D_, 2, CALL) INSR_DISPATCH_O(D_, 3, CALL)
+#define INSR_DISPATCH_ALL(CALL) INSR_DISPATCH_ORD(1, CALL) INSR_DISPATCH_ORD(2, CALL) INSR_DISPATCH_ORD(3, CALL)
+
+int generic_forward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
+                    float *y, float *jac, float *h2, float *ws, void *stream) {
+    INSR_DISPATCH_ALL((launch_generic_fwd<D, O, ORDER>(dm, theta, x, N, y, jac, h2, ws, stream)))
+    return fail(INSR_ERR_UNSUPPORTED, "no generic forward kernel for D=%d O=%d order=%d", dm.D, dm.O, order);
+}
+
+int generic_backward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
+                     const float *gy, const float *gjac, const float *gh2, float *gtheta, float *gx,
+                     float *ws, void *stream) {
+    INSR_DISPATCH_ALL((launch_generic_bwd<D, O, ORDER>(dm, theta, x, N, gy, gjac, gh2, gtheta, gx, ws, stream)))
+    return fail(INSR_ERR_UNSUPPORTED, "no generic backward kernel for D=%d O=%d order=%d", dm.D, dm.O, order);
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int insr_version(void) { return INSR_ABI_VERSION; }
+
+const char *insr_last_error(void) { return g_err; }
+
+int64_t insr_launch_count(int reset) {
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int64_t insr_siren_theta_size(const insr_siren_desc *desc) {
+    SirenDims dm;
+    if (validate(desc, 0, 0, &dm)) return 0;
+    return insr_theta_size(dm);
+}
+
+int insr_siren_kernel_family(const insr_siren_desc *desc, int order, int backward) {
+    SirenDims dm;
+    int rc = validate(desc, 0, order, &dm);
+    if (rc) return rc;
+    if (desc->flags & INSR_FLAG_FORCE_GENERIC) return 0;
+    return insr_fused_supported(dm, order, backward) ? 1 : 0;
+}
+
+size_t insr_siren_workspace_bytes(const insr_siren_desc *desc, int64_t n_points, int order, int backward) {
+    SirenDims dm;
+    if (validate(desc, n_points, order, &dm)) return 0;
+    if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_fused_supported(dm, order, backward))
+        return insr_fused_ws_bytes(dm, n_points, order, backward);
+    return generic_ws_bytes(dm, n_points, order, backward);
+}
+
+int insr_siren_forward(const insr_siren_desc *desc, const float *theta, const float *x, int64_t n_points,
+                       int order, float *y, float *jac, float *h2, void *workspace, size_t workspace_bytes,
+                       void *stream) {
+    SirenDims dm;
+    int rc = validate(desc, n_points, order, &dm);
+    if (rc) return rc;
+    if (!theta || !x || !y) return fail(INSR_ERR_NULL, "theta, x and y must not be NULL");
+    if (order >= INSR_ORDER_JAC && !jac) return fail(INSR_ERR_NULL, "jac must not be NULL for order >= 1");
+    if (order >= INSR_ORDER_LAP && !h2) return fail(INSR_ERR_NULL, "h2 must not be NULL for order >= 2");
+    if (!aligned16(theta) || !aligned16(x) || !aligned16(y) || !aligned16(jac) || !aligned16(h2))
+        return fail(INSR_ERR_ALIGN, "all device buffers must be 16-byte aligned");
+    if ((rc = check_device())) return rc;
+    if (n_points == 0) return 0;
+    const size_t need = insr_siren_workspace_bytes(desc, n_points, order, 0);
+    if (need && (!workspace || workspace_bytes < need))
+        return fail(INSR_ERR_WORKSPACE, "forward needs %zu workspace bytes, got %zu", need, workspace_bytes);
+    if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_fused_supported(dm, order, 0)) {
+        rc = insr_fused_forward(dm, order, theta, x, n_points, y, jac, h2, (float *)workspace, stream, &g_launches);
+        if (rc == INSR_ERR_UNSUPPORTED) return fail(rc, "fused forward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
+        if (rc) return rc;
+        return check_cuda("fused forward");
+    }
+    return generic_forward(dm, order, theta, x, n_points, y, jac, h2, (float *)workspace, stream);
+}
+
+int insr_siren_backward(const insr_siren_desc *desc, const float *theta, const float *x, int64_t n_points,
+                        int order, const float *gy, const float *gjac, const float *gh2, float *gtheta,
+                        float *gx, void *workspace, size_t workspace_bytes, void *stream) {
+    SirenDims dm;
+    int rc = validate(desc, n_points, order, &dm);
+    if (rc) return rc;
+    if (!theta || !x || !gtheta) return fail(INSR_ERR_NULL, "theta, x and gtheta must not be NULL");
+    if (!aligned16(theta) || !aligned16(x) || !aligned16(gtheta) || !aligned16(gy) || !aligned16(gjac) ||
+        !aligned16(gh2) || !aligned16(gx))
+        return fail(INSR_ERR_ALIGN, "all device buffers must be 16-byte aligned");
+    if ((rc = check_device())) return rc;
+    if (n_points == 0) return 0;
+    const size_t need = insr_siren_workspace_bytes(desc, n_points, order, 1);
+    if (need && (!workspace || workspace_bytes < need))
+        return fail(INSR_ERR_WORKSPACE, "backward needs %zu workspace bytes, got %zu", need, workspace_bytes);
+    if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_fused_supported(dm, order, 1)) {
+        rc = insr_fused_backward(dm, order, theta, x, n_points, gy, gjac, gh2, gtheta, gx,
+                                 (float *)workspace, stream, &g_launches);
+        if (rc == INSR_ERR_UNSUPPORTED) return fail(rc, "fused backward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
+        if (rc) return rc;
+        return check_cuda("fused backward");
+    }
+    return generic_backward(dm, order, theta, x, n_points, gy, gjac, gh2, gtheta, gx, (float *)workspace, stream);
+}
+
+int insr_siren_lsq_step(const insr_siren_desc *desc, const float *theta, const float *x, int64_t n_points,
+                        int order, int n_res, const float *coef_host, const float *target, float scale,
+                        float *loss_out, float *gtheta, void *workspace, size_t workspace_bytes,
+                        void *stream) {
+    SirenDims dm;
+    int rc = validate(desc, n_points, order, &dm);
+    if (rc) return rc;
+    if (order > INSR_ORDER_LAP) return fail(INSR_ERR_ORDER, "lsq_step supports orders 0..2");
+    if (n_res < 1 || n_res > 4) return fail(INSR_ERR_SHAPE, "n_res=%d outside [1,4]", n_res);
+    if (!theta || !x || !coef_host || !loss_out || !gtheta)
+        return fail(INSR_ERR_NULL, "theta, x, coef_host, loss_out and gtheta must not be NULL");
+    if ((rc = check_device())) return rc;
+    if (n_points == 0) return 0;
+    (void)target; (void)scale; (void)workspace; (void)workspace_bytes; (void)stream;
+    rc = insr_fused_lsq_step(dm, order, n_res, coef_host, theta, x, n_points, target, scale, loss_out,
+                             gtheta, (float *)workspace, workspace_bytes, stream, &g_launches);
+    if (rc == INSR_ERR_UNSUPPORTED)
+        return fail(rc, "lsq_step: no fused kernel for D=%d O=%d H=%d L=%d order=%d", dm.D, dm.O, dm.H, dm.L, order);
+    if (rc) return rc;
+    return check_cuda("fused lsq_step");
+}
+
+}  // extern "C"
