@@ -1,0 +1,146 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs / workspace with the PyTorch caching
+allocator, pass raw device pointers and the current CUDA stream.  PyTorch is plumbing here
+(device memory, streams); all arithmetic happens in libinsr_b200.so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import ORDER_HESS, ORDER_JAC, ORDER_LAP, ORDER_VALUE  # noqa: F401
+
+
+def _require_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError(
+            "insr_pde_b200 runs on CUDA (sm_100a) tensors only; got a tensor on "
+            f"'{t.device}'. There is no CPU fallback.")
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _DeviceGuard:
+    def __init__(self, device):
+        self.g = torch.cuda.device(device) if device.type == "cuda" else None
+
+    def __enter__(self):
+        if self.g is not None:
+            self.g.__enter__()
+
+    def __exit__(self, *a):
+        if self.g is not None:
+            self.g.__exit__(*a)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _workspace(nbytes, device):
+    if nbytes == 0:
+        return None, 0
+    ws = torch.empty(nbytes + 16, dtype=torch.uint8, device=device)
+    return ws, nbytes
+
+
+def _check_input(t, name, shape=None):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    return t
+
+
+def out_shapes(desc, n, order):
+    D, O = desc.in_features, desc.out_features
+    shapes = [(n, O)]
+    if order >= ORDER_JAC:
+        shapes.append((n, O, D))
+    if order == ORDER_LAP:
+        shapes.append((n, O))
+    if order == ORDER_HESS:
+        shapes.append((n, O, D, D))
+    return shapes
+
+
+def siren_forward(desc, theta, x, order):
+    """theta: flat (P,), x: (N, D) -> tuple (y[, jac[, h2]])"""
+    lib = _lib.get_lib()
+    _require_cuda(x)
+    x = _check_input(x, "x")
+    theta = _check_input(theta, "theta")
+    n = x.shape[0]
+    if x.dim() != 2 or x.shape[1] != desc.in_features:
+        raise ValueError(f"x must be (N, {desc.in_features}), got {tuple(x.shape)}")
+    if theta.numel() != lib.theta_size(desc):
+        raise ValueError(f"theta has {theta.numel()} elements, expected {lib.theta_size(desc)}")
+    outs = [torch.empty(s, dtype=torch.float32, device=x.device) for s in out_shapes(desc, n, order)]
+    if n == 0:
+        return tuple(outs)
+    with _DeviceGuard(x.device):
+        ws, nb = _workspace(lib.workspace_bytes(desc, n, order, False), x.device)
+        y = outs[0]
+        jac = outs[1] if order >= ORDER_JAC else None
+        h2 = outs[2] if order >= ORDER_LAP else None
+        lib.forward(desc, theta.data_ptr(), x.data_ptr(), n, order, y.data_ptr(), _ptr(jac), _ptr(h2),
+                    _ptr(ws), nb, _stream(x.device))
+    return tuple(outs)
+
+
+def siren_backward(desc, theta, x, order, gy=None, gjac=None, gh2=None, need_gx=False, gtheta=None):
+    """returns (gtheta flat (P,), gx (N, D) or None).  If ``gtheta`` is given the parameter
+    gradient is accumulated into it (it must be a flat fp32 buffer of P elements)."""
+    lib = _lib.get_lib()
+    _require_cuda(x)
+    x = _check_input(x, "x")
+    theta = _check_input(theta, "theta")
+    n = x.shape[0]
+    shapes = out_shapes(desc, n, order)
+    gy = _check_input(gy, "gy", shapes[0])
+    gjac = _check_input(gjac, "gjac", shapes[1]) if order >= ORDER_JAC else None
+    gh2 = _check_input(gh2, "gh2", shapes[2]) if order >= ORDER_LAP else None
+    if gtheta is None:
+        gtheta = torch.zeros(theta.numel(), dtype=torch.float32, device=x.device)
+    gx = torch.empty_like(x) if need_gx else None
+    if n == 0:
+        return gtheta, gx
+    with _DeviceGuard(x.device):
+        ws, nb = _workspace(lib.workspace_bytes(desc, n, order, True), x.device)
+        lib.backward(desc, theta.data_ptr(), x.data_ptr(), n, order, _ptr(gy), _ptr(gjac), _ptr(gh2),
+                     gtheta.data_ptr(), _ptr(gx), _ptr(ws), nb, _stream(x.device))
+    return gtheta, gx
+
+
+def siren_lsq_step(desc, theta, x, order, coef_y, coef_jac, coef_lap, target, scale, loss_out=None,
+                   gtheta=None):
+    """fused residual + loss + backward (see include/insr_b200.h: insr_siren_lsq_step).
+    coef_y: (R, O), coef_jac: (R, O, D), coef_lap: (R, O) python nested lists / tensors (host)."""
+    lib = _lib.get_lib()
+    _require_cuda(x)
+    x = _check_input(x, "x")
+    theta = _check_input(theta, "theta")
+    n = x.shape[0]
+    D, O = desc.in_features, desc.out_features
+    cy = torch.as_tensor(coef_y, dtype=torch.float32).reshape(-1, O)
+    R = cy.shape[0]
+    cj = torch.zeros(R, O, D) if coef_jac is None else torch.as_tensor(coef_jac, dtype=torch.float32).reshape(R, O, D)
+    cl = torch.zeros(R, O) if coef_lap is None else torch.as_tensor(coef_lap, dtype=torch.float32).reshape(R, O)
+    coef = cy.flatten().tolist() + cj.flatten().tolist() + cl.flatten().tolist()
+    target = _check_input(target, "target", (n, R)) if target is not None else None
+    if loss_out is None:
+        loss_out = torch.zeros(1, dtype=torch.float32, device=x.device)
+    if gtheta is None:
+        gtheta = torch.zeros(theta.numel(), dtype=torch.float32, device=x.device)
+    if n == 0:
+        return loss_out, gtheta
+    with _DeviceGuard(x.device):
+        ws, nb = _workspace(lib.workspace_bytes(desc, n, order, True), x.device)
+        lib.lsq_step(desc, theta.data_ptr(), x.data_ptr(), n, order, R, coef, _ptr(target), float(scale),
+                     loss_out.data_ptr(), gtheta.data_ptr(), _ptr(ws), nb, _stream(x.device))
+    return loss_out, gtheta

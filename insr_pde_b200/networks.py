@@ -1,0 +1,135 @@
+"""Drop-in replacements for base/networks.py:12-100 (``get_network``, ``Sine``, ``MLP`` and the
+sine initialisers) whose forward runs the fused sm_100a SIREN kernels.
+
+Same constructor, same ``forward(coords, weights=None)``, same module tree (so ``state_dict``
+keys stay ``net.{0,2,4,...}.{weight,bias}`` and checkpoints written by base/baseModel.py:137-162
+interchange with the reference), same RNG consumption at construction (the same
+``torch.manual_seed`` gives the same initial weights as the reference).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+from .function import FieldSource, evaluate
+from ._ops import ORDER_VALUE
+
+OMEGA = 30.0
+
+
+def get_network(cfg, in_features, out_features):
+    """base/networks.py:12-17"""
+    if cfg.network == "siren":
+        return MLP(in_features, out_features, cfg.num_hidden_layers, cfg.hidden_features,
+                   nonlinearity=cfg.nonlinearity)
+    raise NotImplementedError
+
+
+class Sine(nn.Module):
+    """base/networks.py:21-27.  Kept in the module tree for state_dict/index compatibility; the
+    fused kernel applies sin(30 z) itself, this module's forward is only used if someone
+    calls ``net.net`` directly."""
+
+    def forward(self, input):
+        return torch.sin(OMEGA * input)
+
+
+def sine_init(m):
+    """base/networks.py:80-85"""
+    with torch.no_grad():
+        if hasattr(m, "weight"):
+            num_input = m.weight.size(-1)
+            m.weight.uniform_(-math.sqrt(6 / num_input) / OMEGA, math.sqrt(6 / num_input) / OMEGA)
+
+
+def first_layer_sine_init(m):
+    """base/networks.py:88-93"""
+    with torch.no_grad():
+        if hasattr(m, "weight"):
+            num_input = m.weight.size(-1)
+            m.weight.uniform_(-1 / num_input, 1 / num_input)
+
+
+class MLP(nn.Module):
+    """SIREN field  Linear(D,H)+sine, L x [Linear(H,H)+sine], Linear(H,O)  (base/networks.py:30-71)
+    evaluated by the fused CUDA kernels.  Only the configuration the reference's configs ever
+    request is on the B200 path: ``nonlinearity='sine'``, ``outermost_linear=True``
+    (config.py:97-100); anything else raises -- there is no second code path."""
+
+    def __init__(self, in_features, out_features, num_hidden_layers, hidden_features,
+                 outermost_linear=True, nonlinearity="relu", weight_init=None):
+        super().__init__()
+        if nonlinearity != "sine" or not outermost_linear:
+            raise NotImplementedError(
+                "insr_pde_b200.MLP implements the SIREN variant only (nonlinearity='sine', "
+                "outermost_linear=True) -- the only one reachable from config.py:97-100")
+        self.first_layer_init = None
+        self.weight_init = weight_init if weight_init is not None else sine_init
+        layers = [nn.Linear(in_features, hidden_features), Sine()]
+        for _ in range(num_hidden_layers):
+            layers += [nn.Linear(hidden_features, hidden_features), Sine()]
+        layers.append(nn.Linear(hidden_features, out_features))
+        self.net = nn.Sequential(*layers)
+        self.net.apply(self.weight_init)
+        self.net[0].apply(first_layer_sine_init)
+
+        self.in_features, self.out_features = in_features, out_features
+        self.hidden_features, self.num_hidden_layers = hidden_features, num_hidden_layers
+        self.desc = _lib.make_desc(in_features, out_features, hidden_features, num_hidden_layers, OMEGA)
+        self._flat = None
+        self._slices = None
+
+    # ------------------------------------------------------------------ flat parameter view
+    def param_slices(self):
+        """[(offset, numel, shape)] of every parameter inside the flat theta vector
+        (nn.Module.parameters() order = the layout documented in include/insr_b200.h)."""
+        if self._slices is None:
+            off, out = 0, []
+            for p in self.parameters():
+                out.append((off, p.numel(), tuple(p.shape)))
+                off += p.numel()
+            self._slices = out
+        return self._slices
+
+    def flat_theta(self):
+        """One contiguous fp32 buffer aliasing every parameter.  The reference re-homes the
+        parameters every time step (``net.cpu() ... net.cuda()``, base/baseModel.py:146-147) and
+        copies state dicts between nets (fluid/model.py:64,69), so the aliasing is re-checked
+        on every call and rebuilt when it no longer holds; no device pointer is cached across
+        calls by the native library."""
+        params = list(self.parameters())
+        slices = self.param_slices()
+        flat = self._flat
+        ok = flat is not None and flat.device == params[0].device
+        if ok:
+            base = flat.data_ptr()
+            for p, (off, _, _) in zip(params, slices):
+                if p.data_ptr() != base + 4 * off:
+                    ok = False
+                    break
+        if not ok:
+            with torch.no_grad():
+                flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in params])
+                for p, (off, numel, shape) in zip(params, slices):
+                    p.data = flat[off:off + numel].view(shape)
+            self._flat = flat
+        return flat
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, coords, weights=None):
+        lead = coords.shape[:-1]
+        x2d = coords.reshape(-1, self.in_features)
+        if x2d.dtype != torch.float32:
+            x2d = x2d.float()
+        x2d = x2d.contiguous()
+        y = evaluate(self, x2d, ORDER_VALUE)[0]
+        out = y.reshape(*lead, self.out_features)
+        if torch.is_grad_enabled() and coords.requires_grad:
+            # (the tag deliberately does not hold `out` itself: no tensor <-> attribute cycle)
+            out._insr_source = FieldSource(self, coords, x2d)
+        if weights is not None:
+            out = out * weights
+        return out

@@ -1,0 +1,141 @@
+"""Run the UNMODIFIED reference (main.py, */model.py, base/baseModel.py) on the fused kernels.
+
+``install(reference_root)`` puts the reference tree on sys.path, provides stub modules for
+its optional third-party imports that are absent in this image (plotting / logging / mesh
+I/O -- none is on the hot path), imports ``base`` and rebinds
+
+    base.networks.get_network, base.baseModel.get_network, base.get_network, base.MLP
+    base.diff_ops.{gradient,divergence,laplace,jacobian,hessian} and their re-exports in base
+
+to this package *before* ``advection`` / ``fluid`` / ``elasticity`` bind them by name
+(``from base import gradient, ...``: fluid/model.py:5-6, advection/model.py:5,
+elasticity/model.py:11).  ``run_main(argv)`` then executes the reference's own main.py.
+
+Nothing here touches the kernels; it is the integration shim a maintainer of the reference
+would replace by two import lines.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import runpy
+import sys
+import types
+
+from . import diff_ops, networks
+
+_DIFF_NAMES = ("gradient", "divergence", "laplace", "jacobian", "hessian")
+
+
+class _Sink:
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Sink()
+
+    def __getattr__(self, name):
+        return _Sink()
+
+    def __iter__(self):
+        return iter((_Sink(), _Sink()))
+
+
+def _stub_module(name, **attrs):
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+
+    def _missing(key):
+        if key.startswith("__"):
+            raise AttributeError(key)
+        return _Sink()
+
+    mod.__getattr__ = _missing
+    sys.modules[name] = mod
+    return mod
+
+
+def _ensure_optional_modules():
+    """the reference imports these at module import time; none is used by the hot path"""
+    def have(name):
+        try:
+            importlib.import_module(name)
+            return True
+        except Exception:
+            return False
+
+    if not have("pytorch3d"):
+        p3 = _stub_module("pytorch3d")
+        p3.ops = _stub_module("pytorch3d.ops", knn_points=None, knn_gather=None)
+    if not have("tensorboardX"):
+        _stub_module("tensorboardX", SummaryWriter=_Sink)
+    if not have("matplotlib"):
+        mpl = _stub_module("matplotlib")
+        for sub in ("pyplot", "cm", "colors"):
+            setattr(mpl, sub, _stub_module(f"matplotlib.{sub}"))
+    for name in ("meshio", "open3d"):
+        if not have(name):
+            _stub_module(name)
+
+
+def _shim_torch():
+    """torch >= 2.7 removed ReduceLROnPlateau(verbose=) used at base/baseModel.py:61-62"""
+    import inspect
+    import torch
+
+    sched = torch.optim.lr_scheduler
+    if "verbose" not in inspect.signature(sched.ReduceLROnPlateau.__init__).parameters:
+        base_cls = sched.ReduceLROnPlateau
+
+        class ReduceLROnPlateau(base_cls):
+            def __init__(self, *a, verbose=None, **k):
+                super().__init__(*a, **k)
+
+        sched.ReduceLROnPlateau = ReduceLROnPlateau
+
+
+def install(reference_root: str):
+    """rebind the reference's field + operator layer to the fused implementation; returns the
+    imported ``base`` package."""
+    reference_root = os.path.abspath(reference_root)
+    if not os.path.isfile(os.path.join(reference_root, "base", "networks.py")):
+        raise FileNotFoundError(f"no INSR-PDE tree at {reference_root}")
+    if reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    _ensure_optional_modules()
+    _shim_torch()
+    base = importlib.import_module("base")
+    ref_networks = importlib.import_module("base.networks")
+    ref_model = importlib.import_module("base.baseModel")
+    ref_diff = importlib.import_module("base.diff_ops")
+    for holder in (ref_networks, ref_model, base):
+        holder.get_network = networks.get_network
+    for holder in (ref_networks, base):
+        holder.MLP = networks.MLP
+    for name in _DIFF_NAMES:
+        fn = getattr(diff_ops, name)
+        setattr(ref_diff, name, fn)
+        setattr(ref_networks, name, fn)     # networks.py does ``from .diff_ops import *``
+        setattr(base, name, fn)
+    return base
+
+
+def run_main(argv, reference_root: str):
+    """python main.py <argv>  of the reference, unchanged, on the fused kernels"""
+    install(reference_root)
+    old_argv, old_cwd = sys.argv, os.getcwd()
+    sys.argv = [os.path.join(reference_root, "main.py"), *argv]
+    os.chdir(reference_root)     # config.py:55-57 copies *.py relative to cwd; mesh paths are relative
+    try:
+        runpy.run_path(sys.argv[0], run_name="__main__")
+    finally:
+        sys.argv = old_argv
+        os.chdir(old_cwd)
+
+
+if __name__ == "__main__":
+    root = os.environ.get("INSR_REFERENCE_ROOT")
+    if not root:
+        raise SystemExit("set INSR_REFERENCE_ROOT to the INSR-PDE checkout; usage: "
+                         "python -m insr_pde_b200.patch fluid --tag ... (main.py arguments)")
+    run_main(sys.argv[1:], root)

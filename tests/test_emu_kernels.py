@@ -1,0 +1,101 @@
+"""Kernel sources executed under the host SIMT emulator (tests/emu) and compared with the
+fp64 oracle: catches indexing / layout / synchronisation mistakes in the CUDA code without a
+GPU.  The real parity tests run on the B200 (test_gpu_parity.py)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from insr_pde_b200 import _lib
+from oracle import siren_fwdmode as fm
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def make_theta(rng, D, O, H, L):
+    parts = []
+    for li, (o, i) in enumerate(fm.layer_shapes(D, O, H, L)):
+        bound = 1.0 / i if li == 0 else np.sqrt(6.0 / i) / 30.0
+        parts.append(rng.uniform(-bound, bound, o * i))
+        parts.append(rng.uniform(-1, 1, o) / np.sqrt(i))
+    return np.concatenate(parts).astype(np.float32)
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def run_case(lib, D, O, H, L, N, order, flags=0, seed=0):
+    rng = np.random.default_rng(seed)
+    desc = _lib.make_desc(D, O, H, L, flags=flags)
+    theta = make_theta(rng, D, O, H, L)
+    assert lib.theta_size(desc) == theta.size
+    x = rng.uniform(-1, 1, (N, D)).astype(np.float32)
+    y = np.full((N, O), np.nan, np.float32)
+    jac = np.full((N, O, D), np.nan, np.float32)
+    h2 = np.full((N, O) if order == 2 else (N, O, D, D), np.nan, np.float32)
+    nb = lib.workspace_bytes(desc, N, order, False)
+    ws = np.zeros(nb // 4 + 8, np.float32)
+    lib.forward(desc, ptr(theta), ptr(x), N, order, ptr(y), ptr(jac) if order >= 1 else None,
+                ptr(h2) if order >= 2 else None, ptr(ws), nb, None)
+    ref = fm.forward(theta.astype(np.float64), x.astype(np.float64), D, O, H, L, order)
+    errs = {"y": rel(y, ref["y"])}
+    if order >= 1:
+        errs["jac"] = rel(jac, ref["jac"])
+    if order == 2:
+        errs["lap"] = rel(h2, ref["lap"])
+    if order == 3:
+        errs["hess"] = rel(h2, ref["hess"])
+    gy = rng.standard_normal((N, O)).astype(np.float32)
+    gj = rng.standard_normal((N, O, D)).astype(np.float32)
+    gh = rng.standard_normal(h2.shape).astype(np.float32)
+    gth = np.zeros(theta.size, np.float32)
+    gx = np.full((N, D), np.nan, np.float32)
+    nb = lib.workspace_bytes(desc, N, order, True)
+    ws = np.zeros(nb // 4 + 8, np.float32)
+    lib.backward(desc, ptr(theta), ptr(x), N, order, ptr(gy), ptr(gj) if order >= 1 else None,
+                 ptr(gh) if order >= 2 else None, ptr(gth), ptr(gx), ptr(ws), nb, None)
+    kw = dict(gy=gy)
+    if order >= 1:
+        kw["gjac"] = gj
+    if order == 2:
+        kw["glap"] = gh
+    if order == 3:
+        kw["ghess"] = gh
+    gref, gxref = fm.backward(theta.astype(np.float64), x.astype(np.float64), D, O, H, L, order, **kw)
+    errs["gtheta"] = rel(gth, gref)
+    errs["gx"] = rel(gx, gxref)
+    assert max(errs.values()) < 1e-4, errs
+    return errs
+
+
+GENERIC_CASES = [
+    (2, 1, 32, 3, 150, 2), (1, 1, 20, 2, 70, 1), (2, 2, 32, 3, 130, 0), (3, 3, 66, 3, 40, 1),
+    (2, 2, 68, 3, 40, 3), (3, 1, 24, 5, 33, 3), (2, 1, 8, 0, 50, 2), (2, 1, 130, 1, 40, 2),
+]
+
+
+@pytest.mark.parametrize("case", GENERIC_CASES)
+def test_generic_family_under_emulation(emu_library, case):
+    run_case(emu_library, *case, flags=_lib.FLAG_FORCE_GENERIC)
+
+
+def test_backward_accumulates_and_null_cotangents(emu_library):
+    lib = emu_library
+    rng = np.random.default_rng(3)
+    D, O, H, L, N = 2, 2, 16, 1, 40
+    desc = _lib.make_desc(D, O, H, L, flags=_lib.FLAG_FORCE_GENERIC)
+    theta = make_theta(rng, D, O, H, L)
+    x = rng.uniform(-1, 1, (N, D)).astype(np.float32)
+    gj = rng.standard_normal((N, O, D)).astype(np.float32)
+    nb = lib.workspace_bytes(desc, N, 1, True)
+    ws = np.zeros(nb // 4 + 8, np.float32)
+    g1 = np.zeros(theta.size, np.float32)
+    lib.backward(desc, ptr(theta), ptr(x), N, 1, None, ptr(gj), None, ptr(g1), None, ptr(ws), nb, None)
+    g2 = g1.copy()
+    lib.backward(desc, ptr(theta), ptr(x), N, 1, None, ptr(gj), None, ptr(g2), None, ptr(ws), nb, None)
+    assert rel(g2, 2 * g1) < 1e-5
+    gref, _ = fm.backward(theta.astype(np.float64), x.astype(np.float64), D, O, H, L, 1, gjac=gj)
+    assert rel(g1, gref) < 1e-4

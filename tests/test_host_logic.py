@@ -1,0 +1,181 @@
+"""Host-side logic (drop-in MLP, autograd boundary, diff_ops fast/generic paths, parameter
+aliasing) exercised on CPU tensors with the C-ABI calls routed to the emulation build.
+The arithmetic checked here is the kernel sources' (under emulation) -- the product parity
+tests against the oracle on the real device are in test_gpu_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+import insr_pde_b200 as ib
+from conftest import load_golden
+from oracle import closures, torch_port as tp
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def pair(D, O, H, L, seed=0):
+    torch.manual_seed(seed)
+    ours = ib.MLP(D, O, L, H, nonlinearity="sine")
+    ref = tp.RefMLP(D, O, L, H)
+    ref.load_state_dict(ours.state_dict())
+    return ours, ref
+
+
+def flat_grad(net):
+    return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()])
+
+
+def test_state_dict_keys_and_init_stream_match_reference_layout():
+    torch.manual_seed(5)
+    ours = ib.MLP(2, 1, 3, 32, nonlinearity="sine")
+    assert list(ours.state_dict().keys()) == [f"net.{i}.{k}" for i in (0, 2, 4, 6, 8) for k in ("weight", "bias")]
+    g = load_golden("op_fluid_pres")     # reference MLP built under torch.manual_seed(102)
+    torch.manual_seed(102)
+    again = ib.MLP(2, 1, 3, 32, nonlinearity="sine")
+    assert np.array_equal(again.flat_theta().numpy(), g["theta"])
+    with pytest.raises(NotImplementedError):
+        ib.MLP(2, 1, 3, 32)              # reference default nonlinearity='relu' is not on this path
+
+
+def test_flat_theta_realiases_after_rehoming(emu_backend):
+    net, ref = pair(2, 1, 8, 1)
+    th0 = net.flat_theta()
+    assert all(p.data_ptr() == th0.data_ptr() + 4 * off for p, (off, _, _) in zip(net.parameters(), net.param_slices()))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+    x = torch.rand(10, 2).requires_grad_(True)
+    net(x).sum().backward()
+    opt.step()
+    assert net.flat_theta() is th0 and torch.equal(th0, torch.cat([p.detach().reshape(-1) for p in net.parameters()]))
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net.double().float()                 # re-homes every parameter like net.cpu()/net.cuda() does
+    th1 = net.flat_theta()
+    assert th1 is not th0
+    net.load_state_dict(sd)
+    assert torch.equal(net.flat_theta(), th1)
+    ref.load_state_dict(net.state_dict())
+    assert rel(net(x).detach(), ref(x).detach()) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 20, 2), (2, 2, 32, 3), (2, 1, 32, 3), (3, 3, 12, 2)])
+def test_dropin_diff_ops_fast_and_generic_paths(emu_backend, shape):
+    D, O, H, L = shape
+    net, ref = pair(D, O, H, L, seed=3)
+    torch.manual_seed(1)
+    x = (torch.rand(48, D) * 2 - 1).requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    y, yr = net(x), ref(xr)
+    assert rel(y.detach(), yr.detach()) < 1e-5
+    # fast paths (y is tagged with its source)
+    assert rel(ib.gradient(y, x).detach(), tp.gradient(yr, xr).detach()) < 1e-5
+    assert rel(ib.jacobian(y, x)[0].detach(), tp.jacobian(yr, xr)[0].detach()) < 1e-5
+    assert rel(ib.laplace(y, x).detach(), tp.laplace(yr, xr).detach()) < 2e-5
+    if O == D:
+        assert rel(ib.divergence(y, x).detach(), tp.divergence(yr, xr).detach()) < 1e-5
+    # generic paths: the reference's own autograd.grad calls, through SirenFn's differentiable backward
+    y2 = net(x) * 1.0          # loses the tag
+    assert rel(tp.gradient(y2, x).detach(), tp.gradient(yr, xr).detach()) < 1e-5
+    assert rel(tp.jacobian(y2, x)[0].detach(), tp.jacobian(yr, xr)[0].detach()) < 1e-5
+    assert rel(tp.laplace(y2, x).detach(), tp.laplace(yr, xr).detach()) < 2e-5
+    # parameter gradients of a loss mixing value, first and second derivatives
+    for fast in (True, False):
+        net.zero_grad(); ref.zero_grad()
+        yy = net(x) if fast else net(x) * 1.0
+        ops = ib if fast else tp
+        loss = (yy ** 2).mean() + (ops.gradient(yy, x) ** 2).mean() + 0.1 * (ops.laplace(yy, x) ** 2).mean()
+        loss.backward()
+        yr = ref(xr)
+        lr = (yr ** 2).mean() + (tp.gradient(yr, xr) ** 2).mean() + 0.1 * (tp.laplace(yr, xr) ** 2).mean()
+        lr.backward()
+        assert abs(float(loss) - float(lr)) < 1e-5 * abs(float(lr))
+        assert rel(flat_grad(net), flat_grad(ref)) < 5e-5, fast
+
+
+def test_grid_shaped_coords_and_hessian(emu_backend):
+    net, ref = pair(2, 2, 16, 1, seed=4)
+    grid = ib.sample_uniform(6, 2, flatten=False).requires_grad_(True)      # (6, 6, 2) like fluid/model.py:30-31
+    gr = grid.detach().clone().requires_grad_(True)
+    u, ur = net(grid), ref(gr)
+    assert u.shape == (6, 6, 2)
+    j, st = ib.jacobian(u, grid)
+    jr, _ = tp.jacobian(ur, gr)
+    assert st == 0 and j.shape == (6, 6, 2, 2) and rel(j.detach(), jr.detach()) < 1e-5
+    x3 = torch.rand(1, 20, 2).requires_grad_(True)
+    h, _ = ib.hessian(net(x3), x3)
+    hr, _ = tp.hessian(ref(x3.detach().clone().requires_grad_(True) if False else x3), x3)
+    assert h.shape == (1, 20, 2, 2, 2) and rel(h.detach(), hr.detach()) < 2e-5
+
+
+def test_elasticity_pattern_jacobian_of_net_plus_x(emu_backend):
+    net, ref = pair(2, 2, 16, 2, seed=6)
+    x = (torch.rand(40, 2) * 2 - 1).requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+
+    def energy(n, xx, ops):
+        q = n(xx) + xx
+        F, _ = ops.jacobian(q, xx)
+        s = torch.linalg.svdvals(F)
+        return ((s - 1) ** 2).sum() + 1e1 * ((s.prod(dim=1) - 1) ** 2).sum() + (q ** 2).sum()
+
+    e, er = energy(net, x, ib), energy(ref, xr, tp)
+    e.backward(); er.backward()
+    assert abs(float(e) - float(er)) < 1e-5 * abs(float(er))
+    assert rel(flat_grad(net), flat_grad(ref)) < 5e-5
+
+
+def test_frozen_net_no_grad_and_weights_argument(emu_backend):
+    net, ref = pair(2, 2, 16, 1, seed=7)
+    for p in net.parameters():
+        p.requires_grad_(False)
+    x = torch.rand(9, 2)
+    with torch.no_grad():
+        out = net(x)
+    assert not out.requires_grad and rel(out, ref(x).detach()) < 1e-5
+    w = torch.rand(9, 2)
+    assert rel(net(x, weights=w), (ref(x) * w).detach()) < 1e-5
+    assert net(torch.zeros(0, 2)).shape == (0, 2)
+
+
+def test_fluid_closures_with_dropin_modules(emu_backend):
+    g = load_golden("closure_fluid")
+    dt = float(g["cfg"][0])
+
+    def mk(theta, D, O):
+        n = ib.MLP(D, O, 3, 32, nonlinearity="sine")
+        with torch.no_grad():
+            n.flat_theta().copy_(torch.from_numpy(theta))
+        return n
+
+    vel, prev, pres = mk(g["theta.velocity"], 2, 2), mk(g["theta.velocity_prev"], 2, 2), mk(g["theta.pressure"], 2, 1)
+    for p in prev.parameters():
+        p.requires_grad_(False)
+
+    def s(key, i, name):
+        return torch.from_numpy(g[f"{key}.samples{i}.{name}"]).requires_grad_(True)
+
+    def check(key, loss_dict):
+        vel.zero_grad(); pres.zero_grad()
+        sum(loss_dict.values()).backward()
+        for k, v in loss_dict.items():
+            ref = float(g[f"{key}.loss.{k}"])
+            assert abs(float(v) - ref) < 5e-5 * max(abs(ref), 1e-6), (key, k)
+        for name, net in (("velocity", vel), ("pressure", pres)):
+            gr = g[f"{key}.grad.{name}"]
+            if np.abs(gr).max() > 0:
+                assert rel(flat_grad(net), gr) < 2e-4, (key, name)
+
+    bn = "sample_boundary2D_separate"
+    check("advect_velocity", closures.fluid_advect_velocity(
+        vel, prev, s("advect_velocity", 0, "sample_random"), s("advect_velocity", 1, bn), s("advect_velocity", 2, bn), dt))
+    check("solve_pressure", closures.fluid_solve_pressure(
+        vel, pres, ib, s("solve_pressure", 0, "sample_random"), s("solve_pressure", 1, bn), s("solve_pressure", 2, bn)))
+    check("projection", closures.fluid_projection(
+        vel, prev, pres, ib, s("projection", 0, "sample_random"), s("projection", 1, bn), s("projection", 2, bn)))
+
+
+def test_cpu_tensor_without_backend_patch_is_refused():
+    net = ib.MLP(2, 1, 1, 8, nonlinearity="sine")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.rand(4, 2))
