@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the INSR-PDE hot path on B200.
+
+Metric (BASELINE.json): collocation points / s for SIREN forward + gradient + Laplacian +
+backward.  A "step" is one pass of the hot path over one batch of synthetic collocation
+points: evaluate the field with its Jacobian and Laplacian streams (insr_siren_forward,
+order=LAP), then the reverse sweep for given output cotangents (insr_siren_backward) producing
+the flat parameter gradient; with N > 1 ranks the points are sharded (weights replicated) and
+the per-step parameter gradient is all-reduced with NCCL.
+
+Workload (config.workload): the fluid2Dtlgn pressure network of scripts/fluid2Dtlgn.sh
+(2 -> 1, hidden 32, 3 hidden layers = the `_solve_pressure` closure's operator,
+fluid/model.py:103-125) on `--points` synthetic points per GPU per step (default 2^22, larger
+than L2 together with its outputs and cotangents; the script's own batch is 128^2 = 16384
+points, reported under "script_size").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU)
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (D, O, H, L, order, description)
+    "fluid2Dtlgn.pressure": (2, 1, 32, 3, 2, "fluid2Dtlgn pressure net 2->1 H=32 L=3: y+J+Laplacian fwd + bwd"),
+    "fluid2Dtlgn.velocity": (2, 2, 32, 3, 1, "fluid2Dtlgn velocity net 2->2 H=32 L=3: y+J fwd + bwd"),
+    "advect1D": (1, 1, 20, 2, 1, "advect1D field 1->1 H=20 L=2: y+J fwd + bwd"),
+    "elasticity2Dstretch": (2, 2, 68, 3, 1, "elasticity2Dstretch deformation 2->2 H=68 L=3: y+J fwd + bwd"),
+    "elasticity3Dbunny": (3, 3, 66, 3, 1, "elasticity3Dbunny deformation 3->3 H=66 L=3: y+J fwd + bwd"),
+    "sweep.h64": (2, 1, 64, 3, 2, "synthetic sweep 2->1 H=64 L=3: y+J+Laplacian fwd + bwd"),
+    "sweep.h128": (2, 1, 128, 3, 2, "synthetic sweep 2->1 H=128 L=3: y+J+Laplacian fwd + bwd"),
+    "sweep.h256": (2, 1, 256, 3, 2, "synthetic sweep 2->1 H=256 L=3: y+J+Laplacian fwd + bwd"),
+    "sweep.h512": (2, 1, 512, 5, 2, "synthetic sweep 2->1 H=512 L=5: y+J+Laplacian fwd + bwd"),
+}
+
+
+def flops_fwd_per_point(D, O, H, L, order):
+    """MAC(S) = D*H + S*(L*H^2 + H*O); F_fwd = 2*MAC; F_fwd+bwd = 3*F_fwd"""
+    S = 1 + (D if order >= 1 else 0) + (1 if order == 2 else (D * (D + 1) // 2 if order == 3 else 0))
+    return 2 * (D * H + S * (L * H * H + H * O))
+
+
+def fp32_peak_tflops():
+    sm_mhz, how = 1965.0, "fallback sm_max 1965 MHz"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        sm_mhz, how = float(peaks["sm_max_mhz"]), "MEASURED_PEAKS.json sm_max_mhz"
+    except Exception:
+        pass
+    return 148 * 128 * 2 * sm_mhz * 1e6 / 1e12, how
+
+
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p, self.idx = None, gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # "under load": the upper half of the samples (idle samples before/after the region are lower)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": (max(smax) if smax else None),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_theta(net_shape, device, seed=0):
+    """reference init (sine_init / first_layer_sine_init + default bias init) under manual_seed"""
+    import insr_pde_b200 as ib
+    D, O, H, L = net_shape
+    torch.manual_seed(seed)
+    net = ib.MLP(D, O, L, H, nonlinearity="sine").to(device)
+    return net
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import insr_pde_b200 as ib
+    from insr_pde_b200 import _lib, _ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    D, O, H, L, order, desc_txt = WORKLOADS[args.workload]
+    lib = _lib.get_lib()
+    net = synth_theta((D, O, H, L), dev)
+    theta = net.flat_theta()
+    desc = net.desc
+    P = theta.numel()
+    N = args.points
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = (torch.rand(N, D, generator=gen, device=dev) * 2 - 1).contiguous()
+    cg = torch.Generator(device=dev).manual_seed(4321 + rank)
+    shapes = _ops.out_shapes(desc, N, order)
+    cots = [torch.randn(s, generator=cg, device=dev) / N for s in shapes]
+    gtheta = torch.zeros(P, device=dev)
+
+    def step():
+        outs = _ops.siren_forward(desc, theta, x, order)
+        gtheta.zero_()
+        _ops.siren_backward(desc, theta, x, order, *cots, gtheta=gtheta)
+        if world > 1:
+            dist.all_reduce(gtheta)
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.launch_count(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.launch_count(True) + args.steps * (1 + (1 if world > 1 else 0))   # + zero-fill (+ NCCL)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # sustain the load long enough for the clock sampler when the timed region is short
+    if rank == 0:
+        t_end = time.time() + max(0.0, 1.0 - ms / 1e3)
+        while time.time() < t_end:
+            step()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+    pts_per_s = world * N * args.steps / (ms / 1e3)
+
+    # ---- dominant kernel alone (backward), CUDA events on the launch stream
+    def time_call(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    ws_b = torch.empty(lib.workspace_bytes(desc, N, order, True) + 16, dtype=torch.uint8, device=dev)
+    ws_f = torch.empty(lib.workspace_bytes(desc, N, order, False) + 16, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    outs = [torch.empty(s, device=dev) for s in shapes]
+    optr = [o.data_ptr() for o in outs] + [None] * (3 - len(outs))
+    cptr = [c.data_ptr() for c in cots] + [None] * (3 - len(cots))
+
+    def bwd_only():
+        lib.backward(desc, theta.data_ptr(), x.data_ptr(), N, order, cptr[0], cptr[1], cptr[2], gtheta.data_ptr(),
+                     None, ws_b.data_ptr(), ws_b.numel() - 16, stream)
+
+    def fwd_only():
+        lib.forward(desc, theta.data_ptr(), x.data_ptr(), N, order, optr[0], optr[1], optr[2], ws_f.data_ptr(),
+                    ws_f.numel() - 16, stream)
+
+    reps = max(3, min(args.steps, 20))
+    ms_bwd, ms_fwd = time_call(bwd_only, reps), time_call(fwd_only, reps)
+    f_fwd = flops_fwd_per_point(D, O, H, L, order)
+    peak, peak_how = fp32_peak_tflops()
+    ach_bwd = 2 * f_fwd * N / (ms_bwd / 1e3) / 1e12
+    ach_fwd = f_fwd * N / (ms_fwd / 1e3) / 1e12
+    import math
+    bytes_pt = 4 * (D + 2 * sum(math.prod(s[1:]) for s in shapes))   # x + outputs written + cotangents read
+    hbm, hbm_how = hbm_peak_gbs()
+    roofline = {
+        "bound": "fp32", "kernel": "siren backward (recompute + dgrad + wgrad)",
+        "achieved": round(ach_bwd, 3), "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(ach_bwd / peak, 4),
+        "traffic": None, "peak_source": f"148 SM x 128 lanes x 2 x {peak_how}",
+        "algorithmic_flops_per_point": {"fwd": f_fwd, "bwd": 2 * f_fwd},
+        "ms_per_launch": {"bwd": round(ms_bwd, 4), "fwd": round(ms_fwd, 4)},
+        "fwd_kernel": {"achieved": round(ach_fwd, 3), "frac": round(ach_fwd / peak, 4)},
+        "step_frac": round(3 * f_fwd * N * args.steps / (ms / 1e3) / 1e12 / peak, 4),
+        "hbm": {"algorithmic_bytes_per_point": bytes_pt,
+                "achieved_gbs": round(bytes_pt * N / ((ms_bwd + ms_fwd) / 1e3) / 1e9, 1), "peak_gbs": hbm, "peak_source": hbm_how},
+        "kernel_family": {"fwd": lib.kernel_family(desc, order, False), "bwd": lib.kernel_family(desc, order, True)},
+    }
+
+    # ---- end to end through the public API with HOST buffers (rank-local shard)
+    Ne = args.e2e_points or N
+    xh = (torch.rand(Ne, D) * 2 - 1).pin_memory()
+    th = torch.randn(Ne, 1).pin_memory()
+    grad_host = torch.empty(P).pin_memory()
+
+    def e2e_step():
+        xd = xh.to(dev, non_blocking=True).requires_grad_(True)
+        td = th.to(dev, non_blocking=True)
+        for p in net.parameters():
+            p.grad = None
+        y = net(xd)
+        loss = torch.mean((td - ib.laplace(y, xd)) ** 2) + torch.mean(ib.gradient(y, xd) ** 2) if order == 2 else \
+            torch.mean((y - td) ** 2) + (torch.mean(ib.gradient(y, xd) ** 2) if order >= 1 else 0.0)
+        loss.backward()
+        g = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+        if world > 1:
+            dist.all_reduce(g)
+        grad_host.copy_(g, non_blocking=True)
+        return float(loss)            # device -> host read of the step's result (syncs)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    k_e = max(2, min(args.steps, 10))
+    t0 = time.perf_counter()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(k_e):
+        e2e_step()
+    b.record()
+    barrier()
+    ms_e = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    e2e = {"value": round(world * Ne * k_e / (float(ms_e.item()) / 1e3), 1), "unit": "points/s",
+           "h2d_bytes_per_step": int(xh.numel() * 4 + th.numel() * 4), "d2h_bytes_per_step": int(P * 4 + 4),
+           "points_per_step_per_gpu": Ne, "steps": k_e,
+           "api": "MLP.forward + diff_ops.laplace/gradient + loss.backward() (autograd boundary), pinned host buffers"}
+
+    # ---- the script's own batch size (128^2 points / iteration), launch-latency bound
+    Ns = 16384
+    xs = x[:Ns].contiguous()
+    cs = [c[:Ns].contiguous() for c in cots]
+
+    def small_step():
+        _ops.siren_forward(desc, theta, xs, order)
+        gtheta.zero_()
+        _ops.siren_backward(desc, theta, xs, order, *cs, gtheta=gtheta)
+
+    ms_small = time_call(small_step, 50)
+    script = {"points": Ns, "us_per_step": round(ms_small * 1e3, 2), "points_per_s": round(Ns / (ms_small / 1e3), 1)}
+
+    # ---- CPU baseline (oracle port of the reference algorithm), rank 0, bounded sample
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_reference(args.workload, budget_s=args.cpu_budget)
+
+    if rank == 0:
+        line = {
+            "metric": "collocation points/s (SIREN fwd + grad + Laplacian + bwd)", "value": round(pts_per_s, 1),
+            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc_txt}", "points_per_step_per_gpu": N,
+                       "global_points_per_step": world * N, "params": P,
+                       "parallelism": f"dp{world} (points sharded, weights replicated, NCCL all-reduce of the flat gradient)",
+                       "l2": "inputs + outputs + cotangents per step exceed the 126 MB L2" if N >= (1 << 22) else "flushed by size only if points >= 2^22",
+                       "init": "reference sine init, torch.manual_seed(0); points U[-1,1]^D seed 1234; cotangents randn/N seed 4321"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "script_size": script,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference(workload, budget_s=15.0, n_points=16384, threads=None):
+    """the reference algorithm (oracle.torch_port: nn.Linear + sin(30x) + nested autograd.grad)
+    on the host cores, on a bounded sample of the workload"""
+    from oracle import torch_port as tp
+    D, O, H, L, order, _ = WORKLOADS[workload]
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    torch.manual_seed(0)
+    net = tp.RefMLP(D, O, L, H)
+    x = (torch.rand(n_points, D) * 2 - 1).requires_grad_(True)
+    gy = torch.randn(n_points, O) / n_points
+    gj = torch.randn(n_points, O, D) / n_points
+    gl = torch.randn(n_points, 1) / n_points
+
+    def step():
+        net.zero_grad()
+        y = net(x)
+        loss = (gy * y).sum()
+        if order >= 1:
+            jac, _ = tp.jacobian(y, x)
+            loss = loss + (gj * jac).sum()
+        if order >= 2:
+            loss = loss + (gl * tp.laplace(y, x)).sum()
+        loss.backward()
+
+    step(); step()
+    t0, n = time.perf_counter(), 0
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 200:
+            break
+    return {"value": round(n_points * n / el, 1), "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": f"{n} steps of {n_points} points ({workload}); oracle.torch_port = the reference's algorithm "
+                      f"(nn.Linear + sin(30x) + nested autograd.grad) in torch {torch.__version__} CPU fp32",
+            "ms_per_step": round(el / n * 1e3, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    D, O, H, L, order, desc_txt = WORKLOADS[args.workload]
+    n_points = 16384
+    per_step_budget = 1.0
+    res = cpu_reference(args.workload, budget_s=max(5.0, min(120.0, per_step_budget * (args.steps + args.warmup))),
+                        n_points=n_points)
+    line = {
+        "impl": "reference", "metric": "collocation points/s (SIREN fwd + grad + Laplacian + bwd)",
+        "value": res["value"], "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc_txt}", "points_per_step": n_points,
+                   "note": "reference = Python/PyTorch; its tree cannot travel to the GPU box, so the oracle port of its "
+                           "algorithm is timed on the host cores (bounded sample)"},
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fluid2Dtlgn.pressure", choices=sorted(WORKLOADS))
+    ap.add_argument("--points", type=int, default=1 << 22, help="collocation points per GPU per step")
+    ap.add_argument("--e2e-points", type=int, default=0)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
