@@ -200,9 +200,9 @@ def test_closures_advection_on_device():
     field, prev = _mk(g["theta.field"], 1, 1, 20, 2), _mk(g["theta.field_prev"], 1, 1, 20, 2)
     for p in prev.parameters():
         p.requires_grad_(False)
-    x = dev(g["advect.samples0.sample_random"]).requires_grad_(True) * length / 2     # non-leaf, as advection/model.py:27
     xb = dev(g["advect.samples1.sample_boundary"]) * length / 2
     for ops in (ib, tp):
+        x = dev(g["advect.samples0.sample_random"]).requires_grad_(True) * length / 2     # non-leaf, as advection/model.py:27
         field.zero_grad()
         ld = closures.advect_step(field, prev, ops, x, xb, dt, vel)
         sum(ld.values()).backward()
