@@ -242,3 +242,36 @@ def test_checkpoint_roundtrip_like_base_model(tmp_path):
     ref = tp.RefMLP(2, 2, 3, 32)
     ref.load_state_dict(sd)                      # same keys as the reference module tree
     assert rel(before, ref(x.cpu())) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(2, 1, 32, 3, 5000, 2, 1), (2, 2, 32, 3, 4097, 1, 2), (1, 1, 20, 2, 3000, 1, 1), (2, 2, 32, 2, 777, 0, 2)])
+def test_fused_lsq_step_matches_oracle(case):
+    """insr_siren_lsq_step: loss = scale * sum_{n,c} r^2 and its parameter gradient in ONE kernel"""
+    D, O, H, L, N, order, R = case
+    rng = np.random.default_rng(11)
+    torch.manual_seed(2)
+    net = ib.MLP(D, O, L, H, nonlinearity="sine").cuda()
+    theta = net.flat_theta()
+    x = dev(rng.uniform(-1, 1, (N, D)))
+    cy = rng.standard_normal((R, O)).astype(np.float32)
+    cj = rng.standard_normal((R, O, D)).astype(np.float32) if order >= 1 else np.zeros((R, O, D), np.float32)
+    cl = rng.standard_normal((R, O)).astype(np.float32) if order == 2 else np.zeros((R, O), np.float32)
+    target = rng.standard_normal((N, R)).astype(np.float32)
+    scale = 1.0 / (N * R)
+    loss, gth = _ops.siren_lsq_step(net.desc, theta, x, order, cy, cj, cl, dev(target), scale)
+    th64, x64 = theta.double().cpu().numpy(), x.double().cpu().numpy()
+    out = fm.forward(th64, x64, D, O, H, L, order)
+    r = out["y"] @ cy.T.astype(np.float64) - target
+    kw = {}
+    if order >= 1:
+        r = r + np.einsum("nod,rod->nr", out["jac"], cj.astype(np.float64))
+    if order == 2:
+        r = r + out["lap"] @ cl.T.astype(np.float64)
+    kw["gy"] = 2 * scale * r @ cy.astype(np.float64)
+    if order >= 1:
+        kw["gjac"] = 2 * scale * np.einsum("nr,rod->nod", r, cj.astype(np.float64))
+    if order == 2:
+        kw["glap"] = 2 * scale * r @ cl.astype(np.float64)
+    gref, _ = fm.backward(th64, x64, D, O, H, L, order, **kw)
+    assert abs(float(loss) - scale * (r ** 2).sum()) < 1e-5 * scale * (r ** 2).sum()
+    assert rel(gth, gref) < TOL

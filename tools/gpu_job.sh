@@ -1,0 +1,17 @@
+#!/bin/bash
+# one gpurun call: tests, bench, launch list, one full capture of the top kernel
+mkdir -p gpurun_out
+TAG=${1:-run}
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$TAG.log
+tail -4 gpurun_out/pytest_gpu_$TAG.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+cat gpurun_out/bench_$TAG.json
+if [ "$2" == "ncu" ]; then
+  python tools/prof_one.py --points 1048576 --reps 2 --lsq > gpurun_out/prof_plain_$TAG.log 2>&1 && \
+  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv \
+      python tools/prof_one.py --points 1048576 --reps 2 --lsq > gpurun_out/ncu_list_$TAG.log 2>&1
+  python tools/prof_one.py --points 262144 --reps 1 --lsq > gpurun_out/prof_plain2_$TAG.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:k_fused -c 3 -f -o gpurun_out/prof_$TAG \
+      python tools/prof_one.py --points 262144 --reps 1 --lsq > gpurun_out/ncu_full_$TAG.log 2>&1
+  tail -3 gpurun_out/ncu_list_$TAG.log gpurun_out/ncu_full_$TAG.log
+fi
