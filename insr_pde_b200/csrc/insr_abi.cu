@@ -9,6 +9,17 @@
 #include "insr_b200.h"
 #include "siren_generic.cuh"
 #include "siren_fused.cuh"
+#ifdef INSR_SINGLE_TU   // emulation build: everything in one translation unit
+#define INSR_INST_D 1
+#define INSR_INST_O 1
+#include "siren_fused_inst.cuh"
+#define INSR_INST_D 2
+#define INSR_INST_O 1
+#include "siren_fused_inst.cuh"
+#define INSR_INST_D 2
+#define INSR_INST_O 2
+#include "siren_fused_inst.cuh"
+#endif
 
 namespace {
 

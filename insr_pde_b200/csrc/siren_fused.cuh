@@ -58,9 +58,10 @@ __host__ __device__ inline int off_B(int L, int l) { return L * HP * HP + l * HP
 __host__ __device__ inline int off_W1(int L) { return L * HP * HP + L * HP; }
 __host__ __device__ inline int off_WO(int L) { return off_W1(L) + HP * 4; }
 __host__ __device__ inline int off_BO(int L) { return off_WO(L) + 3 * HP; }
-// per-warp region: A[S*256] | T[(L+1)*(S+1)*256] (bwd only) | XS[32] | G[128]
-__host__ __device__ inline int warp_floats(int S, int L, bool bwd) {
-    return S * 256 + (bwd ? (L + 1) * (S + 1) * 256 : 0) + 32 + 128;
+// per-warp region: A[S*TP*256] | T[(L+1)*(S+1)*256] (bwd only, TP == 1) | XS[32] | G[128]
+// TP = points per lane (a warp tile covers 8*TP points)
+__host__ __device__ inline int warp_floats(int S, int TP, int L, bool bwd) {
+    return S * TP * 256 + (bwd ? (L + 1) * (S + 1) * 256 : 0) + 32 + 128;
 }
 
 // swizzled float offset of element k of a 32-float row whose swizzle key is `key`
@@ -110,13 +111,13 @@ struct WarpSm {
     float *A, *T, *XS, *G;
 };
 
-template <int S>
+template <int S, int TP>
 __device__ inline WarpSm warp_view(float *sm, int L, int warp, bool bwd) {
     WarpSm v;
     v.W = sm; v.Bv = sm + off_B(L, 0); v.W1 = sm + off_W1(L); v.WO = sm + off_WO(L); v.BO = sm + off_BO(L);
-    float *base = sm + ((w_floats(L) + 3) & ~3) + (size_t)warp * warp_floats(S, L, bwd);
+    float *base = sm + ((w_floats(L) + 3) & ~3) + (size_t)warp * warp_floats(S, TP, L, bwd);
     v.A = base;
-    v.T = base + S * 256;
+    v.T = base + S * TP * 256;
     v.XS = v.T + (bwd ? (L + 1) * (S + 1) * 256 : 0);
     v.G = v.XS + 32;
     return v;
@@ -215,63 +216,79 @@ __device__ __forceinline__ void tape_load(const float *Tl, int lane, int h, floa
         tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
     }
 }
-// operand rows [s*8+pg][32] (swizzle key pg): write the lane's neurons 8*jg+4h .. +3 of every stream
-template <int S>
-__device__ __forceinline__ void operand_store(float *buf, int pg, int jg, int h, const float (&a)[S][4]) {
+// operand rows [(s*TP+t)*8+pg][32] (swizzle key pg): write the lane's neurons 8*jg+4h .. +3 of every
+// stream of its point t
+template <int S, int TP = 1>
+__device__ __forceinline__ void operand_store(float *buf, int pg, int jg, int h, const float (&a)[S][4], int t = 0) {
     INSR_PRAGMA_UNROLL
     for (int s = 0; s < S; ++s)
-        sts4(buf + (s * 8 + pg) * HP + ((((2 * jg + h) ^ pg) & 7) << 2), a[s][0], a[s][1], a[s][2], a[s][3]);
+        sts4(buf + ((s * TP + t) * 8 + pg) * HP + ((((2 * jg + h) ^ pg) & 7) << 2), a[s][0], a[s][1], a[s][2], a[s][3]);
 }
 
 // ---- first sine layer (D -> H): tangents are the columns of W1, second order is zero ------
-template <int D, int ORDER, bool STASH>
-__device__ __forceinline__ void layer0(const WarpSm &ws, int lane, const float (&xv)[D]) {
+template <int D, int ORDER, bool STASH, int TP = 1>
+__device__ __forceinline__ void layer0(const WarpSm &ws, int lane, const float (&xv)[TP][D]) {
     typedef StreamCfg<D, ORDER> C;
     const int pg = lane >> 2, jg = lane & 3;
     INSR_PRAGMA_UNROLL
     for (int h = 0; h < 2; ++h) {
-        float z[C::S][4], a[C::S][4], tv[C::S + 1][4];
+        float4 w[4];
         INSR_PRAGMA_UNROLL
-        for (int c = 0; c < 4; ++c) {
-            const float4 w = lds4(ws.W1 + (8 * jg + 4 * h + c) * 4);
-            float acc = w.w;
+        for (int c = 0; c < 4; ++c) w[c] = lds4(ws.W1 + (8 * jg + 4 * h + c) * 4);
+        INSR_PRAGMA_UNROLL
+        for (int t = 0; t < TP; ++t) {
+            float z[C::S][4], a[C::S][4], tv[C::S + 1][4];
             INSR_PRAGMA_UNROLL
-            for (int d = 0; d < D; ++d) acc = fmaf(f4get(w, d), xv[d], acc);
-            z[0][c] = acc;
-            INSR_PRAGMA_UNROLL
-            for (int d = 0; d < C::ND; ++d) z[1 + d][c] = f4get(w, d);
-            if constexpr (ORDER == 2) z[1 + C::ND][c] = 0.f;
+            for (int c = 0; c < 4; ++c) {
+                float acc = w[c].w;
+                INSR_PRAGMA_UNROLL
+                for (int d = 0; d < D; ++d) acc = fmaf(f4get(w[c], d), xv[t][d], acc);
+                z[0][c] = acc;
+                INSR_PRAGMA_UNROLL
+                for (int d = 0; d < C::ND; ++d) z[1 + d][c] = f4get(w[c], d);
+                if constexpr (ORDER == 2) z[1 + C::ND][c] = 0.f;
+            }
+            act4<D, ORDER>(z, a, tv);
+            operand_store<C::S, TP>(ws.A, pg, jg, h, a, t);
+            if (STASH) tape_store<C::S + 1>(ws.T, lane, h, tv);
         }
-        act4<D, ORDER>(z, a, tv);
-        operand_store<C::S>(ws.A, pg, jg, h, a);
-        if (STASH) tape_store<C::S + 1>(ws.T, lane, h, tv);
     }
 }
 
-// ---- forward contraction: acc[i][s] = sum_k W[8jg+i][k] * A[s][pg][k] ---------------------
-template <int S>
-__device__ __forceinline__ void gemm_fwd(const float *Wl, const float *A, int pg, int jg, float (&acc)[8][S]) {
+// ---- forward contraction: acc[t][i][s] = sum_k W[8jg+i][k] * A[s][t][pg][k] -----------------
+// rolled over the 8 chunks of 4 reduction indices: the body (TP*S + 8 LDS.128, 32*TP*S FFMA)
+// stays resident in the instruction cache
+template <int S, int TP>
+__device__ __forceinline__ void gemm_fwd(const float *Wl, const float *A, int pg, int jg, float (&acc)[TP][8][S]) {
     INSR_PRAGMA_UNROLL
-    for (int i = 0; i < 8; ++i)
+    for (int t = 0; t < TP; ++t)
         INSR_PRAGMA_UNROLL
-        for (int s = 0; s < S; ++s) acc[i][s] = 0.f;
-    INSR_PRAGMA_UNROLL
+        for (int i = 0; i < 8; ++i)
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) acc[t][i][s] = 0.f;
+    const float *arow = A + pg * HP;
+    const float *wrow = Wl + (8 * jg) * HP;
+    INSR_PRAGMA_UNROLL_N(unroll 1)
     for (int c = 0; c < 8; ++c) {
-        const float *ap = A + pg * HP + (((c ^ pg) & 7) << 2);
-        const float *wp = Wl + (8 * jg) * HP + (((c ^ jg) & 7) << 2);
-        float4 a[S];
+        const float *ap = arow + (((c ^ pg) & 7) << 2);
+        const float *wp = wrow + (((c ^ jg) & 7) << 2);
+        float4 a[TP][S];
         INSR_PRAGMA_UNROLL
-        for (int s = 0; s < S; ++s) a[s] = lds4(ap + s * 8 * HP);
+        for (int t = 0; t < TP; ++t)
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) a[t][s] = lds4(ap + (s * TP + t) * 8 * HP);
         INSR_PRAGMA_UNROLL
         for (int i = 0; i < 8; ++i) {
             const float4 w = lds4(wp + i * HP);
             INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s) {
-                float t = acc[i][s];
-                t = fmaf(w.x, a[s].x, t); t = fmaf(w.y, a[s].y, t);
-                t = fmaf(w.z, a[s].z, t); t = fmaf(w.w, a[s].w, t);
-                acc[i][s] = t;
-            }
+            for (int t = 0; t < TP; ++t)
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s) {
+                    float v = acc[t][i][s];
+                    v = fmaf(w.x, a[t][s].x, v); v = fmaf(w.y, a[t][s].y, v);
+                    v = fmaf(w.z, a[t][s].z, v); v = fmaf(w.w, a[t][s].w, v);
+                    acc[t][i][s] = v;
+                }
         }
     }
 }
@@ -285,9 +302,10 @@ __device__ __forceinline__ void gemm_dgrad(const float *Wl, const float *Zb, int
         for (int s = 0; s < S; ++s)
             INSR_PRAGMA_UNROLL
             for (int c = 0; c < 4; ++c) ab[h][s][c] = 0.f;
-    INSR_PRAGMA_UNROLL
+    const float *zrow = Zb + pg * HP;
+    INSR_PRAGMA_UNROLL_N(unroll 1)
     for (int c = 0; c < 8; ++c) {            // chunk of 4 reduction indices j = 4c .. 4c+3 (row key c>>1)
-        const float *zp = Zb + pg * HP + (((c ^ pg) & 7) << 2);
+        const float *zp = zrow + (((c ^ pg) & 7) << 2);
         float4 z[S];
         INSR_PRAGMA_UNROLL
         for (int s = 0; s < S; ++s) z[s] = lds4(zp + s * 8 * HP);
@@ -314,126 +332,153 @@ __device__ __forceinline__ void gemm_dgrad(const float *Wl, const float *Zb, int
 template <int S>
 __device__ __forceinline__ void gemm_wgrad(const float *Zb, const float *A, int lane, float (&gw)[4][8], float (&gb)[4]) {
     const int jt = lane >> 2, kt = lane & 3;
-    INSR_PRAGMA_UNROLL
-    for (int r = 0; r < S * 8; ++r) {
-        const int key = r & 7;
-        const float4 z = lds4(Zb + r * HP + (((jt ^ key) & 7) << 2));
-        const float4 a0 = lds4(A + r * HP + ((((2 * kt) ^ key) & 7) << 2));
-        const float4 a1 = lds4(A + r * HP + ((((2 * kt + 1) ^ key) & 7) << 2));
-        const float zz[4] = {z.x, z.y, z.z, z.w};
+    INSR_PRAGMA_UNROLL_N(unroll 1)
+    for (int r0 = 0; r0 < S * 8; r0 += 4) {
         INSR_PRAGMA_UNROLL
-        for (int a = 0; a < 4; ++a) {
-            gw[a][0] = fmaf(zz[a], a0.x, gw[a][0]); gw[a][1] = fmaf(zz[a], a0.y, gw[a][1]);
-            gw[a][2] = fmaf(zz[a], a0.z, gw[a][2]); gw[a][3] = fmaf(zz[a], a0.w, gw[a][3]);
-            gw[a][4] = fmaf(zz[a], a1.x, gw[a][4]); gw[a][5] = fmaf(zz[a], a1.y, gw[a][5]);
-            gw[a][6] = fmaf(zz[a], a1.z, gw[a][6]); gw[a][7] = fmaf(zz[a], a1.w, gw[a][7]);
-        }
-        if (r < 8 && kt == 0) {     // value-stream rows feed the bias gradient
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = r0 + rr;
+            const int key = rr | (r0 & 4);           // == r & 7
+            const float4 z = lds4(Zb + r * HP + (((jt ^ key) & 7) << 2));
+            const float4 a0 = lds4(A + r * HP + ((((2 * kt) ^ key) & 7) << 2));
+            const float4 a1 = lds4(A + r * HP + ((((2 * kt + 1) ^ key) & 7) << 2));
+            const float zz[4] = {z.x, z.y, z.z, z.w};
             INSR_PRAGMA_UNROLL
-            for (int a = 0; a < 4; ++a) gb[a] += zz[a];
+            for (int a = 0; a < 4; ++a) {
+                gw[a][0] = fmaf(zz[a], a0.x, gw[a][0]); gw[a][1] = fmaf(zz[a], a0.y, gw[a][1]);
+                gw[a][2] = fmaf(zz[a], a0.z, gw[a][2]); gw[a][3] = fmaf(zz[a], a0.w, gw[a][3]);
+                gw[a][4] = fmaf(zz[a], a1.x, gw[a][4]); gw[a][5] = fmaf(zz[a], a1.y, gw[a][5]);
+                gw[a][6] = fmaf(zz[a], a1.z, gw[a][6]); gw[a][7] = fmaf(zz[a], a1.w, gw[a][7]);
+            }
+            if (r0 < 8 && kt == 0) {                 // value-stream rows feed the bias gradient
+                INSR_PRAGMA_UNROLL
+                for (int a = 0; a < 4; ++a) gb[a] += zz[a];
+            }
         }
     }
 }
 
 // ---- hidden sine layers, forward (with optional tape) ---------------------------------------
-template <int D, int ORDER, bool STASH>
+template <int D, int ORDER, bool STASH, int TP = 1>
 __device__ __forceinline__ void hidden_forward(const WarpSm &ws, int L, int lane) {
     typedef StreamCfg<D, ORDER> C;
     constexpr int S = C::S;
     const int pg = lane >> 2, jg = lane & 3;
     INSR_PRAGMA_UNROLL_N(unroll 1)
     for (int l = 0; l < L; ++l) {
-        float acc[8][S];
-        gemm_fwd<S>(ws.W + off_W(l), ws.A, pg, jg, acc);
+        float acc[TP][8][S];
+        gemm_fwd<S, TP>(ws.W + off_W(l), ws.A, pg, jg, acc);
         __syncwarp();                                   // every lane has finished reading A
         INSR_PRAGMA_UNROLL
         for (int h = 0; h < 2; ++h) {
             const float4 b = lds4(ws.Bv + l * HP + 8 * jg + 4 * h);
-            float z[S][4], a[S][4], tv[S + 1][4];
             INSR_PRAGMA_UNROLL
-            for (int c = 0; c < 4; ++c) {
-                z[0][c] = acc[4 * h + c][0] + f4get(b, c);
+            for (int t = 0; t < TP; ++t) {
+                float z[S][4], a[S][4], tv[S + 1][4];
                 INSR_PRAGMA_UNROLL
-                for (int s = 1; s < S; ++s) z[s][c] = acc[4 * h + c][s];
+                for (int c = 0; c < 4; ++c) {
+                    z[0][c] = acc[t][4 * h + c][0] + f4get(b, c);
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 1; s < S; ++s) z[s][c] = acc[t][4 * h + c][s];
+                }
+                act4<D, ORDER>(z, a, tv);
+                operand_store<S, TP>(ws.A, pg, jg, h, a, t);
+                if (STASH) tape_store<S + 1>(ws.T + (l + 1) * (S + 1) * 256, lane, h, tv);
             }
-            act4<D, ORDER>(z, a, tv);
-            operand_store<S>(ws.A, pg, jg, h, a);
-            if (STASH) tape_store<S + 1>(ws.T + (l + 1) * (S + 1) * 256, lane, h, tv);
         }
         __syncwarp();
     }
 }
 
-// ---- output layer: out[o][s] = sum_j WO[o][j] * a_L[s][pg][j] (+ bias on the value stream) --
-template <int O, int S>
-__device__ __forceinline__ void output_forward(const WarpSm &ws, int lane, float (&out)[O][S]) {
+// ---- output layer: out[t][o][s] = sum_j WO[o][j] * a_L[s][t][pg][j] (+ bias on the value stream)
+template <int O, int S, int TP = 1>
+__device__ __forceinline__ void output_forward(const WarpSm &ws, int lane, float (&out)[TP][O][S]) {
     const int pg = lane >> 2, jg = lane & 3;
     INSR_PRAGMA_UNROLL
-    for (int o = 0; o < O; ++o)
+    for (int t = 0; t < TP; ++t)
         INSR_PRAGMA_UNROLL
-        for (int s = 0; s < S; ++s) out[o][s] = 0.f;
+        for (int o = 0; o < O; ++o)
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) out[t][o][s] = 0.f;
     INSR_PRAGMA_UNROLL
     for (int h = 0; h < 2; ++h) {
-        float4 a[S];
         INSR_PRAGMA_UNROLL
-        for (int s = 0; s < S; ++s) a[s] = lds4(ws.A + (s * 8 + pg) * HP + ((((2 * jg + h) ^ pg) & 7) << 2));
-        INSR_PRAGMA_UNROLL
-        for (int o = 0; o < O; ++o) {
-            const float4 w = lds4(ws.WO + o * HP + 8 * jg + 4 * h);
+        for (int t = 0; t < TP; ++t) {
+            float4 a[S];
             INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s) {
-                float t = out[o][s];
-                t = fmaf(w.x, a[s].x, t); t = fmaf(w.y, a[s].y, t);
-                t = fmaf(w.z, a[s].z, t); t = fmaf(w.w, a[s].w, t);
-                out[o][s] = t;
+            for (int s = 0; s < S; ++s)
+                a[s] = lds4(ws.A + ((s * TP + t) * 8 + pg) * HP + ((((2 * jg + h) ^ pg) & 7) << 2));
+            INSR_PRAGMA_UNROLL
+            for (int o = 0; o < O; ++o) {
+                const float4 w = lds4(ws.WO + o * HP + 8 * jg + 4 * h);
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s) {
+                    float v = out[t][o][s];
+                    v = fmaf(w.x, a[s].x, v); v = fmaf(w.y, a[s].y, v);
+                    v = fmaf(w.z, a[s].z, v); v = fmaf(w.w, a[s].w, v);
+                    out[t][o][s] = v;
+                }
             }
         }
     }
     INSR_PRAGMA_UNROLL
-    for (int o = 0; o < O; ++o) {
+    for (int t = 0; t < TP; ++t)
         INSR_PRAGMA_UNROLL
-        for (int s = 0; s < S; ++s) {
-            float t = out[o][s];
-            t += __shfl_xor_sync(0xffffffffu, t, 1);
-            t += __shfl_xor_sync(0xffffffffu, t, 2);
-            out[o][s] = t;
+        for (int o = 0; o < O; ++o) {
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) {
+                float v = out[t][o][s];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                out[t][o][s] = v;
+            }
+            out[t][o][0] += ws.BO[o];
         }
-        out[o][0] += ws.BO[o];
-    }
 }
+
+// points per lane of the forward kernel: 8 x 8 register tiles (TP*S ~ 8 rows x 8 neurons) give
+// >= 4 FFMA per float delivered by shared memory, the balance point of the 128 B/clk LSU pipe
+template <int S> struct FwdTile { static constexpr int TP = (S >= 3) ? 2 : (S == 2 ? 4 : 8); };
+constexpr int FWD_WARPS = 12;
 
 // =============================================================================================
 // forward kernel
 // =============================================================================================
 template <int D, int O, int ORDER>
-__global__ void __launch_bounds__(MAX_WARPS * 32, 2) k_fused_fwd(Params p) {
+__global__ void __launch_bounds__(FWD_WARPS * 32, 1) k_fused_fwd(Params p) {
     typedef StreamCfg<D, ORDER> C;
     constexpr int S = C::S;
+    constexpr int TP = FwdTile<S>::TP;
     INSR_DYN_SMEM(float, sm);
     stage_weights(p, sm);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pg = lane >> 2, jg = lane & 3;
     const int L = p.dm.L;
-    const WarpSm ws = warp_view<S>(sm, L, warp, false);
-    const int64_t ntiles = (p.N + PW - 1) / PW;
+    const WarpSm ws = warp_view<S, TP>(sm, L, warp, false);
+    const int64_t ntiles = (p.N + PW * TP - 1) / (PW * TP);
     const int64_t stride = (int64_t)gridDim.x * p.nwarps;
     for (int64_t tile = (int64_t)blockIdx.x * p.nwarps + warp; tile < ntiles; tile += stride) {
-        const int64_t n = tile * PW + pg;
-        const bool valid = n < p.N;
-        float xv[D];
+        float xv[TP][D];
         INSR_PRAGMA_UNROLL
-        for (int d = 0; d < D; ++d) xv[d] = valid ? __ldg(p.x + n * D + d) : 0.f;
-        layer0<D, ORDER, false>(ws, lane, xv);
-        __syncwarp();
-        hidden_forward<D, ORDER, false>(ws, L, lane);
-        float out[O][S];
-        output_forward<O, S>(ws, lane, out);
-        if (valid) {
-            // the 4 lanes of a point share the stores: lane jg writes output o == jg (O <= 3)
+        for (int t = 0; t < TP; ++t) {
+            const int64_t n = tile * (PW * TP) + t * 8 + pg;
             INSR_PRAGMA_UNROLL
-            for (int o = 0; o < O; ++o)
-                if (jg == o) insr_store_outputs<D, O, ORDER>(n, o, out[o], p.y, p.jac, p.h2);
+            for (int d = 0; d < D; ++d) xv[t][d] = (n < p.N) ? __ldg(p.x + n * D + d) : 0.f;
+        }
+        layer0<D, ORDER, false, TP>(ws, lane, xv);
+        __syncwarp();
+        hidden_forward<D, ORDER, false, TP>(ws, L, lane);
+        float out[TP][O][S];
+        output_forward<O, S, TP>(ws, lane, out);
+        INSR_PRAGMA_UNROLL
+        for (int t = 0; t < TP; ++t) {
+            const int64_t n = tile * (PW * TP) + t * 8 + pg;
+            if (n < p.N) {
+                // the 4 lanes of a point share the stores: lane jg writes output o == jg (O <= 3)
+                INSR_PRAGMA_UNROLL
+                for (int o = 0; o < O; ++o)
+                    if (jg == o) insr_store_outputs<D, O, ORDER>(n, o, out[t][o], p.y, p.jac, p.h2);
+            }
         }
         __syncwarp();                                   // A is rewritten by the next tile
     }
@@ -454,7 +499,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) k_fused_bwd(Params p) {
     const int pg = lane >> 2, jg = lane & 3;     // forward / dgrad ownership
     const int jt = lane >> 2, kt = lane & 3;     // weight-gradient ownership
     const int L = p.dm.L;
-    const WarpSm ws = warp_view<S>(sm, L, warp, true);
+    const WarpSm ws = warp_view<S, 1>(sm, L, warp, true);
 
     // persistent partial sums (registers, whole launch)
     float gw[LMAX_BWD][4][8], gb[LMAX_BWD][4];
@@ -475,23 +520,24 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) k_fused_bwd(Params p) {
     for (int64_t tile = (int64_t)blockIdx.x * p.nwarps + warp; tile < ntiles; tile += stride) {
         const int64_t n = tile * PW + pg;
         const bool valid = n < p.N;
-        float xv[D];
+        float xv[1][D];
         INSR_PRAGMA_UNROLL
-        for (int d = 0; d < D; ++d) xv[d] = valid ? __ldg(p.x + n * D + d) : 0.f;
+        for (int d = 0; d < D; ++d) xv[0][d] = valid ? __ldg(p.x + n * D + d) : 0.f;
         if (jg == 0) {
             INSR_PRAGMA_UNROLL
-            for (int d = 0; d < D; ++d) ws.XS[pg * 4 + d] = xv[d];
+            for (int d = 0; d < D; ++d) ws.XS[pg * 4 + d] = xv[0][d];
         }
         // ---------------- forward with tape
-        layer0<D, ORDER, true>(ws, lane, xv);
+        layer0<D, ORDER, true, 1>(ws, lane, xv);
         __syncwarp();
-        hidden_forward<D, ORDER, true>(ws, L, lane);
+        hidden_forward<D, ORDER, true, 1>(ws, L, lane);
 
         // ---------------- output-layer cotangents g[o][s]
         float g[O][S];
         if constexpr (LSQ) {
-            float out[O][S];
-            output_forward<O, S>(ws, lane, out);
+            float out1[1][O][S];
+            output_forward<O, S, 1>(ws, lane, out1);
+            float (&out)[O][S] = out1[0];
             INSR_PRAGMA_UNROLL
             for (int o = 0; o < O; ++o)
                 INSR_PRAGMA_UNROLL
@@ -559,30 +605,34 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) k_fused_bwd(Params p) {
             }
         }
 
-        // ---------------- reverse sweep through the hidden layers (static unroll: gw[l] are registers)
-        INSR_PRAGMA_UNROLL
-        for (int l = LMAX_BWD; l >= 1; --l) {
-            if (l <= L) {
-                float *Tl = ws.T + l * TV * 256;
-                INSR_PRAGMA_UNROLL
-                for (int h = 0; h < 2; ++h) {
-                    float tv[TV][4];
-                    tape_load<TV>(Tl, lane, h, tv);
-                    adj4<D, ORDER>(tv, ab[h]);
-                }
-                __syncwarp();                           // tape of layer l consumed; A / previous Zb no longer read
-                float *Zb = Tl;                         // zbar operand reuses the tape slot of layer l
-                INSR_PRAGMA_UNROLL
-                for (int h = 0; h < 2; ++h) {
-                    operand_store<S>(Zb, pg, jg, h, ab[h]);
-                    float tv[TV][4], a[S][4];
-                    tape_load<TV>(Tl - TV * 256, lane, h, tv);
-                    a_from_tape4<D, ORDER>(tv, a);
-                    operand_store<S>(ws.A, pg, jg, h, a);   // a_{l-1}: the input of hidden layer l
-                }
-                __syncwarp();
-                gemm_dgrad<S>(ws.W + off_W(l - 1), Zb, pg, jg, ab);
-                gemm_wgrad<S>(Zb, ws.A, lane, gw[l - 1], gb[l - 1]);
+        // ---------------- reverse sweep through the hidden layers.  Runtime loop (small code, resident in
+        // the instruction cache); only the weight-gradient call is switched statically because its
+        // accumulators gw[l] are registers
+        INSR_PRAGMA_UNROLL_N(unroll 1)
+        for (int l = L; l >= 1; --l) {
+            float *Tl = ws.T + l * TV * 256;
+            INSR_PRAGMA_UNROLL
+            for (int h = 0; h < 2; ++h) {
+                float tv[TV][4];
+                tape_load<TV>(Tl, lane, h, tv);
+                adj4<D, ORDER>(tv, ab[h]);
+            }
+            __syncwarp();                               // tape of layer l consumed; A / previous Zb no longer read
+            float *Zb = Tl;                             // zbar operand reuses the tape slot of layer l
+            INSR_PRAGMA_UNROLL
+            for (int h = 0; h < 2; ++h) {
+                operand_store<S>(Zb, pg, jg, h, ab[h]);
+                float tv[TV][4], a[S][4];
+                tape_load<TV>(Tl - TV * 256, lane, h, tv);
+                a_from_tape4<D, ORDER>(tv, a);
+                operand_store<S>(ws.A, pg, jg, h, a);   // a_{l-1}: the input of hidden layer l
+            }
+            __syncwarp();
+            gemm_dgrad<S>(ws.W + off_W(l - 1), Zb, pg, jg, ab);
+            switch (l) {
+                case 1: gemm_wgrad<S>(Zb, ws.A, lane, gw[0], gb[0]); break;
+                case 2: gemm_wgrad<S>(Zb, ws.A, lane, gw[1], gb[1]); break;
+                default: gemm_wgrad<S>(Zb, ws.A, lane, gw[2], gb[2]); break;
             }
         }
         // ---------------- first sine layer
@@ -692,12 +742,12 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) k_fused_bwd(Params p) {
 // =============================================================================================
 inline bool shape_instantiated(int D, int O) { return (D == 1 && O == 1) || (D == 2 && O == 1) || (D == 2 && O == 2); }
 
-inline size_t smem_bytes(int S, int L, bool bwd, int nwarps) {
-    return ((size_t)((w_floats(L) + 3) & ~3) + (size_t)nwarps * warp_floats(S, L, bwd)) * sizeof(float);
+inline size_t smem_bytes(int S, int TP, int L, bool bwd, int nwarps) {
+    return ((size_t)((w_floats(L) + 3) & ~3) + (size_t)nwarps * warp_floats(S, TP, L, bwd)) * sizeof(float);
 }
-inline int pick_warps(int S, int L, bool bwd) {
-    int nw = MAX_WARPS;
-    while (nw > 1 && smem_bytes(S, L, bwd, nw) > SMEM_LIMIT) --nw;
+inline int pick_warps(int S, int TP, int L, bool bwd, int max_warps) {
+    int nw = max_warps;
+    while (nw > 1 && smem_bytes(S, TP, L, bwd, nw) > SMEM_LIMIT) --nw;
     return nw;
 }
 
@@ -715,13 +765,14 @@ inline int sm_count() {
 template <int D, int O, int ORDER>
 int launch_fwd(Params &p, void *stream, int64_t *launches) {
     constexpr int S = StreamCfg<D, ORDER>::S;
-    p.nwarps = MAX_WARPS;
-    const size_t smem = smem_bytes(S, p.dm.L, false, p.nwarps);
+    constexpr int TP = FwdTile<S>::TP;
+    p.nwarps = pick_warps(S, TP, p.dm.L, false, FWD_WARPS);
+    const size_t smem = smem_bytes(S, TP, p.dm.L, false, p.nwarps);
     auto kfn = k_fused_fwd<D, O, ORDER>;
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int64_t tiles = (p.N + PW - 1) / PW;
+    const int64_t tiles = (p.N + PW * TP - 1) / (PW * TP);
     int64_t ctas = (tiles + p.nwarps - 1) / p.nwarps;
-    const int64_t cap = (int64_t)2 * sm_count();
+    const int64_t cap = (int64_t)sm_count();
     if (ctas > cap) ctas = cap;
     INSR_LAUNCH(kfn, dim3((unsigned)ctas), dim3(p.nwarps * 32), smem, stream, p);
     ++*launches;
@@ -731,8 +782,8 @@ int launch_fwd(Params &p, void *stream, int64_t *launches) {
 template <int D, int O, int ORDER, bool LSQ>
 int launch_bwd(Params &p, void *stream, int64_t *launches) {
     constexpr int S = StreamCfg<D, ORDER>::S;
-    p.nwarps = pick_warps(S, p.dm.L, true);
-    const size_t smem = smem_bytes(S, p.dm.L, true, p.nwarps);
+    p.nwarps = pick_warps(S, 1, p.dm.L, true, MAX_WARPS);
+    const size_t smem = smem_bytes(S, 1, p.dm.L, true, p.nwarps);
     auto kfn = k_fused_bwd<D, O, ORDER, LSQ>;
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int64_t tiles = (p.N + PW - 1) / PW;
@@ -742,17 +793,6 @@ int launch_bwd(Params &p, void *stream, int64_t *launches) {
     ++*launches;
     return 0;
 }
-
-#define INSR_FUSED_CASE(D_, O_, ORD_, CALL)                                      \
-    if (p.dm.D == D_ && p.dm.O == O_ && order == ORD_) {                         \
-        constexpr int D = D_, O = O_, ORDER = ORD_;                              \
-        (void)D; (void)O; (void)ORDER;                                           \
-        return CALL;                                                             \
-    }
-#define INSR_FUSED_ALL(CALL)                                                     \
-    INSR_FUSED_CASE(1, 1, 0, CALL) INSR_FUSED_CASE(1, 1, 1, CALL) INSR_FUSED_CASE(1, 1, 2, CALL) \
-    INSR_FUSED_CASE(2, 1, 0, CALL) INSR_FUSED_CASE(2, 1, 1, CALL) INSR_FUSED_CASE(2, 1, 2, CALL) \
-    INSR_FUSED_CASE(2, 2, 0, CALL) INSR_FUSED_CASE(2, 2, 1, CALL) INSR_FUSED_CASE(2, 2, 2, CALL)
 
 }  // namespace insr_fused
 
@@ -765,33 +805,41 @@ inline bool insr_fused_supported(const SirenDims &dm, int order, int backward) {
 
 inline size_t insr_fused_ws_bytes(const SirenDims &, int64_t, int, int) { return 0; }
 
+// one translation unit per (D, O) pair instantiates the kernels (siren_fused_inst.cuh) so that
+// nvcc can build them in parallel; kind: 0 = forward, 1 = backward, 2 = lsq step
+int insr_fused_run_11(int kind, insr_fused::Params &p, int order, void *stream, int64_t *launches);
+int insr_fused_run_21(int kind, insr_fused::Params &p, int order, void *stream, int64_t *launches);
+int insr_fused_run_22(int kind, insr_fused::Params &p, int order, void *stream, int64_t *launches);
+
+inline int insr_fused_run(int kind, insr_fused::Params &p, int order, void *stream, int64_t *launches) {
+    if (p.dm.D == 1 && p.dm.O == 1) return insr_fused_run_11(kind, p, order, stream, launches);
+    if (p.dm.D == 2 && p.dm.O == 1) return insr_fused_run_21(kind, p, order, stream, launches);
+    if (p.dm.D == 2 && p.dm.O == 2) return insr_fused_run_22(kind, p, order, stream, launches);
+    return -6;
+}
+
 inline int insr_fused_forward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
                               float *y, float *jac, float *h2, float *, void *stream, int64_t *launches) {
-    using namespace insr_fused;
-    Params p{};
+    insr_fused::Params p{};
     p.dm = dm; p.theta = theta; p.x = x; p.N = N; p.y = y; p.jac = jac; p.h2 = h2;
-    INSR_FUSED_ALL((launch_fwd<D, O, ORDER>(p, stream, launches)))
-    return -6;
+    return insr_fused_run(0, p, order, stream, launches);
 }
 
 inline int insr_fused_backward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
                                const float *gy, const float *gjac, const float *gh2, float *gtheta, float *gx,
                                float *, void *stream, int64_t *launches) {
-    using namespace insr_fused;
-    Params p{};
+    insr_fused::Params p{};
     p.dm = dm; p.theta = theta; p.x = x; p.N = N; p.gy = gy; p.gjac = gjac; p.gh2 = gh2;
     p.gtheta = gtheta; p.gx = gx;
-    INSR_FUSED_ALL((launch_bwd<D, O, ORDER, false>(p, stream, launches)))
-    return -6;
+    return insr_fused_run(1, p, order, stream, launches);
 }
 
 // coef_host: cy (n_res x O) | cj (n_res x O x D) | cl (n_res x O)  ->  coef[c][o][s]
 inline int insr_fused_lsq_step(const SirenDims &dm, int order, int n_res, const float *coef_host,
                                const float *theta, const float *x, int64_t N, const float *target, float scale,
                                float *loss_out, float *gtheta, float *, size_t, void *stream, int64_t *launches) {
-    using namespace insr_fused;
     if (!insr_fused_supported(dm, order, 1)) return -6;
-    Params p{};
+    insr_fused::Params p{};
     p.dm = dm; p.theta = theta; p.x = x; p.N = N; p.gtheta = gtheta; p.gx = nullptr;
     p.target = target; p.scale = scale; p.loss_out = loss_out; p.n_res = n_res;
     const int D = dm.D, O = dm.O, S = insr_nstreams(D, order);
@@ -804,9 +852,5 @@ inline int insr_fused_lsq_step(const SirenDims &dm, int order, int n_res, const 
                 for (int d = 0; d < D; ++d) dst[1 + d] = cj[(c * O + o) * D + d];
             if (order == 2) dst[1 + D] = cl[c * O + o];
         }
-    {
-        constexpr bool kLsq = true;
-        INSR_FUSED_ALL((launch_bwd<D, O, ORDER, kLsq>(p, stream, launches)))
-    }
-    return -6;
+    return insr_fused_run(2, p, order, stream, launches);
 }

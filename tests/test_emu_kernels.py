@@ -99,3 +99,63 @@ def test_backward_accumulates_and_null_cotangents(emu_library):
     assert rel(g2, 2 * g1) < 1e-5
     gref, _ = fm.backward(theta.astype(np.float64), x.astype(np.float64), D, O, H, L, 1, gjac=gj)
     assert rel(g1, gref) < 1e-4
+
+
+FUSED_CASES = [
+    (2, 1, 32, 3, 70, 2), (2, 1, 32, 3, 8, 0), (1, 1, 20, 2, 100, 1), (2, 2, 32, 3, 45, 1),
+    (2, 2, 20, 1, 30, 2), (1, 1, 7, 3, 19, 2),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_fused_family_under_emulation(emu_library, case):
+    D, O, H, L, N, order = case
+    desc = _lib.make_desc(D, O, H, L)
+    assert emu_library.kernel_family(desc, order, True) == 1 and emu_library.kernel_family(desc, order, False) == 1
+    run_case(emu_library, *case)
+
+
+def test_family_dispatch_rules(emu_library):
+    fam = emu_library.kernel_family
+    assert fam(_lib.make_desc(2, 1, 32, 3), 2, True) == 1
+    assert fam(_lib.make_desc(2, 1, 32, 3, flags=_lib.FLAG_FORCE_GENERIC), 2, True) == 0
+    assert fam(_lib.make_desc(2, 1, 33, 3), 2, True) == 0        # wider than the resident-weights kernel
+    assert fam(_lib.make_desc(2, 1, 32, 4), 2, True) == 0        # deeper than the register-resident gW partials
+    assert fam(_lib.make_desc(2, 1, 32, 4), 2, False) == 1
+    assert fam(_lib.make_desc(2, 1, 32, 3), 3, True) == 0        # full Hessian streams: generic
+    assert fam(_lib.make_desc(3, 3, 32, 3), 1, True) == 0
+
+
+@pytest.mark.parametrize("case", [(2, 1, 32, 3, 50, 2, 1), (2, 2, 32, 3, 37, 1, 2), (1, 1, 20, 2, 64, 1, 1), (2, 2, 32, 2, 20, 0, 2)])
+def test_fused_lsq_step_under_emulation(emu_library, case):
+    lib = emu_library
+    D, O, H, L, N, order, R = case
+    rng = np.random.default_rng(5)
+    desc = _lib.make_desc(D, O, H, L)
+    theta = make_theta(rng, D, O, H, L)
+    x = rng.uniform(-1, 1, (N, D)).astype(np.float32)
+    cy = rng.standard_normal((R, O)).astype(np.float32)
+    cj = rng.standard_normal((R, O, D)).astype(np.float32) if order >= 1 else np.zeros((R, O, D), np.float32)
+    cl = rng.standard_normal((R, O)).astype(np.float32) if order == 2 else np.zeros((R, O), np.float32)
+    target = rng.standard_normal((N, R)).astype(np.float32)
+    scale = 1.0 / (N * R)
+    loss = np.zeros(1, np.float32)
+    gth = np.zeros(theta.size, np.float32)
+    coef = cy.ravel().tolist() + cj.ravel().tolist() + cl.ravel().tolist()
+    lib.lsq_step(desc, ptr(theta), ptr(x), N, order, R, coef, ptr(target), scale, ptr(loss), ptr(gth), None, 0, None)
+    out = fm.forward(theta.astype(np.float64), x.astype(np.float64), D, O, H, L, order)
+    r = out["y"] @ cy.T.astype(np.float64) - target
+    kw = {}
+    if order >= 1:
+        r = r + np.einsum("nod,rod->nr", out["jac"], cj.astype(np.float64))
+    if order == 2:
+        r = r + out["lap"] @ cl.T.astype(np.float64)
+    kw["gy"] = 2 * scale * r @ cy.astype(np.float64)
+    if order >= 1:
+        kw["gjac"] = 2 * scale * np.einsum("nr,rod->nod", r, cj.astype(np.float64))
+    if order == 2:
+        kw["glap"] = 2 * scale * r @ cl.astype(np.float64)
+    gref, _ = fm.backward(theta.astype(np.float64), x.astype(np.float64), D, O, H, L, order, **kw)
+    ref_loss = scale * (r ** 2).sum()
+    assert abs(float(loss[0]) - ref_loss) < 1e-5 * abs(ref_loss)
+    assert rel(gth, gref) < 1e-4

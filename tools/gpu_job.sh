@@ -13,5 +13,5 @@ if [ "$2" == "ncu" ]; then
   python tools/prof_one.py --points 262144 --reps 1 --lsq > gpurun_out/prof_plain2_$TAG.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:k_fused -c 3 -f -o gpurun_out/prof_$TAG \
       python tools/prof_one.py --points 262144 --reps 1 --lsq > gpurun_out/ncu_full_$TAG.log 2>&1
-  tail -3 gpurun_out/ncu_list_$TAG.log gpurun_out/ncu_full_$TAG.log
+  tail -n 3 gpurun_out/ncu_list_$TAG.log; tail -n 3 gpurun_out/ncu_full_$TAG.log
 fi
