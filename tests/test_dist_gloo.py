@@ -1,0 +1,96 @@
+"""world_size-2 gloo test of the data-parallel host logic (CPU): sharded points + one flat
+all-reduce reproduce the single-process gradient and keep replicas identical through Adam."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from insr_pde_b200 import dist as idist
+    from oracle import closures, torch_port as tp
+    torch.set_num_threads(1)
+    r, w = idist.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)                               # identical replicas
+    vel, pres = tp.RefMLP(2, 2, 3, 16), tp.RefMLP(2, 1, 3, 16)
+    g = torch.Generator().manual_seed(7)               # identical GLOBAL sample set on every rank
+    x_all = torch.rand(256, 2, generator=g) * 2 - 1
+    bcx = tp.sample_boundary2D_separate(8, "horizontal")
+    bcy = tp.sample_boundary2D_separate(8, "vertical")
+    dist.broadcast(bcx, 0); dist.broadcast(bcy, 0)
+    opt = torch.optim.Adam(list(vel.parameters()) + list(pres.parameters()), lr=1e-3)
+    reducer = idist.GradAllReducer([vel, pres])
+    reducer.install(opt)
+    for it in range(3):
+        x = idist.shard_points(x_all).clone().requires_grad_(True)
+        assert x.shape[0] == 256 // world
+        loss = closures.fluid_solve_pressure(vel, pres, tp, x, bcx.clone().requires_grad_(True),
+                                             bcy.clone().requires_grad_(True))
+        opt.zero_grad()
+        sum(loss.values()).backward()
+        if it == 0:
+            g_local = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in pres.parameters()]).clone()
+            extra = reducer.allreduce(extra_scalars=torch.stack([v.detach() for v in loss.values()]))
+            g_red = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in pres.parameters()]).clone()
+            np.savez(os.path.join(out_dir, f"rank{rank}.npz"), g_local=g_local.numpy(), g_red=g_red.numpy(),
+                     extra=extra.numpy())
+            opt.zero_grad()
+            sum(closures.fluid_solve_pressure(vel, pres, tp, x, bcx.clone().requires_grad_(True),
+                                              bcy.clone().requires_grad_(True)).values()).backward()
+        opt.step()                                      # pre-hook all-reduces
+    theta = torch.cat([p.detach().reshape(-1) for p in pres.parameters()])
+    np.save(os.path.join(out_dir, f"theta{rank}.npy"), theta.numpy())
+    dist.destroy_process_group()
+
+
+def test_sharded_gradients_match_single_process(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert np.array_equal(r0["g_red"], r1["g_red"]) and np.array_equal(r0["extra"], r1["extra"])
+    assert np.allclose(r0["g_red"], 0.5 * (r0["g_local"] + r1["g_local"]), rtol=1e-5, atol=1e-7)
+    assert not np.allclose(r0["g_local"], r1["g_local"])
+    # replicas stay bit-identical through the optimizer
+    assert np.array_equal(np.load(tmp_path / "theta0.npy"), np.load(tmp_path / "theta1.npy"))
+    # and equal the single-process run on the full batch (the bc terms are identical on every rank)
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import closures, torch_port as tp
+    torch.manual_seed(0)
+    vel, pres = tp.RefMLP(2, 2, 3, 16), tp.RefMLP(2, 1, 3, 16)
+    g = torch.Generator().manual_seed(7)
+    x_all = (torch.rand(256, 2, generator=g) * 2 - 1).requires_grad_(True)
+    # same boundary points as the workers drew (rank 0's draw after manual_seed(0) + net construction)
+    bcx = tp.sample_boundary2D_separate(8, "horizontal").requires_grad_(True)
+    bcy = tp.sample_boundary2D_separate(8, "vertical").requires_grad_(True)
+    loss = closures.fluid_solve_pressure(vel, pres, tp, x_all, bcx, bcy)
+    sum(loss.values()).backward()
+    g_full = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in pres.parameters()]).numpy()
+    assert np.abs(g_full - r0["g_red"]).max() <= 2e-5 * np.abs(g_full).max()
+
+
+def test_shard_partition_is_exact():
+    from insr_pde_b200.sampling import shard
+    x = torch.arange(103 * 2, dtype=torch.float32).reshape(103, 2)
+    for world in (1, 2, 4, 8):
+        parts = [shard(x, r, world) for r in range(world)]
+        assert torch.equal(torch.cat(parts), x)
+        assert max(p.shape[0] for p in parts) - min(p.shape[0] for p in parts) <= 1
