@@ -124,6 +124,57 @@ def synth_theta(net_shape, device, seed=0):
     return net
 
 
+def fluid_timestep_ours(dev, iters, world=1):
+    """seconds per PDE time step of fluid2Dtlgn (fluid/model.py:61-70: advect -> pressure -> projection,
+    `iters` Adam iterations per loop, 128^2 points + 2x162 boundary points per iteration, early stop off)
+    on the fused closures (insr_pde_b200.fused)."""
+    import insr_pde_b200 as ib
+    from insr_pde_b200 import dist as idist, fused
+    torch.manual_seed(0)
+    vel, prev, pres = (ib.MLP(2, o, 3, 32, nonlinearity="sine").to(dev) for o in (2, 2, 1))
+    factory = (lambda nets: idist.GradAllReducer(nets)) if world > 1 else None
+    st = fused.FluidStepper(vel, prev, pres, dt=0.05, sample_resolution=128, lr=1e-4, reducer_factory=factory)
+    st.initialize(fused.taylorgreen_velocity, 20, world)
+    st.step(3, world)                                   # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    h1, h2, h3 = st.step(iters, world)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    return {"sec_per_timestep": round(sec, 4), "iters_per_loop": iters, "loops": 3,
+            "us_per_iteration": round(sec / (3 * iters) * 1e6, 1), "points_per_iteration": 128 * 128,
+            "final_losses": [round(h[-1]["main"], 8) for h in (h1, h2, h3)],
+            "note": "fluid2Dtlgn step on fused lsq closures + torch Adam + ReduceLROnPlateau, host sync per iteration as base/baseModel.py:116"}
+
+
+def fluid_timestep_cpu(iters_measured=3, iters_per_loop=100):
+    """the same time step with the reference algorithm (oracle port) on the host cores; a few
+    iterations per loop are timed and scaled to `iters_per_loop`."""
+    from oracle import closures, torch_port as tp, training
+    torch.manual_seed(0)
+    vel, prev, pres = (tp.RefMLP(2, o, 3, 32) for o in (2, 2, 1))
+    for p in prev.parameters():
+        p.requires_grad_(False)
+
+    def samples():
+        return (tp.sample_random(128 * 128, 2).requires_grad_(True),
+                tp.sample_boundary2D_separate(163, "horizontal").requires_grad_(True),
+                tp.sample_boundary2D_separate(163, "vertical").requires_grad_(True))
+
+    loops = [lambda i: closures.fluid_advect_velocity(vel, prev, *samples(), 0.05),
+             lambda i: closures.fluid_solve_pressure(vel, pres, tp, *samples()),
+             lambda i: closures.fluid_projection(vel, prev, pres, tp, *samples())]
+    per_iter = []
+    for c in loops:
+        training.training_loop(c, [vel, pres], 1, 1e-4)
+        t0 = time.perf_counter()
+        training.training_loop(c, [vel, pres], iters_measured, 1e-4)
+        per_iter.append((time.perf_counter() - t0) / iters_measured)
+    return {"sec_per_timestep": round(sum(per_iter) * iters_per_loop, 3), "iters_per_loop": iters_per_loop,
+            "ms_per_iteration": [round(t * 1e3, 2) for t in per_iter], "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"{iters_measured} timed iterations per loop, scaled to {iters_per_loop}"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     import insr_pde_b200 as ib
@@ -186,13 +237,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    # sustain the load long enough for the clock sampler when the timed region is short
-    if rank == 0:
-        t_end = time.time() + max(0.0, 1.0 - ms / 1e3)
-        while time.time() < t_end:
-            step()
-        torch.cuda.synchronize()
-        clocks = sampler.stop()
+    # sustain the load long enough for the clock sampler when the timed region is short.  The step
+    # contains a collective for N > 1, so EVERY rank runs the same (deterministic) number of extra steps.
+    n_extra = int(max(0.0, 1000.0 - ms) / max(ms / args.steps, 1e-3)) + 1
+    for _ in range(min(n_extra, 2000)):
+        step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     pts_per_s = world * N * args.steps / (ms / 1e3)
 
     # ---- dominant kernel alone (backward), CUDA events on the launch stream
@@ -298,6 +349,13 @@ def run_ours(args):
     ms_small = time_call(small_step, 50)
     script = {"points": Ns, "us_per_step": round(ms_small * 1e3, 2), "points_per_s": round(Ns / (ms_small / 1e3), 1)}
 
+    # ---- seconds per PDE time step (second half of BASELINE.json's metric): fluid2Dtlgn, fixed iterations
+    timestep = None
+    if args.timestep_iters > 0:
+        timestep = fluid_timestep_ours(dev, args.timestep_iters, world)
+        if rank == 0 and not args.no_cpu_baseline:
+            timestep["cpu_reference"] = fluid_timestep_cpu(3, args.timestep_iters)
+
     # ---- CPU baseline (oracle port of the reference algorithm), rank 0, bounded sample
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -315,7 +373,7 @@ def run_ours(args):
                        "l2": "inputs + outputs + cotangents per step exceed the 126 MB L2" if N >= (1 << 22) else "flushed by size only if points >= 2^22",
                        "init": "reference sine init, torch.manual_seed(0); points U[-1,1]^D seed 1234; cotangents randn/N seed 4321"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "script_size": script,
+            "cpu_baseline": cpu, "script_size": script, "timestep": timestep,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -397,6 +455,7 @@ def main():
     ap.add_argument("--e2e-points", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timestep-iters", type=int, default=100, help="Adam iterations per training loop of the fluid2Dtlgn time-step measurement (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -15,7 +15,7 @@
 #define INSR_LAUNCH(kfn, grid, block, smem, stream, ...) \
     kfn<<<(grid), (block), (smem), reinterpret_cast<cudaStream_t>(stream)>>>(__VA_ARGS__)
 #define INSR_DYN_SMEM(type, name) \
-    extern __shared__ __align__(16) unsigned char insr_dyn_smem_raw[]; \
+    extern __shared__ __align__(128) unsigned char insr_dyn_smem_raw[]; \
     type *name = reinterpret_cast<type *>(insr_dyn_smem_raw)
 #define INSR_PRAGMA_UNROLL _Pragma("unroll")
 #define INSR_PRAGMA_UNROLL_N(n) _Pragma(#n)

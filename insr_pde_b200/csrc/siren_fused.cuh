@@ -73,6 +73,25 @@ __device__ __forceinline__ void sts4(float *p, float a, float b, float c, float 
 }
 __device__ __forceinline__ float f4get(const float4 &v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
 
+// explicit shared-memory byte addresses: lets the swizzle be ONE xor on the address and the row
+// offset an immediate of the load (operand buffers are 128-byte aligned, rows are 128 bytes)
+#ifdef INSR_CPU_EMU
+typedef uintptr_t saddr_t;
+__device__ inline saddr_t saddr(const void *p) { return reinterpret_cast<uintptr_t>(p); }
+template <int OFF>
+__device__ inline float4 lds4a(saddr_t a) { return *reinterpret_cast<const float4 *>(a + OFF); }
+#else
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t saddr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+template <int OFF>
+__device__ __forceinline__ float4 lds4a(saddr_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF));
+    return v;
+}
+#endif
+
 // ---- stage all weights into shared memory (omega folded into the sine layers) -----------
 __device__ inline void stage_weights(const Params &p, float *sm) {
     const SirenDims &dm = p.dm;
@@ -115,7 +134,7 @@ template <int S, int TP>
 __device__ inline WarpSm warp_view(float *sm, int L, int warp, bool bwd) {
     WarpSm v;
     v.W = sm; v.Bv = sm + off_B(L, 0); v.W1 = sm + off_W1(L); v.WO = sm + off_WO(L); v.BO = sm + off_BO(L);
-    float *base = sm + ((w_floats(L) + 3) & ~3) + (size_t)warp * warp_floats(S, TP, L, bwd);
+    float *base = sm + ((w_floats(L) + 31) & ~31) + (size_t)warp * warp_floats(S, TP, L, bwd);
     v.A = base;
     v.T = base + S * TP * 256;
     v.XS = v.T + (bwd ? (L + 1) * (S + 1) * 256 : 0);
@@ -328,32 +347,48 @@ __device__ __forceinline__ void gemm_dgrad(const float *Wl, const float *Zb, int
 }
 
 // ---- weight-gradient contraction over the tile's S*8 rows.  lane (jt, kt) = (lane>>2, lane&3)
-// accumulates gw[a][b] += sum_rows Zb[row][4jt+a] * A[row][8kt+b]  and (kt==0) gb[a] += value-stream rows
+// accumulates gw[a][b] += sum_rows Zb[row][4jt+a] * A[row][8kt+b]  and (kt==0) gb[a] += value-stream rows.
+// Row r has swizzle key r&7, so with the row index static inside a group of 8 the swizzle is one xor
+// of an immediate on a lane-constant address and the row offset is an immediate of the load.
+template <int RR, bool BIAS>
+__device__ __forceinline__ void wgrad_row(saddr_t zb, saddr_t ab, bool bias_lane, float (&gw)[4][8], float (&gb)[4]) {
+    const saddr_t za = zb ^ (saddr_t)(RR << 4);
+    const saddr_t aa = ab ^ (saddr_t)(RR << 4);
+    const float4 z = lds4a<RR * 128>(za);
+    const float4 a0 = lds4a<RR * 128>(aa);
+    const float4 a1 = lds4a<RR * 128 + ((RR & 1) ? -16 : 16)>(aa);     // chunk 2kt+1 == (2kt) ^ 1
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+    INSR_PRAGMA_UNROLL
+    for (int a = 0; a < 4; ++a) {
+        gw[a][0] = fmaf(zz[a], a0.x, gw[a][0]); gw[a][1] = fmaf(zz[a], a0.y, gw[a][1]);
+        gw[a][2] = fmaf(zz[a], a0.z, gw[a][2]); gw[a][3] = fmaf(zz[a], a0.w, gw[a][3]);
+        gw[a][4] = fmaf(zz[a], a1.x, gw[a][4]); gw[a][5] = fmaf(zz[a], a1.y, gw[a][5]);
+        gw[a][6] = fmaf(zz[a], a1.z, gw[a][6]); gw[a][7] = fmaf(zz[a], a1.w, gw[a][7]);
+    }
+    if (BIAS) {
+        if (bias_lane) {
+            INSR_PRAGMA_UNROLL
+            for (int a = 0; a < 4; ++a) gb[a] += zz[a];
+        }
+    }
+}
+template <bool BIAS>
+__device__ __forceinline__ void wgrad_rows8(saddr_t zb, saddr_t ab, bool bias_lane, float (&gw)[4][8], float (&gb)[4]) {
+    wgrad_row<0, BIAS>(zb, ab, bias_lane, gw, gb); wgrad_row<1, BIAS>(zb, ab, bias_lane, gw, gb);
+    wgrad_row<2, BIAS>(zb, ab, bias_lane, gw, gb); wgrad_row<3, BIAS>(zb, ab, bias_lane, gw, gb);
+    wgrad_row<4, BIAS>(zb, ab, bias_lane, gw, gb); wgrad_row<5, BIAS>(zb, ab, bias_lane, gw, gb);
+    wgrad_row<6, BIAS>(zb, ab, bias_lane, gw, gb); wgrad_row<7, BIAS>(zb, ab, bias_lane, gw, gb);
+}
 template <int S>
 __device__ __forceinline__ void gemm_wgrad(const float *Zb, const float *A, int lane, float (&gw)[4][8], float (&gb)[4]) {
     const int jt = lane >> 2, kt = lane & 3;
+    saddr_t zb = saddr(Zb) + (saddr_t)(jt << 4);            // chunk jt of row 0 (key 0)
+    saddr_t ab = saddr(A) + (saddr_t)(kt << 5);             // chunk 2kt of row 0
+    wgrad_rows8<true>(zb, ab, kt == 0, gw, gb);             // rows 0..7: the value stream (bias gradient)
     INSR_PRAGMA_UNROLL_N(unroll 1)
-    for (int r0 = 0; r0 < S * 8; r0 += 4) {
-        INSR_PRAGMA_UNROLL
-        for (int rr = 0; rr < 4; ++rr) {
-            const int r = r0 + rr;
-            const int key = rr | (r0 & 4);           // == r & 7
-            const float4 z = lds4(Zb + r * HP + (((jt ^ key) & 7) << 2));
-            const float4 a0 = lds4(A + r * HP + ((((2 * kt) ^ key) & 7) << 2));
-            const float4 a1 = lds4(A + r * HP + ((((2 * kt + 1) ^ key) & 7) << 2));
-            const float zz[4] = {z.x, z.y, z.z, z.w};
-            INSR_PRAGMA_UNROLL
-            for (int a = 0; a < 4; ++a) {
-                gw[a][0] = fmaf(zz[a], a0.x, gw[a][0]); gw[a][1] = fmaf(zz[a], a0.y, gw[a][1]);
-                gw[a][2] = fmaf(zz[a], a0.z, gw[a][2]); gw[a][3] = fmaf(zz[a], a0.w, gw[a][3]);
-                gw[a][4] = fmaf(zz[a], a1.x, gw[a][4]); gw[a][5] = fmaf(zz[a], a1.y, gw[a][5]);
-                gw[a][6] = fmaf(zz[a], a1.z, gw[a][6]); gw[a][7] = fmaf(zz[a], a1.w, gw[a][7]);
-            }
-            if (r0 < 8 && kt == 0) {                 // value-stream rows feed the bias gradient
-                INSR_PRAGMA_UNROLL
-                for (int a = 0; a < 4; ++a) gb[a] += zz[a];
-            }
-        }
+    for (int g = 1; g < S; ++g) {
+        zb += 8 * 128; ab += 8 * 128;
+        wgrad_rows8<false>(zb, ab, false, gw, gb);
     }
 }
 
@@ -686,50 +721,56 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) k_fused_bwd(Params p) {
         __syncwarp();                                   // XS / A / tape are rewritten by the next tile
     }
 
-    // ---------------- CTA reduction of the register partials, then one red.global per parameter
+    // ---------------- CTA reduction of the register partials, then one red.global per parameter.
+    // Deterministic inside the CTA: warps take turns adding their registers into one shared copy
+    // (inside a warp every lane owns distinct parameters, so plain read-modify-write suffices).
     __syncthreads();
     const SirenDims dm = p.dm;
     const int H = dm.H;
     const int P = (int)insr_theta_size(dm);
-    float *red = sm + ((w_floats(L) + 3) & ~3);         // reuse the (now idle) per-warp regions
+    float *red = sm + ((w_floats(L) + 31) & ~31);       // reuse the (now idle) per-warp regions
     for (int i = threadIdx.x; i < P + 1; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
     const float w = dm.omega;
-    INSR_PRAGMA_UNROLL
-    for (int l = 1; l <= LMAX_BWD; ++l) {
-        if (l <= L) {
-            const int wo = (int)insr_w_offset(dm, l), bo = (int)insr_b_offset(dm, l);
+    for (int turn = 0; turn < p.nwarps; ++turn) {
+        if (warp == turn) {
+            INSR_PRAGMA_UNROLL
+            for (int l = 1; l <= LMAX_BWD; ++l) {
+                if (l <= L) {
+                    const int wo = (int)insr_w_offset(dm, l), bo = (int)insr_b_offset(dm, l);
+                    INSR_PRAGMA_UNROLL
+                    for (int a = 0; a < 4; ++a) {
+                        const int j = 4 * jt + a;
+                        if (j < H) {
+                            INSR_PRAGMA_UNROLL
+                            for (int b = 0; b < 8; ++b) {
+                                const int k = 8 * kt + b;
+                                if (k < H) red[wo + j * H + k] += w * gw[l - 1][a][b];
+                            }
+                            if (kt == 0) red[bo + j] += w * gb[l - 1][a];
+                        }
+                    }
+                }
+            }
             INSR_PRAGMA_UNROLL
             for (int a = 0; a < 4; ++a) {
                 const int j = 4 * jt + a;
                 if (j < H) {
-                    INSR_PRAGMA_UNROLL
-                    for (int b = 0; b < 8; ++b) {
-                        const int k = 8 * kt + b;
-                        if (k < H) atomicAdd(red + wo + j * H + k, w * gw[l - 1][a][b]);
-                    }
-                    if (kt == 0) atomicAdd(red + bo + j, w * gb[l - 1][a]);
+                    if (kt == 0) red[(int)insr_b_offset(dm, 0) + j] += w * g1[a];
+                    else if (kt <= D) red[(int)insr_w_offset(dm, 0) + j * D + (kt - 1)] += w * g1[a];
+                    if (kt < O) red[(int)insr_w_offset(dm, L + 1) + kt * H + j] += gwo[a];
                 }
             }
+            if (jt == 0 && kt < O) red[(int)insr_b_offset(dm, L + 1) + kt] += gbo;
+            if (LSQ) {
+                float t = loss_acc;
+                INSR_PRAGMA_UNROLL
+                for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+                if (lane == 0) red[P] += t;
+            }
         }
+        __syncthreads();
     }
-    INSR_PRAGMA_UNROLL
-    for (int a = 0; a < 4; ++a) {
-        const int j = 4 * jt + a;
-        if (j < H) {
-            if (kt == 0) atomicAdd(red + (int)insr_b_offset(dm, 0) + j, w * g1[a]);
-            else if (kt <= D) atomicAdd(red + (int)insr_w_offset(dm, 0) + j * D + (kt - 1), w * g1[a]);
-            if (kt < O) atomicAdd(red + (int)insr_w_offset(dm, L + 1) + kt * H + j, gwo[a]);
-        }
-    }
-    if (jt == 0 && kt < O) atomicAdd(red + (int)insr_b_offset(dm, L + 1) + kt, gbo);
-    if (LSQ) {
-        float t = loss_acc;
-        INSR_PRAGMA_UNROLL
-        for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
-        if (lane == 0) atomicAdd(red + P, t);
-    }
-    __syncthreads();
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         const float v = red[i];
         if (v != 0.f) atomicAdd(p.gtheta + i, v);
@@ -743,7 +784,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) k_fused_bwd(Params p) {
 inline bool shape_instantiated(int D, int O) { return (D == 1 && O == 1) || (D == 2 && O == 1) || (D == 2 && O == 2); }
 
 inline size_t smem_bytes(int S, int TP, int L, bool bwd, int nwarps) {
-    return ((size_t)((w_floats(L) + 3) & ~3) + (size_t)nwarps * warp_floats(S, TP, L, bwd)) * sizeof(float);
+    return ((size_t)((w_floats(L) + 31) & ~31) + (size_t)nwarps * warp_floats(S, TP, L, bwd)) * sizeof(float);
 }
 inline int pick_warps(int S, int TP, int L, bool bwd, int max_warps) {
     int nw = max_warps;

@@ -1,0 +1,217 @@
+"""Fused loss closures: the mean-square residual losses of the advection
+and fluid models evaluated by ``insr_siren_lsq_step`` -- forward streams, residual, loss partial
+and reverse sweep in ONE kernel per term, no autograd graph, no activation recompute, no
+y/J/lap round trip through HBM.  Gradients are accumulated straight into a flat buffer that the
+parameters' ``.grad`` alias, so ``torch.optim.Adam`` (one fused update per net) consumes them
+unchanged.
+
+Each function mirrors one ``@_training_loop`` closure of the reference on EXPLICIT samples and
+returns the same ``loss_dict`` (device scalars):
+
+  advect_initialize      advection/model.py:43-52      advect_step          advection/model.py:68-91
+  fluid_initialize       fluid/model.py:43-52          fluid_advect_velocity fluid/model.py:72-101
+  fluid_solve_pressure   fluid/model.py:103-125        fluid_projection     fluid/model.py:127-151
+
+``TrainingLoop`` restates the caller (base/baseModel.py:55-62, 73-81, 104-134): fresh Adam +
+ReduceLROnPlateau(factor .1, patience 500, min_lr 1e-8) per loop, ``scheduler.step(main)``,
+optional early stop at lr <= 1.1e-8.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _ops
+from ._ops import ORDER_JAC, ORDER_LAP, ORDER_VALUE
+
+
+# ------------------------------------------------------------------------------------------------
+# flat gradient plumbing
+# ------------------------------------------------------------------------------------------------
+def flat_grad(net):
+    """One flat fp32 gradient buffer per net whose slices ARE the parameters' .grad (re-created
+    if an optimizer's zero_grad(set_to_none=True) dropped them or the net moved device)."""
+    theta = net.flat_theta()
+    buf = getattr(net, "_flat_grad", None)
+    ok = buf is not None and buf.device == theta.device and buf.numel() == theta.numel()
+    if ok:
+        for p, (off, numel, shape) in zip(net.parameters(), net.param_slices()):
+            if p.grad is None or p.grad.data_ptr() != buf.data_ptr() + 4 * off:
+                ok = False
+                break
+    if not ok:
+        if buf is None or buf.device != theta.device or buf.numel() != theta.numel():
+            buf = torch.zeros_like(theta)
+            net._flat_grad = buf
+        for p, (off, numel, shape) in zip(net.parameters(), net.param_slices()):
+            p.grad = buf[off:off + numel].view(shape)
+    return buf
+
+
+def zero_grads(*nets):
+    for n in nets:
+        flat_grad(n).zero_()
+
+
+def lsq(net, x, order, cy, cj=None, cl=None, target=None, scale=None):
+    """loss = scale * sum_{n,c} (sum_o cy[c,o] y + cj[c,o,:].J + cl[c,o] lap - target[n,c])^2 ;
+    d loss / d theta is ACCUMULATED into flat_grad(net); returns the loss (1-element tensor)."""
+    x = x.detach().reshape(-1, net.in_features).contiguous()
+    rows = len(cy)
+    if scale is None:
+        scale = 1.0 / (x.shape[0] * rows)
+    if target is not None:
+        target = target.detach().reshape(x.shape[0], rows).contiguous().float()
+    loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+    _ops.siren_lsq_step(net.desc, net.flat_theta(), x, order, cy, cj, cl, target, scale,
+                        loss_out=loss, gtheta=flat_grad(net))
+    return loss[0]
+
+
+def evaluate(net, x, order):
+    """(y[, J[, lap]]) of a (frozen) net without autograd"""
+    x = x.detach().reshape(-1, net.in_features).contiguous()
+    return _ops.siren_forward(net.desc, net.flat_theta(), x, order)
+
+
+def _eye(n):
+    return [[1.0 if i == j else 0.0 for j in range(n)] for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------------
+# advection (1-D, constant velocity)
+# ------------------------------------------------------------------------------------------------
+def advect_initialize(field, samples, init_values):
+    return {"main": lsq(field, samples, ORDER_VALUE, [[1.0]], target=init_values)}
+
+
+def advect_step(field, field_prev, samples, boundary_samples, dt, vel):
+    """midpoint residual  (u - u_prev)/dt + vel (u_x + u_prev_x)/2  and Dirichlet band"""
+    u_prev, j_prev = evaluate(field_prev, samples, ORDER_JAC)
+    target = u_prev / dt - (0.5 * vel) * j_prev[:, :, 0]
+    main = lsq(field, samples, ORDER_JAC, [[1.0 / dt]], cj=[[[0.5 * vel]]], target=target)
+    bc = lsq(field, boundary_samples, ORDER_VALUE, [[1.0]])
+    return {"main": main, "bc": bc}
+
+
+# ------------------------------------------------------------------------------------------------
+# fluid (2-D inviscid Euler, operator splitting)
+# ------------------------------------------------------------------------------------------------
+def _no_slip_bc(velocity, bc_x, bc_y):
+    return lsq(velocity, bc_x, ORDER_VALUE, [[1.0, 0.0]]) + lsq(velocity, bc_y, ORDER_VALUE, [[0.0, 1.0]])
+
+
+def fluid_initialize(velocity, samples, init_values):
+    return {"main": lsq(velocity, samples, ORDER_VALUE, _eye(2), target=init_values)}
+
+
+def fluid_advect_velocity(velocity, velocity_prev, samples, bc_x, bc_y, dt):
+    """semi-Lagrangian: u(x) = u_prev(clamp(x - u_prev(x) dt))"""
+    x = samples.detach().reshape(-1, 2)
+    (u_prev,) = evaluate(velocity_prev, x, ORDER_VALUE)
+    back = torch.clamp(x - u_prev * dt, min=-1.0, max=1.0)
+    (u_adv,) = evaluate(velocity_prev, back, ORDER_VALUE)
+    main = lsq(velocity, x, ORDER_VALUE, _eye(2), target=u_adv)
+    return {"main": main, "bc": _no_slip_bc(velocity, bc_x, bc_y)}
+
+
+def fluid_solve_pressure(velocity, pressure, samples, bc_x, bc_y):
+    """lap p = div u, Neumann band"""
+    _, jac_u = evaluate(velocity, samples, ORDER_JAC)
+    div_u = jac_u[:, 0, 0] + jac_u[:, 1, 1]
+    main = lsq(pressure, samples, ORDER_LAP, [[0.0]], cl=[[1.0]], target=div_u)
+    bc = lsq(pressure, bc_x, ORDER_JAC, [[0.0]], cj=[[[1.0, 0.0]]]) + \
+        lsq(pressure, bc_y, ORDER_JAC, [[0.0]], cj=[[[0.0, 1.0]]])
+    return {"main": main, "bc": bc}
+
+
+def fluid_projection(velocity, velocity_prev, pressure, samples, bc_x, bc_y):
+    """u <- u_prev - grad p"""
+    (u_prev,) = evaluate(velocity_prev, samples, ORDER_VALUE)
+    _, jac_p = evaluate(pressure, samples, ORDER_JAC)
+    target = u_prev - jac_p[:, 0, :]
+    main = lsq(velocity, samples, ORDER_VALUE, _eye(2), target=target)
+    return {"main": main, "bc": _no_slip_bc(velocity, bc_x, bc_y)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the caller: one @_training_loop
+# ------------------------------------------------------------------------------------------------
+class TrainingLoop:
+    """fresh Adam + ReduceLROnPlateau per loop over the nets' parameters (base/baseModel.py:55-62);
+    ``closure(i)`` must accumulate gradients via ``lsq`` and return the loss_dict."""
+
+    def __init__(self, nets, lr, early_stop=False, reducer=None):
+        self.nets = list(nets)
+        self.reducer = reducer
+        self.early_stop = early_stop
+        for n in self.nets:
+            flat_grad(n)
+        self.opt = torch.optim.Adam([{"params": n.parameters(), "lr": lr} for n in self.nets])
+        self.sched = torch.optim.lr_scheduler.ReduceLROnPlateau(self.opt, factor=0.1, min_lr=1e-8, patience=500)
+
+    def run(self, closure, n_iters, on_step=None):
+        hist = []
+        for i in range(n_iters):
+            zero_grads(*self.nets)
+            loss_dict = closure(i)
+            if self.reducer is not None:
+                self.reducer.allreduce()
+            self.opt.step()
+            values = {k: float(v) for k, v in loss_dict.items()}        # host sync, as base/baseModel.py:116
+            self.sched.step(values["main"])
+            hist.append(values)
+            if on_step is not None:
+                on_step(i, values)
+            if self.early_stop and self.opt.param_groups[0]["lr"] <= 1.1e-8:
+                break
+        return hist
+
+
+class FluidStepper:
+    """Fluid2DModel.step (fluid/model.py:61-70) on the fused closures, with the reference's sampling
+    (base/sampling.py) and schedule; used for the seconds-per-timestep measurement."""
+
+    def __init__(self, velocity, velocity_prev, pressure, dt=0.05, sample_resolution=128, lr=1e-4, reducer_factory=None):
+        self.vel, self.prev, self.pres = velocity, velocity_prev, pressure
+        self.dt, self.sr, self.lr = dt, sample_resolution, lr
+        self.reducer_factory = reducer_factory
+        for p in self.prev.parameters():
+            p.requires_grad_(False)
+
+    def _samples(self, n_shard_div=1):
+        from . import sampling
+        dev = next(self.vel.parameters()).device
+        n = self.sr ** 2
+        x = sampling.sample_random(n // n_shard_div, 2, device=dev)
+        bx = sampling.sample_boundary2D_separate(n // 100, "horizontal", device=dev)
+        by = sampling.sample_boundary2D_separate(n // 100, "vertical", device=dev)
+        return x, bx, by
+
+    def _loop(self, nets, closure, n_iters, world=1):
+        red = self.reducer_factory(nets) if self.reducer_factory else None
+        return TrainingLoop(nets, self.lr, reducer=red).run(closure, n_iters)
+
+    def initialize(self, init_fn, n_iters, world=1):
+        def c(i):
+            x, _, _ = self._samples(world)
+            return fluid_initialize(self.vel, x, init_fn(x))
+        return self._loop([self.vel], c, n_iters)
+
+    def step(self, n_iters, world=1):
+        """advect -> pressure solve -> projection; returns the three loss histories"""
+        nets = [self.vel, self.pres]
+        self.prev.load_state_dict(self.vel.state_dict())
+        h1 = self._loop(nets, lambda i: fluid_advect_velocity(self.vel, self.prev, *self._samples(world), self.dt), n_iters)
+        h2 = self._loop(nets, lambda i: fluid_solve_pressure(self.vel, self.pres, *self._samples(world)), n_iters)
+        self.prev.load_state_dict(self.vel.state_dict())
+        h3 = self._loop(nets, lambda i: fluid_projection(self.vel, self.prev, self.pres, *self._samples(world)), n_iters)
+        return h1, h2, h3
+
+
+def taylorgreen_velocity(samples):
+    """fluid/examples.py:17-31 with rescale=True"""
+    px = (samples[..., 0] + 1) * math.pi
+    py = (samples[..., 1] + 1) * math.pi
+    return torch.stack([torch.sin(px) * torch.cos(py) / math.pi, -torch.cos(px) * torch.sin(py) / math.pi], dim=-1)

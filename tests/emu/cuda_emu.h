@@ -74,7 +74,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
                     c.warp_barrier.emplace_back(new std::barrier<>(lanes));
                     c.warp_xchg.emplace_back(32, 0u);
                 }
-                c.dyn_smem.assign(smem + 16, 0);
+                c.dyn_smem.assign(smem + 128, 0);
                 ctx() = &c;
                 std::vector<std::thread> ts;
                 ts.reserve(nthreads);
@@ -96,7 +96,7 @@ inline unsigned linear_tid() {
 }
 inline void *dyn_smem() {
     auto p = reinterpret_cast<uintptr_t>(ctx()->dyn_smem.data());
-    return reinterpret_cast<void *>((p + 15) & ~uintptr_t(15));
+    return reinterpret_cast<void *>((p + 127) & ~uintptr_t(127));
 }
 }  // namespace insr_emu
 

@@ -275,3 +275,19 @@ def test_fused_lsq_step_matches_oracle(case):
     gref, _ = fm.backward(th64, x64, D, O, H, L, order, **kw)
     assert abs(float(loss) - scale * (r ** 2).sum()) < 1e-5 * scale * (r ** 2).sum()
     assert rel(gth, gref) < TOL
+
+
+def test_fused_closures_match_reference_goldens_on_device():
+    from test_host_logic import check_fused_closures_against_goldens
+    check_fused_closures_against_goldens("cuda")
+
+
+def test_fused_stepper_runs_on_device():
+    from insr_pde_b200 import fused
+    torch.manual_seed(0)
+    vel, prev, pres = (ib.MLP(2, o, 3, 32, nonlinearity="sine").cuda() for o in (2, 2, 1))
+    stepper = fused.FluidStepper(vel, prev, pres, dt=0.05, sample_resolution=128, lr=1e-4)
+    h0 = stepper.initialize(fused.taylorgreen_velocity, 50)
+    assert h0[-1]["main"] < h0[0]["main"]
+    h1, h2, h3 = stepper.step(5)
+    assert all(np.isfinite(list(d.values())).all() for d in h1 + h2 + h3)

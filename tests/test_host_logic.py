@@ -179,3 +179,82 @@ def test_cpu_tensor_without_backend_patch_is_refused():
     net = ib.MLP(2, 1, 1, 8, nonlinearity="sine")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         net(torch.rand(4, 2))
+
+
+def _mk_golden_net(theta, D, O, H, L, device="cpu"):
+    n = ib.MLP(D, O, L, H, nonlinearity="sine").to(device)
+    with torch.no_grad():
+        n.flat_theta().copy_(torch.from_numpy(theta).to(device))
+    return n
+
+
+def check_fused_closures_against_goldens(device):
+    """shared with the GPU test: fused lsq closures reproduce the reference closures' loss_dict and gradients"""
+    from insr_pde_b200 import fused
+    g = load_golden("closure_fluid")
+    dt = float(g["cfg"][0])
+    vel = _mk_golden_net(g["theta.velocity"], 2, 2, 32, 3, device)
+    prev = _mk_golden_net(g["theta.velocity_prev"], 2, 2, 32, 3, device)
+    pres = _mk_golden_net(g["theta.pressure"], 2, 1, 32, 3, device)
+
+    def s(key, i, name):
+        return torch.from_numpy(g[f"{key}.samples{i}.{name}"]).to(device)
+
+    def check(key, fn, tol=2e-4):
+        fused.zero_grads(vel, pres)
+        loss_dict = fn()
+        for k, v in loss_dict.items():
+            ref = float(g[f"{key}.loss.{k}"])
+            assert abs(float(v) - ref) < 1e-4 * max(abs(ref), 1e-6), (key, k, float(v), ref)
+        for name, net in (("velocity", vel), ("pressure", pres)):
+            gr = g[f"{key}.grad.{name}"]
+            got = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).cpu().numpy()
+            if np.abs(gr).max() > 0:
+                assert rel(got, gr) < tol, (key, name, rel(got, gr))
+            else:
+                assert np.abs(got).max() == 0
+
+    bn = "sample_boundary2D_separate"
+    x0 = s("initialize", 0, "sample_random")
+    check("initialize", lambda: fused.fluid_initialize(vel, x0, fused.taylorgreen_velocity(x0)))
+    check("advect_velocity", lambda: fused.fluid_advect_velocity(
+        vel, prev, s("advect_velocity", 0, "sample_random"), s("advect_velocity", 1, bn), s("advect_velocity", 2, bn), dt))
+    check("solve_pressure", lambda: fused.fluid_solve_pressure(
+        vel, pres, s("solve_pressure", 0, "sample_random"), s("solve_pressure", 1, bn), s("solve_pressure", 2, bn)))
+    check("projection", lambda: fused.fluid_projection(
+        vel, prev, pres, s("projection", 0, "sample_random"), s("projection", 1, bn), s("projection", 2, bn)))
+
+    g = load_golden("closure_advection")
+    dt, velc, length, sr = (float(v) for v in g["cfg"])
+    field = _mk_golden_net(g["theta.field"], 1, 1, 20, 2, device)
+    fprev = _mk_golden_net(g["theta.field_prev"], 1, 1, 20, 2, device)
+    x = torch.from_numpy(g["initialize.samples0.sample_random"]).to(device) * length / 2
+    fused.zero_grads(field)
+    ld = fused.advect_initialize(field, x, torch.exp(-0.5 * (x + 1.5) ** 2 / 0.01))
+    assert abs(float(ld["main"]) - float(g["initialize.loss.main"])) < 1e-4 * float(g["initialize.loss.main"])
+    assert rel(torch.cat([p.grad.reshape(-1) for p in field.parameters()]).cpu(), g["initialize.grad.field"]) < 2e-4
+    x = torch.from_numpy(g["advect.samples0.sample_random"]).to(device) * length / 2
+    xb = torch.from_numpy(g["advect.samples1.sample_boundary"]).to(device) * length / 2
+    fused.zero_grads(field)
+    ld = fused.advect_step(field, fprev, x, xb, dt, velc)
+    assert abs(float(ld["main"]) - float(g["advect.loss.main"])) < 1e-4 * float(g["advect.loss.main"])
+    assert abs(float(ld["bc"]) - float(g["advect.loss.bc"])) < 1e-4 * float(g["advect.loss.bc"])
+    assert rel(torch.cat([p.grad.reshape(-1) for p in field.parameters()]).cpu(), g["advect.grad.field"]) < 2e-4
+
+
+def test_fused_closures_match_reference_goldens_emulated(emu_backend):
+    check_fused_closures_against_goldens("cpu")
+
+
+def test_fused_training_loop_and_stepper_emulated(emu_backend):
+    from insr_pde_b200 import fused
+    torch.manual_seed(0)
+    vel, prev, pres = (ib.MLP(2, o, 3, 32, nonlinearity="sine") for o in (2, 2, 1))
+    stepper = fused.FluidStepper(vel, prev, pres, dt=0.05, sample_resolution=16, lr=1e-3)
+    h0 = stepper.initialize(fused.taylorgreen_velocity, 6)
+    assert h0[-1]["main"] < h0[0]["main"]                      # Adam on the flat gradient actually descends
+    before = pres.flat_theta().clone()
+    h1, h2, h3 = stepper.step(3)
+    assert len(h1) == len(h2) == len(h3) == 3 and all(np.isfinite(list(d.values())).all() for d in h1 + h2 + h3)
+    assert not torch.equal(before, pres.flat_theta())
+    assert torch.equal(prev.flat_theta(), prev.flat_theta()) and not any(p.requires_grad for p in prev.parameters())
