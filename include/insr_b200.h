@@ -125,7 +125,8 @@ int insr_siren_lsq_step(const insr_siren_desc *desc, const float *theta, const f
                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* introspection used by bench.py / tests: which kernel family a call would dispatch to.
- * returns 0 = generic, 1 = fused resident-weights kernel; negative = error. */
+ * returns 0 = generic, 1 = fused resident-weights kernels (H <= 32), 2 = tiled shared-memory GEMM
+ * kernels (32 < H <= 512); negative = error. */
 int insr_siren_kernel_family(const insr_siren_desc *desc, int order, int backward);
 
 /* number of kernel launches issued by this library on the calling thread since the last

@@ -9,7 +9,9 @@
 #include "insr_b200.h"
 #include "siren_generic.cuh"
 #include "siren_fused.cuh"
-#ifdef INSR_SINGLE_TU   // emulation build: everything in one translation unit
+#include "siren_tiled_api.h"
+#ifdef INSR_SINGLE_TU
+#include "siren_tiled.cuh"   // emulation build: everything in one translation unit
 #define INSR_INST_D 1
 #define INSR_INST_O 1
 #include "siren_fused_inst.cuh"
@@ -19,6 +21,7 @@
 #define INSR_INST_D 2
 #define INSR_INST_O 2
 #include "siren_fused_inst.cuh"
+#include "siren_tiled_inst.cuh"
 #endif
 
 namespace {
@@ -190,14 +193,17 @@ int insr_siren_kernel_family(const insr_siren_desc *desc, int order, int backwar
     int rc = validate(desc, 0, order, &dm);
     if (rc) return rc;
     if (desc->flags & INSR_FLAG_FORCE_GENERIC) return 0;
-    return insr_fused_supported(dm, order, backward) ? 1 : 0;
+    if (insr_fused_supported(dm, order, backward)) return 1;
+    return insr_tiled_supported(dm, order) ? 2 : 0;
 }
 
 size_t insr_siren_workspace_bytes(const insr_siren_desc *desc, int64_t n_points, int order, int backward) {
     SirenDims dm;
     if (validate(desc, n_points, order, &dm)) return 0;
-    if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_fused_supported(dm, order, backward))
-        return insr_fused_ws_bytes(dm, n_points, order, backward);
+    if (!(desc->flags & INSR_FLAG_FORCE_GENERIC)) {
+        if (insr_fused_supported(dm, order, backward)) return insr_fused_ws_bytes(dm, n_points, order, backward);
+        if (insr_tiled_supported(dm, order)) return insr_tiled_ws_bytes(dm, n_points, order, backward);
+    }
     return generic_ws_bytes(dm, n_points, order, backward);
 }
 
@@ -223,6 +229,11 @@ int insr_siren_forward(const insr_siren_desc *desc, const float *theta, const fl
         if (rc) return rc;
         return check_cuda("fused forward");
     }
+    if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_tiled_supported(dm, order)) {
+        rc = insr_tiled_forward(dm, order, theta, x, n_points, y, jac, h2, (float *)workspace, stream, &g_launches);
+        if (rc) return fail(rc, "tiled forward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
+        return check_cuda("tiled forward");
+    }
     return generic_forward(dm, order, theta, x, n_points, y, jac, h2, (float *)workspace, stream);
 }
 
@@ -247,6 +258,12 @@ int insr_siren_backward(const insr_siren_desc *desc, const float *theta, const f
         if (rc == INSR_ERR_UNSUPPORTED) return fail(rc, "fused backward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
         if (rc) return rc;
         return check_cuda("fused backward");
+    }
+    if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_tiled_supported(dm, order)) {
+        rc = insr_tiled_backward(dm, order, theta, x, n_points, gy, gjac, gh2, gtheta, gx, (float *)workspace, stream,
+                                 &g_launches);
+        if (rc) return fail(rc, "tiled backward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
+        return check_cuda("tiled backward");
     }
     return generic_backward(dm, order, theta, x, n_points, gy, gjac, gh2, gtheta, gx, (float *)workspace, stream);
 }

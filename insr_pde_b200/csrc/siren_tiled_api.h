@@ -1,0 +1,43 @@
+// siren_tiled_api.h -- what the ABI unit needs from the tiled family: workspace sizing and the
+// non-template entry points (the kernels themselves are in siren_tiled.cuh, compiled in their own unit)
+#pragma once
+#include "siren_common.cuh"
+
+namespace insr_tiled {
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// points per chunk: bound the workspace to ~1.5 GB
+inline int64_t chunk_points(const SirenDims &dm, int S, bool bwd, int64_t N) {
+    const int HP = (dm.H + 7) & ~7;
+    const size_t per_point = (size_t)S * HP * sizeof(float) * (bwd ? (2 * (dm.L + 1) + 2) : 2) + (bwd ? 16 * 4 * 4 : 0);
+    int64_t nc = (int64_t)(((size_t)1536 << 20) / per_point);
+    nc = nc / 1024 * 1024;
+    if (nc < 1024) nc = 1024;
+    const int64_t need = round_up(N, 1024);
+    return nc < need ? nc : need;
+}
+
+// row capacity of the workspace buffers: the chunk plus slack for the last (partial) CTA tile
+inline int64_t capacity(int64_t chunk) { return chunk + 256; }
+
+inline size_t ws_bytes(const SirenDims &dm, int order, bool bwd, int64_t N) {
+    const int S = insr_nstreams(dm.D, order);
+    const int HP = (dm.H + 7) & ~7;
+    const int64_t NCp = capacity(chunk_points(dm, S, bwd, N));
+    const size_t buf = (size_t)S * NCp * HP;
+    size_t floats = bwd ? buf * (2 * (dm.L + 1) + 2) + (size_t)dm.O * S * NCp : buf * 2;
+    return floats * sizeof(float) + 256;
+}
+
+}  // namespace insr_tiled
+
+// non-template entry points, defined in siren_tiled_inst.cuh (own translation unit under nvcc)
+int insr_tiled_forward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N, float *y,
+                       float *jac, float *h2, float *ws, void *stream, int64_t *launches);
+int insr_tiled_backward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
+                        const float *gy, const float *gjac, const float *gh2, float *gtheta, float *gx, float *ws,
+                        void *stream, int64_t *launches);
+inline bool insr_tiled_supported(const SirenDims &dm, int order) { return dm.H > 32 && dm.H <= 512 && order <= 3; }
+inline size_t insr_tiled_ws_bytes(const SirenDims &dm, int64_t N, int order, int backward) {
+    return insr_tiled::ws_bytes(dm, order, backward != 0, N);
+}

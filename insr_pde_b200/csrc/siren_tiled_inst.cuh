@@ -1,0 +1,19 @@
+// siren_tiled_inst.cuh -- instantiation + dispatch of the tiled family for every (D, O, order).
+#define INSR_TILED_CASE(D_, O_, ORD_, CALL) \
+    if (dm.D == D_ && dm.O == O_ && order == ORD_) { constexpr int D = D_, O = O_, ORDER = ORD_; \
+        (void)D; (void)O; (void)ORDER; return CALL; }
+#define INSR_TILED_O(D_, ORD_, CALL) INSR_TILED_CASE(D_, 1, ORD_, CALL) INSR_TILED_CASE(D_, 2, ORD_, CALL) INSR_TILED_CASE(D_, 3, ORD_, CALL)
+#define INSR_TILED_ORD(D_, CALL) INSR_TILED_O(D_, 0, CALL) INSR_TILED_O(D_, 1, CALL) INSR_TILED_O(D_, 2, CALL) INSR_TILED_O(D_, 3, CALL)
+#define INSR_TILED_ALL(CALL) INSR_TILED_ORD(1, CALL) INSR_TILED_ORD(2, CALL) INSR_TILED_ORD(3, CALL)
+
+int insr_tiled_forward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N, float *y,
+                       float *jac, float *h2, float *ws, void *stream, int64_t *launches) {
+    INSR_TILED_ALL((insr_tiled::run_forward<D, O, ORDER>(dm, theta, x, N, y, jac, h2, ws, stream, launches)))
+    return -6;
+}
+int insr_tiled_backward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
+                        const float *gy, const float *gjac, const float *gh2, float *gtheta, float *gx, float *ws,
+                        void *stream, int64_t *launches) {
+    INSR_TILED_ALL((insr_tiled::run_backward<D, O, ORDER>(dm, theta, x, N, gy, gjac, gh2, gtheta, gx, ws, stream, launches)))
+    return -6;
+}

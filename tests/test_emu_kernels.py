@@ -115,11 +115,27 @@ def test_fused_family_under_emulation(emu_library, case):
     run_case(emu_library, *case)
 
 
+TILED_CASES = [
+    (2, 2, 68, 3, 150, 1), (2, 1, 64, 2, 300, 2), (3, 3, 66, 2, 100, 1), (2, 1, 40, 1, 77, 0),
+    (2, 1, 136, 1, 60, 2), (3, 1, 72, 2, 50, 3), (1, 1, 33, 1, 40, 2),
+]
+
+
+@pytest.mark.parametrize("case", TILED_CASES)
+def test_tiled_family_under_emulation(emu_library, case):
+    D, O, H, L, N, order = case
+    desc = _lib.make_desc(D, O, H, L)
+    assert emu_library.kernel_family(desc, order, True) == 2 and emu_library.kernel_family(desc, order, False) == 2
+    run_case(emu_library, *case)
+
+
 def test_family_dispatch_rules(emu_library):
     fam = emu_library.kernel_family
     assert fam(_lib.make_desc(2, 1, 32, 3), 2, True) == 1
     assert fam(_lib.make_desc(2, 1, 32, 3, flags=_lib.FLAG_FORCE_GENERIC), 2, True) == 0
-    assert fam(_lib.make_desc(2, 1, 33, 3), 2, True) == 0        # wider than the resident-weights kernel
+    assert fam(_lib.make_desc(2, 1, 33, 3), 2, True) == 2        # wider than the resident-weights kernel: tiled GEMM family
+    assert fam(_lib.make_desc(3, 3, 512, 5), 3, True) == 2
+    assert fam(_lib.make_desc(2, 1, 64, 3, flags=_lib.FLAG_FORCE_GENERIC), 2, True) == 0
     assert fam(_lib.make_desc(2, 1, 32, 4), 2, True) == 0        # deeper than the register-resident gW partials
     assert fam(_lib.make_desc(2, 1, 32, 4), 2, False) == 1
     assert fam(_lib.make_desc(2, 1, 32, 3), 3, True) == 0        # full Hessian streams: generic
