@@ -77,26 +77,56 @@ __device__ __forceinline__ void gemm_mainloop(const Geo &g, const float *__restr
             INSR_PRAGMA_UNROLL
             for (int c = 0; c < TN; ++c) acc[s][t][c] = 0.f;
     const int tid = threadIdx.x;
+    // per-thread staging assignments (independent of the slab): <= 4 float4 of A, <= 4 scalars of B
+    constexpr int MAXA = 4, MAXB = 4;
     const int a_items = S * g.BP * 2;          // float4 loads per slab: (row, half)
     const int b_items = g.BN * BK;             // scalar loads per slab
+    const float *a_src[MAXA];
+    int a_dst[MAXA], b_kk[MAXB], b_col[MAXB];
+    INSR_PRAGMA_UNROLL
+    for (int i = 0; i < MAXA; ++i) {
+        const int idx = tid + i * NT;
+        const int r = idx >> 1, q = idx & 1;
+        const int s = r / g.BP, p = r - s * g.BP;
+        a_src[i] = (idx < a_items) ? Ain + ((int64_t)s * NCp + p_tile0 + p) * g.HP + 4 * q : nullptr;
+        a_dst[i] = (4 * q) * g.AST + r;
+    }
+    INSR_PRAGMA_UNROLL
+    for (int i = 0; i < MAXB; ++i) {
+        const int idx = tid + i * NT;
+        b_kk[i] = (idx < b_items) ? idx / g.BN : -1;
+        b_col[i] = idx - (idx / g.BN) * g.BN;
+    }
+    float4 ra[MAXA];
+    float rb[MAXB];
+    auto gload = [&](int k0) {                 // global -> registers (next slab, overlaps the FFMA loop)
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < MAXA; ++i)
+            if (a_src[i]) ra[i] = ld4(a_src[i] + k0);
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < MAXB; ++i)
+            if (b_kk[i] >= 0) rb[i] = bfetch(k0 + b_kk[i], b_col[i]);
+    };
+    auto sstore = [&]() {                      // registers -> shared (A transposed: smA[kk][s*BP + p])
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < MAXA; ++i)
+            if (a_src[i]) {
+                float *dst = smA + a_dst[i];
+                dst[0] = ra[i].x; dst[g.AST] = ra[i].y; dst[2 * g.AST] = ra[i].z; dst[3 * g.AST] = ra[i].w;
+            }
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < MAXB; ++i)
+            if (b_kk[i] >= 0) smB[b_kk[i] * g.BST + b_col[i]] = rb[i];
+    };
+    gload(0);
+    sstore();
+    __syncthreads();
     for (int k0 = 0; k0 < K; k0 += BK) {
-        // ---- stage the A slab transposed: smA[kk][s*BP + p]
-        for (int idx = tid; idx < a_items; idx += NT) {
-            const int r = idx >> 1, q = idx & 1;
-            const int s = r / g.BP, p = r - s * g.BP;
-            const float4 v = ld4(Ain + ((int64_t)s * NCp + p_tile0 + p) * g.HP + k0 + 4 * q);
-            float *dst = smA + (4 * q) * g.AST + r;
-            dst[0] = v.x; dst[g.AST] = v.y; dst[2 * g.AST] = v.z; dst[3 * g.AST] = v.w;
-        }
-        // ---- stage the B slab: smB[kk][col]
-        for (int idx = tid; idx < b_items; idx += NT) {
-            const int kk = idx / g.BN, col = idx - kk * g.BN;
-            smB[kk * g.BST + col] = bfetch(k0 + kk, col);
-        }
-        __syncthreads();
+        const bool more = k0 + BK < K;
+        if (more) gload(k0 + BK);
         if (active) {
             const float *ap = smA + TP * rt;
-            const float *bp = smB + TN * ct;
+            const float *bp = smB + 4 * ct;          // columns 4ct..4ct+3 and 4CT+4ct..: conflict-free LDS.128
             INSR_PRAGMA_UNROLL
             for (int kk = 0; kk < BK; ++kk) {
                 float a[S][TP];
@@ -112,7 +142,7 @@ __device__ __forceinline__ void gemm_mainloop(const Geo &g, const float *__restr
                         a[s][0] = ap[kk * g.AST + s * g.BP];
                     }
                 }
-                const float4 b0 = ld4(bp + kk * g.BST), b1 = ld4(bp + kk * g.BST + 4);
+                const float4 b0 = ld4(bp + kk * g.BST), b1 = ld4(bp + kk * g.BST + 4 * g.CT);
                 const float b[TN] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s)
@@ -122,7 +152,11 @@ __device__ __forceinline__ void gemm_mainloop(const Geo &g, const float *__restr
                         for (int c = 0; c < TN; ++c) acc[s][t][c] = fmaf(a[s][t], b[c], acc[s][t][c]);
             }
         }
-        __syncthreads();
+        __syncthreads();                       // everyone is done reading the current slab
+        if (more) {
+            sstore();
+            __syncthreads();
+        }
     }
 }
 
@@ -175,7 +209,7 @@ __global__ void __launch_bounds__(NT) k_tiled_layer0(SirenDims dm, int HP, const
 // T2: hidden sine layer forward: GEMM + bias + activation.  grid = (NCp / BP, panels)
 // ---------------------------------------------------------------------------------------------
 template <int D, int ORDER>
-__global__ void __launch_bounds__(NT) k_tiled_fwd(SirenDims dm, Geo g, const float *__restrict__ W,
+__global__ void __launch_bounds__(NT, (StreamCfg<D, ORDER>::S <= 3) ? 2 : 1) k_tiled_fwd(SirenDims dm, Geo g, const float *__restrict__ W,
                                                   const float *__restrict__ bias, const float *__restrict__ Ain,
                                                   int64_t NCp, float *__restrict__ Zpre, float *__restrict__ Aout) {
     typedef StreamCfg<D, ORDER> C;
@@ -195,15 +229,14 @@ __global__ void __launch_bounds__(NT) k_tiled_fwd(SirenDims dm, Geo g, const flo
     };
     gemm_mainloop<S, TP>(g, Ain, NCp, p_tile0, g.HP, bfetch, smA, smB, rt, ct, active, acc);
     if (!active) return;
-    const int jc = j0 + TN * ct;
-    if (jc >= g.HP) return;
+    const int jcA = j0 + 4 * ct, jcB = j0 + 4 * g.CT + 4 * ct;      // the thread's two groups of 4 columns
     INSR_PRAGMA_UNROLL
     for (int t = 0; t < TP; ++t) {
         const int64_t p = p_tile0 + TP * rt + t;
         float zo[S][TN], ao[S][TN];
         INSR_PRAGMA_UNROLL
         for (int c = 0; c < TN; ++c) {
-            const int j = jc + c;
+            const int j = (c < 4) ? (jcA + c) : (jcB + c - 4);
             float z[S], a[S];
             const float bj = (j < H) ? __ldg(bias + j) : 0.f;
             z[0] = dm.omega * (acc[0][t][c] + bj);
@@ -215,13 +248,15 @@ __global__ void __launch_bounds__(NT) k_tiled_fwd(SirenDims dm, Geo g, const flo
         }
         INSR_PRAGMA_UNROLL
         for (int s = 0; s < S; ++s) {
-            const int64_t off = ((int64_t)s * NCp + p) * g.HP + jc;
-            if (Zpre) {
-                st4(Zpre + off, zo[s][0], zo[s][1], zo[s][2], zo[s][3]);
-                st4(Zpre + off + 4, zo[s][4], zo[s][5], zo[s][6], zo[s][7]);
+            const int64_t row = ((int64_t)s * NCp + p) * g.HP;
+            if (jcA < g.HP) {
+                if (Zpre) st4(Zpre + row + jcA, zo[s][0], zo[s][1], zo[s][2], zo[s][3]);
+                st4(Aout + row + jcA, ao[s][0], ao[s][1], ao[s][2], ao[s][3]);
             }
-            st4(Aout + off, ao[s][0], ao[s][1], ao[s][2], ao[s][3]);
-            st4(Aout + off + 4, ao[s][4], ao[s][5], ao[s][6], ao[s][7]);
+            if (jcB < g.HP) {
+                if (Zpre) st4(Zpre + row + jcB, zo[s][4], zo[s][5], zo[s][6], zo[s][7]);
+                st4(Aout + row + jcB, ao[s][4], ao[s][5], ao[s][6], ao[s][7]);
+            }
         }
     }
 }
@@ -335,7 +370,7 @@ __global__ void __launch_bounds__(NT) k_tiled_out_bwd(SirenDims dm, int HP, cons
 //     abar[m][k] = omega * sum_j zbar_l[m][j] W_l[j][k]   ->   zbar_{l-1} = adj(Zpre_{l-1}, abar)
 // ---------------------------------------------------------------------------------------------
 template <int D, int ORDER>
-__global__ void __launch_bounds__(NT) k_tiled_dgrad(SirenDims dm, Geo g, const float *__restrict__ W,
+__global__ void __launch_bounds__(NT, (StreamCfg<D, ORDER>::S <= 3) ? 2 : 1) k_tiled_dgrad(SirenDims dm, Geo g, const float *__restrict__ W,
                                                     const float *__restrict__ ZBin, int64_t NCp,
                                                     const float *__restrict__ ZprePrev, float *__restrict__ ZBout) {
     typedef StreamCfg<D, ORDER> C;
@@ -355,16 +390,17 @@ __global__ void __launch_bounds__(NT) k_tiled_dgrad(SirenDims dm, Geo g, const f
     };
     gemm_mainloop<S, TP>(g, ZBin, NCp, p_tile0, g.HP, bfetch, smA, smB, rt, ct, active, acc);
     if (!active) return;
-    const int kc = k0c + TN * ct;
-    if (kc >= g.HP) return;
+    const int kcA = k0c + 4 * ct, kcB = k0c + 4 * g.CT + 4 * ct;
+    const bool inA = kcA < g.HP, inB = kcB < g.HP;
     INSR_PRAGMA_UNROLL
     for (int t = 0; t < TP; ++t) {
         const int64_t p = p_tile0 + TP * rt + t;
         float zin[S][TN], zo[S][TN];
         INSR_PRAGMA_UNROLL
         for (int s = 0; s < S; ++s) {
-            const float4 v0 = ld4(ZprePrev + ((int64_t)s * NCp + p) * g.HP + kc);
-            const float4 v1 = ld4(ZprePrev + ((int64_t)s * NCp + p) * g.HP + kc + 4);
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v0 = inA ? ld4(ZprePrev + ((int64_t)s * NCp + p) * g.HP + kcA) : zero4;
+            const float4 v1 = inB ? ld4(ZprePrev + ((int64_t)s * NCp + p) * g.HP + kcB) : zero4;
             zin[s][0] = v0.x; zin[s][1] = v0.y; zin[s][2] = v0.z; zin[s][3] = v0.w;
             zin[s][4] = v1.x; zin[s][5] = v1.y; zin[s][6] = v1.z; zin[s][7] = v1.w;
         }
@@ -374,14 +410,15 @@ __global__ void __launch_bounds__(NT) k_tiled_dgrad(SirenDims dm, Geo g, const f
             INSR_PRAGMA_UNROLL
             for (int s = 0; s < S; ++s) { ab[s] = dm.omega * acc[s][t][c]; z[s] = zin[s][c]; }
             insr_sine_bwd<D, ORDER>(z, ab, zb);
+            const int k = (c < 4) ? (kcA + c) : (kcB + c - 4);
             INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s) zo[s][c] = (kc + c < H) ? zb[s] : 0.f;
+            for (int s = 0; s < S; ++s) zo[s][c] = (k < H) ? zb[s] : 0.f;
         }
         INSR_PRAGMA_UNROLL
         for (int s = 0; s < S; ++s) {
-            const int64_t off = ((int64_t)s * NCp + p) * g.HP + kc;
-            st4(ZBout + off, zo[s][0], zo[s][1], zo[s][2], zo[s][3]);
-            st4(ZBout + off + 4, zo[s][4], zo[s][5], zo[s][6], zo[s][7]);
+            const int64_t row = ((int64_t)s * NCp + p) * g.HP;
+            if (inA) st4(ZBout + row + kcA, zo[s][0], zo[s][1], zo[s][2], zo[s][3]);
+            if (inB) st4(ZBout + row + kcB, zo[s][4], zo[s][5], zo[s][6], zo[s][7]);
         }
     }
 }
@@ -415,28 +452,45 @@ __global__ void __launch_bounds__(NT) k_tiled_wgrad(SirenDims dm, int HP, int S,
     // rows of the reduction are (s, p) with p < nv; slabs of WG_R points of one stream
     const int slabs_per_stream = (nv + WG_R - 1) / WG_R;
     const int total = S * slabs_per_stream;
-    for (int sl = blockIdx.z; sl < total; sl += rsplit) {
+    // software pipeline: the next slab's 2+2 float4 are fetched into registers while the current
+    // slab is being contracted out of shared memory
+    float4 rz[2], ra[2];
+    auto gload = [&](int sl) {
         const int s = sl / slabs_per_stream;
         const int p0 = (sl - s * slabs_per_stream) * WG_R;
-        // 32 rows x 64 columns per operand = 512 float4 each: 2 + 2 per thread
         INSR_PRAGMA_UNROLL
         for (int i = 0; i < 2; ++i) {
             const int idx = tid + i * NT;
             const int r = idx >> 4, c4 = (idx & 15) * 4;
             const int64_t row = (int64_t)s * NCp + p0 + r;
             const bool rv = p0 + r < nv;
-            float4 z = make_float4(0.f, 0.f, 0.f, 0.f), a = z;
-            if (rv && j0 + c4 < HP) z = ld4(ZB + row * HP + j0 + c4);
-            if (rv && k0 + c4 < HP) a = ld4(Act + row * HP + k0 + c4);
-            st4(&smZ[r][c4], z.x, z.y, z.z, z.w);
-            st4(&smA[r][c4], a.x, a.y, a.z, a.w);
+            rz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ra[i] = rz[i];
+            if (rv && j0 + c4 < HP) rz[i] = ld4(ZB + row * HP + j0 + c4);
+            if (rv && k0 + c4 < HP) ra[i] = ld4(Act + row * HP + k0 + c4);
         }
-        __syncthreads();
+    };
+    auto sstore = [&]() {
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * NT;
+            const int r = idx >> 4, c4 = (idx & 15) * 4;
+            st4(&smZ[r][c4], rz[i].x, rz[i].y, rz[i].z, rz[i].w);
+            st4(&smA[r][c4], ra[i].x, ra[i].y, ra[i].z, ra[i].w);
+        }
+    };
+    int sl = blockIdx.z;
+    if (sl < total) { gload(sl); sstore(); }
+    __syncthreads();
+    for (; sl < total; sl += rsplit) {
+        const int s = sl / slabs_per_stream;
+        const bool more = sl + rsplit < total;
+        if (more) gload(sl + rsplit);
         INSR_PRAGMA_UNROLL
         for (int rr = 0; rr < WG_R / 4; ++rr) {
             const int r = grp * (WG_R / 4) + rr;
-            const float4 z0 = ld4(&smZ[r][8 * jt]), z1 = ld4(&smZ[r][8 * jt + 4]);
-            const float4 a0 = ld4(&smA[r][8 * kt]), a1 = ld4(&smA[r][8 * kt + 4]);
+            const float4 z0 = ld4(&smZ[r][4 * jt]), z1 = ld4(&smZ[r][32 + 4 * jt]);     // interleaved 4+4 columns:
+            const float4 a0 = ld4(&smA[r][4 * kt]), a1 = ld4(&smA[r][32 + 4 * kt]);     // conflict-free LDS.128
             const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
             const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             INSR_PRAGMA_UNROLL
@@ -449,6 +503,7 @@ __global__ void __launch_bounds__(NT) k_tiled_wgrad(SirenDims dm, int HP, int S,
             for (int r = 0; r < WG_R; ++r) bsum += smZ[r][tid];
         }
         __syncthreads();
+        if (more) { sstore(); __syncthreads(); }
     }
     // combine the 4 groups through shared memory (reuse smZ/smA as a 64x64 tile), then red.global
     float *tile = smbuf;
@@ -458,7 +513,9 @@ __global__ void __launch_bounds__(NT) k_tiled_wgrad(SirenDims dm, int HP, int S,
             for (int a = 0; a < 8; ++a)
                 INSR_PRAGMA_UNROLL
                 for (int b = 0; b < 8; ++b) {
-                    float *dst = tile + (8 * jt + a) * WG_T + 8 * kt + b;
+                    const int jj = (a < 4) ? (4 * jt + a) : (32 + 4 * jt + a - 4);
+                    const int kk = (b < 4) ? (4 * kt + b) : (32 + 4 * kt + b - 4);
+                    float *dst = tile + jj * WG_T + kk;
                     *dst = (gsel == 0 ? 0.f : *dst) + acc[a][b];
                 }
         }
