@@ -59,6 +59,8 @@ else:
     Model = ref.elasticity.ElasticityModel
     spy_training_loop(Model, ["_initialize", "_solve_deformation"])
 model = Model(cfg)
+if pde == "elasticity":
+    model.sample_resolution_init = 12       # the reference hard-codes 500 (250k+250k points) for the zero-fit
 net = next(iter(model._trainable_networks.values()))
 model.initialize()
 model.step()
