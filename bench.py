@@ -133,7 +133,8 @@ def fluid_timestep_ours(dev, iters, world=1):
     torch.manual_seed(0)
     vel, prev, pres = (ib.MLP(2, o, 3, 32, nonlinearity="sine").to(dev) for o in (2, 2, 1))
     factory = (lambda nets: idist.GradAllReducer(nets)) if world > 1 else None
-    st = fused.FluidStepper(vel, prev, pres, dt=0.05, sample_resolution=128, lr=1e-4, reducer_factory=factory)
+    st = fused.FluidStepper(vel, prev, pres, dt=0.05, sample_resolution=128, lr=1e-4, reducer_factory=factory,
+                            graphed=(world == 1))
     st.initialize(fused.taylorgreen_velocity, 20, world)
     st.step(3, world)                                   # warm-up
     torch.cuda.synchronize()
@@ -144,7 +145,9 @@ def fluid_timestep_ours(dev, iters, world=1):
     return {"sec_per_timestep": round(sec, 4), "iters_per_loop": iters, "loops": 3,
             "us_per_iteration": round(sec / (3 * iters) * 1e6, 1), "points_per_iteration": 128 * 128,
             "final_losses": [round(h[-1]["main"], 8) for h in (h1, h2, h3)],
-            "note": "fluid2Dtlgn step on fused lsq closures + torch Adam + ReduceLROnPlateau, host sync per iteration as base/baseModel.py:116"}
+            "note": ("fluid2Dtlgn step on fused lsq closures; one CUDA graph per iteration (sampling + closures + "
+                     "device Adam + device ReduceLROnPlateau), losses read back in bulk") if world == 1 else
+                    "fluid2Dtlgn step on fused lsq closures + torch Adam + flat-gradient all-reduce, host sync per iteration"}
 
 
 def fluid_timestep_cpu(iters_measured=3, iters_per_loop=100):

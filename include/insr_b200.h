@@ -124,6 +124,20 @@ int insr_siren_lsq_step(const insr_siren_desc *desc, const float *theta, const f
                         const float *target, float scale, float *loss_out, float *gtheta,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * Optimiser side of one iteration, on the device (so a whole iteration can be one CUDA graph):
+ * `sched` is 4 device floats {lr, best, num_bad_epochs, step}.
+ *   insr_adam_step     torch.optim.Adam(amsgrad=False, weight_decay=0) on a flat vector, reading lr and the
+ *                      step index from `sched`                           (base/baseModel.py:60, :79)
+ *   insr_plateau_step  ReduceLROnPlateau(mode='min', threshold_mode='rel', cooldown=0).step(loss) updating
+ *                      sched[0..2], and sched[3] += 1                    (base/baseModel.py:61-62, :81)
+ * Call order per iteration: insr_adam_step for every net, then insr_plateau_step once.
+ */
+int insr_adam_step(float *theta, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                   const float *sched, float beta1, float beta2, float eps, void *stream);
+int insr_plateau_step(const float *loss, float *sched, float factor, int patience, float threshold,
+                      float min_lr, float eps, void *stream);
+
 /* introspection used by bench.py / tests: which kernel family a call would dispatch to.
  * returns 0 = generic, 1 = fused resident-weights kernels (H <= 32), 2 = tiled shared-memory GEMM
  * kernels (32 < H <= 512); negative = error. */

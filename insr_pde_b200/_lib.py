@@ -19,7 +19,7 @@ FLAG_FORCE_GENERIC = 1
 EXPORTS = [
     "insr_version", "insr_last_error", "insr_siren_theta_size", "insr_siren_workspace_bytes",
     "insr_siren_forward", "insr_siren_backward", "insr_siren_lsq_step", "insr_siren_kernel_family",
-    "insr_launch_count",
+    "insr_launch_count", "insr_adam_step", "insr_plateau_step",
 ]
 
 
@@ -61,6 +61,11 @@ class Library:
                                           _vp, ctypes.c_float, _vp, _vp, _vp, _sz, _vp]
         c.insr_siren_kernel_family.restype = _i32
         c.insr_siren_kernel_family.argtypes = [_dp, _i32, _i32]
+        _f = ctypes.c_float
+        c.insr_adam_step.restype = _i32
+        c.insr_adam_step.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _vp]
+        c.insr_plateau_step.restype = _i32
+        c.insr_plateau_step.argtypes = [_vp, _vp, _f, _i32, _f, _f, _f, _vp]
         c.insr_launch_count.restype = _i64
         c.insr_launch_count.argtypes = [_i32]
 
@@ -90,6 +95,12 @@ class Library:
     def backward(self, desc, theta, x, n, order, gy, gjac, gh2, gtheta, gx, ws, ws_bytes, stream):
         self.check(self.cdll.insr_siren_backward(ctypes.byref(desc), theta, x, n, order, gy, gjac, gh2,
                                                  gtheta, gx, ws, ws_bytes, stream))
+
+    def adam_step(self, theta, grad, m, v, n, sched, beta1, beta2, eps, stream):
+        self.check(self.cdll.insr_adam_step(theta, grad, m, v, n, sched, beta1, beta2, eps, stream))
+
+    def plateau_step(self, loss, sched, factor, patience, threshold, min_lr, eps, stream):
+        self.check(self.cdll.insr_plateau_step(loss, sched, factor, patience, threshold, min_lr, eps, stream))
 
     def lsq_step(self, desc, theta, x, n, order, n_res, coef, target, scale, loss_out, gtheta, ws,
                  ws_bytes, stream):

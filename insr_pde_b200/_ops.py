@@ -144,3 +144,22 @@ def siren_lsq_step(desc, theta, x, order, coef_y, coef_jac, coef_lap, target, sc
         lib.lsq_step(desc, theta.data_ptr(), x.data_ptr(), n, order, R, coef, _ptr(target), float(scale),
                      loss_out.data_ptr(), gtheta.data_ptr(), _ptr(ws), nb, _stream(x.device))
     return loss_out, gtheta
+
+
+def adam_step(theta, grad, exp_avg, exp_avg_sq, sched, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adam semantics on a flat fp32 vector; lr and step index are read from the device
+    tensor ``sched`` = [lr, best, num_bad_epochs, step] (include/insr_b200.h: insr_adam_step)"""
+    lib = _lib.get_lib()
+    _require_cuda(theta)
+    with _DeviceGuard(theta.device):
+        lib.adam_step(theta.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), theta.numel(),
+                      sched.data_ptr(), beta1, beta2, eps, _stream(theta.device))
+
+
+def plateau_step(loss, sched, factor=0.1, patience=500, threshold=1e-4, min_lr=1e-8, eps=1e-8):
+    """ReduceLROnPlateau(mode='min', threshold_mode='rel').step(loss) on the device + step counter bump"""
+    lib = _lib.get_lib()
+    _require_cuda(sched)
+    with _DeviceGuard(sched.device):
+        lib.plateau_step(loss.data_ptr(), sched.data_ptr(), factor, int(patience), threshold, min_lr, eps,
+                         _stream(sched.device))

@@ -10,6 +10,7 @@
 #include "siren_generic.cuh"
 #include "siren_fused.cuh"
 #include "siren_tiled_api.h"
+#include "optim_kernels.cuh"
 #ifdef INSR_SINGLE_TU
 #include "siren_tiled.cuh"   // emulation build: everything in one translation unit
 #define INSR_INST_D 1
@@ -288,6 +289,33 @@ int insr_siren_lsq_step(const insr_siren_desc *desc, const float *theta, const f
         return fail(rc, "lsq_step: no fused kernel for D=%d O=%d H=%d L=%d order=%d", dm.D, dm.O, dm.H, dm.L, order);
     if (rc) return rc;
     return check_cuda("fused lsq_step");
+}
+
+int insr_adam_step(float *theta, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                   const float *sched, float beta1, float beta2, float eps, void *stream) {
+    if (!theta || !grad || !exp_avg || !exp_avg_sq || !sched) return fail(INSR_ERR_NULL, "adam_step: NULL buffer");
+    if (n < 0) return fail(INSR_ERR_SHAPE, "adam_step: n=%lld", (long long)n);
+    int rc = check_device();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    auto kfn = k_adam_step;
+    INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(256), 0, stream, theta, grad, exp_avg, exp_avg_sq, n, sched, beta1,
+                beta2, eps);
+    ++g_launches;
+    return check_cuda("k_adam_step");
+}
+
+int insr_plateau_step(const float *loss, float *sched, float factor, int patience, float threshold, float min_lr,
+                      float eps, void *stream) {
+    if (!loss || !sched) return fail(INSR_ERR_NULL, "plateau_step: NULL buffer");
+    int rc = check_device();
+    if (rc) return rc;
+    auto kfn = k_plateau_step;
+    INSR_LAUNCH(kfn, dim3(1), dim3(32), 0, stream, loss, sched, factor, patience, threshold, min_lr, eps);
+    ++g_launches;
+    return check_cuda("k_plateau_step");
 }
 
 }  // extern "C"

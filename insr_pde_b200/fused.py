@@ -169,14 +169,89 @@ class TrainingLoop:
         return hist
 
 
+class DeviceOptimizer:
+    """Adam + ReduceLROnPlateau with ALL state on the device (insr_adam_step / insr_plateau_step):
+    no host synchronisation per iteration, graph-capturable.  One schedule shared by every net,
+    like the reference's single scheduler over all param groups (base/baseModel.py:55-62)."""
+
+    def __init__(self, nets, lr, betas=(0.9, 0.999), eps=1e-8, factor=0.1, patience=500, threshold=1e-4,
+                 min_lr=1e-8):
+        self.nets = list(nets)
+        self.betas, self.eps = betas, eps
+        self.factor, self.patience, self.threshold, self.min_lr = factor, patience, threshold, min_lr
+        dev = next(self.nets[0].parameters()).device
+        self.sched = torch.tensor([lr, float("inf"), 0.0, 0.0], dtype=torch.float32, device=dev)
+        self.state = []
+        for n in self.nets:
+            theta = n.flat_theta()
+            self.state.append((n, theta, flat_grad(n), torch.zeros_like(theta), torch.zeros_like(theta)))
+
+    def step(self, main_loss):
+        for _, theta, grad, m, v in self.state:
+            _ops.adam_step(theta, grad, m, v, self.sched, self.betas[0], self.betas[1], self.eps)
+        _ops.plateau_step(main_loss.reshape(1), self.sched, self.factor, self.patience, self.threshold,
+                          self.min_lr, 1e-8)
+
+    @property
+    def lr(self):
+        return float(self.sched[0])          # host sync
+
+
+class GraphedLoop:
+    """One @_training_loop with the whole iteration -- sampling, fused closures, Adam, LR schedule, loss
+    logging -- captured once as a CUDA graph and replayed: the per-iteration host work is one
+    cudaGraphLaunch.  Loss values are written to a device ring and read back in bulk; the early-stop test
+    (lr <= 1.1e-8, base/baseModel.py:132-134) is evaluated every ``check_every`` iterations."""
+
+    def __init__(self, nets, lr, closure, capacity=20000):
+        self.nets, self.closure = list(nets), closure
+        self.opt = DeviceOptimizer(self.nets, lr)
+        self.capacity = capacity
+        self.hist = None
+        self.idx = torch.zeros(1, dtype=torch.long, device=self.opt.sched.device)
+        self.graph = None
+
+    def _iteration(self):
+        zero_grads(*self.nets)
+        loss_dict = self.closure()
+        vals = torch.stack([loss_dict[k].reshape(()) for k in loss_dict]).reshape(1, -1)
+        if self.hist is None:
+            self.hist = torch.zeros(self.capacity, vals.shape[1], device=vals.device)
+        self.hist.index_copy_(0, self.idx, vals)
+        self.idx += 1
+        self.opt.step(loss_dict["main"])
+        return list(loss_dict.keys())
+
+    def run(self, n_iters, early_stop=False, check_every=100):
+        keys = self._iteration()                       # iteration 0 eagerly (also warms everything up)
+        done = 1
+        if n_iters > 1:
+            if self.graph is None:
+                torch.cuda.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._iteration()
+            while done < n_iters:
+                burst = min(check_every, n_iters - done)
+                for _ in range(burst):
+                    self.graph.replay()
+                done += burst
+                if early_stop and self.opt.lr <= 1.1e-8:
+                    break
+        h = self.hist[:done].cpu()
+        return [{k: float(h[i, j]) for j, k in enumerate(keys)} for i in range(done)]
+
+
 class FluidStepper:
     """Fluid2DModel.step (fluid/model.py:61-70) on the fused closures, with the reference's sampling
     (base/sampling.py) and schedule; used for the seconds-per-timestep measurement."""
 
-    def __init__(self, velocity, velocity_prev, pressure, dt=0.05, sample_resolution=128, lr=1e-4, reducer_factory=None):
+    def __init__(self, velocity, velocity_prev, pressure, dt=0.05, sample_resolution=128, lr=1e-4, reducer_factory=None,
+                 graphed=False):
         self.vel, self.prev, self.pres = velocity, velocity_prev, pressure
         self.dt, self.sr, self.lr = dt, sample_resolution, lr
         self.reducer_factory = reducer_factory
+        self.graphed = graphed and reducer_factory is None
         for p in self.prev.parameters():
             p.requires_grad_(False)
 
@@ -190,6 +265,8 @@ class FluidStepper:
         return x, bx, by
 
     def _loop(self, nets, closure, n_iters, world=1):
+        if self.graphed:
+            return GraphedLoop(nets, self.lr, lambda: closure(0)).run(n_iters)
         red = self.reducer_factory(nets) if self.reducer_factory else None
         return TrainingLoop(nets, self.lr, reducer=red).run(closure, n_iters)
 

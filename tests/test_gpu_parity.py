@@ -291,3 +291,25 @@ def test_fused_stepper_runs_on_device():
     assert h0[-1]["main"] < h0[0]["main"]
     h1, h2, h3 = stepper.step(5)
     assert all(np.isfinite(list(d.values())).all() for d in h1 + h2 + h3)
+
+
+def test_graphed_loop_equals_eager_loop_on_fixed_samples():
+    """the CUDA-graphed iteration (device Adam + device plateau scheduler) follows the eager torch loop"""
+    from insr_pde_b200 import fused
+    torch.manual_seed(0)
+    x = torch.rand(4096, 2, device="cuda") * 2 - 1
+    bx = ib.sample_boundary2D_separate(40, "horizontal", device="cuda")
+    by = ib.sample_boundary2D_separate(40, "vertical", device="cuda")
+
+    def make():
+        torch.manual_seed(1)
+        return [ib.MLP(2, o, 3, 32, nonlinearity="sine").cuda() for o in (2, 1)]
+
+    (v1, p1), (v2, p2) = make(), make()
+    h_eager = fused.TrainingLoop([v1, p1], 1e-3).run(lambda i: fused.fluid_solve_pressure(v1, p1, x, bx, by), 30)
+    h_graph = fused.GraphedLoop([v2, p2], 1e-3, lambda: fused.fluid_solve_pressure(v2, p2, x, bx, by)).run(30)
+    assert len(h_graph) == 30
+    for a, b in zip(h_eager, h_graph):
+        assert abs(a["main"] - b["main"]) < 1e-4 * abs(a["main"]) and abs(a["bc"] - b["bc"]) < 1e-4 * abs(a["bc"]) + 1e-9
+    assert rel(p2.flat_theta(), p1.flat_theta()) < 1e-5
+    assert h_graph[-1]["main"] < h_graph[0]["main"]

@@ -258,3 +258,28 @@ def test_fused_training_loop_and_stepper_emulated(emu_backend):
     assert len(h1) == len(h2) == len(h3) == 3 and all(np.isfinite(list(d.values())).all() for d in h1 + h2 + h3)
     assert not torch.equal(before, pres.flat_theta())
     assert torch.equal(prev.flat_theta(), prev.flat_theta()) and not any(p.requires_grad for p in prev.parameters())
+
+
+def test_device_optimizer_matches_torch_adam_and_plateau(emu_backend):
+    """insr_adam_step / insr_plateau_step reproduce torch.optim.Adam + ReduceLROnPlateau (base/baseModel.py:55-81)"""
+    from insr_pde_b200 import _ops
+    torch.manual_seed(0)
+    n = 257
+    theta = torch.randn(n)
+    ref_p = torch.nn.Parameter(theta.clone())
+    opt = torch.optim.Adam([ref_p], lr=1e-2)
+    sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=0.1, min_lr=1e-8, patience=3)
+    m, v = torch.zeros(n), torch.zeros(n)
+    sched = torch.tensor([1e-2, float("inf"), 0.0, 0.0])
+    losses = [1.0, 0.9, 0.95, 0.95, 0.96, 0.97, 0.98, 0.5, 0.6, 0.6, 0.6, 0.6, 0.6, 0.6, 0.6, 0.6, 0.6, 0.6]
+    for it, lv in enumerate(losses):
+        g = torch.randn(n) * (1 + it)
+        ref_p.grad = g.clone()
+        opt.step()
+        sch.step(lv)
+        _ops.adam_step(theta, g, m, v, sched)
+        _ops.plateau_step(torch.tensor([lv]), sched, factor=0.1, patience=3, min_lr=1e-8)
+        assert abs(float(sched[0]) - opt.param_groups[0]["lr"]) < 1e-12 + 1e-6 * opt.param_groups[0]["lr"], it
+        assert float((theta - ref_p.detach()).abs().max()) < 2e-6, it
+    assert opt.param_groups[0]["lr"] < 1e-2          # the schedule actually fired
+    assert float(sched[3]) == len(losses)
