@@ -299,6 +299,25 @@ def run_ours(args):
         "kernel_family": {"fwd": lib.kernel_family(desc, order, False), "bwd": lib.kernel_family(desc, order, True)},
     }
 
+    # ---- fused closure step (insr_siren_lsq_step): forward streams + residual + loss + backward in ONE kernel
+    fused_closure = None
+    if lib.kernel_family(desc, order, True) == 1:
+        from insr_pde_b200 import fused
+        tgt = torch.randn(N, 1, generator=cg, device=dev)
+        loss_buf = torch.zeros(1, device=dev)
+        O_ = desc.out_features
+        cyc = [[0.0] * O_] if order == 2 else [[1.0] * O_]
+        clc = [[1.0] * O_] if order == 2 else None
+
+        def lsq_only():
+            _ops.siren_lsq_step(desc, theta, x, order, cyc, None, clc, tgt, 1.0 / N, loss_out=loss_buf, gtheta=gtheta)
+
+        ms_lsq = time_call(lsq_only, reps)
+        fused_closure = {"ms_per_step": round(ms_lsq, 4), "points_per_s": round(world * N / (ms_lsq / 1e3), 1),
+                         "achieved_tflops": round(3 * f_fwd * N / (ms_lsq / 1e3) / 1e12, 3),
+                         "frac": round(3 * f_fwd * N / (ms_lsq / 1e3) / 1e12 / peak, 4),
+                         "kernel": "k_fused_bwd<..., LSQ=true>: loss = mean((lap - target)^2) and d loss/d theta, no recompute, no output round trip"}
+
     # ---- end to end through the public API with HOST buffers (rank-local shard)
     Ne = args.e2e_points or N
     xh = (torch.rand(Ne, D) * 2 - 1).pin_memory()
@@ -376,7 +395,7 @@ def run_ours(args):
                        "l2": "inputs + outputs + cotangents per step exceed the 126 MB L2" if N >= (1 << 22) else "flushed by size only if points >= 2^22",
                        "init": "reference sine init, torch.manual_seed(0); points U[-1,1]^D seed 1234; cotangents randn/N seed 4321"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "script_size": script, "timestep": timestep,
+            "cpu_baseline": cpu, "script_size": script, "timestep": timestep, "fused_closure": fused_closure,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
