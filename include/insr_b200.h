@@ -75,6 +75,7 @@ typedef struct insr_siren_desc {
 
 #define INSR_FLAG_NONE 0
 #define INSR_FLAG_FORCE_GENERIC 1 /* use the generic (any-H) kernels even where a fused one exists */
+#define INSR_FLAG_TENSOR 2        /* forward of the H <= 32 family on tcgen05/TMEM (3xTF32 split, FP32 accumulate) */
 
 int insr_version(void);
 const char *insr_last_error(void);

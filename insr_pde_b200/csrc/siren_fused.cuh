@@ -860,10 +860,11 @@ inline int insr_fused_run(int kind, insr_fused::Params &p, int order, void *stre
 }
 
 inline int insr_fused_forward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
-                              float *y, float *jac, float *h2, float *, void *stream, int64_t *launches) {
+                              float *y, float *jac, float *h2, float *, void *stream, int64_t *launches,
+                              bool tensor = false) {
     insr_fused::Params p{};
     p.dm = dm; p.theta = theta; p.x = x; p.N = N; p.y = y; p.jac = jac; p.h2 = h2;
-    return insr_fused_run(0, p, order, stream, launches);
+    return insr_fused_run(tensor ? 3 : 0, p, order, stream, launches);
 }
 
 inline int insr_fused_backward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
