@@ -296,7 +296,8 @@ def run_ours(args):
         "step_frac": round(3 * f_fwd * N * args.steps / (ms / 1e3) / 1e12 / peak, 4),
         "hbm": {"algorithmic_bytes_per_point": bytes_pt,
                 "achieved_gbs": round(bytes_pt * N / ((ms_bwd + ms_fwd) / 1e3) / 1e9, 1), "peak_gbs": hbm, "peak_source": hbm_how},
-        "kernel_family": {"fwd": lib.kernel_family(desc, order, False), "bwd": lib.kernel_family(desc, order, True)},
+        "kernel_family": {"fwd": lib.kernel_family(desc, order, False), "bwd": lib.kernel_family(desc, order, True),
+                          "fwd_pipe": "tcgen05 3xTF32 (TMEM accumulators)" if lib.kernel_family(desc, order, False) == 1 else "fp32 ffma"},
     }
 
     # ---- fused closure step (insr_siren_lsq_step): forward streams + residual + loss + backward in ONE kernel

@@ -226,7 +226,7 @@ int insr_siren_forward(const insr_siren_desc *desc, const float *theta, const fl
         return fail(INSR_ERR_WORKSPACE, "forward needs %zu workspace bytes, got %zu", need, workspace_bytes);
     if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_fused_supported(dm, order, 0)) {
         rc = insr_fused_forward(dm, order, theta, x, n_points, y, jac, h2, (float *)workspace, stream, &g_launches,
-                                (desc->flags & INSR_FLAG_TENSOR) != 0);
+                                (desc->flags & INSR_FLAG_NO_TENSOR) == 0);
         if (rc == INSR_ERR_UNSUPPORTED) return fail(rc, "fused forward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
         if (rc) return rc;
         return check_cuda("fused forward");

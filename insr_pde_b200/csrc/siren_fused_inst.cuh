@@ -8,7 +8,9 @@ int INSR_INST_CAT(insr_fused_run_, INSR_INST_D, INSR_INST_O)(int kind, insr_fuse
                                                             void *stream, int64_t *launches) {
     using namespace insr_fused;
     constexpr int D = INSR_INST_D, O = INSR_INST_O;
-#ifndef INSR_CPU_EMU
+#ifdef INSR_CPU_EMU
+    if (kind == 3) kind = 0;             // the emulator has no tensor cores: FFMA forward
+#else
     if (kind == 3) {                     // tcgen05 / TMEM 3xTF32 forward (siren_tc.cuh)
         switch (order) {
             case 0: return insr_tc::launch_tc_fwd<D, O, 0>(p, stream, launches);

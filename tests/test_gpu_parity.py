@@ -16,7 +16,7 @@ from test_oracle_golden import ELAS, OPS, elasticity_case
 
 pytestmark = pytest.mark.gpu
 TOL = 3e-5
-FAMILIES = [0, _lib.FLAG_FORCE_GENERIC]
+FAMILIES = [0, _lib.FLAG_NO_TENSOR, _lib.FLAG_FORCE_GENERIC]   # default (tcgen05 forward where available), FFMA-only, generic
 
 
 def rel(a, b):

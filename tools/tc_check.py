@@ -15,10 +15,10 @@ for (D, O, H, L, order, N) in [(2, 1, 32, 3, 2, 1000), (2, 2, 32, 3, 1, 777), (1
     net = ib.MLP(D, O, L, H, nonlinearity="sine").cuda()
     theta = net.flat_theta()
     x = torch.rand(N, D, device="cuda") * 2 - 1
-    d_tc = _lib.make_desc(D, O, H, L, flags=_lib.FLAG_TENSOR)
+    d_tc = _lib.make_desc(D, O, H, L)
     outs_tc = _ops.siren_forward(d_tc, theta, x, order)
     torch.cuda.synchronize()
-    outs_ff = _ops.siren_forward(net.desc, theta, x, order)
+    outs_ff = _ops.siren_forward(_lib.make_desc(D, O, H, L, flags=_lib.FLAG_NO_TENSOR), theta, x, order)
     ref = fm.forward(theta.double().cpu().numpy(), x.double().cpu().numpy(), D, O, H, L, order)
     names = ["y", "jac", "lap"][:len(outs_tc)]
     print((D, O, H, L, order, N), {k: (f"tc {rel(a, ref[k]):.1e}", f"ffma {rel(b, ref[k]):.1e}") for k, a, b in zip(names, outs_tc, outs_ff)}, flush=True)
@@ -28,7 +28,7 @@ D, O, H, L, order, N = 2, 1, 32, 3, 2, 1 << 22
 net = ib.MLP(D, O, L, H, nonlinearity="sine").cuda()
 theta = net.flat_theta()
 x = torch.rand(N, D, device="cuda") * 2 - 1
-for flags, name in ((0, "ffma"), (_lib.FLAG_TENSOR, "tcgen05")):
+for flags, name in ((_lib.FLAG_NO_TENSOR, "ffma"), (0, "tcgen05")):
     desc = _lib.make_desc(D, O, H, L, flags=flags)
     for _ in range(3):
         _ops.siren_forward(desc, theta, x, order)
