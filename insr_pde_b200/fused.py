@@ -192,6 +192,13 @@ class DeviceOptimizer:
         _ops.plateau_step(main_loss.reshape(1), self.sched, self.factor, self.patience, self.threshold,
                           self.min_lr, 1e-8)
 
+    def reset(self, lr):
+        """fresh optimiser + scheduler state (the reference builds new ones per training loop)"""
+        self.sched.copy_(torch.tensor([lr, float("inf"), 0.0, 0.0]))
+        for _, _, _, m, v in self.state:
+            m.zero_()
+            v.zero_()
+
     @property
     def lr(self):
         return float(self.sched[0])          # host sync
@@ -222,10 +229,19 @@ class GraphedLoop:
         self.opt.step(loss_dict["main"])
         return list(loss_dict.keys())
 
+    def reset(self, lr):
+        """reuse the captured graph for a new training loop: only the optimiser state and the log restart"""
+        self.opt.reset(lr)
+        self.idx.zero_()
+
     def run(self, n_iters, early_stop=False, check_every=100):
-        keys = self._iteration()                       # iteration 0 eagerly (also warms everything up)
-        done = 1
-        if n_iters > 1:
+        if self.graph is None:
+            keys = self._iteration()                   # iteration 0 eagerly (also warms everything up)
+            self.keys = keys
+            done = 1
+        else:
+            keys, done = self.keys, 0
+        if n_iters > done:
             if self.graph is None:
                 torch.cuda.synchronize()
                 self.graph = torch.cuda.CUDAGraph()
@@ -264,9 +280,14 @@ class FluidStepper:
         by = sampling.sample_boundary2D_separate(n // 100, "vertical", device=dev)
         return x, bx, by
 
-    def _loop(self, nets, closure, n_iters, world=1):
+    def _loop(self, nets, closure, n_iters, world=1, key=None):
         if self.graphed:
-            return GraphedLoop(nets, self.lr, lambda: closure(0)).run(n_iters)
+            loops = self.__dict__.setdefault("_loops", {})
+            if key not in loops:                       # capture once per closure kind, replay for every time step
+                loops[key] = GraphedLoop(nets, self.lr, lambda: closure(0))
+            else:
+                loops[key].reset(self.lr)
+            return loops[key].run(n_iters)
         red = self.reducer_factory(nets) if self.reducer_factory else None
         return TrainingLoop(nets, self.lr, reducer=red).run(closure, n_iters)
 
@@ -274,16 +295,19 @@ class FluidStepper:
         def c(i):
             x, _, _ = self._samples(world)
             return fluid_initialize(self.vel, x, init_fn(x))
-        return self._loop([self.vel], c, n_iters)
+        return self._loop([self.vel], c, n_iters, key="initialize")
 
     def step(self, n_iters, world=1):
         """advect -> pressure solve -> projection; returns the three loss histories"""
         nets = [self.vel, self.pres]
         self.prev.load_state_dict(self.vel.state_dict())
-        h1 = self._loop(nets, lambda i: fluid_advect_velocity(self.vel, self.prev, *self._samples(world), self.dt), n_iters)
-        h2 = self._loop(nets, lambda i: fluid_solve_pressure(self.vel, self.pres, *self._samples(world)), n_iters)
+        h1 = self._loop(nets, lambda i: fluid_advect_velocity(self.vel, self.prev, *self._samples(world), self.dt), n_iters,
+                        key="advect")
+        h2 = self._loop(nets, lambda i: fluid_solve_pressure(self.vel, self.pres, *self._samples(world)), n_iters,
+                        key="pressure")
         self.prev.load_state_dict(self.vel.state_dict())
-        h3 = self._loop(nets, lambda i: fluid_projection(self.vel, self.prev, self.pres, *self._samples(world)), n_iters)
+        h3 = self._loop(nets, lambda i: fluid_projection(self.vel, self.prev, self.pres, *self._samples(world)), n_iters,
+                        key="project")
         return h1, h2, h3
 
 

@@ -9,6 +9,7 @@ interchange with the reference), same RNG consumption at construction (the same
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 from torch import nn
@@ -78,7 +79,9 @@ class MLP(nn.Module):
 
         self.in_features, self.out_features = in_features, out_features
         self.hidden_features, self.num_hidden_layers = hidden_features, num_hidden_layers
-        self.desc = _lib.make_desc(in_features, out_features, hidden_features, num_hidden_layers, OMEGA)
+        # INSR_NO_TENSOR=1 keeps the forward on the FP32 FFMA kernels instead of tcgen05 (3xTF32)
+        flags = _lib.FLAG_NO_TENSOR if os.environ.get("INSR_NO_TENSOR", "0") == "1" else 0
+        self.desc = _lib.make_desc(in_features, out_features, hidden_features, num_hidden_layers, OMEGA, flags)
         self._flat = None
         self._slices = None
 

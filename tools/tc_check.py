@@ -40,3 +40,19 @@ for flags, name in ((_lib.FLAG_NO_TENSOR, "ffma"), (0, "tcgen05")):
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 10
     print(name, f"{ms:.3f} ms  {N / ms / 1e3:.1f} Mpts/s  {24960 * N / ms / 1e9:.1f} TFLOP/s algorithmic", flush=True)
+
+# small-batch latency (script sizes)
+for N in (16384, 324, 162):
+    x = torch.rand(N, D, device="cuda") * 2 - 1
+    for flags, name in ((_lib.FLAG_NO_TENSOR, "ffma"), (0, "tcgen05")):
+        desc = _lib.make_desc(D, O, H, L, flags=flags)
+        for order_ in (0, 2):
+            for _ in range(5):
+                _ops.siren_forward(desc, theta, x, order_)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(50):
+                _ops.siren_forward(desc, theta, x, order_)
+            b.record(); torch.cuda.synchronize()
+            print(f"N={N} order={order_} {name}: {a.elapsed_time(b) / 50 * 1e3:.1f} us/call", flush=True)
