@@ -75,6 +75,7 @@ typedef struct insr_siren_desc {
 
 #define INSR_FLAG_NONE 0
 #define INSR_FLAG_FORCE_GENERIC 1 /* use the generic (any-H) kernels even where a fused one exists */
+#define INSR_FLAG_TENSOR_BWD 4    /* also run backward / lsq_step of the H <= 32 family on tcgen05 (tape in the workspace) */
 #define INSR_FLAG_NO_TENSOR 2     /* keep the H <= 32 family on the FP32 FFMA kernels (default: the forward runs on
                                      tcgen05/TMEM with a 3xTF32 split and FP32 accumulation, same 1e-4 parity) */
 

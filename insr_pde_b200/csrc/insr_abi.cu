@@ -256,7 +256,8 @@ int insr_siren_backward(const insr_siren_desc *desc, const float *theta, const f
         return fail(INSR_ERR_WORKSPACE, "backward needs %zu workspace bytes, got %zu", need, workspace_bytes);
     if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_fused_supported(dm, order, 1)) {
         rc = insr_fused_backward(dm, order, theta, x, n_points, gy, gjac, gh2, gtheta, gx,
-                                 (float *)workspace, stream, &g_launches);
+                                 (float *)workspace, stream, &g_launches,
+                                 (desc->flags & INSR_FLAG_TENSOR_BWD) && !(desc->flags & INSR_FLAG_NO_TENSOR));
         if (rc == INSR_ERR_UNSUPPORTED) return fail(rc, "fused backward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
         if (rc) return rc;
         return check_cuda("fused backward");
@@ -283,9 +284,14 @@ int insr_siren_lsq_step(const insr_siren_desc *desc, const float *theta, const f
         return fail(INSR_ERR_NULL, "theta, x, coef_host, loss_out and gtheta must not be NULL");
     if ((rc = check_device())) return rc;
     if (n_points == 0) return 0;
-    (void)target; (void)scale; (void)workspace; (void)workspace_bytes; (void)stream;
+    const bool tensor = (desc->flags & INSR_FLAG_TENSOR_BWD) && !(desc->flags & INSR_FLAG_NO_TENSOR);
+    if (tensor) {
+        const size_t need = insr_siren_workspace_bytes(desc, n_points, order, 1);
+        if (!workspace || workspace_bytes < need)
+            return fail(INSR_ERR_WORKSPACE, "lsq_step needs %zu workspace bytes, got %zu", need, workspace_bytes);
+    }
     rc = insr_fused_lsq_step(dm, order, n_res, coef_host, theta, x, n_points, target, scale, loss_out,
-                             gtheta, (float *)workspace, workspace_bytes, stream, &g_launches);
+                             gtheta, (float *)workspace, workspace_bytes, stream, &g_launches, tensor);
     if (rc == INSR_ERR_UNSUPPORTED)
         return fail(rc, "lsq_step: no fused kernel for D=%d O=%d H=%d L=%d order=%d", dm.D, dm.O, dm.H, dm.L, order);
     if (rc) return rc;

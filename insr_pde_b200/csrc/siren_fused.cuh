@@ -49,6 +49,7 @@ struct Params {
     int n_res;
     float coef[MAX_COEF];                // lsq: coef[c][o][s]
     int nwarps;
+    void *ws;                            // tensor-core backward: tape scratch
 };
 
 // ---- shared-memory map (float offsets) ------------------------------------------------
@@ -844,7 +845,12 @@ inline bool insr_fused_supported(const SirenDims &dm, int order, int backward) {
     return dm.L <= (backward ? LMAX_BWD : LMAX_FWD);
 }
 
-inline size_t insr_fused_ws_bytes(const SirenDims &, int64_t, int, int) { return 0; }
+// the tensor-core backward keeps its tape in a per-CTA global scratch: (L+1) * 4 (S+1) float4 per thread
+inline size_t insr_fused_ws_bytes(const SirenDims &dm, int64_t, int order, int backward) {
+    if (!backward) return 0;
+    const int S = insr_nstreams(dm.D, order);
+    return (size_t)insr_fused::sm_count() * (size_t)(dm.L + 1) * 4 * (S + 1) * 256 * 16 + 256;
+}
 
 // one translation unit per (D, O) pair instantiates the kernels (siren_fused_inst.cuh) so that
 // nvcc can build them in parallel; kind: 0 = forward, 1 = backward, 2 = lsq step
@@ -869,20 +875,21 @@ inline int insr_fused_forward(const SirenDims &dm, int order, const float *theta
 
 inline int insr_fused_backward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
                                const float *gy, const float *gjac, const float *gh2, float *gtheta, float *gx,
-                               float *, void *stream, int64_t *launches) {
+                               float *ws, void *stream, int64_t *launches, bool tensor = false) {
     insr_fused::Params p{};
     p.dm = dm; p.theta = theta; p.x = x; p.N = N; p.gy = gy; p.gjac = gjac; p.gh2 = gh2;
-    p.gtheta = gtheta; p.gx = gx;
-    return insr_fused_run(1, p, order, stream, launches);
+    p.gtheta = gtheta; p.gx = gx; p.ws = ws;
+    return insr_fused_run(tensor ? 4 : 1, p, order, stream, launches);
 }
 
 // coef_host: cy (n_res x O) | cj (n_res x O x D) | cl (n_res x O)  ->  coef[c][o][s]
 inline int insr_fused_lsq_step(const SirenDims &dm, int order, int n_res, const float *coef_host,
                                const float *theta, const float *x, int64_t N, const float *target, float scale,
-                               float *loss_out, float *gtheta, float *, size_t, void *stream, int64_t *launches) {
+                               float *loss_out, float *gtheta, float *ws, size_t, void *stream, int64_t *launches,
+                               bool tensor = false) {
     if (!insr_fused_supported(dm, order, 1)) return -6;
     insr_fused::Params p{};
-    p.dm = dm; p.theta = theta; p.x = x; p.N = N; p.gtheta = gtheta; p.gx = nullptr;
+    p.dm = dm; p.theta = theta; p.x = x; p.N = N; p.gtheta = gtheta; p.gx = nullptr; p.ws = ws;
     p.target = target; p.scale = scale; p.loss_out = loss_out; p.n_res = n_res;
     const int D = dm.D, O = dm.O, S = insr_nstreams(D, order);
     const float *cy = coef_host, *cj = coef_host + n_res * O, *cl = cj + n_res * O * D;
@@ -894,5 +901,5 @@ inline int insr_fused_lsq_step(const SirenDims &dm, int order, int n_res, const 
                 for (int d = 0; d < D; ++d) dst[1 + d] = cj[(c * O + o) * D + d];
             if (order == 2) dst[1 + D] = cl[c * O + o];
         }
-    return insr_fused_run(2, p, order, stream, launches);
+    return insr_fused_run(tensor ? 5 : 2, p, order, stream, launches);
 }

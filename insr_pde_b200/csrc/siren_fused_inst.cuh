@@ -9,13 +9,27 @@ int INSR_INST_CAT(insr_fused_run_, INSR_INST_D, INSR_INST_O)(int kind, insr_fuse
     using namespace insr_fused;
     constexpr int D = INSR_INST_D, O = INSR_INST_O;
 #ifdef INSR_CPU_EMU
-    if (kind == 3) kind = 0;             // the emulator has no tensor cores: FFMA forward
+    if (kind == 3) kind = 0;             // the emulator has no tensor cores: FFMA kernels
+    if (kind == 4) kind = 1;
+    if (kind == 5) kind = 2;
 #else
     if (kind == 3) {                     // tcgen05 / TMEM 3xTF32 forward (siren_tc.cuh)
         switch (order) {
             case 0: return insr_tc::launch_tc_fwd<D, O, 0>(p, stream, launches);
             case 1: return insr_tc::launch_tc_fwd<D, O, 1>(p, stream, launches);
             case 2: return insr_tc::launch_tc_fwd<D, O, 2>(p, stream, launches);
+        }
+        return -6;
+    }
+    if (kind == 4 || kind == 5) {        // tcgen05 backward / fused closure; p.ws carries the tape scratch
+        float *ws = reinterpret_cast<float *>(p.ws);
+        switch (order * 2 + (kind - 4)) {
+            case 0: return insr_tc::launch_tc_bwd<D, O, 0, false>(p, ws, stream, launches);
+            case 1: return insr_tc::launch_tc_bwd<D, O, 0, true>(p, ws, stream, launches);
+            case 2: return insr_tc::launch_tc_bwd<D, O, 1, false>(p, ws, stream, launches);
+            case 3: return insr_tc::launch_tc_bwd<D, O, 1, true>(p, ws, stream, launches);
+            case 4: return insr_tc::launch_tc_bwd<D, O, 2, false>(p, ws, stream, launches);
+            case 5: return insr_tc::launch_tc_bwd<D, O, 2, true>(p, ws, stream, launches);
         }
         return -6;
     }
