@@ -1,20 +1,34 @@
-// siren_tc.cuh -- tcgen05 / TMEM forward kernel for the resident-weights family (H <= 32).
+// siren_tc.cuh -- tcgen05 / TMEM kernels for the resident-weights family (H <= 32).
 //
 // Why: ncu shows the FFMA kernels limited by shared-memory delivery (LDS wavefronts), not by the
-// FP32 pipe; the 5th-gen tensor cores read their operands straight from shared memory through
-// descriptors.  Single-pass TF32 misses the 1e-4 parity target, so every hidden-layer
-// contraction is done as a 3xTF32 split:  a = a_hi + a_lo (a_hi = fp32 with the 13 low mantissa bits
-// cleared, a_lo = a - a_hi exact),  a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo  accumulated in FP32 in
-// TMEM (dropped term ~2^-22 relative).
+// FP32 pipe; the 5th-gen tensor cores take their operands from shared memory descriptors or from TMEM.
+// Single-pass TF32 misses the 1e-4 parity target, so every hidden-layer contraction of
+// the forward pass and of the data gradient is a 3xTF32 split:  a = a_hi + a_lo (a_hi = fp32 with the 13
+// low mantissa bits cleared, a_lo = a - a_hi exact),  a.w ~= a_hi.w_hi + a_hi.w_lo + a_lo.w_hi
+// accumulated in FP32 in TMEM (dropped term ~2^-22 relative).
 //
 // Mapping.  CTA tile = 128 collocation points = the M dimension of tcgen05.mma (one TMEM lane per
 // point).  Each forward-mode stream s is its own MMA chain  D_s[128 x 32] = A_s[128 x 32] . W^T
 // into TMEM columns [32 s, 32 s + 32), so a thread (= one point) reads ALL streams of its neurons
-// with tcgen05.ld and runs the sine-stream algebra in registers, then writes the next layer's
-// operand -- already split into hi / lo -- back to shared memory in the UMMA K-major canonical
-// layout (8 x 16-byte core matrices, LBO = 128 B along K, SBO = 1024 B along M/N).  256 threads:
-// warps w and w+4 share TMEM lanes 32 (w%4) .. +31 and split the 32 neurons in two halves.
-// One elected thread issues the 3 x 4 x S MMAs of a layer and commits them to an mbarrier.
+// with tcgen05.ld and runs the sine-stream algebra in registers.  256 threads: warps w and w+4 share
+// TMEM lanes 32 (w%4) .. +31 and split the 32 neurons in two halves.
+//
+// Measured on the B200 (tools/probe/*.cu, profiles/r1_tcgen05_probes.txt) and designed around:
+//   * an MMA whose A operand comes from shared memory costs 32 + N/4 cycles (operand fetch at 128 B/clk:
+//     40 cycles at N = 32), the same MMA with A in TMEM costs N/2 = 16 cycles.  So the hi part of every
+//     activation operand is written back to TMEM with tcgen05.st (columns [32 S + 32 s, ..)) and used by
+//     two MMAs (x W_hi, x W_lo); only the lo part goes through shared memory (UMMA K-major canonical
+//     layout: 8 x 16-byte core matrices, LBO = 128 B along K, SBO = 1024 B along M/N).
+//   * kind::tf32 ignores MN-major ("transposed") operands: the MMA contributes exactly zero.  The data
+//     gradient therefore uses a second, explicitly transposed copy of the weights.  kind::f16 (bf16) does
+//     honour MN-major operands, so the weight gradient -- a reduction over POINTS, i.e. over the rows of
+//     the natural [point][neuron] layout -- runs in bf16 with both operands split in two bf16 levels
+//     (z = z1 + z2, a = a1 + a2, |error| <= 2^-17 per operand, all four cross products kept):
+//         D[64 x 64] += [z1 | z2]^T . [a1 | a2]      (M = 64 = 2 levels x 32 neurons, N likewise, K = points)
+//     read MN-major from rows of 128 bytes in the 128-byte swizzle; the accumulators of all layers stay in
+//     TMEM for the whole launch.
+//   * tcgen05.mma must be issued from a warp-uniform branch by ONE elected lane (elect.sync): a
+//     `tid == 0` branch makes nvcc wrap every MMA in a divergence "waterfall" loop (~100 cycles each).
 //
 // Only compiled by nvcc (inline PTX); the host-side SIMT emulation does not cover this file.
 #pragma once
@@ -29,10 +43,10 @@ constexpr int TILE_M = 128;
 constexpr int THREADS = 256;
 constexpr int OP_BYTES = TILE_M * HP * 4;          // one 128 x 32 fp32 operand: 16 KB
 constexpr int W_BYTES = HP * HP * 4;               // one 32 x 32 weight operand: 4 KB
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 // kind::tf32, D = F32, A/B = TF32, both K-major, N = 32, M = 128
-constexpr uint32_t IDESC_DGRAD = IDESC | (1u << 16);                 // B operand MN-major (W read "transposed")
-constexpr uint32_t IDESC_WGRAD = IDESC | (1u << 15) | (1u << 16);    // A and B MN-major (reduction over points)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16, D = F32, A/B = BF16, both MN-major, N = 64, M = 64
+constexpr uint32_t IDESC_WG = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -41,21 +55,37 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46);
 }
+// MN-major, 128-byte swizzle: rows of 128 B (64 bf16 along M/N), 8 rows (K) per 1024-byte atom, SBO = 1024 B
+// between 8-row groups along K (probe2: element (n, k) at (k>>3)*1024 + (k&7)*128 + (((n>>3) ^ (k&7)) << 4) + (n&7)*2)
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // byte offset of element (row, k) inside a K-major canonical operand
 __device__ __forceinline__ int op_off(int row, int k) { return (row >> 3) * 1024 + (k >> 2) * 128 + (row & 7) * 16 + (k & 3) * 4; }
 
-// the same 8 x 16-byte core matrices read MN-major (M/N index contiguous inside the 16 bytes, the 8 rows
-// are the K index): leading (K-group) offset 1024 B, stride (M/N-group) offset 128 B
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
-           ((uint64_t)1 << 46);
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate,
-                                         uint32_t idesc = IDESC) {
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_wg(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC_WG), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
@@ -78,74 +108,54 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     INSR_PRAGMA_UNROLL
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                    "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                    "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
 
-// write 4 consecutive neurons (k = 4 kg .. 4 kg + 3) of one stream of row `row`, split hi / lo
-__device__ __forceinline__ void store_split4(unsigned char *op_hi, unsigned char *op_lo, int row, int kg,
-                                             const float (&a)[4]) {
-    float h[4], l[4];
+// 8 consecutive neurons (k = 8 g .. 8 g + 7; g = 0..3) of one stream of row `row`: the hi part goes to TMEM
+// (8 columns at a_tmem), the lo part to the K-major shared-memory operand
+__device__ __forceinline__ void store_split8(uint32_t a_tmem, unsigned char *op_lo, int row, int g, const float (&a)[8]) {
+    float h[8], l[8];
     INSR_PRAGMA_UNROLL
-    for (int c = 0; c < 4; ++c) { h[c] = tf32_hi(a[c]); l[c] = a[c] - h[c]; }
-    const int off = (row >> 3) * 1024 + kg * 128 + (row & 7) * 16;
-    *reinterpret_cast<float4 *>(op_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+    for (int c = 0; c < 8; ++c) { h[c] = tf32_hi(a[c]); l[c] = a[c] - h[c]; }
+    tmem_st8(a_tmem, h);
+    const int off = (row >> 3) * 1024 + (2 * g) * 128 + (row & 7) * 16;
     *reinterpret_cast<float4 *>(op_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<float4 *>(op_lo + off + 128) = make_float4(l[4], l[5], l[6], l[7]);
 }
 
-// shared-memory map (bytes)
-struct Smem {
-    int w_hi, w_lo, bias, w1, wo, bo, a_hi, a_lo, part, mbar, tmem, total;
-};
-__host__ __device__ inline Smem smem_map(int L, int S, int O) {
-    Smem m;
-    int o = 0;
-    m.w_hi = o; o += L * W_BYTES;
-    m.w_lo = o; o += L * W_BYTES;
-    m.a_hi = o; o += S * OP_BYTES;
-    m.a_lo = o; o += S * OP_BYTES;
-    m.bias = o; o += L * HP * 4;
-    m.w1 = o; o += HP * 16;
-    m.wo = o; o += 3 * HP * 4;
-    m.bo = o; o += 16;
-    m.part = o; o += TILE_M * 16 * 4;          // output-layer partials of the upper neuron half: [128][<=16]
-    m.mbar = o; o += 16;
-    m.tmem = o; o += 16;
-    m.total = o;
-    return m;
-}
-
-template <int D, int O, int ORDER>
-__global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(Params p, int tmem_cols) {
-    typedef StreamCfg<D, ORDER> C;
-    constexpr int S = C::S;
-    extern __shared__ __align__(1024) unsigned char smraw[];
-    const SirenDims dm = p.dm;
-    const int L = dm.L, H = dm.H;
-    const Smem M = smem_map(L, S, O);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = 32 * (warp & 3) + lane;            // TMEM lane == point inside the tile
-    const int half = warp >> 2;                        // neurons 16 half .. 16 half + 15
-    float *biasS = reinterpret_cast<float *>(smraw + M.bias);
-    float *w1S = reinterpret_cast<float *>(smraw + M.w1);
-    float *woS = reinterpret_cast<float *>(smraw + M.wo);
-    float *boS = reinterpret_cast<float *>(smraw + M.bo);
-    float *partS = reinterpret_cast<float *>(smraw + M.part);
-    const uint32_t mbar = s32(smraw + M.mbar);
-
-    // ---- stage weights: hidden layers split hi / lo in UMMA K-major layout (omega folded in)
-    const float w = dm.omega;
-    for (int idx = tid; idx < L * HP * HP; idx += THREADS) {
-        const int l = idx / (HP * HP), j = (idx / HP) % HP, k = idx % HP;
-        float v = 0.f;
-        if (j < H && k < H) v = w * p.theta[insr_w_offset(dm, l + 1) + (int64_t)j * H + k];
-        const float hi = tf32_hi(v);
-        *reinterpret_cast<float *>(smraw + M.w_hi + l * W_BYTES + op_off(j, k)) = hi;
-        *reinterpret_cast<float *>(smraw + M.w_lo + l * W_BYTES + op_off(j, k)) = v - hi;
+// the 12 MMAs of one stream of one hidden-layer contraction: D (32 columns) = A . B^T with A_hi in TMEM
+// (32 columns at a_tmem), A_lo and B_hi / B_lo K-major in shared memory
+__device__ __forceinline__ void issue_stream(uint32_t d_tmem, uint32_t a_tmem, uint32_t alo, uint32_t bhi, uint32_t blo) {
+    INSR_PRAGMA_UNROLL
+    for (int ks = 0; ks < 4; ++ks) {                  // K = 8 per instruction: 8 TMEM columns / two 16-byte core matrices
+        mma_tf32_ts(d_tmem, a_tmem + 8 * ks, umma_desc(bhi + 256 * ks), ks > 0);
+        mma_tf32_ts(d_tmem, a_tmem + 8 * ks, umma_desc(blo + 256 * ks), 1);
+        mma_tf32_ss(d_tmem, umma_desc(alo + 256 * ks), umma_desc(bhi + 256 * ks), 1);
     }
+}
+
+__host__ __device__ inline int pow2_cols(int c) {
+    int r = 32;
+    while (r < c) r <<= 1;
+    return r;
+}
+
+// stage the small operands shared by the forward and the backward kernel
+__device__ __forceinline__ void stage_small(const Params &p, float *biasS, float *w1S, float *woS, float *boS) {
+    const SirenDims &dm = p.dm;
+    const int L = dm.L, H = dm.H, D = dm.D, O = dm.O, tid = threadIdx.x;
+    const float w = dm.omega;
     for (int idx = tid; idx < L * HP; idx += THREADS) {
         const int l = idx / HP, j = idx % HP;
         biasS[idx] = (j < H) ? w * p.theta[insr_b_offset(dm, l + 1) + j] : 0.f;
@@ -164,6 +174,68 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(Params p, int tmem_cols) 
         woS[idx] = (o < O && j < H) ? p.theta[insr_w_offset(dm, L + 1) + (int64_t)o * H + j] : 0.f;
     }
     if (tid < 4) boS[tid] = (tid < O) ? p.theta[insr_b_offset(dm, L + 1) + tid] : 0.f;
+}
+// hidden-layer weights split hi / lo in the UMMA K-major layout (omega folded in); transposed = B operand of
+// the data gradient (row = input neuron k, reduction index = output neuron j)
+__device__ __forceinline__ void stage_hidden(const Params &p, unsigned char *whi, unsigned char *wlo, bool transposed) {
+    const SirenDims &dm = p.dm;
+    const int L = dm.L, H = dm.H;
+    const float w = dm.omega;
+    for (int idx = threadIdx.x; idx < L * HP * HP; idx += THREADS) {
+        const int l = idx / (HP * HP), j = (idx / HP) % HP, k = idx % HP;
+        float v = 0.f;
+        if (j < H && k < H) v = w * p.theta[insr_w_offset(dm, l + 1) + (int64_t)j * H + k];
+        const float hi = tf32_hi(v);
+        const int off = l * W_BYTES + (transposed ? op_off(k, j) : op_off(j, k));
+        *reinterpret_cast<float *>(whi + off) = hi;
+        *reinterpret_cast<float *>(wlo + off) = v - hi;
+    }
+}
+
+// =============================================================================================
+// forward kernel: 2 CTAs per SM (one's MMAs overlap the other's epilogue), 256 TMEM columns each
+// =============================================================================================
+struct Smem {
+    int w_hi, w_lo, a_lo, bias, w1, wo, bo, part, mbar, tmem, total;
+};
+__host__ __device__ inline Smem smem_map(int L, int S) {
+    Smem m;
+    int o = 0;
+    m.w_hi = o; o += L * W_BYTES;
+    m.w_lo = o; o += L * W_BYTES;
+    m.a_lo = o; o += S * OP_BYTES;
+    m.bias = o; o += L * HP * 4;
+    m.w1 = o; o += HP * 16;
+    m.wo = o; o += 3 * HP * 4;
+    m.bo = o; o += 16;
+    m.part = o; o += TILE_M * 16 * 4;          // output-layer partials of the upper neuron half: [128][<=16]
+    m.mbar = o; o += 16;
+    m.tmem = o; o += 16;
+    m.total = o;
+    return m;
+}
+
+template <int D, int O, int ORDER>
+__global__ void __launch_bounds__(THREADS, 2) k_tc_fwd(Params p, int tmem_cols) {
+    typedef StreamCfg<D, ORDER> C;
+    constexpr int S = C::S;
+    constexpr int ABASE = 32 * S;                      // TMEM columns of the hi operand
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    const SirenDims dm = p.dm;
+    const int L = dm.L;
+    const Smem M = smem_map(L, S);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = 32 * (warp & 3) + lane;            // TMEM lane == point inside the tile
+    const int half = warp >> 2;                        // neurons 16 half .. 16 half + 15
+    float *biasS = reinterpret_cast<float *>(smraw + M.bias);
+    float *w1S = reinterpret_cast<float *>(smraw + M.w1);
+    float *woS = reinterpret_cast<float *>(smraw + M.wo);
+    float *boS = reinterpret_cast<float *>(smraw + M.bo);
+    float *partS = reinterpret_cast<float *>(smraw + M.part);
+    const uint32_t mbar = s32(smraw + M.mbar);
+
+    stage_hidden(p, smraw + M.w_hi, smraw + M.w_lo, false);
+    stage_small(p, biasS, w1S, woS, boS);
 
     // ---- TMEM allocation (warp 0) + mbarrier init
     if (warp == 0) {
@@ -191,59 +263,66 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(Params p, int tmem_cols) 
         INSR_PRAGMA_UNROLL
         for (int d = 0; d < D; ++d) xv[d] = valid ? __ldg(p.x + n * D + d) : 0.f;
 
-        float alast[S][16];                              // post-activations of the current layer (this thread's 16 neurons)
-        // ---- first sine layer (FFMA): 4 groups of 4 neurons
+        // ---- first sine layer (FFMA): 2 groups of 8 neurons
         INSR_PRAGMA_UNROLL
-        for (int g4 = 0; g4 < 4; ++g4) {
-            float z[S][4], a[S][4], tv[S + 1][4];
+        for (int g8 = 0; g8 < 2; ++g8) {
+            float a8[S][8];
             INSR_PRAGMA_UNROLL
-            for (int c = 0; c < 4; ++c) {
-                const int j = 16 * half + 4 * g4 + c;
-                const float4 wv = *reinterpret_cast<const float4 *>(w1S + j * 4);
-                float acc = wv.w;
+            for (int q = 0; q < 2; ++q) {
+                float z[S][4], a[S][4], tv[S + 1][4];
                 INSR_PRAGMA_UNROLL
-                for (int d = 0; d < D; ++d) acc = fmaf(insr_fused::f4get(wv, d), xv[d], acc);
-                z[0][c] = acc;
+                for (int c = 0; c < 4; ++c) {
+                    const int j = 16 * half + 8 * g8 + 4 * q + c;
+                    const float4 wv = *reinterpret_cast<const float4 *>(w1S + j * 4);
+                    float acc = wv.w;
+                    INSR_PRAGMA_UNROLL
+                    for (int d = 0; d < D; ++d) acc = fmaf(insr_fused::f4get(wv, d), xv[d], acc);
+                    z[0][c] = acc;
+                    INSR_PRAGMA_UNROLL
+                    for (int d = 0; d < C::ND; ++d) z[1 + d][c] = insr_fused::f4get(wv, d);
+                    if constexpr (ORDER == 2) z[1 + C::ND][c] = 0.f;
+                }
+                insr_fused::act4<D, ORDER>(z, a, tv);
                 INSR_PRAGMA_UNROLL
-                for (int d = 0; d < C::ND; ++d) z[1 + d][c] = insr_fused::f4get(wv, d);
-                if constexpr (ORDER == 2) z[1 + C::ND][c] = 0.f;
+                for (int s = 0; s < S; ++s)
+                    INSR_PRAGMA_UNROLL
+                    for (int c = 0; c < 4; ++c) a8[s][4 * q + c] = a[s][c];
             }
-            insr_fused::act4<D, ORDER>(z, a, tv);
             INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s) {
-                store_split4(smraw + M.a_hi + s * OP_BYTES, smraw + M.a_lo + s * OP_BYTES, row, 4 * half + g4, a[s]);
-                INSR_PRAGMA_UNROLL
-                for (int c = 0; c < 4; ++c) alast[s][4 * g4 + c] = a[s][c];
-            }
+            for (int s = 0; s < S; ++s)
+                store_split8(tmem_row + ABASE + 32 * s + 16 * half + 8 * g8, smraw + M.a_lo + s * OP_BYTES, row, 2 * half + g8, a8[s]);
         }
+        float out[O][S];
+        INSR_PRAGMA_UNROLL
+        for (int o = 0; o < O; ++o)
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) out[o][s] = 0.f;
+
         // ---- hidden layers on the tensor cores
         for (int l = 0; l < L; ++l) {
+            tmem_st_wait();
             fence_async_smem();                          // generic-proxy operand writes -> visible to the async proxy
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after();
-                const uint32_t whi = s32(smraw + M.w_hi + l * W_BYTES), wlo = s32(smraw + M.w_lo + l * W_BYTES);
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) {
-                    const uint32_t ahi = s32(smraw + M.a_hi + s * OP_BYTES), alo = s32(smraw + M.a_lo + s * OP_BYTES);
-                    const uint32_t d = tmem_base + 32 * s;
+                if (elect_one()) {
+                    const uint32_t whi = s32(smraw + M.w_hi + l * W_BYTES), wlo = s32(smraw + M.w_lo + l * W_BYTES);
                     INSR_PRAGMA_UNROLL
-                    for (int ks = 0; ks < 4; ++ks) {      // K = 8 per instruction: two 16-byte core matrices = 256 B
-                        mma_tf32(d, umma_desc(ahi + 256 * ks), umma_desc(whi + 256 * ks), ks > 0);
-                        mma_tf32(d, umma_desc(alo + 256 * ks), umma_desc(whi + 256 * ks), 1);
-                        mma_tf32(d, umma_desc(ahi + 256 * ks), umma_desc(wlo + 256 * ks), 1);
-                    }
+                    for (int s = 0; s < S; ++s)
+                        issue_stream(tmem_base + 32 * s, tmem_base + ABASE + 32 * s, s32(smraw + M.a_lo + s * OP_BYTES), whi, wlo);
+                    mma_commit(mbar);
                 }
-                mma_commit(mbar);
+                __syncwarp();
             }
             mbar_wait(mbar, phase);
             phase ^= 1;
             tc_fence_after();
+            const bool last = (l == L - 1);
             // ---- epilogue: 2 groups of 8 neurons of this thread's half
             INSR_PRAGMA_UNROLL
             for (int g8 = 0; g8 < 2; ++g8) {
-                float zz[S][8];
+                float zz[S][8], a8[S][8];
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s) tmem_ld8(tmem_row + 32 * s + 16 * half + 8 * g8, zz[s]);
                 tmem_ld_wait();
@@ -259,32 +338,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(Params p, int tmem_cols) 
                     }
                     insr_fused::act4<D, ORDER>(z, a, tv);
                     INSR_PRAGMA_UNROLL
-                    for (int s = 0; s < S; ++s) {
-                        store_split4(smraw + M.a_hi + s * OP_BYTES, smraw + M.a_lo + s * OP_BYTES, row,
-                                     4 * half + 2 * g8 + q, a[s]);
+                    for (int s = 0; s < S; ++s)
                         INSR_PRAGMA_UNROLL
-                        for (int c = 0; c < 4; ++c) alast[s][8 * g8 + 4 * q + c] = a[s][c];
-                    }
+                        for (int c = 0; c < 4; ++c) a8[s][4 * q + c] = a[s][c];
+                }
+                if (last) {                              // output layer (FFMA) folded into the last epilogue
+                    INSR_PRAGMA_UNROLL
+                    for (int o = 0; o < O; ++o)
+                        INSR_PRAGMA_UNROLL
+                        for (int s = 0; s < S; ++s)
+                            INSR_PRAGMA_UNROLL
+                            for (int i = 0; i < 8; ++i) out[o][s] = fmaf(woS[o * HP + 16 * half + 8 * g8 + i], a8[s][i], out[o][s]);
+                } else {
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s)
+                        store_split8(tmem_row + ABASE + 32 * s + 16 * half + 8 * g8, smraw + M.a_lo + s * OP_BYTES, row, 2 * half + g8, a8[s]);
                 }
             }
         }
-        // ---- output layer (FFMA): this thread's 16 neurons, then combine the two halves
-        float out[O][S];
-        INSR_PRAGMA_UNROLL
-        for (int o = 0; o < O; ++o)
-            INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s) {
-                float acc = 0.f;
-                INSR_PRAGMA_UNROLL
-                for (int i = 0; i < 16; ++i) acc = fmaf(woS[o * HP + 16 * half + i], alast[s][i], acc);
-                out[o][s] = acc;
-            }
+        // ---- combine the two neuron halves
         if (half == 1) {
             INSR_PRAGMA_UNROLL
             for (int o = 0; o < O; ++o)
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s) partS[row * 16 + o * S + s] = out[o][s];
         }
+        tc_fence_before();
         __syncthreads();
         if (half == 0 && valid) {
             INSR_PRAGMA_UNROLL
@@ -295,7 +374,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(Params p, int tmem_cols) 
                 insr_store_outputs<D, O, ORDER>(n, o, out[o], p.y, p.jac, p.h2);
             }
         }
-        __syncthreads();                                 // partS / operands are rewritten by the next tile
+        __syncthreads();                                 // partS is rewritten by the next tile
+        tc_fence_after();
     }
     // ---- TMEM release
     tc_fence_before();
@@ -305,36 +385,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(Params p, int tmem_cols) 
     }
 }
 
-inline int tmem_columns(int S) {
-    int c = 32;
-    while (c < 32 * S) c <<= 1;
-    return c;
-}
-
 template <int D, int O, int ORDER>
 int launch_tc_fwd(Params &p, void *stream, int64_t *launches) {
     constexpr int S = StreamCfg<D, ORDER>::S;
     static_assert(O * S <= 16, "output partial buffer holds 16 values per point");
-    const Smem M = smem_map(p.dm.L, S, O);
+    const Smem M = smem_map(p.dm.L, S);
     auto kfn = k_tc_fwd<D, O, ORDER>;
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, M.total + 1024);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, M.total);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const int64_t tiles = (p.N + TILE_M - 1) / TILE_M;
-    int64_t ctas = tiles < insr_fused::sm_count() ? tiles : insr_fused::sm_count();
-    kfn<<<dim3((unsigned)ctas), dim3(THREADS), M.total + 1024, reinterpret_cast<cudaStream_t>(stream)>>>(p, tmem_columns(S));
+    const int64_t slots = 2 * (int64_t)insr_fused::sm_count();
+    const int64_t ctas = tiles < slots ? tiles : slots;
+    kfn<<<dim3((unsigned)ctas), dim3(THREADS), M.total, reinterpret_cast<cudaStream_t>(stream)>>>(p, pow2_cols(64 * S));
     ++*launches;
     return 0;
 }
 
 
 // =============================================================================================
-// backward / fused-closure kernel on the tensor cores
-//   forward recompute   D_s = A_s W^T                 (A K-major, W K-major)
-//   data gradient       D_s = Zbar_s W                (Zbar K-major, the SAME W buffer read MN-major)
-//   weight gradient     Wacc_l[j][k] += sum_p Zbar_s[p][j] A_s[p][k]   (both operands read MN-major; the
-//                       accumulators stay in TMEM for the whole launch and are read out once at the end)
+// backward / fused-closure kernel on the tensor cores (one CTA per SM, 512 TMEM columns)
+//   forward recompute   D_s = A_s W^T        3xTF32, A_hi in TMEM, A_lo / W K-major in shared memory
+//   data gradient       D_s = Zbar_s W       the same, against the transposed weight copy
+//   weight gradient     Wacc_l[64 x 64] += [z1|z2]^T [a1|a2]   bf16 x 2 levels, both operands MN-major;
+//                       accumulators stay in TMEM for the whole launch and are read out once at the end
+// TMEM columns: [0, 32 S) accumulators, [32 S, 64 S) hi operand, [64 S, 64 S + 64 L) weight-gradient accumulators.
 // The tape (sin, cos, t_d, t_q per activation) lives in a per-CTA global scratch that stays L2-resident.
 // Thin layers (first / output layer, biases, d loss/d x) are reduced over the 32 points of a warp with a
-// halving butterfly (16 shuffles per 16 values) into 7 persistent registers.
+// halving butterfly (16 shuffles per 16 values) into a few persistent registers.
 // =============================================================================================
 __device__ __forceinline__ float reduce16(float (&v)[16], int lane) {
     // after the call the lane holds the warp-wide sum of value index (lane >> 1) & 15
@@ -368,17 +445,21 @@ __device__ __forceinline__ float reduce16(float (&v)[16], int lane) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+constexpr int NSLOT = 2;                            // weight-gradient operand slots (one stream each)
+constexpr int SLOT_BYTES = 2 * TILE_M * 128;        // ZT (128 points x 128 B) | AT (128 points x 128 B)
+
 struct SmemB {
-    int w_hi, w_lo, x_hi, x_lo, y_hi[2], y_lo[2], bias, w1, wo, bo, part, mbar, tmem, total;
+    int slots, x_lo, w_hi, w_lo, wt_hi, wt_lo, bias, w1, wo, bo, part, mbar, tmem, total;
 };
 __host__ __device__ inline SmemB smem_map_bwd(int L, int S) {
     SmemB m;
     int o = 0;
+    m.slots = o; o += NSLOT * SLOT_BYTES;          // first: 1024-byte aligned (128-byte swizzle atoms)
+    m.x_lo = o; o += S * OP_BYTES;
     m.w_hi = o; o += L * W_BYTES;
     m.w_lo = o; o += L * W_BYTES;
-    m.x_hi = o; o += S * OP_BYTES;
-    m.x_lo = o; o += S * OP_BYTES;
-    for (int i = 0; i < 2; ++i) { m.y_hi[i] = o; o += OP_BYTES; m.y_lo[i] = o; o += OP_BYTES; }
+    m.wt_hi = o; o += L * W_BYTES;
+    m.wt_lo = o; o += L * W_BYTES;
     m.bias = o; o += L * HP * 4;
     m.w1 = o; o += HP * 16;
     m.wo = o; o += 3 * HP * 4;
@@ -392,14 +473,41 @@ __host__ __device__ inline SmemB smem_map_bwd(int L, int S) {
 // tape: per CTA  [(L+1)][4 (S+1)][256] float4
 __host__ __device__ inline size_t tape_float4_per_cta(int L, int S) { return (size_t)(L + 1) * 4 * (S + 1) * THREADS; }
 
+// two bf16 levels of 16 values -> 2 x 8 packed words
+__device__ __forceinline__ void split_bf16x2(const float (&v)[16], uint32_t (&l1)[8], uint32_t (&l2)[8]) {
+    INSR_PRAGMA_UNROLL
+    for (int i = 0; i < 8; ++i) {
+        uint32_t w1, w2;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+        const float r0 = v[2 * i] - __uint_as_float(w1 << 16);
+        const float r1 = v[2 * i + 1] - __uint_as_float(w1 & 0xFFFF0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w2) : "f"(r1), "f"(r0));
+        l1[i] = w1; l2[i] = w2;
+    }
+}
+// write this thread's 16 neurons (two levels) of one stream into a [point][64 bf16] operand with 128-byte swizzle:
+// chunks 2 half, 2 half + 1 hold level 1, chunks 4 + 2 half, 5 + 2 half level 2
+__device__ __forceinline__ void store_wg_operand(unsigned char *buf, int row, int half, const float (&v)[16]) {
+    uint32_t l1[8], l2[8];
+    split_bf16x2(v, l1, l2);
+    unsigned char *r = buf + row * 128;
+    const int key = row & 7;
+    *reinterpret_cast<uint4 *>(r + (((2 * half) ^ key) << 4)) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+    *reinterpret_cast<uint4 *>(r + (((2 * half + 1) ^ key) << 4)) = make_uint4(l1[4], l1[5], l1[6], l1[7]);
+    *reinterpret_cast<uint4 *>(r + (((4 + 2 * half) ^ key) << 4)) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+    *reinterpret_cast<uint4 *>(r + (((5 + 2 * half) ^ key) << 4)) = make_uint4(l2[4], l2[5], l2[6], l2[7]);
+}
+
 template <int D, int O, int ORDER, bool LSQ>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restrict__ tape_all, int tmem_cols) {
     typedef StreamCfg<D, ORDER> C;
     constexpr int S = C::S;
     constexpr int TV = S + 1;
     constexpr int NQ = 4 * TV;                       // float4 tape slots per thread per layer
+    constexpr int ABASE = 32 * S, WBASE = 64 * S;
     static_assert(O * S <= 8, "partial buffers hold 8 values per point and half");
-    extern __shared__ __align__(1024) unsigned char smraw[];
+    extern __shared__ __align__(1024) unsigned char smraw_[];
+    unsigned char *smraw = smraw_ + ((1024u - (s32(smraw_) & 1023u)) & 1023u);     // 128-byte swizzle atoms: 1024-byte aligned
     const SirenDims dm = p.dm;
     const int L = dm.L, H = dm.H;
     const SmemB M = smem_map_bwd(L, S);
@@ -414,34 +522,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
     const uint32_t mbarD = s32(smraw + M.mbar), mbarY0 = mbarD + 8, mbarY1 = mbarD + 16;
     float4 *tape = tape_all + (size_t)blockIdx.x * tape_float4_per_cta(L, S);
 
-    // ---- stage weights (as in the forward kernel)
-    const float w = dm.omega;
-    for (int idx = tid; idx < L * HP * HP; idx += THREADS) {
-        const int l = idx / (HP * HP), j = (idx / HP) % HP, k = idx % HP;
-        float v = 0.f;
-        if (j < H && k < H) v = w * p.theta[insr_w_offset(dm, l + 1) + (int64_t)j * H + k];
-        const float hi = tf32_hi(v);
-        *reinterpret_cast<float *>(smraw + M.w_hi + l * W_BYTES + op_off(j, k)) = hi;
-        *reinterpret_cast<float *>(smraw + M.w_lo + l * W_BYTES + op_off(j, k)) = v - hi;
-    }
-    for (int idx = tid; idx < L * HP; idx += THREADS) {
-        const int l = idx / HP, j = idx % HP;
-        biasS[idx] = (j < H) ? w * p.theta[insr_b_offset(dm, l + 1) + j] : 0.f;
-    }
-    for (int idx = tid; idx < HP * 4; idx += THREADS) {
-        const int j = idx >> 2, d = idx & 3;
-        float v = 0.f;
-        if (j < H) {
-            if (d < D) v = w * p.theta[insr_w_offset(dm, 0) + (int64_t)j * D + d];
-            else if (d == 3) v = w * p.theta[insr_b_offset(dm, 0) + j];
-        }
-        w1S[idx] = v;
-    }
-    for (int idx = tid; idx < 3 * HP; idx += THREADS) {
-        const int o = idx / HP, j = idx % HP;
-        woS[idx] = (o < O && j < H) ? p.theta[insr_w_offset(dm, L + 1) + (int64_t)o * H + j] : 0.f;
-    }
-    if (tid < 4) boS[tid] = (tid < O) ? p.theta[insr_b_offset(dm, L + 1) + tid] : 0.f;
+    stage_hidden(p, smraw + M.w_hi, smraw + M.w_lo, false);
+    stage_hidden(p, smraw + M.wt_hi, smraw + M.wt_lo, true);
+    stage_small(p, biasS, w1S, woS, boS);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -458,7 +541,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smraw + M.tmem);
     const uint32_t tmem_row = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-    const uint32_t tmem_wacc = tmem_base + 32 * S;                // L blocks of 32 columns
     uint32_t phD = 0, phY[2] = {0, 0};
     bool pendY[2] = {false, false};
     uint32_t wacc_mask = 0;                                       // bit l-1: Wacc_l holds data
@@ -474,7 +556,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
     auto wait_y = [&](int slot) {
         if (pendY[slot]) { mbar_wait(slot ? mbarY1 : mbarY0, phY[slot]); phY[slot] ^= 1; pendY[slot] = false; }
     };
-    auto publish_and_sync = [&]() {          // operand writes (generic proxy) -> async proxy, then CTA barrier
+    auto publish_and_sync = [&]() {          // operand writes (generic proxy / tcgen05.st) -> MMA, then CTA barrier
+        tmem_st_wait();
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -487,60 +570,65 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
         float xv[D];
         INSR_PRAGMA_UNROLL
         for (int d = 0; d < D; ++d) xv[d] = valid ? __ldg(p.x + n * D + d) : 0.f;
-        wait_y(0); wait_y(1);                              // previous tile's weight-gradient MMAs still read X
 
-        float alast[S][16];
         // ================= forward with tape =================
         INSR_PRAGMA_UNROLL
-        for (int g4 = 0; g4 < 4; ++g4) {
-            float z[S][4], a[S][4], tv[TV][4];
+        for (int g8 = 0; g8 < 2; ++g8) {
+            float a8[S][8];
             INSR_PRAGMA_UNROLL
-            for (int c = 0; c < 4; ++c) {
-                const int j = 16 * half + 4 * g4 + c;
-                const float4 wv = *reinterpret_cast<const float4 *>(w1S + j * 4);
-                float acc = wv.w;
+            for (int q = 0; q < 2; ++q) {
+                const int g4 = 2 * g8 + q;
+                float z[S][4], a[S][4], tv[TV][4];
                 INSR_PRAGMA_UNROLL
-                for (int d = 0; d < D; ++d) acc = fmaf(insr_fused::f4get(wv, d), xv[d], acc);
-                z[0][c] = acc;
+                for (int c = 0; c < 4; ++c) {
+                    const int j = 16 * half + 4 * g4 + c;
+                    const float4 wv = *reinterpret_cast<const float4 *>(w1S + j * 4);
+                    float acc = wv.w;
+                    INSR_PRAGMA_UNROLL
+                    for (int d = 0; d < D; ++d) acc = fmaf(insr_fused::f4get(wv, d), xv[d], acc);
+                    z[0][c] = acc;
+                    INSR_PRAGMA_UNROLL
+                    for (int d = 0; d < C::ND; ++d) z[1 + d][c] = insr_fused::f4get(wv, d);
+                    if constexpr (ORDER == 2) z[1 + C::ND][c] = 0.f;
+                }
+                insr_fused::act4<D, ORDER>(z, a, tv);
                 INSR_PRAGMA_UNROLL
-                for (int d = 0; d < C::ND; ++d) z[1 + d][c] = insr_fused::f4get(wv, d);
-                if constexpr (ORDER == 2) z[1 + C::ND][c] = 0.f;
+                for (int t = 0; t < TV; ++t) tape[(size_t)(g4 * TV + t) * THREADS + tid] = make_float4(tv[t][0], tv[t][1], tv[t][2], tv[t][3]);
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s)
+                    INSR_PRAGMA_UNROLL
+                    for (int c = 0; c < 4; ++c) a8[s][4 * q + c] = a[s][c];
             }
-            insr_fused::act4<D, ORDER>(z, a, tv);
             INSR_PRAGMA_UNROLL
-            for (int t = 0; t < TV; ++t) tape[(size_t)(g4 * TV + t) * THREADS + tid] = make_float4(tv[t][0], tv[t][1], tv[t][2], tv[t][3]);
-            INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s) {
-                store_split4(smraw + M.x_hi + s * OP_BYTES, smraw + M.x_lo + s * OP_BYTES, row, 4 * half + g4, a[s]);
-                INSR_PRAGMA_UNROLL
-                for (int c = 0; c < 4; ++c) alast[s][4 * g4 + c] = a[s][c];
-            }
+            for (int s = 0; s < S; ++s)
+                store_split8(tmem_row + ABASE + 32 * s + 16 * half + 8 * g8, smraw + M.x_lo + s * OP_BYTES, row, 2 * half + g8, a8[s]);
         }
+        float out[O][S];                                   // LSQ: this thread's share of the outputs
+        INSR_PRAGMA_UNROLL
+        for (int o = 0; o < O; ++o)
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) out[o][s] = 0.f;
         for (int l = 0; l < L; ++l) {
             publish_and_sync();
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after();
-                const uint32_t whi = s32(smraw + M.w_hi + l * W_BYTES), wlo = s32(smraw + M.w_lo + l * W_BYTES);
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) {
-                    const uint32_t ahi = s32(smraw + M.x_hi + s * OP_BYTES), alo = s32(smraw + M.x_lo + s * OP_BYTES);
-                    const uint32_t d = tmem_base + 32 * s;
+                if (elect_one()) {
+                    const uint32_t whi = s32(smraw + M.w_hi + l * W_BYTES), wlo = s32(smraw + M.w_lo + l * W_BYTES);
                     INSR_PRAGMA_UNROLL
-                    for (int ks = 0; ks < 4; ++ks) {
-                        mma_tf32(d, umma_desc(ahi + 256 * ks), umma_desc(whi + 256 * ks), ks > 0);
-                        mma_tf32(d, umma_desc(alo + 256 * ks), umma_desc(whi + 256 * ks), 1);
-                        mma_tf32(d, umma_desc(ahi + 256 * ks), umma_desc(wlo + 256 * ks), 1);
-                    }
+                    for (int s = 0; s < S; ++s)
+                        issue_stream(tmem_base + 32 * s, tmem_base + ABASE + 32 * s, s32(smraw + M.x_lo + s * OP_BYTES), whi, wlo);
+                    mma_commit(mbarD);
                 }
-                mma_commit(mbarD);
+                __syncwarp();
             }
             mbar_wait(mbarD, phD);
             phD ^= 1;
             tc_fence_after();
+            const bool last = (l == L - 1);
             float4 *tl = tape + (size_t)(l + 1) * NQ * THREADS;
             INSR_PRAGMA_UNROLL
             for (int g8 = 0; g8 < 2; ++g8) {
-                float zz[S][8];
+                float zz[S][8], a8[S][8];
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s) tmem_ld8(tmem_row + 32 * s + 16 * half + 8 * g8, zz[s]);
                 tmem_ld_wait();
@@ -559,28 +647,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
                     INSR_PRAGMA_UNROLL
                     for (int t = 0; t < TV; ++t) tl[(size_t)(g4 * TV + t) * THREADS + tid] = make_float4(tv[t][0], tv[t][1], tv[t][2], tv[t][3]);
                     INSR_PRAGMA_UNROLL
-                    for (int s = 0; s < S; ++s) {
-                        store_split4(smraw + M.x_hi + s * OP_BYTES, smraw + M.x_lo + s * OP_BYTES, row, 4 * half + g4, a[s]);
+                    for (int s = 0; s < S; ++s)
                         INSR_PRAGMA_UNROLL
-                        for (int c = 0; c < 4; ++c) alast[s][4 * g4 + c] = a[s][c];
+                        for (int c = 0; c < 4; ++c) a8[s][4 * q + c] = a[s][c];
+                }
+                if (last) {
+                    if constexpr (LSQ) {
+                        INSR_PRAGMA_UNROLL
+                        for (int o = 0; o < O; ++o)
+                            INSR_PRAGMA_UNROLL
+                            for (int s = 0; s < S; ++s)
+                                INSR_PRAGMA_UNROLL
+                                for (int i = 0; i < 8; ++i) out[o][s] = fmaf(woS[o * HP + 16 * half + 8 * g8 + i], a8[s][i], out[o][s]);
                     }
+                } else {
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s)
+                        store_split8(tmem_row + ABASE + 32 * s + 16 * half + 8 * g8, smraw + M.x_lo + s * OP_BYTES, row, 2 * half + g8, a8[s]);
                 }
             }
         }
         // ================= output layer: cotangents g[o][s] =================
         float g[O][S];
         if constexpr (LSQ) {
-            float out[O][S];
             INSR_PRAGMA_UNROLL
             for (int o = 0; o < O; ++o)
                 INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) {
-                    float acc = 0.f;
-                    INSR_PRAGMA_UNROLL
-                    for (int i = 0; i < 16; ++i) acc = fmaf(woS[o * HP + 16 * half + i], alast[s][i], acc);
-                    out[o][s] = acc;
-                    partS[(half * TILE_M + row) * 8 + o * S + s] = acc;
-                }
+                for (int s = 0; s < S; ++s) partS[(half * TILE_M + row) * 8 + o * S + s] = out[o][s];
             __syncthreads();
             INSR_PRAGMA_UNROLL
             for (int o = 0; o < O; ++o) {
@@ -617,24 +710,40 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
                 }
             }
         }
-        // output-layer gradients (this thread's 16 neurons) and the cotangent of the last sine layer
+        // output-layer gradients (this thread's 16 neurons; a_L recomputed from the tape) and the cotangent of
+        // the last sine layer
         float ab[S][16];
-        INSR_PRAGMA_UNROLL
-        for (int o = 0; o < O; ++o) {
-            float v[16];
+        {
+            const float4 *tl = tape + (size_t)L * NQ * THREADS;
+            float v[O][16];
             INSR_PRAGMA_UNROLL
-            for (int i = 0; i < 16; ++i) {
-                float acc = 0.f;
+            for (int g4 = 0; g4 < 4; ++g4) {
+                float tv[TV][4], a[S][4];
                 INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) acc = fmaf(g[o][s], alast[s][i], acc);
-                v[i] = acc;
+                for (int t = 0; t < TV; ++t) {
+                    const float4 q = tl[(size_t)(g4 * TV + t) * THREADS + tid];
+                    tv[t][0] = q.x; tv[t][1] = q.y; tv[t][2] = q.z; tv[t][3] = q.w;
+                }
+                insr_fused::a_from_tape4<D, ORDER>(tv, a);
+                INSR_PRAGMA_UNROLL
+                for (int o = 0; o < O; ++o)
+                    INSR_PRAGMA_UNROLL
+                    for (int c = 0; c < 4; ++c) {
+                        float acc = 0.f;
+                        INSR_PRAGMA_UNROLL
+                        for (int s = 0; s < S; ++s) acc = fmaf(g[o][s], a[s][c], acc);
+                        v[o][4 * g4 + c] = acc;
+                    }
             }
-            acc_gwo[o] += reduce16(v, lane);
-            if (half == 0) {
-                float t = g[o][0];
-                INSR_PRAGMA_UNROLL
-                for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
-                if (lane == o) acc_gbo += t;
+            INSR_PRAGMA_UNROLL
+            for (int o = 0; o < O; ++o) {
+                acc_gwo[o] += reduce16(v[o], lane);
+                if (half == 0) {
+                    float t = g[o][0];
+                    INSR_PRAGMA_UNROLL
+                    for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+                    if (lane == o) acc_gbo += t;
+                }
             }
         }
         INSR_PRAGMA_UNROLL
@@ -677,74 +786,72 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
                 const float r = reduce16(v, lane);
                 if (l == 1) acc_gb[0] += r; else if (l == 2) acc_gb[1] += r; else acc_gb[2] += r;
             }
-            // ---- X <- zbar_l (all streams).  The previous layer's weight-gradient MMAs read X: wait for them.
-            wait_y(0); wait_y(1);
+            // ---- data-gradient operands: zbar_l hi -> TMEM, lo -> shared memory (all streams)
             INSR_PRAGMA_UNROLL
             for (int s = 0; s < S; ++s)
                 INSR_PRAGMA_UNROLL
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    const float a4[4] = {ab[s][4 * g4], ab[s][4 * g4 + 1], ab[s][4 * g4 + 2], ab[s][4 * g4 + 3]};
-                    store_split4(smraw + M.x_hi + s * OP_BYTES, smraw + M.x_lo + s * OP_BYTES, row, 4 * half + g4, a4);
-                }
-            publish_and_sync();
-            const uint32_t whi = s32(smraw + M.w_hi + (l - 1) * W_BYTES), wlo = s32(smraw + M.w_lo + (l - 1) * W_BYTES);
-            if (tid == 0) {                            // data gradient: D_s = Zbar_s . W_l   (B = W read MN-major)
-                tc_fence_after();
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) {
-                    const uint32_t zhi = s32(smraw + M.x_hi + s * OP_BYTES), zlo = s32(smraw + M.x_lo + s * OP_BYTES);
-                    const uint32_t d = tmem_base + 32 * s;
+                for (int g8 = 0; g8 < 2; ++g8) {
+                    float a8[8];
                     INSR_PRAGMA_UNROLL
-                    for (int ks = 0; ks < 4; ++ks) {   // 8 reduction indices j per instruction = one 1024-byte row group of W
-                        mma_tf32(d, umma_desc(zhi + 256 * ks), umma_desc_mn(whi + 1024 * ks), ks > 0, IDESC_DGRAD);
-                        mma_tf32(d, umma_desc(zlo + 256 * ks), umma_desc_mn(whi + 1024 * ks), 1, IDESC_DGRAD);
-                        mma_tf32(d, umma_desc(zhi + 256 * ks), umma_desc_mn(wlo + 1024 * ks), 1, IDESC_DGRAD);
-                    }
+                    for (int i = 0; i < 8; ++i) a8[i] = ab[s][8 * g8 + i];
+                    store_split8(tmem_row + ABASE + 32 * s + 16 * half + 8 * g8, smraw + M.x_lo + s * OP_BYTES, row, 2 * half + g8, a8);
                 }
-                mma_commit(mbarD);
-            }
-            // ---- weight gradient, one stream at a time through the two Y slots: Y <- a_{l-1,s}
+            // ---- weight-gradient operands, one stream per slot: ZT <- zbar_{l,s}, AT <- a_{l-1,s} (from the tape)
             const float4 *tp = tape + (size_t)(l - 1) * NQ * THREADS;
-            float aprev[S][16];
+            const uint32_t wthi = s32(smraw + M.wt_hi + (l - 1) * W_BYTES), wtlo = s32(smraw + M.wt_lo + (l - 1) * W_BYTES);
+            const uint32_t dw = tmem_base + WBASE + 64 * (l - 1);
             INSR_PRAGMA_UNROLL
-            for (int g4 = 0; g4 < 4; ++g4) {
-                float tv[TV][4], a[S][4];
+            for (int s0 = 0; s0 < S; s0 += NSLOT) {
                 INSR_PRAGMA_UNROLL
-                for (int t = 0; t < TV; ++t) {
-                    const float4 v = tp[(size_t)(g4 * TV + t) * THREADS + tid];
-                    tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
-                }
-                insr_fused::a_from_tape4<D, ORDER>(tv, a);
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s)
-                    INSR_PRAGMA_UNROLL
-                    for (int c = 0; c < 4; ++c) aprev[s][4 * g4 + c] = a[s][c];
-            }
-            INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s) {
-                const int slot = s & 1;
-                wait_y(slot);
-                INSR_PRAGMA_UNROLL
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    const float a4[4] = {aprev[s][4 * g4], aprev[s][4 * g4 + 1], aprev[s][4 * g4 + 2], aprev[s][4 * g4 + 3]};
-                    store_split4(smraw + M.y_hi[slot], smraw + M.y_lo[slot], row, 4 * half + g4, a4);
+                for (int u = 0; u < NSLOT; ++u) {
+                    const int s = s0 + u;
+                    if (s < S) {
+                        float av[16];
+                        INSR_PRAGMA_UNROLL
+                        for (int g4 = 0; g4 < 4; ++g4) {       // a_{l-1,s} of this thread's 16 neurons
+                            float tv[TV][4], a[S][4];
+                            INSR_PRAGMA_UNROLL
+                            for (int t = 0; t < TV; ++t) {
+                                const float4 v = tp[(size_t)(g4 * TV + t) * THREADS + tid];
+                                tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
+                            }
+                            insr_fused::a_from_tape4<D, ORDER>(tv, a);
+                            INSR_PRAGMA_UNROLL
+                            for (int c = 0; c < 4; ++c) av[4 * g4 + c] = a[s][c];
+                        }
+                        wait_y(u);                             // the slot's previous weight-gradient MMAs are done
+                        unsigned char *slot = smraw + M.slots + u * SLOT_BYTES;
+                        store_wg_operand(slot, row, half, ab[s]);
+                        store_wg_operand(slot + TILE_M * 128, row, half, av);
+                    }
                 }
                 publish_and_sync();
-                if (tid == 0) {
+                if (warp == 0) {
                     tc_fence_after();
-                    const uint32_t zhi = s32(smraw + M.x_hi + s * OP_BYTES), zlo = s32(smraw + M.x_lo + s * OP_BYTES);
-                    const uint32_t yhi = s32(smraw + M.y_hi[slot]), ylo = s32(smraw + M.y_lo[slot]);
-                    const uint32_t d = tmem_wacc + 32 * (l - 1);
-                    const bool fresh = !((wacc_mask >> (l - 1)) & 1u) && s == 0;
-                    INSR_PRAGMA_UNROLL
-                    for (int pg = 0; pg < 16; ++pg) {   // 8 points per instruction = one 1024-byte row group of both operands
-                        mma_tf32(d, umma_desc_mn(zhi + 1024 * pg), umma_desc_mn(yhi + 1024 * pg), !(fresh && pg == 0), IDESC_WGRAD);
-                        mma_tf32(d, umma_desc_mn(zlo + 1024 * pg), umma_desc_mn(yhi + 1024 * pg), 1, IDESC_WGRAD);
-                        mma_tf32(d, umma_desc_mn(zhi + 1024 * pg), umma_desc_mn(ylo + 1024 * pg), 1, IDESC_WGRAD);
+                    if (elect_one()) {
+                        if (s0 == 0) {                         // data gradient: D_s = Zbar_s . W_l  (B = transposed copy)
+                            INSR_PRAGMA_UNROLL
+                            for (int s = 0; s < S; ++s)
+                                issue_stream(tmem_base + 32 * s, tmem_base + ABASE + 32 * s, s32(smraw + M.x_lo + s * OP_BYTES), wthi, wtlo);
+                            mma_commit(mbarD);
+                        }
+                        INSR_PRAGMA_UNROLL
+                        for (int u = 0; u < NSLOT; ++u) {
+                            if (s0 + u < S) {
+                                const uint32_t zt = s32(smraw + M.slots + u * SLOT_BYTES), at = zt + TILE_M * 128;
+                                const bool fresh = !((wacc_mask >> (l - 1)) & 1u) && (s0 + u == 0);
+                                INSR_PRAGMA_UNROLL
+                                for (int kp = 0; kp < 8; ++kp)          // 16 points per instruction = two 1024-byte atoms
+                                    mma_bf16_wg(dw, umma_desc_mn128(zt + 2048 * kp), umma_desc_mn128(at + 2048 * kp), !(fresh && kp == 0));
+                                mma_commit(u ? mbarY1 : mbarY0);
+                            }
+                        }
                     }
-                    mma_commit(slot ? mbarY1 : mbarY0);
+                    __syncwarp();
                 }
-                pendY[slot] = true;
+                INSR_PRAGMA_UNROLL
+                for (int u = 0; u < NSLOT; ++u)
+                    if (s0 + u < S) pendY[u] = true;
             }
             wacc_mask |= 1u << (l - 1);
             // ---- cotangent of a_{l-1} from the data-gradient accumulators
@@ -808,27 +915,35 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
                 }
             }
         }
-        __syncthreads();                                   // partS reuse by the next tile
+        tc_fence_before();
+        __syncthreads();                                   // partS / tape reuse by the next tile
+        tc_fence_after();
     }
 
     // ================= flush =================
     wait_y(0); wait_y(1);
     tc_fence_after();
     const float wsc = dm.omega;
-    // hidden-layer weight gradients: TMEM lanes 0..31 = output neuron j, 32 columns = input k (warp 0 reads them)
-    if (warp == 0) {
+    // hidden-layer weight gradients.  M = 64 accumulator layout: row r of D sits in TMEM lane 32 (r >> 4) + (r & 15),
+    // so lanes 0..15 of warp quadrant q hold rows 16 q .. 16 q + 15 = level (q >> 1), neurons 16 (q & 1) + lane;
+    // the two warps of a quadrant split the 32 input neurons; columns k (x a1) and 32 + k (x a2) are added.
+    {
+        const int j = 16 * (warp & 1) + lane;
         for (int l = 1; l <= L; ++l) {
             if (!((wacc_mask >> (l - 1)) & 1u)) continue;
             float *gW = p.gtheta + insr_w_offset(dm, l);
             INSR_PRAGMA_UNROLL
-            for (int c8 = 0; c8 < 4; ++c8) {
-                float vals[8];
-                tmem_ld8(tmem_wacc + 32 * (l - 1) + 8 * c8, vals);
+            for (int c8 = 0; c8 < 2; ++c8) {
+                float v1[8], v2[8];
+                tmem_ld8(tmem_row + WBASE + 64 * (l - 1) + 16 * half + 8 * c8, v1);
+                tmem_ld8(tmem_row + WBASE + 64 * (l - 1) + 32 + 16 * half + 8 * c8, v2);
                 tmem_ld_wait();
-                if (lane < H) {
+                if (lane < 16 && j < H) {
                     INSR_PRAGMA_UNROLL
-                    for (int i = 0; i < 8; ++i)
-                        if (8 * c8 + i < H) atomicAdd(gW + (size_t)lane * H + 8 * c8 + i, wsc * vals[i]);
+                    for (int i = 0; i < 8; ++i) {
+                        const int k = 16 * half + 8 * c8 + i;
+                        if (k < H) atomicAdd(gW + (size_t)j * H + k, wsc * (v1[i] + v2[i]));
+                    }
                 }
             }
         }
@@ -868,13 +983,12 @@ int launch_tc_bwd(Params &p, float *ws, void *stream, int64_t *launches) {
     constexpr int S = StreamCfg<D, ORDER>::S;
     const SmemB M = smem_map_bwd(p.dm.L, S);
     auto kfn = k_tc_bwd<D, O, ORDER, LSQ>;
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, M.total);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, M.total + 1024);
     const int64_t tiles = (p.N + TILE_M - 1) / TILE_M;
     int64_t ctas = tiles < insr_fused::sm_count() ? tiles : insr_fused::sm_count();
-    int cols = 32;
-    while (cols < 32 * S + 32 * p.dm.L) cols <<= 1;
+    const int cols = pow2_cols(64 * S + 64 * p.dm.L);
     float4 *tape = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(ws) + 15) & ~uintptr_t(15));
-    kfn<<<dim3((unsigned)ctas), dim3(THREADS), M.total, reinterpret_cast<cudaStream_t>(stream)>>>(p, tape, cols);
+    kfn<<<dim3((unsigned)ctas), dim3(THREADS), M.total + 1024, reinterpret_cast<cudaStream_t>(stream)>>>(p, tape, cols);
     ++*launches;
     return 0;
 }

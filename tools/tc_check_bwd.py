@@ -33,7 +33,7 @@ for (D, O, H, L, order, N) in cases:
     P = theta.numel()
     offs = net.param_slices()
     worst = max(((rel(g_tc[o:o+n], gref[o:o+n]), i) for i, (o, n, _) in enumerate(offs)))
-    print("    worst parameter tensor:", worst, flush=True)
+    print("    per-tensor rel err:", [f"{rel(g_tc[o:o+n], gref[o:o+n]):.1e}" for (o, n, _) in offs], flush=True)
 
 if len(sys.argv) > 2:
     D, O, H, L, order, N = 2, 1, 32, 3, 2, 1 << 22
