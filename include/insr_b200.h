@@ -75,9 +75,11 @@ typedef struct insr_siren_desc {
 
 #define INSR_FLAG_NONE 0
 #define INSR_FLAG_FORCE_GENERIC 1 /* use the generic (any-H) kernels even where a fused one exists */
-#define INSR_FLAG_TENSOR_BWD 4    /* also run backward / lsq_step of the H <= 32 family on tcgen05 (tape in the workspace) */
-#define INSR_FLAG_NO_TENSOR 2     /* keep the H <= 32 family on the FP32 FFMA kernels (default: the forward runs on
-                                     tcgen05/TMEM with a 3xTF32 split and FP32 accumulation, same 1e-4 parity) */
+#define INSR_FLAG_NO_TENSOR 2     /* keep the H <= 32 family on the FP32 FFMA kernels.  Default: forward, backward and
+                                     lsq_step run on tcgen05/TMEM (3xTF32 split for the forward pass and the data
+                                     gradient, 2-level bf16 split for the weight gradient, FP32 accumulation; same
+                                     1e-4 parity; the backward keeps its tape in the workspace) */
+#define INSR_FLAG_FFMA_BWD 4      /* tcgen05 forward, FP32 FFMA backward / lsq_step (A/B measurements) */
 
 int insr_version(void);
 const char *insr_last_error(void);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libinsr_b200.so")
 ORDER_VALUE, ORDER_JAC, ORDER_LAP, ORDER_HESS = 0, 1, 2, 3
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_TENSOR = 2
-FLAG_TENSOR_BWD = 4
+FLAG_FFMA_BWD = 4
 
 EXPORTS = [
     "insr_version", "insr_last_error", "insr_siren_theta_size", "insr_siren_workspace_bytes",

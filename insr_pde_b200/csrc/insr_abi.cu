@@ -257,7 +257,7 @@ int insr_siren_backward(const insr_siren_desc *desc, const float *theta, const f
     if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_fused_supported(dm, order, 1)) {
         rc = insr_fused_backward(dm, order, theta, x, n_points, gy, gjac, gh2, gtheta, gx,
                                  (float *)workspace, stream, &g_launches,
-                                 (desc->flags & INSR_FLAG_TENSOR_BWD) && !(desc->flags & INSR_FLAG_NO_TENSOR));
+                                 !(desc->flags & (INSR_FLAG_FFMA_BWD | INSR_FLAG_NO_TENSOR)));
         if (rc == INSR_ERR_UNSUPPORTED) return fail(rc, "fused backward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
         if (rc) return rc;
         return check_cuda("fused backward");
@@ -284,7 +284,7 @@ int insr_siren_lsq_step(const insr_siren_desc *desc, const float *theta, const f
         return fail(INSR_ERR_NULL, "theta, x, coef_host, loss_out and gtheta must not be NULL");
     if ((rc = check_device())) return rc;
     if (n_points == 0) return 0;
-    const bool tensor = (desc->flags & INSR_FLAG_TENSOR_BWD) && !(desc->flags & INSR_FLAG_NO_TENSOR);
+    const bool tensor = !(desc->flags & (INSR_FLAG_FFMA_BWD | INSR_FLAG_NO_TENSOR));
     if (tensor) {
         const size_t need = insr_siren_workspace_bytes(desc, n_points, order, 1);
         if (!workspace || workspace_bytes < need)

@@ -147,7 +147,7 @@ def test_fused_lsq_step_under_emulation(emu_library, case):
     lib = emu_library
     D, O, H, L, N, order, R = case
     rng = np.random.default_rng(5)
-    desc = _lib.make_desc(D, O, H, L)
+    desc = _lib.make_desc(D, O, H, L, flags=_lib.FLAG_NO_TENSOR)     # the emulator covers the FFMA kernels (no tape workspace)
     theta = make_theta(rng, D, O, H, L)
     x = rng.uniform(-1, 1, (N, D)).astype(np.float32)
     cy = rng.standard_normal((R, O)).astype(np.float32)

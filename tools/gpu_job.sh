@@ -11,7 +11,7 @@ if [ "$2" == "ncu" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv \
       python tools/prof_one.py --points 1048576 --reps 2 --lsq > gpurun_out/ncu_list_$TAG.log 2>&1
   python tools/prof_one.py --points 262144 --reps 1 --lsq > gpurun_out/prof_plain2_$TAG.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:k_fused -c 3 -f -o gpurun_out/prof_$TAG \
+  ncu --set full --clock-control none --import-source on -k regex:"k_tc_|k_fused" -c 3 -f -o gpurun_out/prof_$TAG \
       python tools/prof_one.py --points 262144 --reps 1 --lsq > gpurun_out/ncu_full_$TAG.log 2>&1
   tail -n 3 gpurun_out/ncu_list_$TAG.log; tail -n 3 gpurun_out/ncu_full_$TAG.log
 fi

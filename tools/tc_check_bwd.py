@@ -20,7 +20,7 @@ for (D, O, H, L, order, N) in cases:
     x = torch.rand(N, D, device="cuda") * 2 - 1
     shapes = _ops.out_shapes(net.desc, N, order)
     cots = [torch.randn(s, device="cuda") for s in shapes]
-    d_tc = _lib.make_desc(D, O, H, L, flags=_lib.FLAG_TENSOR_BWD)
+    d_tc = _lib.make_desc(D, O, H, L, flags=0)
     d_ff = _lib.make_desc(D, O, H, L, flags=_lib.FLAG_NO_TENSOR)
     g_tc, gx_tc = _ops.siren_backward(d_tc, theta, x, order, *cots, need_gx=True)
     torch.cuda.synchronize()
@@ -43,7 +43,7 @@ if len(sys.argv) > 2:
     cots = [torch.randn(s, device="cuda") / N for s in _ops.out_shapes(net.desc, N, order)]
     tgt = torch.randn(N, 1, device="cuda")
     gth = torch.zeros_like(theta); loss = torch.zeros(1, device="cuda")
-    for flags, name in ((_lib.FLAG_NO_TENSOR, "ffma"), (_lib.FLAG_TENSOR_BWD, "tcgen05")):
+    for flags, name in ((_lib.FLAG_NO_TENSOR, "ffma"), (0, "tcgen05")):
         desc = _lib.make_desc(D, O, H, L, flags=flags)
         for what, fn in (("bwd", lambda: _ops.siren_backward(desc, theta, x, order, *cots, gtheta=gth)),
                          ("lsq", lambda: _ops.siren_lsq_step(desc, theta, x, order, [[0.0]], None, [[1.0]], tgt, 1.0 / N, loss_out=loss, gtheta=gth))):
