@@ -403,59 +403,61 @@ int launch_tc_fwd(Params &p, void *stream, int64_t *launches) {
 
 
 // =============================================================================================
-// backward / fused-closure kernel on the tensor cores (one CTA per SM, 512 TMEM columns)
-//   forward recompute   D_s = A_s W^T        3xTF32, A_hi in TMEM, A_lo / W K-major in shared memory
+// backward / fused-closure kernel on the tensor cores (one CTA of 512 threads per SM, 512 TMEM columns)
+//   forward recompute   D_s = A_s W^T        3xTF32, A_hi in TMEM, W K-major in shared memory
 //   data gradient       D_s = Zbar_s W       the same, against the transposed weight copy
 //   weight gradient     Wacc_l[64 x 64] += [z1|z2]^T [a1|a2]   bf16 x 2 levels, both operands MN-major;
 //                       accumulators stay in TMEM for the whole launch and are read out once at the end
-// TMEM columns: [0, 32 S) accumulators, [32 S, 64 S) hi operand, [64 S, 64 S + 64 L) weight-gradient accumulators.
-// The tape (sin, cos, t_d, t_q per activation) lives in a per-CTA global scratch that stays L2-resident.
-// Thin layers (first / output layer, biases, d loss/d x) are reduced over the 32 points of a warp with a
-// halving butterfly (16 shuffles per 16 values) into a few persistent registers.
+// Four threads per point (8 neurons each): 16 warps hide the latency of the tape (L2), TMEM and MUFU round trips.
+// TMEM columns: [0, 32 S) accumulators | [32 S, 64 S) hi operand | 32 NLO_T lo operand of the first NLO_T streams
+// (the other streams keep their lo operand in shared memory) | 64 L weight-gradient accumulators.
+// Shared memory: one weight-gradient operand slot per stream (ZT | AT, 32 KB), so that a reverse layer needs a
+// single CTA barrier: operands -> barrier -> data-gradient MMAs, then weight-gradient MMAs (which overlap the next
+// layer's adjoint).  The tape (sin, cos, t_d, t_q per activation) lives in a per-CTA global scratch that stays
+// L2-resident.  Thin layers (first / output layer, biases, d loss/d x) are reduced over the 32 points of a warp
+// with a halving butterfly into a few persistent registers.
 // =============================================================================================
-__device__ __forceinline__ float reduce16(float (&v)[16], int lane) {
-    // after the call the lane holds the warp-wide sum of value index (lane >> 1) & 15
+constexpr int BT = 512;                             // threads of the backward kernel
+constexpr int NT = BT / TILE_M;                     // threads per point
+constexpr int NPT = HP / NT;                        // neurons per thread (8)
+constexpr int LMAX_TC = 3;                          // hidden layers (TMEM budget of the weight-gradient accumulators)
+constexpr int SLOT_BYTES = 2 * TILE_M * 128;        // ZT (128 points x 128 B) | AT (128 points x 128 B)
+__host__ __device__ constexpr int nlo_tmem(int S) { return (512 - 64 * S - 64 * LMAX_TC) / 32 < S ? (512 - 64 * S - 64 * LMAX_TC) / 32 : S; }
+
+__device__ __forceinline__ float reduce8(float (&v)[8], int lane) {
+    // after the call the lane holds the warp-wide sum of value index (lane >> 2) & 7
     INSR_PRAGMA_UNROLL
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
         const bool up = lane & 16;
-        const float send = up ? v[i] : v[i + 8];
-        const float keep = up ? v[i + 8] : v[i];
+        const float send = up ? v[i] : v[i + 4];
+        const float keep = up ? v[i + 4] : v[i];
         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
     INSR_PRAGMA_UNROLL
-    for (int i = 0; i < 4; ++i) {
-        const bool up = lane & 8;
-        const float send = up ? v[i] : v[i + 4];
-        const float keep = up ? v[i + 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    INSR_PRAGMA_UNROLL
     for (int i = 0; i < 2; ++i) {
-        const bool up = lane & 4;
+        const bool up = lane & 8;
         const float send = up ? v[i] : v[i + 2];
         const float keep = up ? v[i + 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
     }
     {
-        const bool up = lane & 2;
+        const bool up = lane & 4;
         const float send = up ? v[0] : v[1];
         const float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
     }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
-
-constexpr int NSLOT = 2;                            // weight-gradient operand slots (one stream each)
-constexpr int SLOT_BYTES = 2 * TILE_M * 128;        // ZT (128 points x 128 B) | AT (128 points x 128 B)
 
 struct SmemB {
     int slots, x_lo, w_hi, w_lo, wt_hi, wt_lo, bias, w1, wo, bo, part, mbar, tmem, total;
 };
-__host__ __device__ inline SmemB smem_map_bwd(int L, int S) {
+__host__ __device__ inline SmemB smem_map_bwd(int L, int S, int PS) {
     SmemB m;
     int o = 0;
-    m.slots = o; o += NSLOT * SLOT_BYTES;          // first: 1024-byte aligned (128-byte swizzle atoms)
-    m.x_lo = o; o += S * OP_BYTES;
+    m.slots = o; o += S * SLOT_BYTES;              // first: 1024-byte aligned (128-byte swizzle atoms)
+    m.x_lo = o; o += (S - nlo_tmem(S)) * OP_BYTES;
     m.w_hi = o; o += L * W_BYTES;
     m.w_lo = o; o += L * W_BYTES;
     m.wt_hi = o; o += L * W_BYTES;
@@ -464,19 +466,19 @@ __host__ __device__ inline SmemB smem_map_bwd(int L, int S) {
     m.w1 = o; o += HP * 16;
     m.wo = o; o += 3 * HP * 4;
     m.bo = o; o += 16;
-    m.part = o; o += 2 * TILE_M * 8 * 4;       // per-half partial outputs / gx: [2][128][8]
+    m.part = o; o += NT * TILE_M * PS * 4;         // per-thread partial outputs / gx: [NT][128][PS]
     m.mbar = o; o += 32;
     m.tmem = o; o += 16;
     m.total = o;
     return m;
 }
-// tape: per CTA  [(L+1)][4 (S+1)][256] float4
-__host__ __device__ inline size_t tape_float4_per_cta(int L, int S) { return (size_t)(L + 1) * 4 * (S + 1) * THREADS; }
+// tape: per CTA  [(L+1)][2 (S+1)][512] float4
+__host__ __device__ inline size_t tape_float4_per_cta(int L, int S) { return (size_t)(L + 1) * 2 * (S + 1) * BT; }
 
-// two bf16 levels of 16 values -> 2 x 8 packed words
-__device__ __forceinline__ void split_bf16x2(const float (&v)[16], uint32_t (&l1)[8], uint32_t (&l2)[8]) {
+// two bf16 levels of 8 values -> 2 x 4 packed words
+__device__ __forceinline__ void split_bf16x2(const float (&v)[8], uint32_t (&l1)[4], uint32_t (&l2)[4]) {
     INSR_PRAGMA_UNROLL
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
         uint32_t w1, w2;
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
         const float r0 = v[2 * i] - __uint_as_float(w1 << 16);
@@ -485,54 +487,118 @@ __device__ __forceinline__ void split_bf16x2(const float (&v)[16], uint32_t (&l1
         l1[i] = w1; l2[i] = w2;
     }
 }
-// write this thread's 16 neurons (two levels) of one stream into a [point][64 bf16] operand with 128-byte swizzle:
-// chunks 2 half, 2 half + 1 hold level 1, chunks 4 + 2 half, 5 + 2 half level 2
-__device__ __forceinline__ void store_wg_operand(unsigned char *buf, int row, int half, const float (&v)[16]) {
-    uint32_t l1[8], l2[8];
+// write this thread's 8 neurons (two levels) of one stream into a [point][64 bf16] operand with 128-byte swizzle:
+// chunk `part` holds level 1, chunk 4 + part level 2
+__device__ __forceinline__ void store_wg_operand(unsigned char *buf, int row, int part, const float (&v)[8]) {
+    uint32_t l1[4], l2[4];
     split_bf16x2(v, l1, l2);
     unsigned char *r = buf + row * 128;
     const int key = row & 7;
-    *reinterpret_cast<uint4 *>(r + (((2 * half) ^ key) << 4)) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
-    *reinterpret_cast<uint4 *>(r + (((2 * half + 1) ^ key) << 4)) = make_uint4(l1[4], l1[5], l1[6], l1[7]);
-    *reinterpret_cast<uint4 *>(r + (((4 + 2 * half) ^ key) << 4)) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
-    *reinterpret_cast<uint4 *>(r + (((5 + 2 * half) ^ key) << 4)) = make_uint4(l2[4], l2[5], l2[6], l2[7]);
+    *reinterpret_cast<uint4 *>(r + ((part ^ key) << 4)) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+    *reinterpret_cast<uint4 *>(r + (((4 + part) ^ key) << 4)) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+}
+// hi part -> TMEM; lo part -> TMEM (lo_tmem != 0) or the K-major shared-memory operand
+template <bool LO_TMEM>
+__device__ __forceinline__ void store_split8b(uint32_t hi_tmem, uint32_t lo_tmem, unsigned char *op_lo, int row, int g, const float (&a)[8]) {
+    float h[8], l[8];
+    INSR_PRAGMA_UNROLL
+    for (int c = 0; c < 8; ++c) { h[c] = tf32_hi(a[c]); l[c] = a[c] - h[c]; }
+    tmem_st8(hi_tmem, h);
+    if constexpr (LO_TMEM) {
+        tmem_st8(lo_tmem, l);
+    } else {
+        const int off = (row >> 3) * 1024 + (2 * g) * 128 + (row & 7) * 16;
+        *reinterpret_cast<float4 *>(op_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<float4 *>(op_lo + off + 128) = make_float4(l[4], l[5], l[6], l[7]);
+    }
+}
+template <bool LO_TMEM>
+__device__ __forceinline__ void issue_stream_b(uint32_t d_tmem, uint32_t hi_tmem, uint32_t lo_tmem, uint32_t alo, uint32_t bhi, uint32_t blo) {
+    INSR_PRAGMA_UNROLL
+    for (int ks = 0; ks < 4; ++ks) {
+        mma_tf32_ts(d_tmem, hi_tmem + 8 * ks, umma_desc(bhi + 256 * ks), ks > 0);
+        mma_tf32_ts(d_tmem, hi_tmem + 8 * ks, umma_desc(blo + 256 * ks), 1);
+        if constexpr (LO_TMEM) mma_tf32_ts(d_tmem, lo_tmem + 8 * ks, umma_desc(bhi + 256 * ks), 1);
+        else mma_tf32_ss(d_tmem, umma_desc(alo + 256 * ks), umma_desc(bhi + 256 * ks), 1);
+    }
 }
 
+// phase timing of warp 0 (debug builds with -DINSR_TC_PROFILE): cycles per phase accumulated into 16 counters that
+// sit right behind the tape scratch (tools/tc_phase_profile.py)
+#ifdef INSR_TC_PROFILE
+#define TCP(k) do { if (tid == 0) { const long long t_ = clock64(); atomicAdd(gprof + (k), (unsigned long long)(t_ - tprev)); tprev = t_; } } while (0)
+#else
+#define TCP(k) do { } while (0)
+#endif
+
 template <int D, int O, int ORDER, bool LSQ>
-__global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restrict__ tape_all, int tmem_cols) {
+__global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__ tape_all) {
     typedef StreamCfg<D, ORDER> C;
     constexpr int S = C::S;
     constexpr int TV = S + 1;
-    constexpr int NQ = 4 * TV;                       // float4 tape slots per thread per layer
-    constexpr int ABASE = 32 * S, WBASE = 64 * S;
-    static_assert(O * S <= 8, "partial buffers hold 8 values per point and half");
+    constexpr int NQ = 2 * TV;                       // float4 tape slots per thread per layer
+    constexpr int NLO = nlo_tmem(S);
+    constexpr int ABASE = 32 * S, LBASE = 64 * S, WBASE = 64 * S + 32 * NLO;
+    constexpr int PS = (O * S > D ? O * S : D);      // partial-buffer stride (floats)
     extern __shared__ __align__(1024) unsigned char smraw_[];
     unsigned char *smraw = smraw_ + ((1024u - (s32(smraw_) & 1023u)) & 1023u);     // 128-byte swizzle atoms: 1024-byte aligned
     const SirenDims dm = p.dm;
     const int L = dm.L, H = dm.H;
-    const SmemB M = smem_map_bwd(L, S);
+    const SmemB M = smem_map_bwd(L, S, PS);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = 32 * (warp & 3) + lane;
-    const int half = warp >> 2;
+    const int row = 32 * (warp & 3) + lane;          // TMEM lane == point inside the tile
+    const int part = warp >> 2;                      // neurons 8 part .. 8 part + 7
     float *biasS = reinterpret_cast<float *>(smraw + M.bias);
     float *w1S = reinterpret_cast<float *>(smraw + M.w1);
     float *woS = reinterpret_cast<float *>(smraw + M.wo);
     float *boS = reinterpret_cast<float *>(smraw + M.bo);
     float *partS = reinterpret_cast<float *>(smraw + M.part);
-    const uint32_t mbarD = s32(smraw + M.mbar), mbarY0 = mbarD + 8, mbarY1 = mbarD + 16;
+    const uint32_t mbarD = s32(smraw + M.mbar), mbarW = mbarD + 8;
     float4 *tape = tape_all + (size_t)blockIdx.x * tape_float4_per_cta(L, S);
+#ifdef INSR_TC_PROFILE
+    unsigned long long *gprof = reinterpret_cast<unsigned long long *>(tape_all + (size_t)gridDim.x * tape_float4_per_cta(L, S));
+    long long tprev = 0;
+#endif
 
-    stage_hidden(p, smraw + M.w_hi, smraw + M.w_lo, false);
-    stage_hidden(p, smraw + M.wt_hi, smraw + M.wt_lo, true);
-    stage_small(p, biasS, w1S, woS, boS);
-
+    // ---- stage the weights (BT threads)
+    {
+        const float w = dm.omega;
+        for (int idx = tid; idx < L * HP * HP; idx += BT) {
+            const int l = idx / (HP * HP), j = (idx / HP) % HP, k = idx % HP;
+            float v = 0.f;
+            if (j < H && k < H) v = w * p.theta[insr_w_offset(dm, l + 1) + (int64_t)j * H + k];
+            const float hi = tf32_hi(v);
+            *reinterpret_cast<float *>(smraw + M.w_hi + l * W_BYTES + op_off(j, k)) = hi;
+            *reinterpret_cast<float *>(smraw + M.w_lo + l * W_BYTES + op_off(j, k)) = v - hi;
+            *reinterpret_cast<float *>(smraw + M.wt_hi + l * W_BYTES + op_off(k, j)) = hi;
+            *reinterpret_cast<float *>(smraw + M.wt_lo + l * W_BYTES + op_off(k, j)) = v - hi;
+        }
+        for (int idx = tid; idx < L * HP; idx += BT) {
+            const int l = idx / HP, j = idx % HP;
+            biasS[idx] = (j < H) ? w * p.theta[insr_b_offset(dm, l + 1) + j] : 0.f;
+        }
+        for (int idx = tid; idx < HP * 4; idx += BT) {
+            const int j = idx >> 2, d = idx & 3;
+            float v = 0.f;
+            if (j < H) {
+                if (d < D) v = w * p.theta[insr_w_offset(dm, 0) + (int64_t)j * D + d];
+                else if (d == 3) v = w * p.theta[insr_b_offset(dm, 0) + j];
+            }
+            w1S[idx] = v;
+        }
+        for (int idx = tid; idx < 3 * HP; idx += BT) {
+            const int o = idx / HP, j = idx % HP;
+            woS[idx] = (o < O && j < H) ? p.theta[insr_w_offset(dm, L + 1) + (int64_t)o * H + j] : 0.f;
+        }
+        if (tid < 4) boS[tid] = (tid < O) ? p.theta[insr_b_offset(dm, L + 1) + tid] : 0.f;
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(s32(smraw + M.tmem)), "r"(tmem_cols) : "memory");
+                     :: "r"(s32(smraw + M.tmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        mbar_init(mbarD, 1); mbar_init(mbarY0, 1); mbar_init(mbarY1, 1);
+        mbar_init(mbarD, 1); mbar_init(mbarW, S);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -541,26 +607,50 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smraw + M.tmem);
     const uint32_t tmem_row = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-    uint32_t phD = 0, phY[2] = {0, 0};
-    bool pendY[2] = {false, false};
+    uint32_t phD = 0, phW = 0;
+    bool pendW = false;
     uint32_t wacc_mask = 0;                                       // bit l-1: Wacc_l holds data
+    {   // zero the weight-gradient accumulators: every weight-gradient MMA accumulates, whichever warp issues it first
+        float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = 8 * part; c < 64 * L; c += 8 * NT) tmem_st8(tmem_row + WBASE + c, zero8);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
-    // persistent thin-layer partial sums: the lane holds value (lane >> 1) & 15 of this thread's neuron half
-    float acc_gwo[O], acc_g1[1 + D], acc_gb[3] = {0.f, 0.f, 0.f};
+    // persistent thin-layer partial sums: the lane holds value (lane >> 2) & 7 of this thread's 8 neurons
+    float acc_gwo[O], acc_g1[1 + D], acc_gb[LMAX_TC] = {0.f, 0.f, 0.f};
     float acc_gbo = 0.f, loss_acc = 0.f;
     INSR_PRAGMA_UNROLL
     for (int o = 0; o < O; ++o) acc_gwo[o] = 0.f;
     INSR_PRAGMA_UNROLL
     for (int d = 0; d <= D; ++d) acc_g1[d] = 0.f;
 
-    auto wait_y = [&](int slot) {
-        if (pendY[slot]) { mbar_wait(slot ? mbarY1 : mbarY0, phY[slot]); phY[slot] ^= 1; pendY[slot] = false; }
-    };
     auto publish_and_sync = [&]() {          // operand writes (generic proxy / tcgen05.st) -> MMA, then CTA barrier
         tmem_st_wait();
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+    };
+    // store the operand (all streams) of the next contraction: this thread's 8 neurons
+    auto store_operand = [&](const float (&a)[S][8]) {
+        INSR_PRAGMA_UNROLL
+        for (int s = 0; s < S; ++s) {
+            if (s < NLO)
+                store_split8b<true>(tmem_row + ABASE + 32 * s + 8 * part, tmem_row + LBASE + 32 * (s < NLO ? s : 0) + 8 * part, nullptr, row, part, a[s]);
+            else
+                store_split8b<false>(tmem_row + ABASE + 32 * s + 8 * part, 0, smraw + M.x_lo + (s >= NLO ? s - NLO : 0) * OP_BYTES, row, part, a[s]);
+        }
+    };
+    auto issue_contraction = [&](uint32_t bhi, uint32_t blo) {
+        INSR_PRAGMA_UNROLL
+        for (int s = 0; s < S; ++s) {
+            if (s < NLO)
+                issue_stream_b<true>(tmem_base + 32 * s, tmem_base + ABASE + 32 * s, tmem_base + LBASE + 32 * (s < NLO ? s : 0), 0, bhi, blo);
+            else
+                issue_stream_b<false>(tmem_base + 32 * s, tmem_base + ABASE + 32 * s, 0, s32(smraw + M.x_lo + (s >= NLO ? s - NLO : 0) * OP_BYTES), bhi, blo);
+        }
     };
 
     const int64_t ntiles = (p.N + TILE_M - 1) / TILE_M;
@@ -570,18 +660,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
         float xv[D];
         INSR_PRAGMA_UNROLL
         for (int d = 0; d < D; ++d) xv[d] = valid ? __ldg(p.x + n * D + d) : 0.f;
+#ifdef INSR_TC_PROFILE
+        if (tid == 0) { tprev = clock64(); atomicAdd(gprof + 15, 1ull); }
+#endif
 
         // ================= forward with tape =================
-        INSR_PRAGMA_UNROLL
-        for (int g8 = 0; g8 < 2; ++g8) {
+        {
             float a8[S][8];
             INSR_PRAGMA_UNROLL
             for (int q = 0; q < 2; ++q) {
-                const int g4 = 2 * g8 + q;
                 float z[S][4], a[S][4], tv[TV][4];
                 INSR_PRAGMA_UNROLL
                 for (int c = 0; c < 4; ++c) {
-                    const int j = 16 * half + 4 * g4 + c;
+                    const int j = NPT * part + 4 * q + c;
                     const float4 wv = *reinterpret_cast<const float4 *>(w1S + j * 4);
                     float acc = wv.w;
                     INSR_PRAGMA_UNROLL
@@ -593,16 +684,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
                 }
                 insr_fused::act4<D, ORDER>(z, a, tv);
                 INSR_PRAGMA_UNROLL
-                for (int t = 0; t < TV; ++t) tape[(size_t)(g4 * TV + t) * THREADS + tid] = make_float4(tv[t][0], tv[t][1], tv[t][2], tv[t][3]);
+                for (int t = 0; t < TV; ++t) tape[(size_t)(q * TV + t) * BT + tid] = make_float4(tv[t][0], tv[t][1], tv[t][2], tv[t][3]);
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s)
                     INSR_PRAGMA_UNROLL
                     for (int c = 0; c < 4; ++c) a8[s][4 * q + c] = a[s][c];
             }
-            INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s)
-                store_split8(tmem_row + ABASE + 32 * s + 16 * half + 8 * g8, smraw + M.x_lo + s * OP_BYTES, row, 2 * half + g8, a8[s]);
+            store_operand(a8);
         }
+        TCP(0);
         float out[O][S];                                   // LSQ: this thread's share of the outputs
         INSR_PRAGMA_UNROLL
         for (int o = 0; o < O; ++o)
@@ -613,59 +703,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
             if (warp == 0) {
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t whi = s32(smraw + M.w_hi + l * W_BYTES), wlo = s32(smraw + M.w_lo + l * W_BYTES);
-                    INSR_PRAGMA_UNROLL
-                    for (int s = 0; s < S; ++s)
-                        issue_stream(tmem_base + 32 * s, tmem_base + ABASE + 32 * s, s32(smraw + M.x_lo + s * OP_BYTES), whi, wlo);
+                    issue_contraction(s32(smraw + M.w_hi + l * W_BYTES), s32(smraw + M.w_lo + l * W_BYTES));
                     mma_commit(mbarD);
                 }
                 __syncwarp();
             }
+            TCP(1);
             mbar_wait(mbarD, phD);
             phD ^= 1;
             tc_fence_after();
+            TCP(2);
             const bool last = (l == L - 1);
-            float4 *tl = tape + (size_t)(l + 1) * NQ * THREADS;
+            float4 *tl = tape + (size_t)(l + 1) * NQ * BT;
+            float zz[S][8], a8[S][8];
             INSR_PRAGMA_UNROLL
-            for (int g8 = 0; g8 < 2; ++g8) {
-                float zz[S][8], a8[S][8];
+            for (int s = 0; s < S; ++s) tmem_ld8(tmem_row + 32 * s + 8 * part, zz[s]);
+            tmem_ld_wait();
+            INSR_PRAGMA_UNROLL
+            for (int q = 0; q < 2; ++q) {
+                float z[S][4], a[S][4], tv[TV][4];
                 INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) tmem_ld8(tmem_row + 32 * s + 16 * half + 8 * g8, zz[s]);
-                tmem_ld_wait();
+                for (int c = 0; c < 4; ++c) {
+                    const int j = NPT * part + 4 * q + c;
+                    z[0][c] = zz[0][4 * q + c] + biasS[l * HP + j];
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 1; s < S; ++s) z[s][c] = zz[s][4 * q + c];
+                }
+                insr_fused::act4<D, ORDER>(z, a, tv);
                 INSR_PRAGMA_UNROLL
-                for (int q = 0; q < 2; ++q) {
-                    float z[S][4], a[S][4], tv[TV][4];
+                for (int t = 0; t < TV; ++t) tl[(size_t)(q * TV + t) * BT + tid] = make_float4(tv[t][0], tv[t][1], tv[t][2], tv[t][3]);
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s)
                     INSR_PRAGMA_UNROLL
-                    for (int c = 0; c < 4; ++c) {
-                        const int j = 16 * half + 8 * g8 + 4 * q + c;
-                        z[0][c] = zz[0][4 * q + c] + biasS[l * HP + j];
-                        INSR_PRAGMA_UNROLL
-                        for (int s = 1; s < S; ++s) z[s][c] = zz[s][4 * q + c];
-                    }
-                    insr_fused::act4<D, ORDER>(z, a, tv);
-                    const int g4 = 2 * g8 + q;
-                    INSR_PRAGMA_UNROLL
-                    for (int t = 0; t < TV; ++t) tl[(size_t)(g4 * TV + t) * THREADS + tid] = make_float4(tv[t][0], tv[t][1], tv[t][2], tv[t][3]);
-                    INSR_PRAGMA_UNROLL
-                    for (int s = 0; s < S; ++s)
-                        INSR_PRAGMA_UNROLL
-                        for (int c = 0; c < 4; ++c) a8[s][4 * q + c] = a[s][c];
-                }
-                if (last) {
-                    if constexpr (LSQ) {
-                        INSR_PRAGMA_UNROLL
-                        for (int o = 0; o < O; ++o)
-                            INSR_PRAGMA_UNROLL
-                            for (int s = 0; s < S; ++s)
-                                INSR_PRAGMA_UNROLL
-                                for (int i = 0; i < 8; ++i) out[o][s] = fmaf(woS[o * HP + 16 * half + 8 * g8 + i], a8[s][i], out[o][s]);
-                    }
-                } else {
-                    INSR_PRAGMA_UNROLL
-                    for (int s = 0; s < S; ++s)
-                        store_split8(tmem_row + ABASE + 32 * s + 16 * half + 8 * g8, smraw + M.x_lo + s * OP_BYTES, row, 2 * half + g8, a8[s]);
-                }
+                    for (int c = 0; c < 4; ++c) a8[s][4 * q + c] = a[s][c];
             }
+            if (last) {
+                if constexpr (LSQ) {
+                    INSR_PRAGMA_UNROLL
+                    for (int o = 0; o < O; ++o)
+                        INSR_PRAGMA_UNROLL
+                        for (int s = 0; s < S; ++s)
+                            INSR_PRAGMA_UNROLL
+                            for (int i = 0; i < 8; ++i) out[o][s] = fmaf(woS[o * HP + NPT * part + i], a8[s][i], out[o][s]);
+                }
+            } else {
+                store_operand(a8);
+            }
+            TCP(3);
         }
         // ================= output layer: cotangents g[o][s] =================
         float g[O][S];
@@ -673,12 +757,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
             INSR_PRAGMA_UNROLL
             for (int o = 0; o < O; ++o)
                 INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) partS[(half * TILE_M + row) * 8 + o * S + s] = out[o][s];
+                for (int s = 0; s < S; ++s) partS[(part * TILE_M + row) * PS + o * S + s] = out[o][s];
             __syncthreads();
             INSR_PRAGMA_UNROLL
             for (int o = 0; o < O; ++o) {
                 INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) out[o][s] += partS[((half ^ 1) * TILE_M + row) * 8 + o * S + s];
+                for (int s = 0; s < S; ++s) {
+                    float acc = 0.f;
+                    INSR_PRAGMA_UNROLL
+                    for (int q = 0; q < NT; ++q) acc += partS[(q * TILE_M + row) * PS + o * S + s];
+                    out[o][s] = acc;
+                }
                 out[o][0] += boS[o];
             }
             INSR_PRAGMA_UNROLL
@@ -692,7 +781,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
                     INSR_PRAGMA_UNROLL
                     for (int s = 0; s < S; ++s) r = fmaf(p.coef[(c * O + o) * S + s], out[o][s], r);
                 if (!valid) r = 0.f;
-                if (half == 0) loss_acc = fmaf(r, r, loss_acc);
+                if (part == 0) loss_acc = fmaf(r, r, loss_acc);
                 const float r2 = 2.f * p.scale * r;
                 INSR_PRAGMA_UNROLL
                 for (int o = 0; o < O; ++o)
@@ -710,19 +799,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
                 }
             }
         }
-        // output-layer gradients (this thread's 16 neurons; a_L recomputed from the tape) and the cotangent of
+        // output-layer gradients (this thread's 8 neurons; a_L recomputed from the tape) and the cotangent of
         // the last sine layer
-        float ab[S][16];
+        float ab[S][8];
         {
-            const float4 *tl = tape + (size_t)L * NQ * THREADS;
-            float v[O][16];
+            const float4 *tl = tape + (size_t)L * NQ * BT;
+            float v[O][8];
             INSR_PRAGMA_UNROLL
-            for (int g4 = 0; g4 < 4; ++g4) {
+            for (int q = 0; q < 2; ++q) {
                 float tv[TV][4], a[S][4];
                 INSR_PRAGMA_UNROLL
                 for (int t = 0; t < TV; ++t) {
-                    const float4 q = tl[(size_t)(g4 * TV + t) * THREADS + tid];
-                    tv[t][0] = q.x; tv[t][1] = q.y; tv[t][2] = q.z; tv[t][3] = q.w;
+                    const float4 u = tl[(size_t)(q * TV + t) * BT + tid];
+                    tv[t][0] = u.x; tv[t][1] = u.y; tv[t][2] = u.z; tv[t][3] = u.w;
                 }
                 insr_fused::a_from_tape4<D, ORDER>(tv, a);
                 INSR_PRAGMA_UNROLL
@@ -732,13 +821,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
                         float acc = 0.f;
                         INSR_PRAGMA_UNROLL
                         for (int s = 0; s < S; ++s) acc = fmaf(g[o][s], a[s][c], acc);
-                        v[o][4 * g4 + c] = acc;
+                        v[o][4 * q + c] = acc;
                     }
             }
             INSR_PRAGMA_UNROLL
             for (int o = 0; o < O; ++o) {
-                acc_gwo[o] += reduce16(v[o], lane);
-                if (half == 0) {
+                acc_gwo[o] += reduce8(v[o], lane);
+                if (part == 0) {
                     float t = g[o][0];
                     INSR_PRAGMA_UNROLL
                     for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
@@ -749,150 +838,136 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
         INSR_PRAGMA_UNROLL
         for (int s = 0; s < S; ++s)
             INSR_PRAGMA_UNROLL
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 float acc = 0.f;
                 INSR_PRAGMA_UNROLL
-                for (int o = 0; o < O; ++o) acc = fmaf(woS[o * HP + 16 * half + i], g[o][s], acc);
+                for (int o = 0; o < O; ++o) acc = fmaf(woS[o * HP + NPT * part + i], g[o][s], acc);
                 ab[s][i] = acc;
             }
 
+        TCP(4);
         // ================= reverse sweep =================
         for (int l = L; l >= 1; --l) {
             // ---- activation adjoint of layer l: ab (cotangent of a_l) -> zbar_l (in place)
-            const float4 *tl = tape + (size_t)l * NQ * THREADS;
+            const float4 *tl = tape + (size_t)l * NQ * BT;
             INSR_PRAGMA_UNROLL
-            for (int g4 = 0; g4 < 4; ++g4) {
+            for (int q = 0; q < 2; ++q) {
                 float tv[TV][4], abq[S][4];
                 INSR_PRAGMA_UNROLL
                 for (int t = 0; t < TV; ++t) {
-                    const float4 v = tl[(size_t)(g4 * TV + t) * THREADS + tid];
+                    const float4 v = tl[(size_t)(q * TV + t) * BT + tid];
                     tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
                 }
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s)
                     INSR_PRAGMA_UNROLL
-                    for (int c = 0; c < 4; ++c) abq[s][c] = ab[s][4 * g4 + c];
+                    for (int c = 0; c < 4; ++c) abq[s][c] = ab[s][4 * q + c];
                 insr_fused::adj4<D, ORDER>(tv, abq);
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s)
                     INSR_PRAGMA_UNROLL
-                    for (int c = 0; c < 4; ++c) ab[s][4 * g4 + c] = abq[s][c];
+                    for (int c = 0; c < 4; ++c) ab[s][4 * q + c] = abq[s][c];
             }
+            TCP(5);
             // bias gradient of layer l: sum over points of the value-stream zbar
             {
-                float v[16];
+                float v[8];
                 INSR_PRAGMA_UNROLL
-                for (int i = 0; i < 16; ++i) v[i] = ab[0][i];
-                const float r = reduce16(v, lane);
+                for (int i = 0; i < 8; ++i) v[i] = ab[0][i];
+                const float r = reduce8(v, lane);
                 if (l == 1) acc_gb[0] += r; else if (l == 2) acc_gb[1] += r; else acc_gb[2] += r;
             }
-            // ---- data-gradient operands: zbar_l hi -> TMEM, lo -> shared memory (all streams)
-            INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s)
+            // ---- data-gradient operands: zbar_l hi / lo (all streams)
+            store_operand(ab);
+            TCP(6);
+            // ---- weight-gradient operands, one slot per stream: ZT <- zbar_{l,s}, AT <- a_{l-1,s} (from the tape)
+            {
+                const float4 *tp = tape + (size_t)(l - 1) * NQ * BT;
+                float av[S][8];
                 INSR_PRAGMA_UNROLL
-                for (int g8 = 0; g8 < 2; ++g8) {
-                    float a8[8];
+                for (int q = 0; q < 2; ++q) {
+                    float tv[TV][4], a[S][4];
                     INSR_PRAGMA_UNROLL
-                    for (int i = 0; i < 8; ++i) a8[i] = ab[s][8 * g8 + i];
-                    store_split8(tmem_row + ABASE + 32 * s + 16 * half + 8 * g8, smraw + M.x_lo + s * OP_BYTES, row, 2 * half + g8, a8);
-                }
-            // ---- weight-gradient operands, one stream per slot: ZT <- zbar_{l,s}, AT <- a_{l-1,s} (from the tape)
-            const float4 *tp = tape + (size_t)(l - 1) * NQ * THREADS;
-            const uint32_t wthi = s32(smraw + M.wt_hi + (l - 1) * W_BYTES), wtlo = s32(smraw + M.wt_lo + (l - 1) * W_BYTES);
-            const uint32_t dw = tmem_base + WBASE + 64 * (l - 1);
-            INSR_PRAGMA_UNROLL
-            for (int s0 = 0; s0 < S; s0 += NSLOT) {
-                INSR_PRAGMA_UNROLL
-                for (int u = 0; u < NSLOT; ++u) {
-                    const int s = s0 + u;
-                    if (s < S) {
-                        float av[16];
-                        INSR_PRAGMA_UNROLL
-                        for (int g4 = 0; g4 < 4; ++g4) {       // a_{l-1,s} of this thread's 16 neurons
-                            float tv[TV][4], a[S][4];
-                            INSR_PRAGMA_UNROLL
-                            for (int t = 0; t < TV; ++t) {
-                                const float4 v = tp[(size_t)(g4 * TV + t) * THREADS + tid];
-                                tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
-                            }
-                            insr_fused::a_from_tape4<D, ORDER>(tv, a);
-                            INSR_PRAGMA_UNROLL
-                            for (int c = 0; c < 4; ++c) av[4 * g4 + c] = a[s][c];
-                        }
-                        wait_y(u);                             // the slot's previous weight-gradient MMAs are done
-                        unsigned char *slot = smraw + M.slots + u * SLOT_BYTES;
-                        store_wg_operand(slot, row, half, ab[s]);
-                        store_wg_operand(slot + TILE_M * 128, row, half, av);
+                    for (int t = 0; t < TV; ++t) {
+                        const float4 v = tp[(size_t)(q * TV + t) * BT + tid];
+                        tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
                     }
-                }
-                publish_and_sync();
-                if (warp == 0) {
-                    tc_fence_after();
-                    if (elect_one()) {
-                        if (s0 == 0) {                         // data gradient: D_s = Zbar_s . W_l  (B = transposed copy)
-                            INSR_PRAGMA_UNROLL
-                            for (int s = 0; s < S; ++s)
-                                issue_stream(tmem_base + 32 * s, tmem_base + ABASE + 32 * s, s32(smraw + M.x_lo + s * OP_BYTES), wthi, wtlo);
-                            mma_commit(mbarD);
-                        }
+                    insr_fused::a_from_tape4<D, ORDER>(tv, a);
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s)
                         INSR_PRAGMA_UNROLL
-                        for (int u = 0; u < NSLOT; ++u) {
-                            if (s0 + u < S) {
-                                const uint32_t zt = s32(smraw + M.slots + u * SLOT_BYTES), at = zt + TILE_M * 128;
-                                const bool fresh = !((wacc_mask >> (l - 1)) & 1u) && (s0 + u == 0);
-                                INSR_PRAGMA_UNROLL
-                                for (int kp = 0; kp < 8; ++kp)          // 16 points per instruction = two 1024-byte atoms
-                                    mma_bf16_wg(dw, umma_desc_mn128(zt + 2048 * kp), umma_desc_mn128(at + 2048 * kp), !(fresh && kp == 0));
-                                mma_commit(u ? mbarY1 : mbarY0);
-                            }
-                        }
-                    }
-                    __syncwarp();
+                        for (int c = 0; c < 4; ++c) av[s][4 * q + c] = a[s][c];
                 }
+                TCP(7);
+                if (pendW) { mbar_wait(mbarW, phW); phW ^= 1; pendW = false; }     // previous weight-gradient MMAs read the slots
                 INSR_PRAGMA_UNROLL
-                for (int u = 0; u < NSLOT; ++u)
-                    if (s0 + u < S) pendY[u] = true;
+                for (int s = 0; s < S; ++s) {
+                    unsigned char *slot = smraw + M.slots + s * SLOT_BYTES;
+                    store_wg_operand(slot, row, part, ab[s]);
+                    store_wg_operand(slot + TILE_M * 128, row, part, av[s]);
+                }
             }
-            wacc_mask |= 1u << (l - 1);
+            TCP(8);
+            publish_and_sync();
+            if (warp == 0) {
+                tc_fence_after();
+                if (elect_one()) {
+                    // data gradient: D_s = Zbar_s . W_l  (B = transposed copy)
+                    issue_contraction(s32(smraw + M.wt_hi + (l - 1) * W_BYTES), s32(smraw + M.wt_lo + (l - 1) * W_BYTES));
+                    mma_commit(mbarD);
+                }
+                __syncwarp();
+            }
+            TCP(9);
             // ---- cotangent of a_{l-1} from the data-gradient accumulators
             mbar_wait(mbarD, phD);
             phD ^= 1;
             tc_fence_after();
-            INSR_PRAGMA_UNROLL
-            for (int g8 = 0; g8 < 2; ++g8) {
-                float zz[S][8];
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) tmem_ld8(tmem_row + 32 * s + 16 * half + 8 * g8, zz[s]);
-                tmem_ld_wait();
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s)
+            TCP(10);
+            // ---- weight gradient of layer l: warp s issues stream s.  A warp that issues blocks on the shallow MMA
+            // queue until most of its MMAs have executed, so the 8 S instructions are spread over S warps (one per
+            // scheduler) and issued when the tensor pipe is idle; they execute under the next layer's adjoint.
+            if (warp < S) {
+                if (elect_one()) {
+                    const uint32_t dw = tmem_base + WBASE + 64 * (l - 1);
+                    const uint32_t zt = s32(smraw + M.slots + warp * SLOT_BYTES), at = zt + TILE_M * 128;
                     INSR_PRAGMA_UNROLL
-                    for (int i = 0; i < 8; ++i) ab[s][8 * g8 + i] = zz[s][i];
+                    for (int kp = 0; kp < 8; ++kp)              // 16 points per instruction = two 1024-byte atoms
+                        mma_bf16_wg(dw, umma_desc_mn128(zt + 2048 * kp), umma_desc_mn128(at + 2048 * kp), 1);
+                    mma_commit(mbarW);
+                }
+                __syncwarp();
             }
+            pendW = true;
+            wacc_mask |= 1u << (l - 1);
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) tmem_ld8(tmem_row + 32 * s + 8 * part, ab[s]);
+            tmem_ld_wait();
+            TCP(11);
         }
         // ================= first sine layer =================
         {
             float gx_part[D];
             INSR_PRAGMA_UNROLL
             for (int d = 0; d < D; ++d) gx_part[d] = 0.f;
-            float v0[16], vd[D > 0 ? D : 1][16];
+            float v0[8], vd[D > 0 ? D : 1][8];
             INSR_PRAGMA_UNROLL
-            for (int g4 = 0; g4 < 4; ++g4) {
+            for (int q = 0; q < 2; ++q) {
                 float tv[TV][4], abq[S][4];
                 INSR_PRAGMA_UNROLL
                 for (int t = 0; t < TV; ++t) {
-                    const float4 v = tape[(size_t)(g4 * TV + t) * THREADS + tid];
+                    const float4 v = tape[(size_t)(q * TV + t) * BT + tid];
                     tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
                 }
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s)
                     INSR_PRAGMA_UNROLL
-                    for (int c = 0; c < 4; ++c) abq[s][c] = ab[s][4 * g4 + c];
+                    for (int c = 0; c < 4; ++c) abq[s][c] = ab[s][4 * q + c];
                 insr_fused::adj4<D, ORDER>(tv, abq);
                 INSR_PRAGMA_UNROLL
                 for (int c = 0; c < 4; ++c) {
-                    const int i = 4 * g4 + c;
-                    const float4 wv = *reinterpret_cast<const float4 *>(w1S + (16 * half + i) * 4);
+                    const int i = 4 * q + c;
+                    const float4 wv = *reinterpret_cast<const float4 *>(w1S + (NPT * part + i) * 4);
                     v0[i] = abq[0][c];
                     INSR_PRAGMA_UNROLL
                     for (int d = 0; d < D; ++d) {
@@ -901,56 +976,59 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
                     }
                 }
             }
-            acc_g1[0] += reduce16(v0, lane);
+            acc_g1[0] += reduce8(v0, lane);
             INSR_PRAGMA_UNROLL
-            for (int d = 0; d < D; ++d) acc_g1[1 + d] += reduce16(vd[d], lane);
+            for (int d = 0; d < D; ++d) acc_g1[1 + d] += reduce8(vd[d], lane);
             if (p.gx) {
                 __syncthreads();                           // partS may still be read by the LSQ combine of slow warps
                 INSR_PRAGMA_UNROLL
-                for (int d = 0; d < D; ++d) partS[(half * TILE_M + row) * 8 + d] = gx_part[d];
+                for (int d = 0; d < D; ++d) partS[(part * TILE_M + row) * PS + d] = gx_part[d];
                 __syncthreads();
-                if (half == 0 && valid) {
+                if (part == 0 && valid) {
                     INSR_PRAGMA_UNROLL
-                    for (int d = 0; d < D; ++d) p.gx[n * D + d] = gx_part[d] + partS[(TILE_M + row) * 8 + d];
+                    for (int d = 0; d < D; ++d) {
+                        float acc = 0.f;
+                        INSR_PRAGMA_UNROLL
+                        for (int q = 0; q < NT; ++q) acc += partS[(q * TILE_M + row) * PS + d];
+                        p.gx[n * D + d] = acc;
+                    }
                 }
             }
         }
         tc_fence_before();
-        __syncthreads();                                   // partS / tape reuse by the next tile
+        __syncthreads();                                   // partS reuse by the next tile
         tc_fence_after();
+        TCP(12);
     }
 
     // ================= flush =================
-    wait_y(0); wait_y(1);
+    if (pendW) { mbar_wait(mbarW, phW); phW ^= 1; pendW = false; }
     tc_fence_after();
     const float wsc = dm.omega;
     // hidden-layer weight gradients.  M = 64 accumulator layout: row r of D sits in TMEM lane 32 (r >> 4) + (r & 15),
     // so lanes 0..15 of warp quadrant q hold rows 16 q .. 16 q + 15 = level (q >> 1), neurons 16 (q & 1) + lane;
-    // the two warps of a quadrant split the 32 input neurons; columns k (x a1) and 32 + k (x a2) are added.
+    // the four warps of a quadrant split the 32 input neurons; columns k (x a1) and 32 + k (x a2) are added.
     {
         const int j = 16 * (warp & 1) + lane;
         for (int l = 1; l <= L; ++l) {
             if (!((wacc_mask >> (l - 1)) & 1u)) continue;
             float *gW = p.gtheta + insr_w_offset(dm, l);
-            INSR_PRAGMA_UNROLL
-            for (int c8 = 0; c8 < 2; ++c8) {
-                float v1[8], v2[8];
-                tmem_ld8(tmem_row + WBASE + 64 * (l - 1) + 16 * half + 8 * c8, v1);
-                tmem_ld8(tmem_row + WBASE + 64 * (l - 1) + 32 + 16 * half + 8 * c8, v2);
-                tmem_ld_wait();
-                if (lane < 16 && j < H) {
-                    INSR_PRAGMA_UNROLL
-                    for (int i = 0; i < 8; ++i) {
-                        const int k = 16 * half + 8 * c8 + i;
-                        if (k < H) atomicAdd(gW + (size_t)j * H + k, wsc * (v1[i] + v2[i]));
-                    }
+            float v1[8], v2[8];
+            tmem_ld8(tmem_row + WBASE + 64 * (l - 1) + 8 * part, v1);
+            tmem_ld8(tmem_row + WBASE + 64 * (l - 1) + 32 + 8 * part, v2);
+            tmem_ld_wait();
+            if (lane < 16 && j < H) {
+                INSR_PRAGMA_UNROLL
+                for (int i = 0; i < 8; ++i) {
+                    const int k = 8 * part + i;
+                    if (k < H) atomicAdd(gW + (size_t)j * H + k, wsc * (v1[i] + v2[i]));
                 }
             }
         }
     }
-    // thin layers: the even lanes hold the totals of neuron 16 half + (lane >> 1); one warp per (half, row block)
-    if ((lane & 1) == 0) {
-        const int j = 16 * half + (lane >> 1);
+    // thin layers: lanes with (lane & 3) == 0 hold the totals of neuron 8 part + (lane >> 2)
+    if ((lane & 3) == 0) {
+        const int j = NPT * part + (lane >> 2);
         if (j < H) {
             INSR_PRAGMA_UNROLL
             for (int o = 0; o < O; ++o) atomicAdd(p.gtheta + insr_w_offset(dm, L + 1) + o * H + j, acc_gwo[o]);
@@ -960,17 +1038,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_bwd(Params p, float4 *__restr
             for (int l = 1; l <= L; ++l) atomicAdd(p.gtheta + insr_b_offset(dm, l) + j, wsc * acc_gb[l - 1]);
         }
     }
-    if (half == 0 && lane < O) atomicAdd(p.gtheta + insr_b_offset(dm, L + 1) + lane, acc_gbo);
+    if (part == 0 && lane < O) atomicAdd(p.gtheta + insr_b_offset(dm, L + 1) + lane, acc_gbo);
     if (LSQ) {
         float t = loss_acc;
         INSR_PRAGMA_UNROLL
         for (int m = 16; m >= 1; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
-        if (lane == 0 && half == 0) atomicAdd(p.loss_out, p.scale * t);
+        if (lane == 0 && part == 0) atomicAdd(p.loss_out, p.scale * t);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -981,14 +1059,15 @@ inline size_t tc_bwd_ws_bytes(int L, int S) {
 template <int D, int O, int ORDER, bool LSQ>
 int launch_tc_bwd(Params &p, float *ws, void *stream, int64_t *launches) {
     constexpr int S = StreamCfg<D, ORDER>::S;
-    const SmemB M = smem_map_bwd(p.dm.L, S);
+    constexpr int PS = (O * S > D ? O * S : D);
+    if (p.dm.L > LMAX_TC) return -6;
+    const SmemB M = smem_map_bwd(p.dm.L, S, PS);
     auto kfn = k_tc_bwd<D, O, ORDER, LSQ>;
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, M.total + 1024);
     const int64_t tiles = (p.N + TILE_M - 1) / TILE_M;
     int64_t ctas = tiles < insr_fused::sm_count() ? tiles : insr_fused::sm_count();
-    const int cols = pow2_cols(64 * S + 64 * p.dm.L);
     float4 *tape = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(ws) + 15) & ~uintptr_t(15));
-    kfn<<<dim3((unsigned)ctas), dim3(THREADS), M.total + 1024, reinterpret_cast<cudaStream_t>(stream)>>>(p, tape, cols);
+    kfn<<<dim3((unsigned)ctas), dim3(BT), M.total + 1024, reinterpret_cast<cudaStream_t>(stream)>>>(p, tape);
     ++*launches;
     return 0;
 }
