@@ -305,6 +305,18 @@ def run_ours(args):
         "kernel_family": {"fwd": lib.kernel_family(desc, order, False), "bwd": lib.kernel_family(desc, order, True),
                           "pipe": tensor_pipe_txt},
     }
+    # DRAM traffic of the dominant kernel: one ncu capture at the bench size, committed under profiles/
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic_tcgen05_v5.json")))
+        want = "k_tc_bwd" if tensor_path else "k_fused_bwd"
+        ks = [k for k in tr["kernels"] if want in k["kernel"] and ", 0>" in k["kernel"]]       # LSQ = false instantiation
+        if ks and tr.get("points") == N and args.workload == "fluid2Dtlgn.pressure":
+            k = ks[-1]                                   # last (warm) launch
+            roofline["traffic"] = int(k["dram_read_bytes"] + k["dram_write_bytes"])
+            roofline["traffic_note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum of {k['kernel']} at {N} points "
+                                        f"({tr['source']}); algorithmic bytes of the backward = {4 * (D + sum(math.prod(sh[1:]) for sh in shapes)) * N}")
+    except Exception:
+        pass
     if tensor_path:
         # executed tensor-pipe work of the backward kernel in bf16-equivalent flops (a TF32 flop costs two bf16
         # flops of pipe time): forward recompute + data gradient = 2 x 3 TF32 products, weight gradient = 4 bf16

@@ -1,5 +1,5 @@
 #!/bin/bash
-# one gpurun call: tests, bench, launch list, one full capture of the top kernel
+# one gpurun call: tests, bench, launch list, one full capture of the top kernels, DRAM traffic at the bench size
 mkdir -p gpurun_out
 TAG=${1:-run}
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$TAG.log
@@ -13,5 +13,8 @@ if [ "$2" == "ncu" ]; then
   python tools/prof_one.py --points 262144 --reps 1 --lsq > gpurun_out/prof_plain2_$TAG.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:"k_tc_|k_fused" -c 3 -f -o gpurun_out/prof_$TAG \
       python tools/prof_one.py --points 262144 --reps 1 --lsq > gpurun_out/ncu_full_$TAG.log 2>&1
-  tail -n 3 gpurun_out/ncu_list_$TAG.log; tail -n 3 gpurun_out/ncu_full_$TAG.log
+  # DRAM traffic of the hot kernels at the bench size (2^22 points), second repetition (warm)
+  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"k_tc_|k_fused" \
+      --csv --log-file gpurun_out/traffic_$TAG.csv python tools/prof_one.py --points 4194304 --reps 2 --lsq > gpurun_out/ncu_traffic_$TAG.log 2>&1
+  tail -n 3 gpurun_out/ncu_list_$TAG.log; tail -n 3 gpurun_out/ncu_full_$TAG.log; tail -n 7 gpurun_out/traffic_$TAG.csv | cut -c1-300
 fi
