@@ -79,7 +79,7 @@ class MLP(nn.Module):
 
         self.in_features, self.out_features = in_features, out_features
         self.hidden_features, self.num_hidden_layers = hidden_features, num_hidden_layers
-        # INSR_NO_TENSOR=1 keeps the forward on the FP32 FFMA kernels instead of tcgen05 (3xTF32)
+        # INSR_NO_TENSOR=1 keeps forward and backward on the FP32 FFMA kernels instead of tcgen05 (3xTF32 / bf16x2)
         flags = _lib.FLAG_NO_TENSOR if os.environ.get("INSR_NO_TENSOR", "0") == "1" else 0
         self.desc = _lib.make_desc(in_features, out_features, hidden_features, num_hidden_layers, OMEGA, flags)
         self._flat = None
