@@ -80,6 +80,39 @@ def _eye(n):
 
 
 # ------------------------------------------------------------------------------------------------
+# parallel branches: the terms of one closure are independent kernels (they only meet in the flat gradient
+# buffer, which every kernel updates with red.global); the boundary terms use a handful of CTAs, so they run
+# beside the interior term on side streams.  Under CUDA-graph capture this becomes a fork / join in the graph.
+# ------------------------------------------------------------------------------------------------
+_side_streams = {}
+
+
+def parallel(ref, *fns):
+    """run fns[0] on the current stream and fns[1:] on side streams (fork after everything enqueued so far,
+    join before returning); sequential for CPU tensors.  Returns the list of results."""
+    if len(fns) == 1 or not ref.is_cuda:
+        return [f() for f in fns]
+    dev = ref.device
+    cur = torch.cuda.current_stream(dev)
+    streams = _side_streams.setdefault(dev.index, [])
+    while len(streams) < len(fns) - 1:
+        streams.append(torch.cuda.Stream(device=dev))
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    out = [None] * len(fns)
+    for k, f in enumerate(fns[1:]):
+        streams[k].wait_event(fork)
+        with torch.cuda.stream(streams[k]):
+            out[k + 1] = f()
+    out[0] = fns[0]()
+    for k in range(len(fns) - 1):
+        done = torch.cuda.Event()
+        done.record(streams[k])
+        cur.wait_event(done)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # advection (1-D, constant velocity)
 # ------------------------------------------------------------------------------------------------
 def advect_initialize(field, samples, init_values):
@@ -88,18 +121,20 @@ def advect_initialize(field, samples, init_values):
 
 def advect_step(field, field_prev, samples, boundary_samples, dt, vel):
     """midpoint residual  (u - u_prev)/dt + vel (u_x + u_prev_x)/2  and Dirichlet band"""
-    u_prev, j_prev = evaluate(field_prev, samples, ORDER_JAC)
-    target = u_prev / dt - (0.5 * vel) * j_prev[:, :, 0]
-    main = lsq(field, samples, ORDER_JAC, [[1.0 / dt]], cj=[[[0.5 * vel]]], target=target)
-    bc = lsq(field, boundary_samples, ORDER_VALUE, [[1.0]])
+    def interior():
+        u_prev, j_prev = evaluate(field_prev, samples, ORDER_JAC)
+        target = u_prev / dt - (0.5 * vel) * j_prev[:, :, 0]
+        return lsq(field, samples, ORDER_JAC, [[1.0 / dt]], cj=[[[0.5 * vel]]], target=target)
+
+    main, bc = parallel(samples, interior, lambda: lsq(field, boundary_samples, ORDER_VALUE, [[1.0]]))
     return {"main": main, "bc": bc}
 
 
 # ------------------------------------------------------------------------------------------------
 # fluid (2-D inviscid Euler, operator splitting)
 # ------------------------------------------------------------------------------------------------
-def _no_slip_bc(velocity, bc_x, bc_y):
-    return lsq(velocity, bc_x, ORDER_VALUE, [[1.0, 0.0]]) + lsq(velocity, bc_y, ORDER_VALUE, [[0.0, 1.0]])
+def _no_slip_terms(velocity, bc_x, bc_y):
+    return (lambda: lsq(velocity, bc_x, ORDER_VALUE, [[1.0, 0.0]]), lambda: lsq(velocity, bc_y, ORDER_VALUE, [[0.0, 1.0]]))
 
 
 def fluid_initialize(velocity, samples, init_values):
@@ -109,30 +144,40 @@ def fluid_initialize(velocity, samples, init_values):
 def fluid_advect_velocity(velocity, velocity_prev, samples, bc_x, bc_y, dt):
     """semi-Lagrangian: u(x) = u_prev(clamp(x - u_prev(x) dt))"""
     x = samples.detach().reshape(-1, 2)
-    (u_prev,) = evaluate(velocity_prev, x, ORDER_VALUE)
-    back = torch.clamp(x - u_prev * dt, min=-1.0, max=1.0)
-    (u_adv,) = evaluate(velocity_prev, back, ORDER_VALUE)
-    main = lsq(velocity, x, ORDER_VALUE, _eye(2), target=u_adv)
-    return {"main": main, "bc": _no_slip_bc(velocity, bc_x, bc_y)}
+
+    def interior():
+        (u_prev,) = evaluate(velocity_prev, x, ORDER_VALUE)
+        back = torch.clamp(x - u_prev * dt, min=-1.0, max=1.0)
+        (u_adv,) = evaluate(velocity_prev, back, ORDER_VALUE)
+        return lsq(velocity, x, ORDER_VALUE, _eye(2), target=u_adv)
+
+    main, bx, by = parallel(x, interior, *_no_slip_terms(velocity, bc_x, bc_y))
+    return {"main": main, "bc": bx + by}
 
 
 def fluid_solve_pressure(velocity, pressure, samples, bc_x, bc_y):
     """lap p = div u, Neumann band"""
-    _, jac_u = evaluate(velocity, samples, ORDER_JAC)
-    div_u = jac_u[:, 0, 0] + jac_u[:, 1, 1]
-    main = lsq(pressure, samples, ORDER_LAP, [[0.0]], cl=[[1.0]], target=div_u)
-    bc = lsq(pressure, bc_x, ORDER_JAC, [[0.0]], cj=[[[1.0, 0.0]]]) + \
-        lsq(pressure, bc_y, ORDER_JAC, [[0.0]], cj=[[[0.0, 1.0]]])
-    return {"main": main, "bc": bc}
+    def interior():
+        _, jac_u = evaluate(velocity, samples, ORDER_JAC)
+        div_u = jac_u[:, 0, 0] + jac_u[:, 1, 1]
+        return lsq(pressure, samples, ORDER_LAP, [[0.0]], cl=[[1.0]], target=div_u)
+
+    main, bx, by = parallel(samples, interior,
+                            lambda: lsq(pressure, bc_x, ORDER_JAC, [[0.0]], cj=[[[1.0, 0.0]]]),
+                            lambda: lsq(pressure, bc_y, ORDER_JAC, [[0.0]], cj=[[[0.0, 1.0]]]))
+    return {"main": main, "bc": bx + by}
 
 
 def fluid_projection(velocity, velocity_prev, pressure, samples, bc_x, bc_y):
     """u <- u_prev - grad p"""
-    (u_prev,) = evaluate(velocity_prev, samples, ORDER_VALUE)
-    _, jac_p = evaluate(pressure, samples, ORDER_JAC)
-    target = u_prev - jac_p[:, 0, :]
-    main = lsq(velocity, samples, ORDER_VALUE, _eye(2), target=target)
-    return {"main": main, "bc": _no_slip_bc(velocity, bc_x, bc_y)}
+    def interior():
+        (u_prev,) = evaluate(velocity_prev, samples, ORDER_VALUE)
+        _, jac_p = evaluate(pressure, samples, ORDER_JAC)
+        target = u_prev - jac_p[:, 0, :]
+        return lsq(velocity, samples, ORDER_VALUE, _eye(2), target=target)
+
+    main, bx, by = parallel(samples, interior, *_no_slip_terms(velocity, bc_x, bc_y))
+    return {"main": main, "bc": bx + by}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -278,7 +323,7 @@ class FluidStepper:
         x = sampling.sample_random(n // n_shard_div, 2, device=dev)
         bx = sampling.sample_boundary2D_separate(n // 100, "horizontal", device=dev)
         by = sampling.sample_boundary2D_separate(n // 100, "vertical", device=dev)
-        return x, bx, by
+        return x, bx, by                     # (same RNG stream order as the reference: not run in parallel)
 
     def _loop(self, nets, closure, n_iters, world=1, key=None):
         if self.graphed:
