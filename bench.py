@@ -201,7 +201,7 @@ def run_ours(args):
     theta = net.flat_theta()
     desc = net.desc
     P = theta.numel()
-    N = args.points
+    N = args.points if args.scaling == "weak" else args.points // world     # strong: the global batch is fixed
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = (torch.rand(N, D, generator=gen, device=dev) * 2 - 1).contiguous()
     cg = torch.Generator(device=dev).manual_seed(4321 + rank)
@@ -413,15 +413,22 @@ def run_ours(args):
             timestep["cpu_reference"] = fluid_timestep_cpu(3, args.timestep_iters)
 
     # ---- CPU baseline (oracle port of the reference algorithm), rank 0, bounded sample
-    cpu = None
+    cpu, torch_gpu = None, None
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_reference(args.workload, budget_s=args.cpu_budget)
+        # like-for-like: the same algorithm as stock PyTorch on this GPU, at the largest size whose
+        # autograd graph fits comfortably
+        try:
+            torch_gpu = cpu_reference(args.workload, budget_s=5.0, n_points=min(N, 1 << 20), device=dev)
+        except Exception as e:                                  # e.g. out of memory on a wide net
+            torch_gpu = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
             "metric": "collocation points/s (SIREN fwd + grad + Laplacian + bwd)", "value": round(pts_per_s, 1),
             "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc_txt}", "points_per_step_per_gpu": N,
                        "global_points_per_step": world * N, "params": P,
@@ -429,27 +436,29 @@ def run_ours(args):
                        "l2": "inputs + outputs + cotangents per step exceed the 126 MB L2" if N >= (1 << 22) else "flushed by size only if points >= 2^22",
                        "init": "reference sine init, torch.manual_seed(0); points U[-1,1]^D seed 1234; cotangents randn/N seed 4321"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "script_size": script, "timestep": timestep, "fused_closure": fused_closure,
+            "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "script_size": script, "timestep": timestep,
+            "fused_closure": fused_closure,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_reference(workload, budget_s=15.0, n_points=16384, threads=None):
+def cpu_reference(workload, budget_s=15.0, n_points=16384, threads=None, device="cpu"):
     """the reference algorithm (oracle.torch_port: nn.Linear + sin(30x) + nested autograd.grad)
-    on the host cores, on a bounded sample of the workload"""
+    on the host cores -- or, device="cuda", as stock PyTorch on the same GPU -- on a bounded sample of the workload"""
     from oracle import torch_port as tp
     D, O, H, L, order, _ = WORKLOADS[workload]
     if threads:
         torch.set_num_threads(threads)
     cores = torch.get_num_threads()
     torch.manual_seed(0)
-    net = tp.RefMLP(D, O, L, H)
-    x = (torch.rand(n_points, D) * 2 - 1).requires_grad_(True)
-    gy = torch.randn(n_points, O) / n_points
-    gj = torch.randn(n_points, O, D) / n_points
-    gl = torch.randn(n_points, 1) / n_points
+    on_gpu = str(device).startswith("cuda")
+    net = tp.RefMLP(D, O, L, H).to(device)
+    x = (torch.rand(n_points, D, device=device) * 2 - 1).requires_grad_(True)
+    gy = torch.randn(n_points, O, device=device) / n_points
+    gj = torch.randn(n_points, O, D, device=device) / n_points
+    gl = torch.randn(n_points, 1, device=device) / n_points
 
     def step():
         net.zero_grad()
@@ -463,16 +472,21 @@ def cpu_reference(workload, budget_s=15.0, n_points=16384, threads=None):
         loss.backward()
 
     step(); step()
+    if on_gpu:
+        torch.cuda.synchronize()
     t0, n = time.perf_counter(), 0
     while True:
         step()
         n += 1
+        if on_gpu:
+            torch.cuda.synchronize()
         el = time.perf_counter() - t0
         if el > budget_s or n >= 200:
             break
+    where = f"stock PyTorch eager on {torch.cuda.get_device_name()}" if on_gpu else "CPU"
     return {"value": round(n_points * n / el, 1), "unit": "points/s", "cores": cores, "kind": "port",
             "sample": f"{n} steps of {n_points} points ({workload}); oracle.torch_port = the reference's algorithm "
-                      f"(nn.Linear + sin(30x) + nested autograd.grad) in torch {torch.__version__} CPU fp32",
+                      f"(nn.Linear + sin(30x) + nested autograd.grad) in torch {torch.__version__} {where} fp32",
             "ms_per_step": round(el / n * 1e3, 2)}
 
 
@@ -508,6 +522,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="fluid2Dtlgn.pressure", choices=sorted(WORKLOADS))
     ap.add_argument("--points", type=int, default=1 << 22, help="collocation points per GPU per step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's scaling run): --points per GPU; strong: --points in total, split over the GPUs")
     ap.add_argument("--e2e-points", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

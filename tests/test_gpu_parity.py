@@ -314,3 +314,60 @@ def test_graphed_loop_equals_eager_loop_on_fixed_samples():
         assert abs(a["main"] - b["main"]) < 1e-4 * abs(a["main"]) and abs(a["bc"] - b["bc"]) < 2e-3 * abs(a["bc"]) + 1e-9
     assert rel(p2.flat_theta(), p1.flat_theta()) < 1e-4
     assert h_graph[-1]["main"] < h_graph[0]["main"]
+
+
+@pytest.mark.parametrize("case", [(2, 1, 32, 3, 127, 2), (2, 1, 32, 3, 129, 2), (2, 2, 32, 2, 40001, 1), (1, 1, 20, 1, 19000, 1),
+                                  (2, 1, 5, 3, 300, 2), (2, 2, 32, 3, 148 * 128 * 2 + 5, 2), (2, 1, 32, 1, 256, 0)])
+def test_tcgen05_tile_boundaries_and_persistent_loop(case):
+    """the tcgen05 kernels (default flags) at ragged tile boundaries (128-point tiles), with H padded to 32, and with
+    more tiles than CTAs (persistent loop: TMEM / tape / operand-slot reuse across tiles): forward, backward with
+    dL/dx, and the fused lsq closure against the fp64 oracle"""
+    D, O, H, L, N, order = case
+    rng = np.random.default_rng(7 * N + H)
+    desc = _lib.make_desc(D, O, H, L)
+    assert _lib.get_lib().kernel_family(desc, order, True) == 1
+    parts = []
+    for li, (o, i) in enumerate(fm.layer_shapes(D, O, H, L)):
+        b = 1.0 / i if li == 0 else np.sqrt(6.0 / i) / 30.0
+        parts += [rng.uniform(-b, b, o * i), rng.uniform(-1, 1, o) / np.sqrt(i)]
+    theta = np.concatenate(parts).astype(np.float32)
+    x = rng.uniform(-1, 1, (N, D)).astype(np.float32)
+    th64, x64 = theta.astype(np.float64), x.astype(np.float64)
+    outs = _ops.siren_forward(desc, dev(theta), dev(x), order)
+    ref = fm.forward(th64, x64, D, O, H, L, order)
+    for o_, k in zip(outs, ["y", "jac", "lap"]):
+        assert rel(o_, ref[k]) < TOL, k
+    cot = [rng.standard_normal(tuple(o.shape)).astype(np.float32) for o in outs]
+    gth, gx = _ops.siren_backward(desc, dev(theta), dev(x), order, *[dev(c) for c in cot], need_gx=True)
+    kw = dict(gy=cot[0])
+    if order >= 1:
+        kw["gjac"] = cot[1]
+    if order == 2:
+        kw["glap"] = cot[2]
+    gref, gxref = fm.backward(th64, x64, D, O, H, L, order, **kw)
+    assert rel(gth, gref) < TOL
+    assert rel(gx, gxref) < TOL
+    # fused closure: r = sum_o cy y_o (+ cj . J) (+ cl lap) - target, loss = scale * sum r^2
+    cy = rng.standard_normal((1, O)).astype(np.float32)
+    cj = rng.standard_normal((1, O, D)).astype(np.float32) if order >= 1 else None
+    cl = rng.standard_normal((1, O)).astype(np.float32) if order == 2 else None
+    target = rng.standard_normal((N, 1)).astype(np.float32)
+    scale = 1.0 / N
+    loss = torch.zeros(1, device="cuda")
+    g2 = torch.zeros(theta.size, device="cuda")
+    _ops.siren_lsq_step(desc, dev(theta), dev(x), order, cy.tolist(), None if cj is None else cj.tolist(),
+                        None if cl is None else cl.tolist(), dev(target), scale, loss_out=loss, gtheta=g2)
+    r = ref["y"] @ cy.T.astype(np.float64) - target
+    kw = {}
+    if order >= 1:
+        r = r + np.einsum("nod,rod->nr", ref["jac"], cj.astype(np.float64))
+        kw["gjac"] = 2 * scale * np.einsum("nr,rod->nod", r, cj.astype(np.float64))
+    if order == 2:
+        r = r + ref["lap"] @ cl.T.astype(np.float64)
+        kw["glap"] = 2 * scale * r @ cl.astype(np.float64)
+    if order >= 1:
+        kw["gjac"] = 2 * scale * np.einsum("nr,rod->nod", r, cj.astype(np.float64))
+    kw["gy"] = 2 * scale * r @ cy.astype(np.float64)
+    gref2, _ = fm.backward(th64, x64, D, O, H, L, order, **kw)
+    assert abs(float(loss[0]) - scale * (r ** 2).sum()) < 1e-5 * abs(scale * (r ** 2).sum())
+    assert rel(g2, gref2) < TOL
