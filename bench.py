@@ -47,6 +47,25 @@ WORKLOADS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def keep_stdout_clean():
+    """ONE JSON line on stdout is the contract: park the real stdout and point fd 1 at stderr, so that library chatter
+    (the NCCL version banner, warnings printed by child threads) cannot land in front of the line"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def flops_fwd_per_point(D, O, H, L, order):
     """MAC(S) = D*H + S*(L*H^2 + H*O); F_fwd = 2*MAC; F_fwd+bwd = 3*F_fwd"""
     S = 1 + (D if order >= 1 else 0) + (1 if order == 2 else (D * (D + 1) // 2 if order == 3 else 0))
@@ -439,7 +458,7 @@ def run_ours(args):
             "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "script_size": script, "timestep": timestep,
             "fused_closure": fused_closure,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -511,7 +530,7 @@ def run_reference(args):
         "cpu_baseline": res,
         "e2e": {"value": res["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -529,6 +548,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timestep-iters", type=int, default=100, help="Adam iterations per training loop of the fluid2Dtlgn time-step measurement (0 = skip)")
     args = ap.parse_args()
+    keep_stdout_clean()
     if args.impl == "reference":
         run_reference(args)
     else:
