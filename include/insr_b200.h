@@ -143,6 +143,19 @@ int insr_adam_step(float *theta, const float *grad, float *exp_avg, float *exp_a
 int insr_plateau_step(const float *loss, float *sched, float factor, int patience, float threshold,
                       float min_lr, float eps, void *stream);
 
+/*
+ * Batched 2x2 / 3x3 singular value decomposition and the fused elasticity energy.
+ * Replaces, in the elasticity closure (elasticity/model.py:143-149):
+ *     U_x, S_x, V_x = torch.svd(jac_x)                                  -> insr_svd_small
+ *     E_arap = r_a * sum((S_x - 1)^2); E_volume = r_v * sum((prod(S_x, 1) - 1)^2)  and their adjoint d E / d jac_x
+ *                                                                       -> insr_elastic_energy
+ *   F (n, d, d) row-major, d in {2, 3};  S (n, d) descending, >= 0;  U, V (n, d, d) with F = U diag(S) V^T (nullable)
+ *   energy: device scalar, ACCUMULATED (+=);  gF (n, d, d) = d energy / d F  (nullable: energy only)
+ */
+int insr_svd_small(const float *F, int64_t n, int d, float *U, float *S, float *V, void *stream);
+int insr_elastic_energy(const float *F, int64_t n, int d, float ratio_arap, float ratio_volume, float *energy,
+                        float *gF, void *stream);
+
 /* introspection used by bench.py / tests: which kernel family a call would dispatch to.
  * returns 0 = generic, 1 = fused resident-weights kernels (H <= 32), 2 = tiled shared-memory GEMM
  * kernels (32 < H <= 512); negative = error. */

@@ -21,7 +21,7 @@ FLAG_FFMA_BWD = 4
 EXPORTS = [
     "insr_version", "insr_last_error", "insr_siren_theta_size", "insr_siren_workspace_bytes",
     "insr_siren_forward", "insr_siren_backward", "insr_siren_lsq_step", "insr_siren_kernel_family",
-    "insr_launch_count", "insr_adam_step", "insr_plateau_step",
+    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy",
 ]
 
 
@@ -68,6 +68,10 @@ class Library:
         c.insr_adam_step.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _vp]
         c.insr_plateau_step.restype = _i32
         c.insr_plateau_step.argtypes = [_vp, _vp, _f, _i32, _f, _f, _f, _vp]
+        c.insr_svd_small.restype = _i32
+        c.insr_svd_small.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp]
+        c.insr_elastic_energy.restype = _i32
+        c.insr_elastic_energy.argtypes = [_vp, _i64, _i32, _f, _f, _vp, _vp, _vp]
         c.insr_launch_count.restype = _i64
         c.insr_launch_count.argtypes = [_i32]
 
@@ -103,6 +107,12 @@ class Library:
 
     def plateau_step(self, loss, sched, factor, patience, threshold, min_lr, eps, stream):
         self.check(self.cdll.insr_plateau_step(loss, sched, factor, patience, threshold, min_lr, eps, stream))
+
+    def svd_small(self, F, n, d, U, S, V, stream):
+        self.check(self.cdll.insr_svd_small(F, n, d, U, S, V, stream))
+
+    def elastic_energy(self, F, n, d, ratio_arap, ratio_volume, energy, gF, stream):
+        self.check(self.cdll.insr_elastic_energy(F, n, d, ratio_arap, ratio_volume, energy, gF, stream))
 
     def lsq_step(self, desc, theta, x, n, order, n_res, coef, target, scale, loss_out, gtheta, ws,
                  ws_bytes, stream):

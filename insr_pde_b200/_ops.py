@@ -163,3 +163,42 @@ def plateau_step(loss, sched, factor=0.1, patience=500, threshold=1e-4, min_lr=1
     with _DeviceGuard(sched.device):
         lib.plateau_step(loss.data_ptr(), sched.data_ptr(), factor, int(patience), threshold, min_lr, eps,
                          _stream(sched.device))
+
+
+def svd_small(F, compute_uv=True):
+    """batched SVD of (..., d, d) fp32 matrices, d in {2, 3}: returns (U, S, V) with F = U diag(S) V^T, S descending
+    (U, V are None when compute_uv is False).  See include/insr_b200.h: insr_svd_small."""
+    lib = _lib.get_lib()
+    _require_cuda(F)
+    d = F.shape[-1]
+    if F.shape[-2] != d or d not in (2, 3):
+        raise ValueError(f"svd_small: expected (..., 2, 2) or (..., 3, 3), got {tuple(F.shape)}")
+    Fc = _check_input(F.reshape(-1, d, d), "F")
+    n = Fc.shape[0]
+    S = torch.empty(n, d, dtype=torch.float32, device=F.device)
+    U = torch.empty(n, d, d, dtype=torch.float32, device=F.device) if compute_uv else None
+    V = torch.empty(n, d, d, dtype=torch.float32, device=F.device) if compute_uv else None
+    if n:
+        with _DeviceGuard(F.device):
+            lib.svd_small(Fc.data_ptr(), n, d, _ptr(U), S.data_ptr(), _ptr(V), _stream(F.device))
+    lead = F.shape[:-2]
+    return (U.reshape(*lead, d, d) if compute_uv else None, S.reshape(*lead, d), V.reshape(*lead, d, d) if compute_uv else None)
+
+
+def elastic_energy(F, ratio_arap, ratio_volume, need_grad=True):
+    """E = ratio_arap sum (S - 1)^2 + ratio_volume sum (prod S - 1)^2 over all (d, d) matrices of F and dE/dF, in one
+    kernel.  Returns (E (1,), gF or None).  See include/insr_b200.h: insr_elastic_energy."""
+    lib = _lib.get_lib()
+    _require_cuda(F)
+    d = F.shape[-1]
+    if F.shape[-2] != d or d not in (2, 3):
+        raise ValueError(f"elastic_energy: expected (..., 2, 2) or (..., 3, 3), got {tuple(F.shape)}")
+    Fc = _check_input(F.reshape(-1, d, d), "F")
+    n = Fc.shape[0]
+    E = torch.zeros(1, dtype=torch.float32, device=F.device)
+    gF = torch.empty_like(Fc) if need_grad else None
+    if n:
+        with _DeviceGuard(F.device):
+            lib.elastic_energy(Fc.data_ptr(), n, d, float(ratio_arap), float(ratio_volume), E.data_ptr(), _ptr(gF),
+                               _stream(F.device))
+    return E, (gF.reshape(F.shape) if need_grad else None)

@@ -11,6 +11,7 @@
 #include "siren_fused.cuh"
 #include "siren_tiled_api.h"
 #include "optim_kernels.cuh"
+#include "linalg_kernels.cuh"
 #ifdef INSR_SINGLE_TU
 #include "siren_tiled.cuh"   // emulation build: everything in one translation unit
 #define INSR_INST_D 1
@@ -323,6 +324,35 @@ int insr_plateau_step(const float *loss, float *sched, float factor, int patienc
     INSR_LAUNCH(kfn, dim3(1), dim3(32), 0, stream, loss, sched, factor, patience, threshold, min_lr, eps);
     ++g_launches;
     return check_cuda("k_plateau_step");
+}
+
+int insr_svd_small(const float *F, int64_t n, int d, float *U, float *S, float *V, void *stream) {
+    if (!F || !S) return fail(INSR_ERR_NULL, "svd_small: F and S must not be NULL");
+    if (n < 0 || (d != 2 && d != 3)) return fail(INSR_ERR_SHAPE, "svd_small: n=%lld d=%d (d must be 2 or 3)", (long long)n, d);
+    int rc = check_device();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    int64_t blocks = (n + 127) / 128;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (d == 2) { auto kfn = k_svd_small<2>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, F, n, U, S, V); }
+    else        { auto kfn = k_svd_small<3>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, F, n, U, S, V); }
+    ++g_launches;
+    return check_cuda("k_svd_small");
+}
+
+int insr_elastic_energy(const float *F, int64_t n, int d, float ratio_arap, float ratio_volume, float *energy,
+                        float *gF, void *stream) {
+    if (!F || !energy) return fail(INSR_ERR_NULL, "elastic_energy: F and energy must not be NULL");
+    if (n < 0 || (d != 2 && d != 3)) return fail(INSR_ERR_SHAPE, "elastic_energy: n=%lld d=%d (d must be 2 or 3)", (long long)n, d);
+    int rc = check_device();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    int64_t blocks = (n + 127) / 128;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (d == 2) { auto kfn = k_elastic_energy<2>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, F, n, ratio_arap, ratio_volume, energy, gF); }
+    else        { auto kfn = k_elastic_energy<3>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, F, n, ratio_arap, ratio_volume, energy, gF); }
+    ++g_launches;
+    return check_cuda("k_elastic_energy");
 }
 
 }  // extern "C"

@@ -181,6 +181,59 @@ def fluid_projection(velocity, velocity_prev, pressure, samples, bc_x, bc_y):
 
 
 # ------------------------------------------------------------------------------------------------
+# elasticity (elasticity/model.py:127-189, elasticity/losses.py): the deformation-gradient energies in one kernel
+# ------------------------------------------------------------------------------------------------
+def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_left, fixed_right, *, dt, timestep, energy,
+                                 ratio_arap, ratio_volume, ratio_kinematics, ratio_constraint, ratio_collide,
+                                 external_force, external_force_timesteps, constraint_offset_right, plane_height,
+                                 circle_center, circle_radius):
+    """the reference closure with ``jacobian -> torch.svd -> (S - 1)^2, (prod S - 1)^2`` replaced by the field's
+    order-1 kernel and ONE ``insr_elastic_energy`` kernel (energy + adjoint, no SVD graph); the remaining terms are the
+    reference's elementwise expressions.  ``samples`` must require grad (the Jacobian is taken w.r.t. it)."""
+    from . import diff_ops, linalg
+    with torch.no_grad():
+        q_prev = prev(samples) + samples
+        q_pp = prev_prev(samples) + samples
+    q = deformation(samples) + samples
+    qdot = (q - q_prev) / dt
+    qdot_prev = (q_prev - q_pp) / dt
+    loss = 0
+    ra = ratio_arap if "arap" in energy else 0.0
+    rv = ratio_volume if "volume" in energy else 0.0
+    if ra or rv:
+        F, _ = diff_ops.jacobian(q, samples)
+        loss = loss + linalg.elastic_energy(F, ra, rv)
+    for term in energy:
+        if term in ("arap", "volume"):
+            continue
+        if term == "kinematics":
+            loss = loss + ratio_kinematics * torch.sum((qdot - qdot_prev) ** 2)
+        elif term == "external":
+            if timestep <= external_force_timesteps:
+                loss = loss - dt * torch.sum(qdot * external_force.reshape(1, -1))
+        elif term == "constraint":
+            loss = loss + ratio_constraint * torch.sum(deformation(fixed_left) ** 2)
+        elif term in ("constraint_right", "constraint_right_compress"):
+            sign = 1.0 if term == "constraint_right" else -1.0
+            loss = loss + ratio_constraint * torch.sum((deformation(fixed_right) - sign * constraint_offset_right.reshape(1, -1)) ** 2)
+        elif term == "collision":                                  # elasticity/losses.py:10-20, masked instead of gathered
+            hit = (q[:, -1] < plane_height).to(q.dtype)
+            loss = loss - dt * ratio_collide * torch.sum(hit * qdot[:, -1] * (plane_height - q[:, -1]))
+        elif term == "collision_sphere":                           # elasticity/losses.py:22-39
+            vec = q - circle_center.reshape(1, -1)
+            dist = torch.sqrt(torch.sum(vec ** 2, dim=1))
+            hit = (dist < circle_radius).to(q.dtype)
+            if q.shape[1] == 2:        # force = ratio * dist * dir = ratio * vec  (dir = vec / dist)
+                loss = loss - dt * ratio_collide * torch.sum(hit[:, None] * qdot * vec)
+            else:                      # losses.py:37 broadcasts (M,1,1) * (M,3) -> (M,M,3): sum_i dist_i * sum_j qdot_j . dir_j
+                dirs = vec / dist[:, None]
+                loss = loss - dt * ratio_collide * torch.sum(hit * dist) * torch.sum(hit[:, None] * qdot * dirs)
+        else:
+            raise NotImplementedError(term)
+    return {"main": loss}
+
+
+# ------------------------------------------------------------------------------------------------
 # the caller: one @_training_loop
 # ------------------------------------------------------------------------------------------------
 class TrainingLoop:

@@ -6,6 +6,7 @@ I/O -- none is on the hot path), imports ``base`` and rebinds
 
     base.networks.get_network, base.baseModel.get_network, base.get_network, base.MLP
     base.diff_ops.{gradient,divergence,laplace,jacobian,hessian} and their re-exports in base
+    torch.svd  (dispatcher: batches of 2x2 / 3x3 fp32 CUDA matrices -> insr_svd_small, elasticity/model.py:144)
 
 to this package *before* ``advection`` / ``fluid`` / ``elasticity`` bind them by name
 (``from base import gradient, ...``: fluid/model.py:5-6, advection/model.py:5,
@@ -92,6 +93,20 @@ def _shim_torch():
                 super().__init__(*a, **k)
 
         sched.ReduceLROnPlateau = ReduceLROnPlateau
+
+    # elasticity/model.py:144 calls torch.svd on the (N, D, D) deformation gradients: route the small fp32 CUDA batches
+    # to the one-kernel SVD (insr_svd_small), everything else to torch's own
+    from . import linalg
+    if not getattr(torch.svd, "_insr_dispatch", False):
+        torch_svd = torch.svd
+
+        def svd(A, *args, **kwargs):
+            if linalg.supports(A) and not args and not kwargs:
+                return linalg.svd(A)
+            return torch_svd(A, *args, **kwargs)
+
+        svd._insr_dispatch = True
+        torch.svd = svd
 
 
 def install(reference_root: str):

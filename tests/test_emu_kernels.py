@@ -175,3 +175,53 @@ def test_fused_lsq_step_under_emulation(emu_library, case):
     ref_loss = scale * (r ** 2).sum()
     assert abs(float(loss[0]) - ref_loss) < 1e-5 * abs(ref_loss)
     assert rel(gth, gref) < 1e-4
+
+
+def _svd_cases(rng, d, n):
+    F = rng.standard_normal((n, d, d)).astype(np.float32)
+    F[: n // 4] = np.eye(d, dtype=np.float32) + 0.05 * F[: n // 4]                 # near identity (the elasticity regime)
+    F[n // 4] = np.eye(d)                                                            # exactly identity: coincident singular values
+    F[n // 4 + 1] = 0.0                                                              # zero matrix
+    F[n // 4 + 2] = np.outer(rng.standard_normal(d), rng.standard_normal(d))         # rank one
+    F[n // 4 + 3, :, 0] *= -1.0                                                      # negative determinant
+    return F
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_svd_small_and_elastic_energy_under_emulation(emu_library, d):
+    """insr_svd_small / insr_elastic_energy (elasticity/model.py:143-147) against numpy's SVD in fp64"""
+    lib = emu_library
+    rng = np.random.default_rng(11 + d)
+    n = 200
+    F = _svd_cases(rng, d, n)
+    U = np.full((n, d, d), np.nan, np.float32); S = np.full((n, d), np.nan, np.float32); V = np.full((n, d, d), np.nan, np.float32)
+    lib.svd_small(ptr(F), n, d, ptr(U), ptr(S), ptr(V), None)
+    Sref = np.linalg.svd(F.astype(np.float64), compute_uv=False)
+    assert np.abs(S - Sref).max() < 2e-6 * max(1.0, Sref.max())
+    assert (S[:, :-1] >= S[:, 1:]).all() and (S >= 0).all()
+    rec = np.einsum("nik,nk,njk->nij", U.astype(np.float64), S.astype(np.float64), V.astype(np.float64))
+    assert np.abs(rec - F).max() < 5e-6 * max(1.0, np.abs(F).max())
+    eye = np.eye(d)
+    assert np.abs(np.einsum("nki,nkj->nij", U, U) - eye).max() < 5e-6
+    assert np.abs(np.einsum("nki,nkj->nij", V, V) - eye).max() < 5e-6
+    # fused energy + adjoint:  E = ra sum (s-1)^2 + rv sum (prod s - 1)^2 ;  dE/dF = U diag(dE/ds) V^T
+    ra, rv = 0.7, 1.3
+    E = np.zeros(1, np.float32); gF = np.full((n, d, d), np.nan, np.float32)
+    lib.elastic_energy(ptr(F), n, d, ra, rv, ptr(E), ptr(gF), None)
+    Eref = ra * ((Sref - 1) ** 2).sum() + rv * ((Sref.prod(1) - 1) ** 2).sum()
+    assert abs(E[0] - Eref) < 1e-5 * abs(Eref)
+    # directional finite difference in fp64 on well-conditioned samples
+    Fd = F.astype(np.float64)
+    Hd = rng.standard_normal(F.shape)
+    def energy(M):
+        s = np.linalg.svd(M, compute_uv=False)
+        return ra * ((s - 1) ** 2).sum(1) + rv * ((s.prod(1) - 1) ** 2)
+    h = 1e-6
+    fd = (energy(Fd + h * Hd) - energy(Fd - h * Hd)) / (2 * h)
+    an = (gF.astype(np.float64) * Hd).sum((1, 2))
+    good = (Sref[:, -1] > 1e-2) & ((Sref[:, :-1] - Sref[:, 1:]).min(1) > 1e-3)       # smooth points of the singular values
+    assert good.sum() > n // 2
+    assert np.abs(fd - an)[good].max() < 2e-4 * np.abs(fd[good]).max()
+    # energy-only call accumulates into the scalar
+    lib.elastic_energy(ptr(F), n, d, ra, rv, ptr(E), None, None)
+    assert abs(E[0] - 2 * Eref) < 2e-5 * abs(Eref)
