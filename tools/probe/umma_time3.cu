@@ -31,7 +31,7 @@ __device__ __forceinline__ void commit(uint32_t mbar) {
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra W;\n\t}\n" :: "r"(mbar), "r"(parity) : "memory");
 }
-struct TCfg { int M, N, a_lt, a_lbo, a_sbo, b_lt, b_lbo, b_sbo, tr, a_step, b_step, iters; };
+struct TCfg { int M, N, a_lt, a_lbo, a_sbo, b_lt, b_lbo, b_sbo, tr, a_step, b_step, iters, count; };
 
 template <int KIND, int TS>
 __global__ void k_time(long long *out, TCfg c) {
@@ -65,6 +65,10 @@ __global__ void k_time(long long *out, TCfg c) {
         }
         if (elect_one()) {
             t0 = clock64();
+            if (c.count > 0) {                 // queue-depth mode: exactly c.count MMAs, no loop-carried arithmetic
+#pragma unroll
+                for (int u = 0; u < 64; ++u) if (u < c.count) mma<KIND, TS>(d[u & 3], a[u & 3], at[u & 3], b[(u >> 2) & 3], id);
+            } else
             for (int it = 0; it < c.iters; ++it) {
 #pragma unroll
                 for (int u = 0; u < 16; ++u) mma<KIND, TS>(d[u & 3], a[u & 3], at[u & 3], b[(u >> 2) & 3], id);
@@ -96,34 +100,52 @@ void run(const char *name, TCfg c, long long *dt) {
     printf("%s: %7.2f cycles/MMA  (issue %6.2f/MMA; 64 MMAs: %lld cycles)\n", name, (double)(r68[0] - r4[0]) / 1024.0, (double)(r68[1] - r4[1]) / 1024.0, r4[0]);
 }
 
+template <int KIND, int TS>
+void depth(const char *name, TCfg c, long long *dt) {
+    cudaFuncSetAttribute(k_time<KIND, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 64);
+    printf("%s: issue cycles / total cycles for R MMAs:", name);
+    for (int R : {1, 2, 4, 6, 8, 12, 16, 24, 32, 48, 64}) {
+        long long r[2];
+        c.count = R; c.iters = 0;
+        for (int rep = 0; rep < 2; ++rep) { k_time<KIND, TS><<<1, 128, 131072 + 64>>>(dt, c); cudaDeviceSynchronize(); }
+        cudaMemcpy(r, dt, 16, cudaMemcpyDeviceToHost);
+        printf("  R=%d %lld/%lld", R, r[1], r[0]);
+    }
+    printf("\n");
+}
+
 int main() {
     long long *dt; cudaMalloc(&dt, 64);
+    depth<1, 0>("queue depth, bf16 SS MN/MN sw128 M64 N64 (32 cycles each)", {64, 64, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0, 0}, dt);
+    depth<0, 1>("queue depth, tf32 TS M128 N32 (16 cycles each)          ", {128, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    depth<0, 0>("queue depth, tf32 SS M128 N32 (40 cycles each)          ", {128, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    depth<0, 0>("queue depth, tf32 SS M128 N256 (128 cycles each)        ", {128, 256, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
     //                                        M    N  a_lt lbo  sbo  b_lt lbo  sbo  tr a_step b_step
-    run<0, 0>("tf32 SS none  M128 N16 ", {128, 16, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<0, 0>("tf32 SS none  M128 N32 ", {128, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<0, 0>("tf32 SS none  M128 N64 ", {128, 64, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<0, 0>("tf32 SS none  M128 N128", {128, 128, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<0, 0>("tf32 SS none  M128 N256", {128, 256, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<0, 0>("tf32 SS none  M64  N32 ", {64, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<0, 0>("tf32 SS none  M64  N64 ", {64, 64, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<0, 0>("tf32 SS sw128 M128 N32 ", {128, 32, 2, 16, 1024, 2, 16, 1024, 0, 32, 32, 0}, dt);
-    run<0, 0>("tf32 SS sw128 M128 N64 ", {128, 64, 2, 16, 1024, 2, 16, 1024, 0, 32, 32, 0}, dt);
-    run<0, 0>("tf32 SS sw128 M128 N256", {128, 256, 2, 16, 1024, 2, 16, 1024, 0, 32, 32, 0}, dt);
-    run<0, 1>("tf32 TS       M128 N32 ", {128, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<0, 1>("tf32 TS       M128 N64 ", {128, 64, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<0, 1>("tf32 TS       M128 N256", {128, 256, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<1, 0>("bf16 SS none  M128 N32 ", {128, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<1, 0>("bf16 SS none  M128 N64 ", {128, 64, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<1, 0>("bf16 SS none  M128 N96 ", {128, 96, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<1, 0>("bf16 SS none  M128 N128", {128, 128, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<1, 0>("bf16 SS none  M128 N256", {128, 256, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<1, 0>("bf16 SS sw128 M128 N32 ", {128, 32, 2, 16, 1024, 2, 16, 1024, 0, 32, 32, 0}, dt);
-    run<1, 0>("bf16 SS sw128 M128 N256", {128, 256, 2, 16, 1024, 2, 16, 1024, 0, 32, 32, 0}, dt);
-    run<1, 1>("bf16 TS       M128 N32 ", {128, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0}, dt);
-    run<1, 0>("bf16 SS MN/MN sw128 M128 N64 ", {128, 64, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0}, dt);
-    run<1, 0>("bf16 SS MN/MN sw128 M128 N96 ", {128, 96, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0}, dt);
-    run<1, 0>("bf16 SS MN/MN sw128 M128 N128", {128, 128, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0}, dt);
-    run<1, 0>("bf16 SS MN/MN sw128 M64  N64 ", {64, 64, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0}, dt);
-    run<1, 0>("bf16 SS MN/MN sw128 M64  N32 ", {64, 32, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0}, dt);
+    run<0, 0>("tf32 SS none  M128 N16 ", {128, 16, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<0, 0>("tf32 SS none  M128 N32 ", {128, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<0, 0>("tf32 SS none  M128 N64 ", {128, 64, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<0, 0>("tf32 SS none  M128 N128", {128, 128, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<0, 0>("tf32 SS none  M128 N256", {128, 256, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<0, 0>("tf32 SS none  M64  N32 ", {64, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<0, 0>("tf32 SS none  M64  N64 ", {64, 64, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<0, 0>("tf32 SS sw128 M128 N32 ", {128, 32, 2, 16, 1024, 2, 16, 1024, 0, 32, 32, 0, 0}, dt);
+    run<0, 0>("tf32 SS sw128 M128 N64 ", {128, 64, 2, 16, 1024, 2, 16, 1024, 0, 32, 32, 0, 0}, dt);
+    run<0, 0>("tf32 SS sw128 M128 N256", {128, 256, 2, 16, 1024, 2, 16, 1024, 0, 32, 32, 0, 0}, dt);
+    run<0, 1>("tf32 TS       M128 N32 ", {128, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<0, 1>("tf32 TS       M128 N64 ", {128, 64, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<0, 1>("tf32 TS       M128 N256", {128, 256, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<1, 0>("bf16 SS none  M128 N32 ", {128, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<1, 0>("bf16 SS none  M128 N64 ", {128, 64, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<1, 0>("bf16 SS none  M128 N96 ", {128, 96, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<1, 0>("bf16 SS none  M128 N128", {128, 128, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<1, 0>("bf16 SS none  M128 N256", {128, 256, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<1, 0>("bf16 SS sw128 M128 N32 ", {128, 32, 2, 16, 1024, 2, 16, 1024, 0, 32, 32, 0, 0}, dt);
+    run<1, 0>("bf16 SS sw128 M128 N256", {128, 256, 2, 16, 1024, 2, 16, 1024, 0, 32, 32, 0, 0}, dt);
+    run<1, 1>("bf16 TS       M128 N32 ", {128, 32, 0, 128, 1024, 0, 128, 1024, 0, 256, 256, 0, 0}, dt);
+    run<1, 0>("bf16 SS MN/MN sw128 M128 N64 ", {128, 64, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0, 0}, dt);
+    run<1, 0>("bf16 SS MN/MN sw128 M128 N96 ", {128, 96, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0, 0}, dt);
+    run<1, 0>("bf16 SS MN/MN sw128 M128 N128", {128, 128, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0, 0}, dt);
+    run<1, 0>("bf16 SS MN/MN sw128 M64  N64 ", {64, 64, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0, 0}, dt);
+    run<1, 0>("bf16 SS MN/MN sw128 M64  N32 ", {64, 32, 2, 8192, 1024, 2, 8192, 1024, 1, 2048, 2048, 0, 0}, dt);
     return 0;
 }
