@@ -156,6 +156,19 @@ int insr_svd_small(const float *F, int64_t n, int d, float *U, float *S, float *
 int insr_elastic_energy(const float *F, int64_t n, int d, float ratio_arap, float ratio_volume, float *energy,
                         float *gF, void *stream);
 
+/*
+ * All collocation-point sets of one iteration in one kernel.  Replaces the torch.rand / scale / shift / cat sequences
+ * of base/sampling.py:14-18 (sample_random) and :21-64 (sample_boundary, sample_boundary2D_separate): every set is
+ * i.i.d. uniform in an axis-aligned box.  Box b holds count[b] points in [lo[b], hi[b])^dim (lo, hi: n_boxes x dim,
+ * host arrays); `out` receives the boxes back to back.  Counter-based Philox4x32-10 keyed by (seed; point index +
+ * point_offset, iteration): `counter` (nullable) is a DEVICE iteration counter read at entry and incremented by the
+ * last CTA to finish (`ticket`: a zeroed device word), so a CUDA-graph replay draws fresh points every time;
+ * point_offset lets a data-parallel rank draw exactly its shard of a global set.
+ * Same distributions as the reference; the random stream is Philox's, not torch's generator.
+ */
+int insr_sample_boxes(int n_boxes, int dim, const int32_t *count, const float *lo, const float *hi, uint64_t seed,
+                      int64_t *counter, uint32_t *ticket, int64_t point_offset, float *out, void *stream);
+
 /* introspection used by bench.py / tests: which kernel family a call would dispatch to.
  * returns 0 = generic, 1 = fused resident-weights kernels (H <= 32), 2 = tiled shared-memory GEMM
  * kernels (32 < H <= 512); negative = error. */

@@ -21,7 +21,7 @@ FLAG_FFMA_BWD = 4
 EXPORTS = [
     "insr_version", "insr_last_error", "insr_siren_theta_size", "insr_siren_workspace_bytes",
     "insr_siren_forward", "insr_siren_backward", "insr_siren_lsq_step", "insr_siren_kernel_family",
-    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy",
+    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes",
 ]
 
 
@@ -72,6 +72,8 @@ class Library:
         c.insr_svd_small.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp]
         c.insr_elastic_energy.restype = _i32
         c.insr_elastic_energy.argtypes = [_vp, _i64, _i32, _f, _f, _vp, _vp, _vp]
+        c.insr_sample_boxes.restype = _i32
+        c.insr_sample_boxes.argtypes = [_i32, _i32, _vp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _i64, _vp, _vp]
         c.insr_launch_count.restype = _i64
         c.insr_launch_count.argtypes = [_i32]
 
@@ -107,6 +109,13 @@ class Library:
 
     def plateau_step(self, loss, sched, factor, patience, threshold, min_lr, eps, stream):
         self.check(self.cdll.insr_plateau_step(loss, sched, factor, patience, threshold, min_lr, eps, stream))
+
+    def sample_boxes(self, counts, lo, hi, dim, seed, counter, ticket, point_offset, out, stream):
+        n = len(counts)
+        c = (ctypes.c_int32 * n)(*counts)
+        l = (ctypes.c_float * (n * dim))(*[v for row in lo for v in row])
+        h = (ctypes.c_float * (n * dim))(*[v for row in hi for v in row])
+        self.check(self.cdll.insr_sample_boxes(n, dim, c, l, h, seed, counter, ticket, point_offset, out, stream))
 
     def svd_small(self, F, n, d, U, S, V, stream):
         self.check(self.cdll.insr_svd_small(F, n, d, U, S, V, stream))

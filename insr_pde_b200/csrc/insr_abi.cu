@@ -12,6 +12,7 @@
 #include "siren_tiled_api.h"
 #include "optim_kernels.cuh"
 #include "linalg_kernels.cuh"
+#include "sampling_kernels.cuh"
 #ifdef INSR_SINGLE_TU
 #include "siren_tiled.cuh"   // emulation build: everything in one translation unit
 #define INSR_INST_D 1
@@ -353,6 +354,31 @@ int insr_elastic_energy(const float *F, int64_t n, int d, float ratio_arap, floa
     else        { auto kfn = k_elastic_energy<3>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, F, n, ratio_arap, ratio_volume, energy, gF); }
     ++g_launches;
     return check_cuda("k_elastic_energy");
+}
+
+int insr_sample_boxes(int n_boxes, int dim, const int32_t *count, const float *lo, const float *hi, uint64_t seed,
+                      int64_t *counter, uint32_t *ticket, int64_t point_offset, float *out, void *stream) {
+    if (!count || !lo || !hi || !out) return fail(INSR_ERR_NULL, "sample_boxes: NULL argument");
+    if (n_boxes < 1 || n_boxes > INSR_MAX_BOXES || dim < 1 || dim > 3)
+        return fail(INSR_ERR_SHAPE, "sample_boxes: n_boxes=%d (1..%d) dim=%d (1..3)", n_boxes, INSR_MAX_BOXES, dim);
+    if (counter && !ticket) return fail(INSR_ERR_NULL, "sample_boxes: a device counter needs a zeroed ticket word");
+    insr_box_set bs{};
+    bs.n_boxes = n_boxes; bs.dim = dim;
+    int64_t total = 0;
+    for (int b = 0; b < n_boxes; ++b) {
+        if (count[b] < 0) return fail(INSR_ERR_SHAPE, "sample_boxes: count[%d]=%d", b, count[b]);
+        bs.count[b] = count[b]; total += count[b];
+        for (int d = 0; d < dim; ++d) { bs.lo[b][d] = lo[b * dim + d]; bs.hi[b][d] = hi[b * dim + d]; }
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    if (total == 0) return 0;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    auto kfn = k_sample_boxes;
+    INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(256), 0, stream, bs, seed, counter, ticket, point_offset, out);
+    ++g_launches;
+    return check_cuda("k_sample_boxes");
 }
 
 }  // extern "C"

@@ -361,11 +361,12 @@ class FluidStepper:
     (base/sampling.py) and schedule; used for the seconds-per-timestep measurement."""
 
     def __init__(self, velocity, velocity_prev, pressure, dt=0.05, sample_resolution=128, lr=1e-4, reducer_factory=None,
-                 graphed=False):
+                 graphed=False, device_sampler=False, seed=0):
         self.vel, self.prev, self.pres = velocity, velocity_prev, pressure
         self.dt, self.sr, self.lr = dt, sample_resolution, lr
         self.reducer_factory = reducer_factory
         self.graphed = graphed and reducer_factory is None
+        self.device_sampler, self.seed, self._samplers = device_sampler, seed, {}
         for p in self.prev.parameters():
             p.requires_grad_(False)
 
@@ -373,6 +374,11 @@ class FluidStepper:
         from . import sampling
         dev = next(self.vel.parameters()).device
         n = self.sr ** 2
+        if self.device_sampler:              # one kernel for the three sets (insr_sample_boxes)
+            if n_shard_div not in self._samplers:
+                self._samplers[n_shard_div] = sampling.BoxSampler(sampling.fluid_sets(n // n_shard_div, n // 100), 2,
+                                                                  seed=self.seed, device=dev)
+            return tuple(self._samplers[n_shard_div].sample())
         x = sampling.sample_random(n // n_shard_div, 2, device=dev)
         bx = sampling.sample_boundary2D_separate(n // 100, "horizontal", device=dev)
         by = sampling.sample_boundary2D_separate(n // 100, "vertical", device=dev)

@@ -54,6 +54,47 @@ def sample_boundary2D_separate(N, side, epsilon=1e-4, device="cpu"):
     return torch.cat([_strip(N // 2, xr, yr, device) for xr, yr in strips], dim=0)
 
 
+class BoxSampler:
+    """Several uniform-in-a-box point sets per call from ONE kernel (insr_sample_boxes): the graph-friendly
+    replacement of the torch.rand / scale / shift / cat sequences above when the reference's exact random stream is
+    not required (same distributions, Philox4x32-10 keyed by seed, point index and a device iteration counter that
+    the kernel bumps itself -- a CUDA-graph replay draws fresh points).
+
+    ``sets``: list of point sets, each a list of boxes ``(count, lo, hi)`` with ``lo`` / ``hi`` of length dim;
+    ``sample()`` returns one (sum of counts, dim) tensor per set (views of one buffer, fresh values on every call)."""
+
+    def __init__(self, sets, dim, seed=0, device="cuda", point_offset=0):
+        from . import _lib
+        self.dim, self.seed, self.point_offset = dim, int(seed), int(point_offset)
+        self.counts, self.lo, self.hi, self.sizes = [], [], [], []
+        for boxes in sets:
+            self.sizes.append(sum(int(b[0]) for b in boxes))
+            for count, lo, hi in boxes:
+                self.counts.append(int(count)); self.lo.append([float(v) for v in lo]); self.hi.append([float(v) for v in hi])
+        self.device = torch.device(device)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._lib = _lib
+
+    def sample(self):
+        lib = self._lib.get_lib()
+        out = torch.empty(sum(self.sizes), self.dim, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            lib.sample_boxes(self.counts, self.lo, self.hi, self.dim, self.seed, self.counter.data_ptr(), self.ticket.data_ptr(),
+                             self.point_offset, out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        return list(torch.split(out, self.sizes, dim=0))
+
+
+def fluid_sets(n_interior, n_boundary, epsilon=1e-4):
+    """the three sets of a fluid iteration: sample_random(n, 2), sample_boundary2D_separate(nb, 'horizontal'),
+    sample_boundary2D_separate(nb, 'vertical')  (fluid/model.py:75-77 etc., base/sampling.py:45-64)"""
+    inner, lo, hi = (-1.0, 1.0), (-1.0 - epsilon, -1.0 + epsilon), (1.0 - epsilon, 1.0 + epsilon)
+    box = lambda n, xr, yr: (n, (xr[0], yr[0]), (xr[1], yr[1]))
+    return [[box(n_interior, inner, inner)],
+            [box(n_boundary // 2, lo, inner), box(n_boundary // 2, hi, inner)],
+            [box(n_boundary // 2, inner, lo), box(n_boundary // 2, inner, hi)]]
+
+
 def shard(points, rank, world_size):
     """contiguous slice [r*N/G, (r+1)*N/G) of a global point set for data-parallel rank r."""
     n = points.shape[0]

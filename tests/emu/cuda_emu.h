@@ -137,6 +137,10 @@ static inline float atomicAdd(float *addr, float v) {
     while (!a->compare_exchange_weak(old, old + v, std::memory_order_relaxed)) {}
     return old;
 }
+static inline unsigned int atomicAdd(unsigned int *addr, unsigned int v) {
+    return reinterpret_cast<std::atomic<unsigned int> *>(addr)->fetch_add(v, std::memory_order_acq_rel);
+}
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 #define __sinf(x) sinf(x)   /* glibc declares __sinf/__cosf itself: use macros */
 #define __cosf(x) cosf(x)

@@ -225,3 +225,35 @@ def test_svd_small_and_elastic_energy_under_emulation(emu_library, d):
     # energy-only call accumulates into the scalar
     lib.elastic_energy(ptr(F), n, d, ra, rv, ptr(E), None, None)
     assert abs(E[0] - 2 * Eref) < 2e-5 * abs(Eref)
+
+
+def test_sample_boxes_under_emulation(emu_library):
+    """insr_sample_boxes (base/sampling.py:14-18, 45-64 distributions): bounds, moments, fresh draws per iteration
+    through the device counter, and shard consistency through point_offset"""
+    lib = emu_library
+    eps = 1e-4
+    counts = [4096, 300, 300]
+    lo = [[-1.0, -1.0], [-1 - eps, -1.0], [1 - eps, -1.0]]
+    hi = [[1.0, 1.0], [-1 + eps, 1.0], [1 + eps, 1.0]]
+    n = sum(counts)
+    counter = np.zeros(1, np.int64); ticket = np.zeros(1, np.uint32)
+    a = np.full((n, 2), np.nan, np.float32); b = np.full((n, 2), np.nan, np.float32)
+    lib.sample_boxes(counts, lo, hi, 2, 1234, ptr(counter), ptr(ticket), 0, ptr(a), None)
+    assert counter[0] == 1 and ticket[0] == 0
+    lib.sample_boxes(counts, lo, hi, 2, 1234, ptr(counter), ptr(ticket), 0, ptr(b), None)
+    assert counter[0] == 2
+    off = 0
+    for c, l, h in zip(counts, lo, hi):
+        blk = a[off:off + c]
+        assert (blk >= np.asarray(l, np.float32) - 1e-7).all() and (blk <= np.asarray(h, np.float32) + 1e-7).all()
+        off += c
+    x = a[:4096]
+    assert abs(x.mean()) < 0.05 and abs(x.var() - 1.0 / 3.0) < 0.03           # U[-1,1]: mean 0, variance 1/3
+    assert abs(np.corrcoef(x[:, 0], x[:, 1])[0, 1]) < 0.06
+    assert not np.array_equal(a, b) and len(np.unique(a[:4096, 0])) > 4000      # fresh draws, no repeats
+    # same seed + same iteration + point offset = the same global stream, whichever rank draws it
+    counter[0] = 0
+    c1 = np.zeros((2048, 2), np.float32); c2 = np.zeros((2048, 2), np.float32)
+    lib.sample_boxes([2048], [lo[0]], [hi[0]], 2, 1234, None, None, 0, ptr(c1), None)
+    lib.sample_boxes([2048], [lo[0]], [hi[0]], 2, 1234, None, None, 2048, ptr(c2), None)
+    assert np.array_equal(np.concatenate([c1, c2]), a[:4096])

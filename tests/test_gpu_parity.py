@@ -448,3 +448,28 @@ def test_closures_elasticity_with_device_svd_and_fused_energy(tag, monkeypatch):
     assert rel(grad2, g["solve_deformation.grad.deformation"]) < 5e-3
     # the fused energy avoids the SVD backward (1 / (s_i^2 - s_j^2) terms): it agrees with the reference at least as well
     assert rel(grad2, grad) < 5e-3
+
+
+def test_box_sampler_on_device_and_under_graph_replay():
+    """insr_sample_boxes: the fluid iteration's three point sets from one kernel; a CUDA-graph replay draws fresh
+    points (device iteration counter), distributions as base/sampling.py"""
+    from insr_pde_b200 import sampling
+    s = sampling.BoxSampler(sampling.fluid_sets(16384, 162), 2, seed=7, device="cuda")
+    x, bx, by = s.sample()
+    assert x.shape == (16384, 2) and bx.shape == (162, 2) and by.shape == (162, 2)
+    assert float(x.abs().max()) <= 1.0 and abs(float(x.mean())) < 0.02 and abs(float(x.var()) - 1 / 3) < 0.02
+    assert float((bx[:, 0].abs() - 1).abs().max()) <= 1.0001e-4 and float(bx[:, 1].abs().max()) <= 1.0
+    assert float((by[:, 1].abs() - 1).abs().max()) <= 1.0001e-4 and float(by[:, 0].abs().max()) <= 1.0
+    assert float(bx[:81, 0].max()) < 0 < float(bx[81:, 0].min())           # left band then right band, as the reference
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    keep = torch.zeros(16384, 2, device="cuda")
+    with torch.cuda.graph(g):
+        xs, _, _ = s.sample()
+        keep.copy_(xs)
+    draws = []
+    for _ in range(3):
+        g.replay()
+        draws.append(keep.clone())
+    assert not torch.equal(draws[0], draws[1]) and not torch.equal(draws[1], draws[2])
+    assert int(s.counter) == 1 + 3
