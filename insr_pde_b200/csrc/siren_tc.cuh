@@ -665,26 +665,30 @@ __global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__
 #endif
 
         // ================= forward with tape =================
+        // Tape traffic (L1 <-> L2) is the largest single cost of this kernel (ablation: 1.8 of 5.0 ms), so the first sine
+        // layer is not taped: it is recomputed from x where it is needed (8 sincos per thread per use).
+        auto layer0 = [&](int q, float (&a)[S][4], float (&tv)[TV][4]) {      // neurons 8 part + 4 q .. + 3
+            float z[S][4];
+            INSR_PRAGMA_UNROLL
+            for (int c = 0; c < 4; ++c) {
+                const int j = NPT * part + 4 * q + c;
+                const float4 wv = *reinterpret_cast<const float4 *>(w1S + j * 4);
+                float acc = wv.w;
+                INSR_PRAGMA_UNROLL
+                for (int d = 0; d < D; ++d) acc = fmaf(insr_fused::f4get(wv, d), xv[d], acc);
+                z[0][c] = acc;
+                INSR_PRAGMA_UNROLL
+                for (int d = 0; d < C::ND; ++d) z[1 + d][c] = insr_fused::f4get(wv, d);
+                if constexpr (ORDER == 2) z[1 + C::ND][c] = 0.f;
+            }
+            insr_fused::act4<D, ORDER>(z, a, tv);
+        };
         {
             float a8[S][8];
             INSR_PRAGMA_UNROLL
             for (int q = 0; q < 2; ++q) {
-                float z[S][4], a[S][4], tv[TV][4];
-                INSR_PRAGMA_UNROLL
-                for (int c = 0; c < 4; ++c) {
-                    const int j = NPT * part + 4 * q + c;
-                    const float4 wv = *reinterpret_cast<const float4 *>(w1S + j * 4);
-                    float acc = wv.w;
-                    INSR_PRAGMA_UNROLL
-                    for (int d = 0; d < D; ++d) acc = fmaf(insr_fused::f4get(wv, d), xv[d], acc);
-                    z[0][c] = acc;
-                    INSR_PRAGMA_UNROLL
-                    for (int d = 0; d < C::ND; ++d) z[1 + d][c] = insr_fused::f4get(wv, d);
-                    if constexpr (ORDER == 2) z[1 + C::ND][c] = 0.f;
-                }
-                insr_fused::act4<D, ORDER>(z, a, tv);
-                INSR_PRAGMA_UNROLL
-                for (int t = 0; t < TV; ++t) tape[(size_t)(q * TV + t) * BT + tid] = make_float4(tv[t][0], tv[t][1], tv[t][2], tv[t][3]);
+                float a[S][4], tv[TV][4];
+                layer0(q, a, tv);
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s)
                     INSR_PRAGMA_UNROLL
@@ -887,12 +891,16 @@ __global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__
                 INSR_PRAGMA_UNROLL
                 for (int q = 0; q < 2; ++q) {
                     float tv[TV][4], a[S][4];
-                    INSR_PRAGMA_UNROLL
-                    for (int t = 0; t < TV; ++t) {
-                        const float4 v = tp[(size_t)(q * TV + t) * BT + tid];
-                        tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
+                    if (l == 1) {
+                        layer0(q, a, tv);
+                    } else {
+                        INSR_PRAGMA_UNROLL
+                        for (int t = 0; t < TV; ++t) {
+                            const float4 v = tp[(size_t)(q * TV + t) * BT + tid];
+                            tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
+                        }
+                        insr_fused::a_from_tape4<D, ORDER>(tv, a);
                     }
-                    insr_fused::a_from_tape4<D, ORDER>(tv, a);
                     INSR_PRAGMA_UNROLL
                     for (int s = 0; s < S; ++s)
                         INSR_PRAGMA_UNROLL
@@ -953,12 +961,8 @@ __global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__
             float v0[8], vd[D > 0 ? D : 1][8];
             INSR_PRAGMA_UNROLL
             for (int q = 0; q < 2; ++q) {
-                float tv[TV][4], abq[S][4];
-                INSR_PRAGMA_UNROLL
-                for (int t = 0; t < TV; ++t) {
-                    const float4 v = tape[(size_t)(q * TV + t) * BT + tid];
-                    tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
-                }
+                float tv[TV][4], abq[S][4], a0[S][4];
+                layer0(q, a0, tv);
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s)
                     INSR_PRAGMA_UNROLL

@@ -1,6 +1,6 @@
 """tcgen05 forward kernel vs the FFMA fused kernel and the fp64 oracle (run on the B200)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import insr_pde_b200 as ib
 from insr_pde_b200 import _lib, _ops

@@ -1,6 +1,6 @@
 """tcgen05 backward / lsq kernels vs the FFMA kernels and the fp64 oracle (run on the B200)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import insr_pde_b200 as ib
 from insr_pde_b200 import _lib, _ops
