@@ -265,6 +265,53 @@ def trajectory_advection(ref):
     print("trajectory advection: last losses", hist["_initialize"][-1], hist["_advect"][-1])
 
 
+def trajectory_fluid(ref):
+    """fluid2Dtlgn (Taylor-Green): K Adam iterations of initialize() + one step() (advect -> pressure -> projection):
+    weights, loss histories and the PER-FRAME velocity field on a uniform grid (the north star's parity clause)."""
+    import fluid.model as mod
+    K, SR, GRID = 12, 20, 12
+    torch.manual_seed(31)
+    cfg = ref_loader.make_cfg("fluid", sample_resolution=SR, max_n_iters=K, lr=1e-4)
+    m = ref.fluid.Fluid2DModel(cfg)
+    theta0 = {"velocity": flat(m.velocity_field.parameters()).numpy().copy(),
+              "pressure": flat(m.pressure_field.parameters()).numpy().copy()}
+    names = ["_initialize", "_advect_velocity", "_solve_pressure", "_projection"]
+    hist = {n: [] for n in names}
+
+    def spy(name):
+        fn = raw_closure(getattr(type(m), name))
+
+        def wrapped(self):
+            d = fn(self)
+            hist[name].append([float(v) for v in d.values()])
+            return d
+        return wrapped
+
+    BaseModel = ref.base.BaseModel
+    for n in names:
+        setattr(type(m), n, BaseModel._training_loop(spy(n)))
+    torch.manual_seed(32)
+    with Recorder(mod, ["sample_random", "sample_boundary2D_separate"]) as r:
+        m.initialize()
+        frame0 = m.sample_field(GRID).detach().numpy().copy()
+        th_init = flat(m.velocity_field.parameters()).numpy().copy()
+        n_init = len(r.log)
+        m.step()
+        frame1 = m.sample_field(GRID).detach().numpy().copy()
+    rec = {"theta0.velocity": theta0["velocity"], "theta0.pressure": theta0["pressure"],
+           "theta_after_init.velocity": th_init,
+           "theta_after_step.velocity": flat(m.velocity_field.parameters()).numpy().copy(),
+           "theta_after_step.pressure": flat(m.pressure_field.parameters()).numpy().copy(),
+           "frame0": frame0, "frame1": frame1,
+           "cfg": np.array([cfg.dt, SR, K, cfg.lr, GRID, n_init])}
+    for n in names:
+        rec["hist" + n] = np.array(hist[n])
+    for i, (name, arr) in enumerate(r.log):
+        rec[f"samples{i:04d}.{name}"] = arr.astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "trajectory_fluid.npz"), **rec)
+    print("trajectory fluid: last losses", {n: hist[n][-1] for n in names}, "samples", len(r.log))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load(cpu=True)
@@ -275,6 +322,7 @@ def main():
     closures_fluid(ref)
     closures_elasticity(ref)
     trajectory_advection(ref)
+    trajectory_fluid(ref)
 
 
 if __name__ == "__main__":

@@ -66,3 +66,51 @@ def replay_advection(make_net, ops, golden, device="cpu"):
     theta_step = torch.cat([p.detach().reshape(-1) for p in field.parameters()]).cpu().numpy()
     return dict(theta_after_init=theta_init, theta_after_step=theta_step, hist_initialize=h_init,
                 hist_advect=h_step)
+
+
+def replay_fluid(make_net, ops, golden, device="cpu"):
+    """initialize() + one step() of Fluid2DModel (fluid/model.py:36-70: advect -> pressure -> projection) on the
+    recorded sample stream of tests/golden/trajectory_fluid.npz; returns weights, loss histories and the per-frame
+    velocity field on the golden's uniform grid (fluid/model.py:28-34 sample_field)."""
+    from . import closures
+    from .torch_port import sample_uniform
+    dt, SR, K, lr, GRID, _ = (float(v) for v in golden["cfg"])
+    K, GRID = int(K), int(GRID)
+    vel = make_net(golden["theta0.velocity"], 2, 2, 32, 3)
+    prev = make_net(golden["theta0.velocity"], 2, 2, 32, 3)
+    pres = make_net(golden["theta0.pressure"], 2, 1, 32, 3)
+    for p in prev.parameters():
+        p.requires_grad_(False)
+    keys = sorted(k for k in golden if k.startswith("samples"))
+    stream = [torch.from_numpy(golden[k]).to(device) for k in keys]
+    pos = [0]
+
+    def nxt(grad=True):
+        t = stream[pos[0]]
+        pos[0] += 1
+        return t.requires_grad_(True) if grad else t
+
+    def flat(net):
+        return torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu().numpy()
+
+    def frame():
+        grid = sample_uniform(GRID, 2, device=device, flatten=False)
+        with torch.no_grad():
+            return vel(grid).cpu().numpy()
+
+    out = {}
+    out["hist_initialize"] = training_loop(lambda i: closures.fluid_initialize(vel, nxt()), [vel, pres], K, lr)
+    out["theta_after_init.velocity"] = flat(vel)
+    out["frame0"] = frame()
+    prev.load_state_dict(vel.state_dict())
+    out["hist_advect_velocity"] = training_loop(
+        lambda i: closures.fluid_advect_velocity(vel, prev, nxt(), nxt(), nxt(), dt), [vel, pres], K, lr)
+    out["hist_solve_pressure"] = training_loop(
+        lambda i: closures.fluid_solve_pressure(vel, pres, ops, nxt(), nxt(), nxt()), [vel, pres], K, lr)
+    prev.load_state_dict(vel.state_dict())
+    out["hist_projection"] = training_loop(
+        lambda i: closures.fluid_projection(vel, prev, pres, ops, nxt(), nxt(), nxt()), [vel, pres], K, lr)
+    out["theta_after_step.velocity"] = flat(vel)
+    out["theta_after_step.pressure"] = flat(pres)
+    out["frame1"] = frame()
+    return out

@@ -51,3 +51,41 @@ def test_fused_modules_follow_reference_trajectory_on_device():
     print("max |dtheta| after init/step:", np.abs(out["theta_after_init"] - g["theta_after_init"]).max(),
           np.abs(out["theta_after_step"] - g["theta_after_step"]).max())
     check(out, g, 5e-5, 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fluid2Dtlgn: initialize() + one step() (advect -> pressure -> projection), 12 Adam iterations per loop (20^2 points) on the sample
+# stream recorded from the REAL reference (tests/golden/trajectory_fluid.npz, oracle/make_goldens.py:trajectory_fluid).
+# North-star clause: per-frame velocity fields within 1e-4 (relative to max |u|) of the reference.
+# ---------------------------------------------------------------------------------------------------------------
+def check_fluid(out, g, atol_theta, rtol_field, rtol_hist):
+    for k in ("theta_after_init.velocity", "theta_after_step.velocity", "theta_after_step.pressure"):
+        assert np.abs(out[k] - g[k]).max() < atol_theta, (k, np.abs(out[k] - g[k]).max())
+    for k in ("frame0", "frame1"):
+        err = np.abs(out[k] - g[k]).max() / np.abs(g[k]).max()
+        assert err < rtol_field, (k, err)
+    for k in ("initialize", "advect_velocity", "solve_pressure", "projection"):
+        a, b = np.array(out["hist_" + k]), g["hist_" + k]
+        assert a.shape == b.shape and np.abs(a - b).max() <= rtol_hist * np.abs(b).max(), k
+
+
+def test_port_replays_reference_fluid_trajectory():
+    g = load_golden("trajectory_fluid")
+    torch.set_num_threads(1)
+    out = training.replay_fluid(lambda th, D, O, H, L: tp.RefMLP(D, O, L, H).load_flat_theta(th), tp, g)
+    check_fluid(out, g, 1e-6, 1e-6, 1e-5)
+
+
+def test_fused_modules_follow_reference_fluid_trajectory_emulated(emu_backend):
+    g = load_golden("trajectory_fluid")
+    out = training.replay_fluid(make_ours("cpu"), ib, g)
+    check_fluid(out, g, 5e-5, 1e-4, 1e-3)
+
+
+@pytest.mark.gpu
+def test_fused_modules_follow_reference_fluid_trajectory_on_device():
+    g = load_golden("trajectory_fluid")
+    out = training.replay_fluid(make_ours("cuda"), ib, g, device="cuda")
+    for k in ("frame0", "frame1"):
+        print(k, "max rel field error:", np.abs(out[k] - g[k]).max() / np.abs(g[k]).max())
+    check_fluid(out, g, 5e-5, 1e-4, 1e-3)
