@@ -234,7 +234,8 @@ int insr_siren_forward(const insr_siren_desc *desc, const float *theta, const fl
         return check_cuda("fused forward");
     }
     if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_tiled_supported(dm, order)) {
-        rc = insr_tiled_forward(dm, order, theta, x, n_points, y, jac, h2, (float *)workspace, stream, &g_launches);
+        rc = insr_tiled_forward(dm, order, theta, x, n_points, y, jac, h2, (float *)workspace, stream, &g_launches,
+                                !(desc->flags & INSR_FLAG_NO_TENSOR));
         if (rc) return fail(rc, "tiled forward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
         return check_cuda("tiled forward");
     }
@@ -266,7 +267,7 @@ int insr_siren_backward(const insr_siren_desc *desc, const float *theta, const f
     }
     if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_tiled_supported(dm, order)) {
         rc = insr_tiled_backward(dm, order, theta, x, n_points, gy, gjac, gh2, gtheta, gx, (float *)workspace, stream,
-                                 &g_launches);
+                                 &g_launches, !(desc->flags & INSR_FLAG_NO_TENSOR));
         if (rc) return fail(rc, "tiled backward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
         return check_cuda("tiled backward");
     }

@@ -24,6 +24,7 @@
 // Points are processed in chunks of NC so that the workspace stays bounded.
 #pragma once
 #include "siren_tiled_api.h"
+#include "siren_wide_tc.cuh"
 
 namespace insr_tiled {
 
@@ -609,8 +610,13 @@ __global__ void __launch_bounds__(NT) k_tiled_gx(SirenDims dm, int HP, const flo
 
 template <int D, int O, int ORDER>
 int run_forward(const SirenDims &dm, const float *theta, const float *x, int64_t N, float *y, float *jac,
-                float *h2, float *ws, void *stream, int64_t *launches) {
+                float *h2, float *ws, void *stream, int64_t *launches, bool tensor) {
     constexpr int S = StreamCfg<D, ORDER>::S;
+#ifdef INSR_CPU_EMU
+    tensor = false;
+#else
+    tensor = tensor && S <= 4;                              // S * NCOL TMEM columns
+#endif
     constexpr int TP = Tile<S>::TP;
     const Geo g = make_geo(dm.H, S, TP);
     const int64_t chunk = chunk_points(dm, S, false, N);
@@ -622,7 +628,7 @@ int run_forward(const SirenDims &dm, const float *theta, const float *x, int64_t
     cudaFuncSetAttribute(kfwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int64_t n0 = 0; n0 < N; n0 += chunk) {
         const int nv = (int)((N - n0 < chunk) ? (N - n0) : chunk);
-        const int64_t rows = round_up(nv, g.BP);                 // tiles actually computed (<= NCp)
+        const int64_t rows = round_up(nv, tensor ? 128 : g.BP);  // tiles actually computed (<= NCp)
         auto k0 = k_tiled_layer0<D, ORDER>;
         const int64_t items = rows * (g.HP / 4);
         INSR_LAUNCH(k0, dim3((unsigned)((items + NT - 1) / NT)), dim3(NT), 0, stream, dm, g.HP, theta, x, n0, nv,
@@ -630,6 +636,16 @@ int run_forward(const SirenDims &dm, const float *theta, const float *x, int64_t
         ++*launches;
         float *in = A0, *out = A1;
         for (int l = 1; l <= dm.L; ++l) {
+#ifndef INSR_CPU_EMU
+            if constexpr (S <= 4) {
+                if (tensor) {
+                    insr_wide::launch_wide<D, ORDER, 0>(dm, theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l), in, NCp, rows,
+                                                        nullptr, nullptr, out, stream, launches);
+                    float *t = in; in = out; out = t;
+                    continue;
+                }
+            }
+#endif
             INSR_LAUNCH(kfwd, dim3((unsigned)(rows / g.BP), g.panels), dim3(NT), smem, stream, dm, g,
                         theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l), in, NCp, (float *)nullptr, out);
             ++*launches;
@@ -646,8 +662,13 @@ int run_forward(const SirenDims &dm, const float *theta, const float *x, int64_t
 template <int D, int O, int ORDER>
 int run_backward(const SirenDims &dm, const float *theta, const float *x, int64_t N, const float *gy,
                  const float *gjac, const float *gh2, float *gtheta, float *gx, float *ws, void *stream,
-                 int64_t *launches) {
+                 int64_t *launches, bool tensor) {
     constexpr int S = StreamCfg<D, ORDER>::S;
+#ifdef INSR_CPU_EMU
+    tensor = false;
+#else
+    tensor = tensor && S <= 4;
+#endif
     constexpr int TP = Tile<S>::TP;
     const Geo g = make_geo(dm.H, S, TP);
     const int L = dm.L;
@@ -669,7 +690,7 @@ int run_backward(const SirenDims &dm, const float *theta, const float *x, int64_
     if (sms <= 0) sms = 148;
     for (int64_t n0 = 0; n0 < N; n0 += chunk) {
         const int nv = (int)((N - n0 < chunk) ? (N - n0) : chunk);
-        const int64_t rows = round_up(nv, g.BP);
+        const int64_t rows = round_up(nv, tensor ? 128 : g.BP);
         const int64_t items = rows * (g.HP / 4);
         const unsigned eg = (unsigned)((items + NT - 1) / NT);
         // ---- forward with tape
@@ -677,6 +698,16 @@ int run_backward(const SirenDims &dm, const float *theta, const float *x, int64_
         INSR_LAUNCH(k0, dim3(eg), dim3(NT), 0, stream, dm, g.HP, theta, x, n0, nv, NCp, Zpre, Act);
         ++*launches;
         for (int l = 1; l <= L; ++l) {
+#ifndef INSR_CPU_EMU
+            if constexpr (S <= 4) {
+                if (tensor) {
+                    insr_wide::launch_wide<D, ORDER, 0>(dm, theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l),
+                                                        Act + (size_t)(l - 1) * buf, NCp, rows, nullptr, Zpre + (size_t)l * buf,
+                                                        Act + (size_t)l * buf, stream, launches);
+                    continue;
+                }
+            }
+#endif
             INSR_LAUNCH(kfwd, dim3((unsigned)(rows / g.BP), g.panels), dim3(NT), smem, stream, dm, g,
                         theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l), Act + (size_t)(l - 1) * buf, NCp,
                         Zpre + (size_t)l * buf, Act + (size_t)l * buf);
@@ -700,9 +731,22 @@ int run_backward(const SirenDims &dm, const float *theta, const float *x, int64_
                         Act + (size_t)(l - 1) * buf, NCp, nv, rsplit, gtheta + insr_w_offset(dm, l),
                         gtheta + insr_b_offset(dm, l));
             ++*launches;
-            INSR_LAUNCH(kdg, dim3((unsigned)(rows / g.BP), g.panels), dim3(NT), smem, stream, dm, g,
-                        theta + insr_w_offset(dm, l), zin, NCp, Zpre + (size_t)(l - 1) * buf, zout);
-            ++*launches;
+#ifndef INSR_CPU_EMU
+            bool done = false;
+            if constexpr (S <= 4) {
+                if (tensor) {
+                    insr_wide::launch_wide<D, ORDER, 1>(dm, theta + insr_w_offset(dm, l), nullptr, zin, NCp, rows,
+                                                        Zpre + (size_t)(l - 1) * buf, nullptr, zout, stream, launches);
+                    done = true;
+                }
+            }
+            if (!done)
+#endif
+            {
+                INSR_LAUNCH(kdg, dim3((unsigned)(rows / g.BP), g.panels), dim3(NT), smem, stream, dm, g,
+                            theta + insr_w_offset(dm, l), zin, NCp, Zpre + (size_t)(l - 1) * buf, zout);
+                ++*launches;
+            }
             float *t = zin; zin = zout; zout = t;
         }
         // ---- thin layers + gx  (zin now holds zbar_0)

@@ -32,11 +32,12 @@ inline size_t ws_bytes(const SirenDims &dm, int order, bool bwd, int64_t N) {
 }  // namespace insr_tiled
 
 // non-template entry points, defined in siren_tiled_inst.cuh (own translation unit under nvcc)
+// tensor = true: hidden-layer GEMMs (forward + data gradient) on tcgen05 where the shape allows (siren_wide_tc.cuh)
 int insr_tiled_forward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N, float *y,
-                       float *jac, float *h2, float *ws, void *stream, int64_t *launches);
+                       float *jac, float *h2, float *ws, void *stream, int64_t *launches, bool tensor = false);
 int insr_tiled_backward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
                         const float *gy, const float *gjac, const float *gh2, float *gtheta, float *gx, float *ws,
-                        void *stream, int64_t *launches);
+                        void *stream, int64_t *launches, bool tensor = false);
 inline bool insr_tiled_supported(const SirenDims &dm, int order) { return dm.H > 32 && dm.H <= 512 && order <= 3; }
 inline size_t insr_tiled_ws_bytes(const SirenDims &dm, int64_t N, int order, int backward) {
     return insr_tiled::ws_bytes(dm, order, backward != 0, N);

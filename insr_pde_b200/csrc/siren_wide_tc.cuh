@@ -1,0 +1,304 @@
+// siren_wide_tc.cuh -- tcgen05 / TMEM hidden-layer GEMMs of the tiled family (32 < H <= 512, S <= 4 streams).
+//
+// Replaces the FFMA GEMM + epilogue kernels k_tiled_fwd / k_tiled_dgrad (siren_tiled.cuh) -- 75 % of that family's
+// time -- with one kernel per hidden layer on the tensor cores, same buffers ([stream][point][HP] fp32 in the
+// caller's workspace), same epilogues, 3xTF32 precision (a = a_hi + a_lo, w = w_hi + w_lo, three products, FP32
+// accumulation in TMEM; see siren_tc.cuh for the measured hardware facts this relies on).
+//
+//   MODE 0  forward layer   D_s[128 x NCOL] = A_s[128 x K] . (omega W)^T      epilogue: + omega b, sine-stream
+//                           activation (insr_sine_fwd), writes the pre-activations (tape) and the post-activations
+//   MODE 1  data gradient   D_s[128 x NCOL] = Zbar_s[128 x K] . (omega W)     epilogue: activation adjoint of the
+//                           previous layer against its tape (insr_sine_bwd), writes zbar_{l-1}
+//
+// CTA = 128 points (TMEM lanes) x one pass of NCOL <= 128 output columns, all S streams (S NCOL <= 512 TMEM columns).
+// The reduction runs in slabs of 32 (one 128-byte swizzle row of fp32): every thread loads its share of the next slab
+// (S A-tiles of 128 x 32 + the weight tile) from HBM / L2 into REGISTERS while the tensor core works on the current
+// one, then splits hi / lo and stores both halves in the K-major 128-byte-swizzle layout (conflict-free 16-byte
+// stores: 8 lanes cover one 128-byte row).  36 MMAs (S = 3) or 48 (S = 4) of N = NCOL per slab, issued by one elected
+// lane of warp 0.  Per layer the kernel moves 4 S HP bytes/point in and 4-8 S HP out against 2 S HP^2 flops: it is
+// HBM-bound for H <= 256.
+//
+// Only compiled by nvcc (inline PTX); the host-side SIMT emulation keeps using the FFMA kernels.
+#pragma once
+#include "siren_tc.cuh"
+
+#ifndef INSR_CPU_EMU
+namespace insr_wide {
+
+using insr_tc::s32;
+constexpr int WT = 256;                 // threads
+constexpr int TILE = 128;               // points per CTA
+constexpr int KS = 32;                  // reduction slab
+constexpr int A_TILE = TILE * KS * 4;   // 16 KB: one 128 x 32 fp32 operand tile
+
+struct WGeo {
+    int HP, NK, NCOL, passes;
+};
+inline WGeo make_wgeo(int H) {
+    WGeo g;
+    g.HP = (H + 7) & ~7;
+    g.NK = (g.HP + KS - 1) / KS;
+    const int hp16 = (g.HP + 15) & ~15;
+    if (hp16 <= 128) { g.NCOL = hp16; g.passes = 1; }
+    else { g.NCOL = 128; g.passes = (g.HP + 127) / 128; }
+    return g;
+}
+inline size_t smem_bytes(int S, int NCOL) {
+    const size_t operands = (size_t)2 * S * A_TILE + (size_t)2 * NCOL * KS * 4 + 64;        // + mbarrier / TMEM slot
+    const size_t staging = (size_t)2 * S * TILE * 36 * 4;                                    // epilogue tiles (reuse the operand region)
+    return (operands > staging ? operands : staging) + 1024;
+}
+
+// byte offset of element (row, kk) of a K-major operand tile in the 128-byte swizzle: rows of 128 B (32 fp32 along K),
+// 8-row atoms of 1024 B, 16-byte chunk index XORed with (row & 7)   (probe2: verified for A and B, k-steps at +32 B)
+__device__ __forceinline__ int sw_off(int row, int kk) {
+    return (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ row) & 7) << 4) + (kk & 3) * 4;
+}
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int D, int ORDER, int MODE>
+__global__ void __launch_bounds__(WT, 1) k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, const float *__restrict__ W,
+                                                   const float *__restrict__ bias, const float *__restrict__ Ain,
+                                                   int64_t NCp, int64_t p_base, const float *__restrict__ Ztape,
+                                                   float *__restrict__ Zout, float *__restrict__ Aout) {
+    typedef StreamCfg<D, ORDER> C;
+    constexpr int S = C::S;
+    static_assert(S <= 4, "S * NCOL must fit the 512 TMEM columns");
+    extern __shared__ __align__(1024) unsigned char smraw_[];
+    unsigned char *sm = smraw_ + ((1024u - (s32(smraw_) & 1023u)) & 1023u);
+    unsigned char *a_hi = sm, *a_lo = sm + S * A_TILE;
+    unsigned char *b_hi = sm + 2 * S * A_TILE, *b_lo = b_hi + NCOL * KS * 4;
+    const uint32_t mbar = s32(b_lo + NCOL * KS * 4), tslot = mbar + 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = dm.H;
+    const float w = dm.omega;
+    const int64_t p0 = p_base + (int64_t)blockIdx.x * TILE;
+    const int j0 = blockIdx.y * NCOL;                   // first output column of this pass
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tslot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        insr_tc::mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    insr_tc::tc_fence_before();
+    __syncthreads();
+    insr_tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(b_lo + NCOL * KS * 4 + 16);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((128u >> 4) << 24);
+
+    // ---- staging assignment: A = S tiles of 128 rows x 8 chunks (16 B) -> 4 S chunks per thread; B = NCOL x 32 scalars
+    constexpr int NA = 4 * S;
+    constexpr int NB = 16;                              // 128 * 32 / 256
+    float4 ra[NA];
+    float rb[NB];
+    auto gload = [&](int k0) {
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < NA; ++i) {
+            const int c = tid + WT * i;                 // chunk index over (stream, row, chunk)
+            const int s = c >> 10, row = (c >> 3) & 127, ch = c & 7;
+            const int k = k0 + 4 * ch;
+            ra[i] = (k < HP) ? __ldg(reinterpret_cast<const float4 *>(Ain + ((int64_t)s * NCp + p0 + row) * HP + k))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < NB; ++i) {
+            const int e = tid + WT * i;
+            float v = 0.f;
+            if (e < NCOL * KS) {
+                if (MODE == 0) {                        // B[n][kk] = omega W[j0 + n][k0 + kk]
+                    const int n = e >> 5, kk = e & 31;
+                    const int j = j0 + n, k = k0 + kk;
+                    if (j < H && k < H) v = w * __ldg(W + (size_t)j * H + k);
+                } else {                                // B[n][kk] = omega W[k0 + kk][j0 + n]   (n = input neuron of the layer)
+                    const int n = e % NCOL, kk = e / NCOL;
+                    const int kin = j0 + n, j = k0 + kk;
+                    if (j < H && kin < H) v = w * __ldg(W + (size_t)j * H + kin);
+                }
+            }
+            rb[i] = v;
+        }
+    };
+    auto sstore = [&]() {
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < NA; ++i) {
+            const int c = tid + WT * i;
+            const int s = c >> 10, row = (c >> 3) & 127, ch = c & 7;
+            const float4 v = ra[i];
+            const float4 h = make_float4(insr_tc::tf32_hi(v.x), insr_tc::tf32_hi(v.y), insr_tc::tf32_hi(v.z), insr_tc::tf32_hi(v.w));
+            const int off = s * A_TILE + (row >> 3) * 1024 + (row & 7) * 128 + (((ch ^ row) & 7) << 4);
+            *reinterpret_cast<float4 *>(a_hi + off) = h;
+            *reinterpret_cast<float4 *>(a_lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < NB; ++i) {
+            const int e = tid + WT * i;
+            if (e < NCOL * KS) {
+                int n, kk;
+                if (MODE == 0) { n = e >> 5; kk = e & 31; } else { n = e % NCOL; kk = e / NCOL; }
+                const float h = insr_tc::tf32_hi(rb[i]);
+                *reinterpret_cast<float *>(b_hi + sw_off(n, kk)) = h;
+                *reinterpret_cast<float *>(b_lo + sw_off(n, kk)) = rb[i] - h;
+            }
+        }
+    };
+
+    uint32_t phase = 0;
+    gload(0);
+    for (int ks = 0; ks < NK; ++ks) {
+        sstore();
+        insr_tc::fence_async_smem();
+        insr_tc::tc_fence_before();
+        __syncthreads();
+        if (ks + 1 < NK) gload((ks + 1) * KS);          // in flight while the tensor core works on slab ks
+        if (warp == 0) {
+            insr_tc::tc_fence_after();
+            if (insr_tc::elect_one()) {
+                const uint32_t bh = s32(b_hi), bl = s32(b_lo);
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s) {
+                    const uint32_t ah = s32(a_hi + s * A_TILE), al = s32(a_lo + s * A_TILE);
+                    const uint32_t d = tmem_base + (uint32_t)(s * NCOL);
+                    INSR_PRAGMA_UNROLL
+                    for (int q = 0; q < 4; ++q) {       // K = 8 per instruction: 32 bytes inside the swizzled row
+                        mma_tf32(d, desc_sw128(ah + 32 * q), desc_sw128(bh + 32 * q), idesc, (ks > 0 || q > 0) ? 1u : 0u);
+                        mma_tf32(d, desc_sw128(al + 32 * q), desc_sw128(bh + 32 * q), idesc, 1u);
+                        mma_tf32(d, desc_sw128(ah + 32 * q), desc_sw128(bl + 32 * q), idesc, 1u);
+                    }
+                }
+                insr_tc::mma_commit(mbar);
+            }
+            __syncwarp();
+        }
+        insr_tc::mbar_wait(mbar, phase);
+        phase ^= 1;
+        insr_tc::tc_fence_after();
+    }
+
+    // ---- epilogue, 32 output columns at a time, staged through shared memory (the operand tiles are free now) so that
+    // every global access is a coalesced 128-byte row segment: a thread owns a point ROW of the accumulators, and a
+    // row-per-lane store to [stream][point][HP] would touch 32 different lines per instruction (measured: 3x slower).
+    //   staging tiles: [tile][128 rows][36 floats] (row stride 144 B = 16 mod 128: conflict-free 16-byte accesses),
+    //   tiles 0..S-1 = tape (MODE 0: Zout, written; MODE 1: Ztape, read), tiles S..2S-1 = Aout
+    constexpr int EC = 32, EST = 36;
+    float *stage = reinterpret_cast<float *>(sm);
+    auto tile_at = [&](int t, int r, int c) -> float * { return stage + ((size_t)t * TILE + r) * EST + c; };
+    const int row = 32 * (warp & 3) + lane;
+    const int half = warp >> 2;                                   // 16 of the 32 columns
+    const uint32_t trow = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int crow = tid >> 3, cch = tid & 7;                     // cooperative copies: 8 lanes per 128-byte row segment
+    for (int cc = 0; cc < NCOL; cc += EC) {
+        const int jc = j0 + cc;                                   // first output column of this chunk
+        if (jc >= HP) break;
+        if (MODE == 1) {                                          // stage the tape of the previous layer
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s)
+                INSR_PRAGMA_UNROLL
+                for (int i = 0; i < 4; ++i) {
+                    const int r = crow + 32 * i, j = jc + 4 * cch;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < HP) v = __ldg(reinterpret_cast<const float4 *>(Ztape + ((int64_t)s * NCp + p0 + r) * HP + j));
+                    *reinterpret_cast<float4 *>(tile_at(s, r, 4 * cch)) = v;
+                }
+            __syncthreads();
+        }
+        INSR_PRAGMA_UNROLL
+        for (int g8 = 0; g8 < 2; ++g8) {
+            const int c0 = 16 * half + 8 * g8;                    // column inside the chunk
+            float acc[S][8], o1[S][8], o2[S][8];
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) insr_tc::tmem_ld8(trow + (uint32_t)(s * NCOL + cc + c0), acc[s]);
+            insr_tc::tmem_ld_wait();
+            if (MODE == 0) {
+                INSR_PRAGMA_UNROLL
+                for (int i = 0; i < 8; ++i) {
+                    float z[S], a[S];
+                    const int j = jc + c0 + i;
+                    const float bj = (j < H) ? w * __ldg(bias + j) : 0.f;
+                    z[0] = acc[0][i] + bj;
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 1; s < S; ++s) z[s] = acc[s][i];
+                    insr_sine_fwd<D, ORDER>(z, a);
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s) { o1[s][i] = z[s]; o2[s][i] = a[s]; }
+                }
+                if (Zout) {
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s) {
+                        *reinterpret_cast<float4 *>(tile_at(s, row, c0)) = make_float4(o1[s][0], o1[s][1], o1[s][2], o1[s][3]);
+                        *reinterpret_cast<float4 *>(tile_at(s, row, c0 + 4)) = make_float4(o1[s][4], o1[s][5], o1[s][6], o1[s][7]);
+                    }
+                }
+            } else {
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s) {
+                    const float4 z0 = *reinterpret_cast<const float4 *>(tile_at(s, row, c0));
+                    const float4 z1 = *reinterpret_cast<const float4 *>(tile_at(s, row, c0 + 4));
+                    o1[s][0] = z0.x; o1[s][1] = z0.y; o1[s][2] = z0.z; o1[s][3] = z0.w;
+                    o1[s][4] = z1.x; o1[s][5] = z1.y; o1[s][6] = z1.z; o1[s][7] = z1.w;
+                }
+                INSR_PRAGMA_UNROLL
+                for (int i = 0; i < 8; ++i) {
+                    float z[S], ab[S], zb[S];
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s) { z[s] = o1[s][i]; ab[s] = acc[s][i]; }
+                    insr_sine_bwd<D, ORDER>(z, ab, zb);
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s) o2[s][i] = zb[s];
+                }
+            }
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) {
+                *reinterpret_cast<float4 *>(tile_at(S + s, row, c0)) = make_float4(o2[s][0], o2[s][1], o2[s][2], o2[s][3]);
+                *reinterpret_cast<float4 *>(tile_at(S + s, row, c0 + 4)) = make_float4(o2[s][4], o2[s][5], o2[s][6], o2[s][7]);
+            }
+        }
+        __syncthreads();
+        INSR_PRAGMA_UNROLL
+        for (int s = 0; s < S; ++s)
+            INSR_PRAGMA_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                const int r = crow + 32 * i, j = jc + 4 * cch;
+                if (j < HP) {
+                    const int64_t g = ((int64_t)s * NCp + p0 + r) * HP + j;
+                    if (MODE == 0 && Zout) *reinterpret_cast<float4 *>(Zout + g) = *reinterpret_cast<const float4 *>(tile_at(s, r, 4 * cch));
+                    *reinterpret_cast<float4 *>(Aout + g) = *reinterpret_cast<const float4 *>(tile_at(S + s, r, 4 * cch));
+                }
+            }
+        __syncthreads();                                          // tiles are rewritten by the next chunk
+    }
+    insr_tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// one hidden layer on the tensor cores; rows = number of point rows to process (multiple of 128, within the buffers)
+template <int D, int ORDER, int MODE>
+int launch_wide(const SirenDims &dm, const float *W, const float *bias, const float *Ain, int64_t NCp, int64_t rows,
+                const float *Ztape, float *Zout, float *Aout, void *stream, int64_t *launches) {
+    constexpr int S = StreamCfg<D, ORDER>::S;
+    const WGeo g = make_wgeo(dm.H);
+    auto kfn = k_wide_tc<D, ORDER, MODE>;
+    const size_t smem = smem_bytes(S, g.NCOL);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kfn<<<dim3((unsigned)(rows / TILE), (unsigned)g.passes), dim3(WT), smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        dm, g.HP, g.NK, g.NCOL, W, bias, Ain, NCp, (int64_t)0, Ztape, Zout, Aout);
+    ++*launches;
+    return 0;
+}
+
+}  // namespace insr_wide
+#endif  // !INSR_CPU_EMU
