@@ -726,11 +726,19 @@ int run_backward(const SirenDims &dm, const float *theta, const float *x, int64_
             int rsplit = (2 * sms + wt * wt - 1) / (wt * wt);
             if (rsplit > slabs) rsplit = slabs;
             if (rsplit < 1) rsplit = 1;
-            auto kwg = k_tiled_wgrad;
-            INSR_LAUNCH(kwg, dim3(wt, wt, rsplit), dim3(NT), 0, stream, dm, g.HP, S, zin,
-                        Act + (size_t)(l - 1) * buf, NCp, nv, rsplit, gtheta + insr_w_offset(dm, l),
-                        gtheta + insr_b_offset(dm, l));
-            ++*launches;
+#ifndef INSR_CPU_EMU
+            if (tensor && insr_wide::wide_wgrad_ok(dm.H)) {
+                insr_wide::launch_wide_wgrad(dm, S, zin, Act + (size_t)(l - 1) * buf, NCp, nv, gtheta + insr_w_offset(dm, l),
+                                             gtheta + insr_b_offset(dm, l), stream, launches);
+            } else
+#endif
+            {
+                auto kwg = k_tiled_wgrad;
+                INSR_LAUNCH(kwg, dim3(wt, wt, rsplit), dim3(NT), 0, stream, dm, g.HP, S, zin,
+                            Act + (size_t)(l - 1) * buf, NCp, nv, rsplit, gtheta + insr_w_offset(dm, l),
+                            gtheta + insr_b_offset(dm, l));
+                ++*launches;
+            }
 #ifndef INSR_CPU_EMU
             bool done = false;
             if constexpr (S <= 4) {

@@ -300,5 +300,195 @@ int launch_wide(const SirenDims &dm, const float *W, const float *bias, const fl
     return 0;
 }
 
+// =============================================================================================
+// weight gradient of a hidden layer of the tiled family, HP <= 128:
+//     gW[j][k] += omega * sum_{s,p} zbar[s][p][j] * act[s][p][k],      gb[j] += omega * sum_p zbar[0][p][j]
+// The reduction runs over POINTS, i.e. over the rows of the [stream][point][HP] buffers: both operands are MN-major,
+// which kind::tf32 does not support (siren_tc.cuh), so -- as in the H <= 32 family -- the operands are split in two
+// bf16 levels (z = z1 + z2, a = a1 + a2, residual <= 2^-17) and all four cross products are kept:
+//     D[jb][kb][128 x 128] += [z1 | z2]^T . [a1 | a2]      (M = 2 levels x 64 neurons, N likewise, K = 16 points)
+// for the <= 2 x 2 blocks of 64 x 64 weights; all accumulators (<= 512 TMEM columns) stay resident while the persistent
+// CTA streams its share of the points (64 points of one stream per stage: loaded to registers while the previous stage
+// is in the tensor core, split, stored as [point][64 bf16] rows in the 128-byte swizzle), and are flushed once:
+// quadrants combined in shared memory, one red.global per weight per CTA.
+// =============================================================================================
+constexpr int WG_PTS = 64;                                   // points per stage
+constexpr int WG_ATOM = WG_PTS * 128;                        // one (block, level) operand: 64 rows x 128 B = 8 KB
+constexpr uint32_t IDESC_WG128 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr, uint32_t lbo) {          // MN-major, 128-byte swizzle
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(WT, 1) k_wide_wgrad(SirenDims dm, int HP, int S, const float *__restrict__ ZB,
+                                                      const float *__restrict__ Act, int64_t NCp, int nv,
+                                                      float *__restrict__ gW, float *__restrict__ gb) {
+    extern __shared__ __align__(1024) unsigned char smraw_[];
+    unsigned char *sm = smraw_ + ((1024u - (s32(smraw_) & 1023u)) & 1023u);
+    const int NBJ = (HP + 63) >> 6;                          // 1 or 2 blocks of 64 neurons
+    unsigned char *zt = sm, *at = sm + 4 * WG_ATOM;          // [block][level][64 x 128 B] each
+    float *bsumS = reinterpret_cast<float *>(sm + 8 * WG_ATOM);                 // 128 floats
+    const uint32_t mbar = s32(sm + 8 * WG_ATOM + 512), tslot = mbar + 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = dm.H;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tslot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        insr_tc::mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 128) bsumS[tid] = 0.f;
+    insr_tc::tc_fence_before();
+    __syncthreads();
+    insr_tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + 8 * WG_ATOM + 512 + 16);
+
+    // staging: per operand 64 rows x 32 chunk slots (16 B of fp32 = 4 neurons); thread -> chunk slot (tid & 31), rows (tid >> 5) + 8 i
+    const int ch = tid & 31, r0 = tid >> 5;
+    const bool ch_ok = 4 * ch < HP;
+    float4 rz[8], ra[8];
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ngroups = (nv + WG_PTS - 1) / WG_PTS;
+    const int64_t nstages = (int64_t)((ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * S;   // this CTA's stages
+    auto stage_coords = [&](int64_t st, int &g, int &s) { g = (int)blockIdx.x + (int)(st / S) * (int)gridDim.x; s = (int)(st % S); };
+    auto gload = [&](int64_t st) {
+        int g, s;
+        stage_coords(st, g, s);
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 8 * i;
+            const int64_t pnt = (int64_t)g * WG_PTS + r;
+            rz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ra[i] = rz[i];
+            if (ch_ok && pnt < nv) {
+                const int64_t off = ((int64_t)s * NCp + pnt) * HP + 4 * ch;
+                rz[i] = __ldg(reinterpret_cast<const float4 *>(ZB + off));
+                ra[i] = __ldg(reinterpret_cast<const float4 *>(Act + off));
+            }
+        }
+    };
+    auto split4 = [&](const float4 &v, uint2 &l1, uint2 &l2) {
+        uint32_t a, b, c, d;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a) : "f"(v.y), "f"(v.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b) : "f"(v.w), "f"(v.z));
+        const float r0_ = v.x - __uint_as_float(a << 16), r1_ = v.y - __uint_as_float(a & 0xFFFF0000u);
+        const float r2_ = v.z - __uint_as_float(b << 16), r3_ = v.w - __uint_as_float(b & 0xFFFF0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(c) : "f"(r1_), "f"(r0_));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(r3_), "f"(r2_));
+        l1 = make_uint2(a, b); l2 = make_uint2(c, d);
+    };
+    auto sstore = [&](int64_t st) {
+        int g, s;
+        stage_coords(st, g, s);
+        if (4 * ch < 64 * NBJ) {
+            const int jb = ch >> 4, jj = (4 * ch) & 63;          // block, neuron inside the block (multiple of 4)
+            INSR_PRAGMA_UNROLL
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 8 * i;
+                const int off = r * 128 + ((((jj >> 3) ^ r) & 7) << 4) + (jj & 7) * 2;
+                uint2 l1, l2;
+                split4(rz[i], l1, l2);
+                *reinterpret_cast<uint2 *>(zt + (jb * 2 + 0) * WG_ATOM + off) = l1;
+                *reinterpret_cast<uint2 *>(zt + (jb * 2 + 1) * WG_ATOM + off) = l2;
+                split4(ra[i], l1, l2);
+                *reinterpret_cast<uint2 *>(at + (jb * 2 + 0) * WG_ATOM + off) = l1;
+                *reinterpret_cast<uint2 *>(at + (jb * 2 + 1) * WG_ATOM + off) = l2;
+                if (s == 0) { bsum.x += rz[i].x; bsum.y += rz[i].y; bsum.z += rz[i].z; bsum.w += rz[i].w; }
+            }
+        }
+    };
+
+    uint32_t phase = 0;
+    if (nstages > 0) gload(0);
+    for (int64_t st = 0; st < nstages; ++st) {
+        sstore(st);
+        insr_tc::fence_async_smem();
+        insr_tc::tc_fence_before();
+        __syncthreads();
+        if (st + 1 < nstages) gload(st + 1);
+        if (warp == 0) {
+            insr_tc::tc_fence_after();
+            if (insr_tc::elect_one()) {
+                for (int jb = 0; jb < NBJ; ++jb)
+                    for (int kb = 0; kb < NBJ; ++kb) {
+                        const uint32_t d = tmem_base + (uint32_t)((jb * NBJ + kb) * 128);
+                        const uint32_t za = s32(zt + jb * 2 * WG_ATOM), aa = s32(at + kb * 2 * WG_ATOM);
+                        INSR_PRAGMA_UNROLL
+                        for (int q = 0; q < 4; ++q) {              // 16 points per instruction = two 1024-byte row groups
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                                :: "r"(d), "l"(desc_mn128(za + 2048 * q, WG_ATOM)), "l"(desc_mn128(aa + 2048 * q, WG_ATOM)),
+                                   "r"(IDESC_WG128), "r"((st > 0 || q > 0) ? 1u : 0u) : "memory");
+                        }
+                    }
+                insr_tc::mma_commit(mbar);
+            }
+            __syncwarp();
+        }
+        insr_tc::mbar_wait(mbar, phase);
+        phase ^= 1;
+        insr_tc::tc_fence_after();
+    }
+
+    // ---- flush: bias gradient, then the weight blocks (quadrants combined in shared memory)
+    if (ch_ok) {
+        atomicAdd(bsumS + 4 * ch + 0, bsum.x); atomicAdd(bsumS + 4 * ch + 1, bsum.y);
+        atomicAdd(bsumS + 4 * ch + 2, bsum.z); atomicAdd(bsumS + 4 * ch + 3, bsum.w);
+    }
+    __syncthreads();
+    if (tid < 128 && tid < H && bsumS[tid] != 0.f) atomicAdd(gb + tid, dm.omega * bsumS[tid]);
+    if (nstages > 0) {
+        float *tile = reinterpret_cast<float *>(sm);             // 64 x 64 floats (operand region is free)
+        const int m = 32 * (warp & 3) + lane;                    // accumulator row: level (m >> 6), neuron (m & 63)
+        const int half = warp >> 2;                              // columns 64 half .. + 63: level of `a`
+        const uint32_t trow = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+        for (int jb = 0; jb < NBJ; ++jb)
+            for (int kb = 0; kb < NBJ; ++kb) {
+                for (int idx = tid; idx < 64 * 64; idx += WT) tile[idx] = 0.f;
+                __syncthreads();
+                INSR_PRAGMA_UNROLL
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    float v[8];
+                    insr_tc::tmem_ld8(trow + (uint32_t)((jb * NBJ + kb) * 128 + 64 * half + 8 * c8), v);
+                    insr_tc::tmem_ld_wait();
+                    INSR_PRAGMA_UNROLL
+                    for (int i = 0; i < 8; ++i) atomicAdd(tile + (m & 63) * 64 + 8 * c8 + i, v[i]);
+                }
+                __syncthreads();
+                for (int idx = tid; idx < 64 * 64; idx += WT) {
+                    const int j = jb * 64 + (idx >> 6), k = kb * 64 + (idx & 63);
+                    const float v = tile[idx];
+                    if (j < H && k < H && v != 0.f) atomicAdd(gW + (size_t)j * H + k, dm.omega * v);
+                }
+                __syncthreads();
+            }
+    }
+    insr_tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+inline bool wide_wgrad_ok(int H) { return ((H + 7) & ~7) <= 128; }
+
+inline int launch_wide_wgrad(const SirenDims &dm, int S, const float *ZB, const float *Act, int64_t NCp, int nv, float *gW,
+                             float *gb, void *stream, int64_t *launches) {
+    const int HP = (dm.H + 7) & ~7;
+    const size_t smem = (size_t)8 * WG_ATOM + 512 + 64 + 1024;
+    cudaFuncSetAttribute(k_wide_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int groups = (nv + WG_PTS - 1) / WG_PTS;
+    const int sms = insr_fused::sm_count();
+    const int ctas = groups < sms ? groups : sms;
+    k_wide_wgrad<<<dim3((unsigned)ctas), dim3(WT), smem, reinterpret_cast<cudaStream_t>(stream)>>>(dm, HP, S, ZB, Act, NCp, nv, gW, gb);
+    ++*launches;
+    return 0;
+}
+
 }  // namespace insr_wide
 #endif  // !INSR_CPU_EMU
