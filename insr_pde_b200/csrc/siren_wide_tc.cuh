@@ -113,19 +113,17 @@ __global__ void __launch_bounds__(WT, 1) k_wide_tc(SirenDims dm, int HP, int NK,
                              : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         INSR_PRAGMA_UNROLL
-        for (int i = 0; i < NB; ++i) {
-            const int e = tid + WT * i;
+        for (int i = 0; i < NB; ++i) {                  // raw weights: omega is applied in sstore (no use of the value here, so the
+            const int e = tid + WT * i;                 // loads stay in flight while the tensor core works)
             float v = 0.f;
-            if (e < NCOL * KS) {
-                if (MODE == 0) {                        // B[n][kk] = omega W[j0 + n][k0 + kk]
-                    const int n = e >> 5, kk = e & 31;
-                    const int j = j0 + n, k = k0 + kk;
-                    if (j < H && k < H) v = w * __ldg(W + (size_t)j * H + k);
-                } else {                                // B[n][kk] = omega W[k0 + kk][j0 + n]   (n = input neuron of the layer)
-                    const int n = e % NCOL, kk = e / NCOL;
-                    const int kin = j0 + n, j = k0 + kk;
-                    if (j < H && kin < H) v = w * __ldg(W + (size_t)j * H + kin);
-                }
+            if (MODE == 0) {                            // B[n][kk] = omega W[j0 + n][k0 + kk]
+                const int n = e >> 5, kk = e & 31;
+                const int j = j0 + n, k = k0 + kk;
+                if (n < NCOL && j < H && k < H) v = __ldg(W + (size_t)j * H + k);
+            } else {                                    // B[n][kk] = omega W[k0 + kk][j0 + n]   (n = input neuron of the layer)
+                const int n = e & 127, kk = e >> 7;
+                const int kin = j0 + n, j = k0 + kk;
+                if (n < NCOL && j < H && kin < H) v = __ldg(W + (size_t)j * H + kin);
             }
             rb[i] = v;
         }
@@ -144,12 +142,13 @@ __global__ void __launch_bounds__(WT, 1) k_wide_tc(SirenDims dm, int HP, int NK,
         INSR_PRAGMA_UNROLL
         for (int i = 0; i < NB; ++i) {
             const int e = tid + WT * i;
-            if (e < NCOL * KS) {
-                int n, kk;
-                if (MODE == 0) { n = e >> 5; kk = e & 31; } else { n = e % NCOL; kk = e / NCOL; }
-                const float h = insr_tc::tf32_hi(rb[i]);
+            int n, kk;
+            if (MODE == 0) { n = e >> 5; kk = e & 31; } else { n = e & 127; kk = e >> 7; }
+            if (n < NCOL) {
+                const float v = w * rb[i];
+                const float h = insr_tc::tf32_hi(v);
                 *reinterpret_cast<float *>(b_hi + sw_off(n, kk)) = h;
-                *reinterpret_cast<float *>(b_lo + sw_off(n, kk)) = rb[i] - h;
+                *reinterpret_cast<float *>(b_lo + sw_off(n, kk)) = v - h;
             }
         }
     };
