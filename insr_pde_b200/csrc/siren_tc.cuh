@@ -663,6 +663,22 @@ __global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__
 #ifdef INSR_TC_PROFILE
         if (tid == 0) { tprev = clock64(); atomicAdd(gprof + 15, 1ull); }
 #endif
+        // HBM latency of the per-point streams is taken off the critical path: this tile's cotangents / targets (needed
+        // after the forward recompute) and the next tile's points are pulled into L2 now (no registers held)
+        if (part == 0) {
+            auto pf = [](const void *q) { asm volatile("prefetch.global.L2 [%0];" :: "l"(q)); };
+            if (valid) {
+                if constexpr (LSQ) {
+                    if (p.target) pf(p.target + n * p.n_res);
+                } else {
+                    if (p.gy) pf(p.gy + n * O);
+                    if (ORDER >= 1 && p.gjac) pf(p.gjac + n * O * D);
+                    if (ORDER >= 2 && p.gh2) pf(p.gh2 + n * O);
+                }
+            }
+            const int64_t nn = n + (int64_t)gridDim.x * TILE_M;
+            if (nn < p.N) pf(p.x + nn * D);
+        }
 
         // ================= forward with tape =================
         // Tape traffic (L1 <-> L2) is the largest single cost of this kernel (ablation: 1.8 of 5.0 ms), so the first sine
