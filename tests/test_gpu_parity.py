@@ -473,3 +473,42 @@ def test_box_sampler_on_device_and_under_graph_replay():
         draws.append(keep.clone())
     assert not torch.equal(draws[0], draws[1]) and not torch.equal(draws[1], draws[2])
     assert int(s.counter) == 1 + 3
+
+
+@pytest.mark.parametrize("case", [(2, 2, 40, 2, 300, 1), (3, 3, 66, 3, 1000, 1), (2, 1, 129, 2, 500, 2), (1, 1, 100, 3, 777, 1),
+                                  (2, 1, 128, 3, 129, 2), (2, 2, 68, 3, 200000, 1), (3, 1, 72, 1, 64, 0), (2, 1, 200, 2, 5, 2)])
+def test_wide_tcgen05_layers_against_fp64_oracle(case):
+    """the tensor-core hidden layers of the 32 < H <= 512 family (k_wide_tc forward / data gradient, k_wide_wgrad for
+    HP <= 128): K padded to 32-slabs, one and two column passes, one and two 64-neuron weight blocks, ragged point
+    tiles, a batch that crosses the workspace chunk (200000 points), against the fp64 oracle; and agreement with the
+    FFMA kernels of the same family"""
+    D, O, H, L, N, order = case
+    rng = np.random.default_rng(3 * N + H)
+    parts = []
+    for li, (o, i) in enumerate(fm.layer_shapes(D, O, H, L)):
+        b = 1.0 / i if li == 0 else np.sqrt(6.0 / i) / 30.0
+        parts += [rng.uniform(-b, b, o * i), rng.uniform(-1, 1, o) / np.sqrt(i)]
+    theta = np.concatenate(parts).astype(np.float32)
+    x = rng.uniform(-1, 1, (N, D)).astype(np.float32)
+    th64, x64 = theta.astype(np.float64), x.astype(np.float64)
+    ref = fm.forward(th64, x64, D, O, H, L, order)
+    res = {}
+    for flags in (0, _lib.FLAG_NO_TENSOR):
+        desc = _lib.make_desc(D, O, H, L, flags=flags)
+        assert _lib.get_lib().kernel_family(desc, order, True) == 2
+        outs = _ops.siren_forward(desc, dev(theta), dev(x), order)
+        for o_, k in zip(outs, ["y", "jac", "lap"]):
+            assert rel(o_, ref[k]) < TOL, (flags, k)
+        cot = [np.random.default_rng(9).standard_normal(tuple(o.shape)).astype(np.float32) for o in outs]
+        gth, gx = _ops.siren_backward(desc, dev(theta), dev(x), order, *[dev(c) for c in cot], need_gx=True)
+        res[flags] = (gth, gx, cot)
+    cot = res[0][2]
+    kw = dict(gy=cot[0])
+    if order >= 1:
+        kw["gjac"] = cot[1]
+    if order == 2:
+        kw["glap"] = cot[2]
+    gref, gxref = fm.backward(th64, x64, D, O, H, L, order, **kw)
+    for flags in res:
+        assert rel(res[flags][0], gref) < TOL, flags
+        assert rel(res[flags][1], gxref) < TOL, flags
