@@ -65,8 +65,11 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// S <= 2 (value-only evaluations of the frozen nets, 1-D fields): 2 CTAs per SM (<= 256 TMEM columns, <= 97 KB each), so one
+// CTA's MMAs and loads overlap the other's epilogue
 template <int D, int ORDER, int MODE>
-__global__ void __launch_bounds__(WT, 1) k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, const float *__restrict__ W,
+__global__ void __launch_bounds__(WT, (StreamCfg<D, ORDER>::S <= 2) ? 2 : 1)
+k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__restrict__ W,
                                                    const float *__restrict__ bias, const float *__restrict__ Ain,
                                                    int64_t NCp, int64_t p_base, const float *__restrict__ Ztape,
                                                    float *__restrict__ Zout, float *__restrict__ Aout) {
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(WT, 1) k_wide_tc(SirenDims dm, int HP, int NK,
     const int j0 = blockIdx.y * NCOL;                   // first output column of this pass
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tslot), "r"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tslot), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(WT, 1) k_wide_tc(SirenDims dm, int HP, int NK,
     insr_tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -293,8 +296,9 @@ int launch_wide(const SirenDims &dm, const float *W, const float *bias, const fl
     auto kfn = k_wide_tc<D, ORDER, MODE>;
     const size_t smem = smem_bytes(S, g.NCOL);
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kfn<<<dim3((unsigned)(rows / TILE), (unsigned)g.passes), dim3(WT), smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dm, g.HP, g.NK, g.NCOL, W, bias, Ain, NCp, (int64_t)0, Ztape, Zout, Aout);
+        dm, g.HP, g.NK, g.NCOL, insr_tc::pow2_cols(S * g.NCOL), W, bias, Ain, NCp, (int64_t)0, Ztape, Zout, Aout);
     ++*launches;
     return 0;
 }
