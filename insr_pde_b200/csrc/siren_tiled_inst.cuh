@@ -17,3 +17,13 @@ int insr_tiled_backward(const SirenDims &dm, int order, const float *theta, cons
     INSR_TILED_ALL((insr_tiled::run_backward<D, O, ORDER>(dm, theta, x, N, gy, gjac, gh2, gtheta, gx, ws, stream, launches, tensor)))
     return -6;
 }
+
+#if defined(INSR_WIDE_PROFILE) && !defined(INSR_CPU_EMU)
+// debug builds only (tools/wide_phase_profile.py): read / reset the phase counters of k_wide_tc
+extern "C" int insr_debug_wide_prof(unsigned long long *out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, insr_wide::g_wide_prof, 16 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(insr_wide::g_wide_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -26,7 +26,8 @@
 namespace insr_wide {
 
 using insr_tc::s32;
-constexpr int WT = 256;                 // threads
+constexpr int WT = 512;                 // threads of k_wide_tc: 16 warps (4 per TMEM lane quadrant) hide the epilogue's latency chains
+constexpr int WGT = 256;                // threads of k_wide_wgrad
 constexpr int TILE = 128;               // points per CTA
 constexpr int KS = 32;                  // reduction slab
 constexpr int A_TILE = TILE * KS * 4;   // 16 KB: one 128 x 32 fp32 operand tile
@@ -67,6 +68,10 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
 
 // S <= 2 (value-only evaluations of the frozen nets, 1-D fields): 2 CTAs per SM (<= 256 TMEM columns, <= 97 KB each), so one
 // CTA's MMAs and loads overlap the other's epilogue
+#ifdef INSR_WIDE_PROFILE
+__device__ unsigned long long g_wide_prof[16];
+#endif
+
 template <int D, int ORDER, int MODE>
 __global__ void __launch_bounds__(WT, (StreamCfg<D, ORDER>::S <= 2) ? 2 : 1)
 k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__restrict__ W,
@@ -102,8 +107,8 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((128u >> 4) << 24);
 
     // ---- staging assignment: A = S tiles of 128 rows x 8 chunks (16 B) -> 4 S chunks per thread; B = NCOL x 32 scalars
-    constexpr int NA = 4 * S;
-    constexpr int NB = 16;                              // 128 * 32 / 256
+    constexpr int NA = 1024 * S / WT;
+    constexpr int NB = 128 * KS / WT;
     float4 ra[NA];
     float rb[NB];
     auto gload = [&](int k0) {
@@ -157,12 +162,22 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
     };
 
     uint32_t phase = 0;
+#ifdef INSR_WIDE_PROFILE
+    unsigned long long *gprof = g_wide_prof;            // phase timing of warp 1 (debug builds; insr_debug_wide_prof)
+    long long tprev = clock64();
+#define WTP(k) do { if (tid == 32 && gprof) { const long long t_ = clock64(); atomicAdd(gprof + (k), (unsigned long long)(t_ - tprev)); tprev = t_; } } while (0)
+#else
+#define WTP(k) do { } while (0)
+#endif
     gload(0);
+    WTP(0);
     for (int ks = 0; ks < NK; ++ks) {
         sstore();
+        WTP(1);
         insr_tc::fence_async_smem();
         insr_tc::tc_fence_before();
         __syncthreads();
+        WTP(2);
         if (ks + 1 < NK) gload((ks + 1) * KS);          // in flight while the tensor core works on slab ks
         if (warp == 0) {
             insr_tc::tc_fence_after();
@@ -183,9 +198,11 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
             }
             __syncwarp();
         }
+        WTP(3);
         insr_tc::mbar_wait(mbar, phase);
         phase ^= 1;
         insr_tc::tc_fence_after();
+        WTP(4);
     }
 
     // ---- epilogue, 32 output columns at a time, staged through shared memory (the operand tiles are free now) so that
@@ -197,27 +214,38 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
     float *stage = reinterpret_cast<float *>(sm);
     auto tile_at = [&](int t, int r, int c) -> float * { return stage + ((size_t)t * TILE + r) * EST + c; };
     const int row = 32 * (warp & 3) + lane;
-    const int half = warp >> 2;                                   // 16 of the 32 columns
+    const int quarter = warp >> 2;                                // 8 of the 32 columns of a chunk
     const uint32_t trow = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-    const int crow = tid >> 3, cch = tid & 7;                     // cooperative copies: 8 lanes per 128-byte row segment
-    for (int cc = 0; cc < NCOL; cc += EC) {
-        const int jc = j0 + cc;                                   // first output column of this chunk
-        if (jc >= HP) break;
-        if (MODE == 1) {                                          // stage the tape of the previous layer
+    const int crow = tid >> 3, cch = tid & 7;                     // cooperative copies: 8 lanes per 128-byte row segment, 64 rows per sweep
+    constexpr int CR = TILE * 8 / WT;                             // row sweeps of a cooperative copy (2)
+    float4 zpre[MODE == 1 ? S : 1][CR];                           // MODE 1: tape chunk in registers
+    auto load_tape_chunk = [&](int jc_) {
+        if (MODE == 1) {
             INSR_PRAGMA_UNROLL
             for (int s = 0; s < S; ++s)
                 INSR_PRAGMA_UNROLL
-                for (int i = 0; i < 4; ++i) {
-                    const int r = crow + 32 * i, j = jc + 4 * cch;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j < HP) v = __ldg(reinterpret_cast<const float4 *>(Ztape + ((int64_t)s * NCp + p0 + r) * HP + j));
-                    *reinterpret_cast<float4 *>(tile_at(s, r, 4 * cch)) = v;
+                for (int i = 0; i < CR; ++i) {
+                    const int r = crow + (WT / 8) * i, j = jc_ + 4 * cch;
+                    zpre[MODE == 1 ? s : 0][i] = (j < HP) ? __ldg(reinterpret_cast<const float4 *>(Ztape + ((int64_t)s * NCp + p0 + r) * HP + j))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-            __syncthreads();
         }
-        INSR_PRAGMA_UNROLL
-        for (int g8 = 0; g8 < 2; ++g8) {
-            const int c0 = 16 * half + 8 * g8;                    // column inside the chunk
+    };
+    load_tape_chunk(j0);
+    for (int cc = 0; cc < NCOL; cc += EC) {
+        const int jc = j0 + cc;                                   // first output column of this chunk
+        if (jc >= HP) break;
+        if (MODE == 1) {                                          // stage the tape of the previous layer (loaded one chunk ahead)
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s)
+                INSR_PRAGMA_UNROLL
+                for (int i = 0; i < CR; ++i)
+                    *reinterpret_cast<float4 *>(tile_at(s, crow + (WT / 8) * i, 4 * cch)) = zpre[MODE == 1 ? s : 0][i];
+            __syncthreads();
+            if (cc + EC < NCOL) load_tape_chunk(jc + EC);         // in flight during this chunk's arithmetic
+        }
+        {
+            const int c0 = 8 * quarter;                           // column inside the chunk
             float acc[S][8], o1[S][8], o2[S][8];
             INSR_PRAGMA_UNROLL
             for (int s = 0; s < S; ++s) insr_tc::tmem_ld8(trow + (uint32_t)(s * NCOL + cc + c0), acc[s]);
@@ -270,8 +298,8 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
         INSR_PRAGMA_UNROLL
         for (int s = 0; s < S; ++s)
             INSR_PRAGMA_UNROLL
-            for (int i = 0; i < 4; ++i) {
-                const int r = crow + 32 * i, j = jc + 4 * cch;
+            for (int i = 0; i < CR; ++i) {
+                const int r = crow + (WT / 8) * i, j = jc + 4 * cch;
                 if (j < HP) {
                     const int64_t g = ((int64_t)s * NCp + p0 + r) * HP + j;
                     if (MODE == 0 && Zout) *reinterpret_cast<float4 *>(Zout + g) = *reinterpret_cast<const float4 *>(tile_at(s, r, 4 * cch));
@@ -280,6 +308,10 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
             }
         __syncthreads();                                          // tiles are rewritten by the next chunk
     }
+    WTP(5);
+#ifdef INSR_WIDE_PROFILE
+    if (tid == 32 && gprof) atomicAdd(gprof + 7, 1ull);
+#endif
     insr_tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -325,7 +357,7 @@ __device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr, uint32_t lbo) {  
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-__global__ void __launch_bounds__(WT, 1) k_wide_wgrad(SirenDims dm, int HP, int S, const float *__restrict__ ZB,
+__global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int S, const float *__restrict__ ZB,
                                                       const float *__restrict__ Act, int64_t NCp, int nv,
                                                       float *__restrict__ gW, float *__restrict__ gb) {
     extern __shared__ __align__(1024) unsigned char smraw_[];
@@ -453,7 +485,7 @@ __global__ void __launch_bounds__(WT, 1) k_wide_wgrad(SirenDims dm, int HP, int 
         const uint32_t trow = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
         for (int jb = 0; jb < NBJ; ++jb)
             for (int kb = 0; kb < NBJ; ++kb) {
-                for (int idx = tid; idx < 64 * 64; idx += WT) tile[idx] = 0.f;
+                for (int idx = tid; idx < 64 * 64; idx += WGT) tile[idx] = 0.f;
                 __syncthreads();
                 INSR_PRAGMA_UNROLL
                 for (int c8 = 0; c8 < 8; ++c8) {
@@ -464,7 +496,7 @@ __global__ void __launch_bounds__(WT, 1) k_wide_wgrad(SirenDims dm, int HP, int 
                     for (int i = 0; i < 8; ++i) atomicAdd(tile + (m & 63) * 64 + 8 * c8 + i, v[i]);
                 }
                 __syncthreads();
-                for (int idx = tid; idx < 64 * 64; idx += WT) {
+                for (int idx = tid; idx < 64 * 64; idx += WGT) {
                     const int j = jb * 64 + (idx >> 6), k = kb * 64 + (idx & 63);
                     const float v = tile[idx];
                     if (j < H && k < H && v != 0.f) atomicAdd(gW + (size_t)j * H + k, dm.omega * v);
@@ -489,7 +521,7 @@ inline int launch_wide_wgrad(const SirenDims &dm, int S, const float *ZB, const 
     const int groups = (nv + WG_PTS - 1) / WG_PTS;
     const int sms = insr_fused::sm_count();
     const int ctas = groups < sms ? groups : sms;
-    k_wide_wgrad<<<dim3((unsigned)ctas), dim3(WT), smem, reinterpret_cast<cudaStream_t>(stream)>>>(dm, HP, S, ZB, Act, NCp, nv, gW, gb);
+    k_wide_wgrad<<<dim3((unsigned)ctas), dim3(WGT), smem, reinterpret_cast<cudaStream_t>(stream)>>>(dm, HP, S, ZB, Act, NCp, nv, gW, gb);
     ++*launches;
     return 0;
 }
