@@ -376,8 +376,13 @@ class FluidStepper:
         n = self.sr ** 2
         if self.device_sampler:              # one kernel for the three sets (insr_sample_boxes)
             if n_shard_div not in self._samplers:
-                self._samplers[n_shard_div] = sampling.BoxSampler(sampling.fluid_sets(n // n_shard_div, n // 100), 2,
-                                                                  seed=self.seed, device=dev)
+                import torch.distributed as tdist
+                rank = tdist.get_rank() if (tdist.is_available() and tdist.is_initialized()) else 0
+                sets = sampling.fluid_sets(n // n_shard_div, n // 100)
+                per_rank = sum(int(bx[0]) for st in sets for bx in st)
+                # every rank draws its own slice of ONE global Philox stream (point index offset by the rank)
+                self._samplers[n_shard_div] = sampling.BoxSampler(sets, 2, seed=self.seed, device=dev,
+                                                                  point_offset=rank * per_rank)
             return tuple(self._samplers[n_shard_div].sample())
         x = sampling.sample_random(n // n_shard_div, 2, device=dev)
         bx = sampling.sample_boundary2D_separate(n // 100, "horizontal", device=dev)
