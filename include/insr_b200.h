@@ -169,6 +169,18 @@ int insr_elastic_energy(const float *F, int64_t n, int d, float ratio_arap, floa
 int insr_sample_boxes(int n_boxes, int dim, const int32_t *count, const float *lo, const float *hi, uint64_t seed,
                       int64_t *counter, uint32_t *ticket, int64_t point_offset, float *out, void *stream);
 
+/*
+ * Points on a triangle (verts_per_elem 3) or tetrahedron (4) mesh.  Replaces elasticity/sampling.py:4-9 ->
+ * torchgp/sample_surface.py:28-52 (Categorical over face areas, weights (1 - sqrt(u), sqrt(u)(1 - v), sqrt(u) v)) and
+ * torchgp/sample_volume.py:9-43 (Categorical over tet volumes, numpy Dirichlet(1,1,1,1) on the host + copy).
+ * V (n_vert, 3) float, elem (n_elem, verts_per_elem) int32, cdf (n_elem) inclusive cumulative area / volume (any
+ * positive normalisation; the kernel scales by its last entry) -- all DEVICE arrays; out (n, dim_out) receives the
+ * first dim_out coordinates (the reference slices [:, 0:dim]).  seed / counter / ticket / point_offset as above.
+ */
+int insr_sample_mesh(const float *V, const int32_t *elem, const float *cdf, int n_elem, int verts_per_elem, int64_t n,
+                     int dim_out, uint64_t seed, int64_t *counter, uint32_t *ticket, int64_t point_offset, float *out,
+                     void *stream);
+
 /* introspection used by bench.py / tests: which kernel family a call would dispatch to.
  * returns 0 = generic, 1 = fused resident-weights kernels (H <= 32), 2 = tiled shared-memory GEMM
  * kernels (32 < H <= 512); negative = error. */

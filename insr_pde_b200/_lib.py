@@ -21,7 +21,7 @@ FLAG_FFMA_BWD = 4
 EXPORTS = [
     "insr_version", "insr_last_error", "insr_siren_theta_size", "insr_siren_workspace_bytes",
     "insr_siren_forward", "insr_siren_backward", "insr_siren_lsq_step", "insr_siren_kernel_family",
-    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes",
+    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes", "insr_sample_mesh",
 ]
 
 
@@ -72,6 +72,8 @@ class Library:
         c.insr_svd_small.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp]
         c.insr_elastic_energy.restype = _i32
         c.insr_elastic_energy.argtypes = [_vp, _i64, _i32, _f, _f, _vp, _vp, _vp]
+        c.insr_sample_mesh.restype = _i32
+        c.insr_sample_mesh.argtypes = [_vp, _vp, _vp, _i32, _i32, _i64, _i32, ctypes.c_uint64, _vp, _vp, _i64, _vp, _vp]
         c.insr_sample_boxes.restype = _i32
         c.insr_sample_boxes.argtypes = [_i32, _i32, _vp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _i64, _vp, _vp]
         c.insr_launch_count.restype = _i64
@@ -116,6 +118,10 @@ class Library:
         l = (ctypes.c_float * (n * dim))(*[v for row in lo for v in row])
         h = (ctypes.c_float * (n * dim))(*[v for row in hi for v in row])
         self.check(self.cdll.insr_sample_boxes(n, dim, c, l, h, seed, counter, ticket, point_offset, out, stream))
+
+    def sample_mesh(self, V, elem, cdf, n_elem, k, n, dim_out, seed, counter, ticket, point_offset, out, stream):
+        self.check(self.cdll.insr_sample_mesh(V, elem, cdf, n_elem, k, n, dim_out, seed, counter, ticket, point_offset,
+                                              out, stream))
 
     def svd_small(self, F, n, d, U, S, V, stream):
         self.check(self.cdll.insr_svd_small(F, n, d, U, S, V, stream))

@@ -382,4 +382,28 @@ int insr_sample_boxes(int n_boxes, int dim, const int32_t *count, const float *l
     return check_cuda("k_sample_boxes");
 }
 
+int insr_sample_mesh(const float *V, const int32_t *elem, const float *cdf, int n_elem, int verts_per_elem, int64_t n,
+                     int dim_out, uint64_t seed, int64_t *counter, uint32_t *ticket, int64_t point_offset, float *out,
+                     void *stream) {
+    if (!V || !elem || !cdf || !out) return fail(INSR_ERR_NULL, "sample_mesh: NULL argument");
+    if (n_elem < 1 || n < 0 || dim_out < 1 || dim_out > 3 || (verts_per_elem != 3 && verts_per_elem != 4))
+        return fail(INSR_ERR_SHAPE, "sample_mesh: n_elem=%d n=%lld dim_out=%d (1..3) verts_per_elem=%d (3 or 4)", n_elem,
+                    (long long)n, dim_out, verts_per_elem);
+    if (counter && !ticket) return fail(INSR_ERR_NULL, "sample_mesh: a device counter needs a zeroed ticket word");
+    int rc = check_device();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (verts_per_elem == 3) {
+        auto kfn = k_sample_mesh<3>;
+        INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(256), 0, stream, V, elem, cdf, n_elem, n, dim_out, seed, counter, ticket, point_offset, out);
+    } else {
+        auto kfn = k_sample_mesh<4>;
+        INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(256), 0, stream, V, elem, cdf, n_elem, n, dim_out, seed, counter, ticket, point_offset, out);
+    }
+    ++g_launches;
+    return check_cuda("k_sample_mesh");
+}
+
 }  // extern "C"

@@ -18,6 +18,7 @@ optional early stop at lr <= 1.1e-8.
 """
 from __future__ import annotations
 
+import gc
 import math
 
 import torch
@@ -189,19 +190,22 @@ def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_le
                                  circle_center, circle_radius):
     """the reference closure with ``jacobian -> torch.svd -> (S - 1)^2, (prod S - 1)^2`` replaced by the field's
     order-1 kernel and ONE ``insr_elastic_energy`` kernel (energy + adjoint, no SVD graph); the remaining terms are the
-    reference's elementwise expressions.  ``samples`` must require grad (the Jacobian is taken w.r.t. it)."""
-    from . import diff_ops, linalg
-    with torch.no_grad():
-        q_prev = prev(samples) + samples
-        q_pp = prev_prev(samples) + samples
-    q = deformation(samples) + samples
+    reference's elementwise expressions."""
+    from . import function, linalg
+    samples = samples.detach().reshape(-1, deformation.in_features).contiguous()
+    q_prev = evaluate(prev, samples, ORDER_VALUE)[0] + samples
+    q_pp = evaluate(prev_prev, samples, ORDER_VALUE)[0] + samples
+    ra = ratio_arap if "arap" in energy else 0.0
+    rv = ratio_volume if "volume" in energy else 0.0
+    # value and Jacobian of the trainable field from ONE order-1 kernel (and one reverse kernel for both cotangents);
+    # jacobian(net(x) + x, x) = J + I, so the points themselves need no gradient and no NaN-status host sync happens
+    outs = function.evaluate(deformation, samples, ORDER_JAC if (ra or rv) else ORDER_VALUE)
+    q = outs[0] + samples
     qdot = (q - q_prev) / dt
     qdot_prev = (q_prev - q_pp) / dt
     loss = 0
-    ra = ratio_arap if "arap" in energy else 0.0
-    rv = ratio_volume if "volume" in energy else 0.0
     if ra or rv:
-        F, _ = diff_ops.jacobian(q, samples)
+        F = outs[1] + torch.eye(samples.shape[1], device=samples.device, dtype=samples.dtype)
         loss = loss + linalg.elastic_energy(F, ra, rv)
     for term in energy:
         if term in ("arap", "volume"):
@@ -236,6 +240,18 @@ def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_le
 # ------------------------------------------------------------------------------------------------
 # the caller: one @_training_loop
 # ------------------------------------------------------------------------------------------------
+def _backward_if_needed(loss_dict):
+    """the fluid / advection closures accumulate d loss / d theta inside their kernels and return detached values; a
+    closure that still carries an autograd graph (elasticity) is differentiated here, summed like _update_network
+    (base/baseModel.py:73-77) -- the accumulation lands in the same flat gradient buffers"""
+    live = [v for v in loss_dict.values() if torch.is_tensor(v) and v.requires_grad]
+    if live:
+        sum(live).backward()
+    for k in loss_dict:
+        if torch.is_tensor(loss_dict[k]):
+            loss_dict[k] = loss_dict[k].detach()
+
+
 class TrainingLoop:
     """fresh Adam + ReduceLROnPlateau per loop over the nets' parameters (base/baseModel.py:55-62);
     ``closure(i)`` must accumulate gradients via ``lsq`` and return the loss_dict."""
@@ -254,6 +270,7 @@ class TrainingLoop:
         for i in range(n_iters):
             zero_grads(*self.nets)
             loss_dict = closure(i)
+            _backward_if_needed(loss_dict)
             if self.reducer is not None:
                 self.reducer.allreduce()
             self.opt.step()
@@ -319,6 +336,7 @@ class GraphedLoop:
     def _iteration(self):
         zero_grads(*self.nets)
         loss_dict = self.closure()
+        _backward_if_needed(loss_dict)
         vals = torch.stack([loss_dict[k].reshape(()) for k in loss_dict]).reshape(1, -1)
         if self.hist is None:
             self.hist = torch.zeros(self.capacity, vals.shape[1], device=vals.device)
@@ -341,10 +359,20 @@ class GraphedLoop:
             keys, done = self.keys, 0
         if n_iters > done:
             if self.graph is None:
+                # a garbage-collection pass that happens to free an OLD CUDAGraph (a dropped stepper is a reference
+                # cycle) while this capture is open calls cudaGraphExecDestroy / cudaFree and invalidates the capture:
+                # collect now, and keep the collector off until the capture has ended
+                gc.collect()
                 torch.cuda.synchronize()
                 self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
-                    self._iteration()
+                gc_was_on = gc.isenabled()
+                gc.disable()
+                try:
+                    with torch.cuda.graph(self.graph):
+                        self._iteration()
+                finally:
+                    if gc_was_on:
+                        gc.enable()
             while done < n_iters:
                 burst = min(check_every, n_iters - done)
                 for _ in range(burst):
@@ -418,6 +446,119 @@ class FluidStepper:
         h3 = self._loop(nets, lambda i: fluid_projection(self.vel, self.prev, self.pres, *self._samples(world)), n_iters,
                         key="project")
         return h1, h2, h3
+
+
+class ElasticityStepper:
+    """ElasticityModel.initialize / step (elasticity/model.py:100-125) on the fused closure: previous-frame hand-over,
+    the reference's sample pattern ('random' and / or 'uniform'; a mesh when ``mesh=(V, F)`` is given), one
+    @_training_loop per time step.  ``graphed=True`` captures the whole iteration (sampling kernel, field kernels, energy
+    kernel, autograd reverse sweep, device Adam + plateau) as one CUDA graph that every later time step replays."""
+
+    def __init__(self, deformation, prev, prev_prev, dim, dt=0.05, sample_resolution=100, lr=1e-4,
+                 sample_pattern=("random", "uniform"), mesh=None, graphed=False, seed=0, **closure_kw):
+        self.defo, self.prev, self.pp = deformation, prev, prev_prev
+        self.dim, self.dt, self.sr, self.lr = dim, dt, sample_resolution, lr
+        self.pattern, self.mesh, self.graphed, self.seed = tuple(sample_pattern), mesh, graphed, seed
+        self.kw = closure_kw
+        self.timestep = 0
+        self._samplers, self._const = {}, {}
+        for net in (self.prev, self.pp):
+            for p in net.parameters():
+                p.requires_grad_(False)
+
+    # --- sampling (elasticity/model.py:198-253) --------------------------------------------------
+    def _device(self):
+        return next(self.defo.parameters()).device
+
+    def _interior(self, resolution):
+        from . import sampling
+        dev, parts = self._device(), []
+        for kind in self.pattern:
+            if kind == "random":
+                if self.mesh is not None:
+                    key = ("mesh",)
+                    if key not in self._samplers:
+                        self._samplers[key] = sampling.MeshSampler(self.mesh[0].to(dev), self.mesh[1].to(dev), self.dim, self.seed)
+                    parts.append(self._samplers[key].sample(resolution ** self.dim))
+                elif self.graphed:
+                    key = ("box", resolution)
+                    if key not in self._samplers:
+                        box = [(resolution ** self.dim, (-1.0,) * self.dim, (1.0,) * self.dim)]
+                        self._samplers[key] = sampling.BoxSampler([box], self.dim, seed=self.seed, device=dev)
+                    parts.append(self._samplers[key].sample()[0])
+                else:
+                    parts.append(sampling.sample_random(resolution ** self.dim, self.dim, device=dev))
+            elif kind == "uniform":
+                key = ("uniform", resolution)
+                if key not in self._const:
+                    self._const[key] = (self.mesh[0][:, :self.dim].to(dev).float().contiguous() if self.mesh is not None
+                                        else sampling.sample_uniform(resolution, self.dim, device=dev))
+                parts.append(self._const[key])
+            else:
+                raise NotImplementedError(kind)
+        return torch.cat(parts, dim=0).requires_grad_(True)
+
+    def _fixed(self, resolution):
+        from . import sampling
+        dev, left, right = self._device(), [], []
+        if self.mesh is not None:
+            return [], []
+        for kind in self.pattern:
+            if kind == "random":
+                if self.graphed:               # both faces from one kernel: a box that is flat in the first coordinate
+                    key = ("fixed", resolution)
+                    if key not in self._samplers:
+                        lo, hi = (-1.0,) * (self.dim - 1), (1.0,) * (self.dim - 1)
+                        sets = [[(resolution, (-1.0,) + lo, (-1.0,) + hi)], [(resolution, (1.0,) + lo, (1.0,) + hi)]]
+                        self._samplers[key] = sampling.BoxSampler(sets, self.dim, seed=self.seed + 1, device=dev)
+                    l, r = self._samplers[key].sample()
+                else:
+                    l = torch.cat((-torch.ones(resolution, 1, device=dev), sampling.sample_random(resolution, self.dim - 1, device=dev)), dim=1)
+                    r = torch.cat((torch.ones(resolution, 1, device=dev), sampling.sample_random(resolution, self.dim - 1, device=dev)), dim=1)
+                left.append(l); right.append(r)
+            elif kind == "uniform":
+                key = ("fixed_uniform", resolution)
+                if key not in self._const:
+                    face = sampling.sample_uniform(resolution, self.dim - 1, device=dev)
+                    one = torch.ones(face.shape[0], 1, device=dev)
+                    self._const[key] = (torch.cat((-one, face), dim=1), torch.cat((one, face), dim=1))
+                left.append(self._const[key][0]); right.append(self._const[key][1])
+        return torch.cat(left, dim=0), torch.cat(right, dim=0)
+
+    # --- the two training loops -----------------------------------------------------------------
+    def _loop(self, closure, n_iters, key):
+        if self.graphed:
+            loops = self.__dict__.setdefault("_loops", {})
+            if key not in loops:
+                loops[key] = GraphedLoop([self.defo], self.lr, lambda: closure(0))
+            else:
+                loops[key].reset(self.lr)
+            return loops[key].run(n_iters)
+        return TrainingLoop([self.defo], self.lr).run(closure, n_iters)
+
+    def initialize(self, n_iters, resolution=None):
+        """fit the zero deformation (elasticity/model.py:108-117), then copy it into both previous frames (:100-105)"""
+        res = resolution or self.sr
+
+        def c(i):
+            return {"main": torch.mean(self.defo(self._interior(res).detach()) ** 2)}      # widths above the lsq kernels
+        hist = self._loop(c, n_iters, ("initialize", res))
+        self.pp.load_state_dict(self.defo.state_dict())
+        self.prev.load_state_dict(self.defo.state_dict())
+        return hist
+
+    def step(self, n_iters):
+        self.timestep += 1
+        self.pp.load_state_dict(self.prev.state_dict())
+        self.prev.load_state_dict(self.defo.state_dict())
+        forced = self.timestep <= self.kw.get("external_force_timesteps", 0)
+
+        def c(i):
+            left, right = self._fixed(self.sr)
+            return elasticity_solve_deformation(self.defo, self.prev, self.pp, self._interior(self.sr), left, right,
+                                                dt=self.dt, timestep=self.timestep, **self.kw)
+        # the external-force term is a host-side branch on the time step: one captured graph per branch
+        return self._loop(c, n_iters, ("solve", forced))
 
 
 def taylorgreen_velocity(samples):

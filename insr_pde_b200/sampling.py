@@ -85,6 +85,50 @@ class BoxSampler:
         return list(torch.split(out, self.sizes, dim=0))
 
 
+def element_measures(V, F):
+    """triangle areas (torchgp/area_weighted_distribution.py:40-42 via per_face_normals.py:33-38) or tetrahedron
+    volumes (torchgp/per_tet_volumes.py:12-19): the weights of the reference's Categorical over elements"""
+    P = V[F.long()]
+    if F.shape[1] == 3:
+        return torch.linalg.norm(torch.linalg.cross(P[:, 0] - P[:, 1], P[:, 1] - P[:, 2]), dim=1) * 0.5
+    if F.shape[1] == 4:
+        a, b, c = P[:, 1] - P[:, 0], P[:, 2] - P[:, 0], P[:, 3] - P[:, 0]
+        return torch.abs(torch.sum(c * torch.linalg.cross(a, b), dim=-1)) / 6
+    raise ValueError("elements must be triangles (n, 3) or tetrahedra (n, 4)")
+
+
+class MeshSampler:
+    """``sample_mesh(V, F, N, distrib)[:, 0:dim]`` (elasticity/sampling.py:4-9, elasticity/model.py:203) from one kernel
+    (insr_sample_mesh): the element by binary search in the cumulative area / volume table, barycentric weights as the
+    reference draws them (triangles) or as normalised exponentials = Dirichlet(1,1,1,1) (tetrahedra), all on the device
+    -- the reference's tetrahedron path calls numpy on the host and copies.  Same distribution, Philox stream."""
+
+    def __init__(self, V, F, dim_out=3, seed=0, point_offset=0):
+        from . import _lib
+        self.V = V.detach().to(torch.float32).contiguous()
+        if self.V.shape[1] < 3:                                   # 2-D meshes carry a zero third coordinate
+            self.V = torch.cat([self.V, self.V.new_zeros(self.V.shape[0], 3 - self.V.shape[1])], dim=1).contiguous()
+        self.F = F.detach().to(torch.int32).contiguous()
+        measure = element_measures(self.V, self.F).double()
+        if not bool((measure > 0).all()):
+            raise ValueError("mesh has degenerate elements (zero area / volume)")
+        self.cdf = (torch.cumsum(measure, 0) / measure.sum()).to(torch.float32).contiguous()
+        self.dim_out, self.seed, self.point_offset = int(dim_out), int(seed), int(point_offset)
+        self.device = self.V.device
+        self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._lib = _lib
+
+    def sample(self, n):
+        lib = self._lib.get_lib()
+        out = torch.empty(n, self.dim_out, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            lib.sample_mesh(self.V.data_ptr(), self.F.data_ptr(), self.cdf.data_ptr(), self.F.shape[0], self.F.shape[1], n,
+                            self.dim_out, self.seed, self.counter.data_ptr(), self.ticket.data_ptr(), self.point_offset,
+                            out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        return out
+
+
 def fluid_sets(n_interior, n_boundary, epsilon=1e-4):
     """the three sets of a fluid iteration: sample_random(n, 2), sample_boundary2D_separate(nb, 'horizontal'),
     sample_boundary2D_separate(nb, 'vertical')  (fluid/model.py:75-77 etc., base/sampling.py:45-64)"""

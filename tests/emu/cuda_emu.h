@@ -144,6 +144,7 @@ static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 #define __sinf(x) sinf(x)   /* glibc declares __sinf/__cosf itself: use macros */
 #define __cosf(x) cosf(x)
+#define __logf(x) logf(x)
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }

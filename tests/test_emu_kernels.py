@@ -257,3 +257,65 @@ def test_sample_boxes_under_emulation(emu_library):
     lib.sample_boxes([2048], [lo[0]], [hi[0]], 2, 1234, None, None, 0, ptr(c1), None)
     lib.sample_boxes([2048], [lo[0]], [hi[0]], 2, 1234, None, None, 2048, ptr(c2), None)
     assert np.array_equal(np.concatenate([c1, c2]), a[:4096])
+
+
+def _cube_tets():
+    """unit cube [0,1]^3 split into 6 tetrahedra around the main diagonal + a stretched copy (different volumes)"""
+    corners = np.array([[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)], np.float32)
+    idx = lambda x, y, z: 4 * x + 2 * y + z
+    perms = [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)]
+    tets = []
+    for p in perms:
+        cur = [0, 0, 0]; path = [idx(*cur)]
+        for ax in p:
+            cur[ax] = 1; path.append(idx(*cur))
+        tets.append(path)
+    far = corners * np.array([3.0, 1.0, 1.0], np.float32) + np.array([2.0, 0.0, 0.0], np.float32)   # [2,5]x[0,1]^2
+    V = np.concatenate([corners, far]).astype(np.float32)
+    T = np.array(tets + [[v + 8 for v in t] for t in tets], np.int32)
+    return V, T
+
+
+def test_sample_mesh_under_emulation(emu_library):
+    """insr_sample_mesh: volume-weighted tetrahedra with Dirichlet(1,1,1,1) weights (torchgp/sample_volume.py:9-43) and
+    area-weighted triangles with the sqrt(u) weights (torchgp/sample_surface.py:28-52) -- points lie inside the mesh,
+    are uniform over it (element frequencies ~ measure, first moments), are fresh per iteration and shard by offset"""
+    lib = emu_library
+    V, T = _cube_tets()
+    P = V[T]
+    vol = np.abs(np.einsum("ij,ij->i", P[:, 3] - P[:, 0], np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]))) / 6
+    cdf = (np.cumsum(vol.astype(np.float64)) / vol.sum()).astype(np.float32)
+    n = 20000
+    counter = np.zeros(1, np.int64); ticket = np.zeros(1, np.uint32)
+    a = np.full((n, 3), np.nan, np.float32); b = np.full((n, 3), np.nan, np.float32)
+    lib.sample_mesh(ptr(V), ptr(T), ptr(cdf), len(T), 4, n, 3, 77, ptr(counter), ptr(ticket), 0, ptr(a), None)
+    lib.sample_mesh(ptr(V), ptr(T), ptr(cdf), len(T), 4, n, 3, 77, ptr(counter), ptr(ticket), 0, ptr(b), None)
+    assert counter[0] == 2 and ticket[0] == 0 and not np.array_equal(a, b)
+    assert np.isfinite(a).all()
+    near = a[:, 0] <= 1.0 + 1e-6
+    far = a[:, 0] >= 2.0 - 1e-6
+    assert (near | far).all()                                              # nothing in the gap between the two boxes
+    assert (a[:, 1:] >= -1e-6).all() and (a[:, 1:] <= 1 + 1e-6).all() and a[:, 0].min() >= -1e-6 and a[:, 0].max() <= 5 + 1e-6
+    assert abs(far.mean() - 0.75) < 0.015                                  # volume 3 of 4
+    # uniform inside each box: mean at the centre, variance (edge^2)/12
+    assert np.abs(a[near].mean(0) - 0.5).max() < 0.02 and np.abs(a[near].var(0) - 1 / 12).max() < 0.01
+    assert np.abs(a[far].mean(0) - np.array([3.5, 0.5, 0.5])).max() < 0.03 and abs(a[far][:, 0].var() - 9 / 12) < 0.03
+    # dim_out slice and rank offset: the second half of a global draw is the draw at offset n/2
+    h = n // 2
+    c2 = np.zeros((h, 2), np.float32)
+    counter[0] = 0
+    lib.sample_mesh(ptr(V), ptr(T), ptr(cdf), len(T), 4, h, 2, 77, None, None, h, ptr(c2), None)
+    assert np.array_equal(c2, a[h:, :2])
+    # triangles: the two faces of the unit square in the plane z = 0 plus a bigger triangle
+    Vt = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [2, 0, 0], [4, 0, 0], [2, 2, 0]], np.float32)
+    Ft = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6]], np.int32)
+    area = np.array([0.5, 0.5, 2.0]); cdf_t = (np.cumsum(area) / area.sum()).astype(np.float32)
+    s = np.full((n, 2), np.nan, np.float32)
+    lib.sample_mesh(ptr(Vt), ptr(Ft), ptr(cdf_t), 3, 3, n, 2, 5, None, None, 0, ptr(s), None)
+    big = s[:, 0] >= 2 - 1e-6
+    assert abs(big.mean() - 2 / 3) < 0.015
+    sq = s[~big]
+    assert (sq >= -1e-6).all() and (sq <= 1 + 1e-6).all() and np.abs(sq.mean(0) - 0.5).max() < 0.02 and np.abs(sq.var(0) - 1 / 12).max() < 0.01
+    tri = s[big]
+    assert ((tri[:, 0] - 2) + tri[:, 1] <= 2 + 1e-5).all() and (tri[:, 1] >= -1e-6).all()
+    assert np.abs(tri.mean(0) - np.array([2 + 2 / 3, 2 / 3])).max() < 0.03     # centroid

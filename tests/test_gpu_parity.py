@@ -475,6 +475,114 @@ def test_box_sampler_on_device_and_under_graph_replay():
     assert int(s.counter) == 1 + 3
 
 
+def _elastic_nets(seed, dim, H):
+    torch.manual_seed(seed)
+    defo = ib.MLP(dim, dim, 3, H, nonlinearity="sine").cuda()
+    prev = ib.MLP(dim, dim, 3, H, nonlinearity="sine").cuda()
+    pp = ib.MLP(dim, dim, 3, H, nonlinearity="sine").cuda()
+    return defo, prev, pp
+
+
+def test_elasticity_stepper_graph_replay_matches_eager_loop():
+    """ElasticityStepper (elasticity/model.py:100-189): the CUDA-graphed iteration (order-1 field kernel, energy kernel,
+    autograd reverse sweep, device Adam + plateau) reproduces the eager loop (torch Adam + ReduceLROnPlateau) on the
+    deterministic 'uniform' sample pattern over two time steps, the second of which drops the external force"""
+    from insr_pde_b200 import fused
+    kw = dict(energy=["arap", "volume", "kinematics", "external", "constraint", "collision_sphere"], ratio_arap=1.0,
+              ratio_volume=0.7, ratio_kinematics=0.5, ratio_constraint=100.0, ratio_collide=3.0,
+              external_force=torch.tensor([0.0, -2.0], device="cuda"), external_force_timesteps=1,
+              constraint_offset_right=torch.tensor([0.3, 0.0], device="cuda"), plane_height=-1.5,
+              circle_center=torch.tensor([0.2, -0.9], device="cuda"), circle_radius=0.5)
+    hist = {}
+    for graphed in (False, True):
+        defo, prev, pp = _elastic_nets(5, 2, 68)
+        st = fused.ElasticityStepper(defo, prev, pp, 2, dt=0.05, sample_resolution=24, lr=1e-4, sample_pattern=("uniform",),
+                                     graphed=graphed, **kw)
+        h0 = st.initialize(6)
+        assert torch.equal(prev.flat_theta(), defo.flat_theta()) and torch.equal(pp.flat_theta(), defo.flat_theta())
+        h1 = st.step(8)
+        h2 = st.step(8)
+        hist[graphed] = ([h["main"] for h in h0], [h["main"] for h in h1], [h["main"] for h in h2], defo.flat_theta().clone())
+    for a, b in zip(hist[False][:3], hist[True][:3]):
+        a, b = np.asarray(a), np.asarray(b)
+        assert np.isfinite(a).all() and np.abs(a - b).max() <= 2e-3 * np.abs(a).max(), (a, b)
+    assert rel(hist[True][3].cpu().numpy(), hist[False][3].cpu().numpy()) < 2e-3
+    assert hist[False][0][-1] < hist[False][0][0]                       # the zero-deformation fit makes progress
+    # random pattern: the device samplers (boxes with a flat first coordinate for the clamped faces) inside the graph
+    defo, prev, pp = _elastic_nets(6, 2, 68)
+    st = fused.ElasticityStepper(defo, prev, pp, 2, sample_resolution=24, sample_pattern=("random", "uniform"), graphed=True, **kw)
+    st.initialize(4)
+    h = st.step(6)
+    assert len(h) == 6 and all(np.isfinite(v["main"]) for v in h)
+    left, right = st._fixed(24)
+    assert left.shape == (48, 2) and bool((left[:, 0] == -1).all()) and bool((right[:, 0] == 1).all())
+    assert float(left[:24, 1].abs().max()) <= 1 and float(left[:24, 1].std()) > 0.3
+    assert int(st._samplers[("box", 24)].counter) >= 6
+
+
+def test_elasticity_stepper_on_a_tetrahedron_mesh():
+    """mesh branch of _sample_in_training (elasticity/model.py:198-207): volume samples from insr_sample_mesh plus the mesh
+    vertices, 3-D field, graphed"""
+    from insr_pde_b200 import fused
+    from test_emu_kernels import _cube_tets
+    Vn, Tn = _cube_tets()
+    V = torch.tensor(Vn[:8] * 2 - 1, device="cuda"); T = torch.tensor(Tn[:6].astype(np.int64), device="cuda")
+    defo, prev, pp = _elastic_nets(7, 3, 66)
+    kw = dict(energy=["arap", "kinematics", "external", "collision"], ratio_arap=1.0, ratio_volume=0.0, ratio_kinematics=0.5,
+              ratio_constraint=0.0, ratio_collide=2.0, external_force=torch.tensor([0.0, 0.0, -1.0], device="cuda"),
+              external_force_timesteps=10, constraint_offset_right=torch.zeros(3, device="cuda"), plane_height=-0.9,
+              circle_center=torch.zeros(3, device="cuda"), circle_radius=0.0)
+    st = fused.ElasticityStepper(defo, prev, pp, 3, sample_resolution=12, mesh=(V, T), graphed=True, **kw)
+    st.initialize(3)
+    x = st._interior(12)
+    assert x.shape == (12 ** 3 + 8, 3) and float(x.abs().max()) <= 1 + 1e-6
+    h = st.step(5)
+    assert len(h) == 5 and all(np.isfinite(v["main"]) for v in h)
+
+
+def test_mesh_sampler_on_device():
+    """insr_sample_mesh behind sampling.MeshSampler (elasticity/sampling.py:4-9): tetrahedra by volume with Dirichlet
+    weights, triangles by area with the reference's sqrt(u) weights; compared with the reference's own recipe restated
+    in torch (Categorical + barycentric weights) through distribution statistics, fresh draws under graph replay"""
+    from insr_pde_b200 import sampling
+    from test_emu_kernels import _cube_tets
+    Vn, Tn = _cube_tets()
+    V, T = torch.tensor(Vn, device="cuda"), torch.tensor(Tn.astype(np.int64), device="cuda")
+    ms = sampling.MeshSampler(V, T, dim_out=3, seed=11)
+    n = 400000
+    p = ms.sample(n)
+    assert p.shape == (n, 3) and bool(torch.isfinite(p).all())
+    far = p[:, 0] >= 2.0 - 1e-6
+    assert bool(((p[:, 0] <= 1 + 1e-6) | far).all()) and float(p[:, 1:].min()) >= -1e-6 and float(p[:, 1:].max()) <= 1 + 1e-6
+    assert abs(float(far.float().mean()) - 0.75) < 0.004
+    # the reference's recipe on the same mesh (sample_volume.py:27-38): moments of both agree
+    vol = sampling.element_measures(V, T)
+    idx = torch.distributions.Categorical(vol / vol.sum()).sample([n])
+    w = torch.distributions.Dirichlet(torch.ones(4, device="cuda")).sample([n])
+    q = (w[:, :, None] * V[T[idx]]).sum(1)
+    assert float((p.mean(0) - q.mean(0)).abs().max()) < 0.01 and float((p.var(0) - q.var(0)).abs().max()) < 0.02
+    counts_p = torch.bincount((p[:, 0] * 2).long().clamp(0, 9), minlength=10).float() / n
+    counts_q = torch.bincount((q[:, 0] * 2).long().clamp(0, 9), minlength=10).float() / n
+    assert float((counts_p - counts_q).abs().max()) < 0.005
+    # surface triangles of a 2-D mesh (vertices with two coordinates), first two coordinates out
+    V2 = torch.tensor([[0, 0], [1, 0], [1, 1], [0, 1]], dtype=torch.float32, device="cuda")
+    F2 = torch.tensor([[0, 1, 2], [0, 2, 3]], device="cuda")
+    tri = sampling.MeshSampler(V2, F2, dim_out=2, seed=3)
+    s1 = tri.sample(100000)
+    assert float(s1.min()) >= -1e-6 and float(s1.max()) <= 1 + 1e-6
+    assert float((s1.mean(0) - 0.5).abs().max()) < 0.01 and float((s1.var(0) - 1 / 12).abs().max()) < 0.005
+    assert abs(float((s1[:, 1] <= s1[:, 0]).float().mean()) - 0.5) < 0.01    # both triangles equally likely
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    keep = torch.zeros(4096, 2, device="cuda")
+    with torch.cuda.graph(g):
+        keep.copy_(tri.sample(4096))
+    g.replay(); d0 = keep.clone(); g.replay()
+    assert not torch.equal(d0, keep)
+    with pytest.raises(ValueError):
+        sampling.MeshSampler(V2, torch.tensor([[0, 1, 1]], device="cuda"))      # degenerate element
+
+
 @pytest.mark.parametrize("case", [(2, 2, 40, 2, 300, 1), (3, 3, 66, 3, 1000, 1), (2, 1, 129, 2, 500, 2), (1, 1, 100, 3, 777, 1),
                                   (2, 1, 128, 3, 129, 2), (2, 2, 68, 3, 200000, 1), (3, 1, 72, 1, 64, 0), (2, 1, 200, 2, 5, 2)])
 def test_wide_tcgen05_layers_against_fp64_oracle(case):

@@ -1,0 +1,62 @@
+"""seconds per elasticity training iteration / time step on one B200 (elasticity2Dstretch and bunny-sized configs):
+ElasticityStepper eager and CUDA-graphed, beside the reference closure restated in stock PyTorch (oracle port) on the
+same GPU.  Usage: python tools/elastic_step_bench.py [iters]"""
+import os, sys, time
+sys.path.insert(0, os.getcwd())
+import numpy as np
+import torch
+import insr_pde_b200 as ib
+from insr_pde_b200 import fused, sampling
+from oracle import closures, torch_port as tp
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+CASES = {
+    "elasticity2Dstretch": dict(dim=2, H=68, sr=100, dt=0.05, energy=["arap", "constraint", "constraint_right", "volume"],
+                                ratio_volume=1e3, ratio_arap=1e0, ratio_constraint=1e4, ratio_kinematics=1e0, ratio_collide=1e0,
+                                ext=[0., 0., 0.], ext_T=5, off=[2.0, 0., 0.], plane=-2.0, center=[0., -2., 0.], radius=1.0),
+    "elasticity3D_bunny_sized": dict(dim=3, H=66, sr=24, dt=0.1, energy=["arap", "kinematics", "collision", "external", "volume"],
+                                     ratio_volume=1e3, ratio_arap=1e2, ratio_constraint=1e3, ratio_kinematics=1e0, ratio_collide=1e6,
+                                     ext=[0., 0., -1e2], ext_T=5, off=[1.0, 0., 0.], plane=-0.9, center=[0., -2., 0.], radius=1.0),
+}
+for name, c in CASES.items():
+    dim = c["dim"]
+    kw = dict(energy=c["energy"], ratio_arap=c["ratio_arap"], ratio_volume=c["ratio_volume"], ratio_kinematics=c["ratio_kinematics"],
+              ratio_constraint=c["ratio_constraint"], ratio_collide=c["ratio_collide"],
+              external_force=torch.tensor(c["ext"][:dim], device="cuda"), external_force_timesteps=c["ext_T"],
+              constraint_offset_right=torch.tensor(c["off"][:dim], device="cuda"), plane_height=c["plane"],
+              circle_center=torch.tensor(c["center"][:dim], device="cuda"), circle_radius=c["radius"])
+    res = {}
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        nets = [ib.MLP(dim, dim, 3, c["H"], nonlinearity="sine").cuda() for _ in range(3)]
+        st = fused.ElasticityStepper(*nets, dim, dt=c["dt"], sample_resolution=c["sr"], graphed=graphed, **kw)
+        st.initialize(5)
+        st.step(10)                                   # warm-up (graph capture happens here)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        h = st.step(K)
+        torch.cuda.synchronize(); res[graphed] = (time.perf_counter() - t0) / K
+        npts = st._interior(c["sr"]).shape[0]
+    # the reference closure in stock PyTorch on the same GPU (autograd jacobian + torch.svd + Adam), fixed samples
+    torch.manual_seed(0)
+    rn = [tp.RefMLP(dim, dim, 3, c["H"]).cuda() for _ in range(3)]
+    for n in rn[1:]:
+        for p in n.parameters():
+            p.requires_grad_(False)
+    opt = torch.optim.Adam(rn[0].parameters(), lr=1e-4)
+    def ref_iter():
+        x = torch.cat([sampling.sample_random(c["sr"] ** dim, dim, device="cuda"), sampling.sample_uniform(c["sr"], dim, device="cuda")]).requires_grad_(True)
+        one = torch.ones(c["sr"], 1, device="cuda")
+        l = torch.cat((-one, sampling.sample_random(c["sr"], dim - 1, device="cuda")), 1)
+        r = torch.cat((one, sampling.sample_random(c["sr"], dim - 1, device="cuda")), 1)
+        opt.zero_grad()
+        loss = closures.elasticity_solve_deformation(rn[0], rn[1], rn[2], tp, x, l, r, dt=c["dt"], timestep=1, **kw)
+        loss["main"].backward(); opt.step()
+        return float(loss["main"])
+    for _ in range(3): ref_iter()
+    kr = max(5, K // 10)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(kr): ref_iter()
+    torch.cuda.synchronize(); tref = (time.perf_counter() - t0) / kr
+    print(f"{name}: {npts} points/iter  eager {res[False]*1e3:.3f} ms/iter  graphed {res[True]*1e3:.3f} ms/iter "
+          f"({npts / res[True] / 1e6:.1f} Mpts/s)  stock PyTorch on the same GPU {tref*1e3:.2f} ms/iter  "
+          f"-> {tref / res[True]:.1f}x", flush=True)
