@@ -80,6 +80,11 @@ typedef struct insr_siren_desc {
                                      gradient, 2-level bf16 split for the weight gradient, FP32 accumulation; same
                                      1e-4 parity; the backward keeps its tape in the workspace) */
 #define INSR_FLAG_FFMA_BWD 4      /* tcgen05 forward, FP32 FFMA backward / lsq_step (A/B measurements) */
+#define INSR_FLAG_KEEP_TAPE 8     /* 32 < H <= 512 family: insr_siren_forward leaves the activations of every layer in the
+                                   * workspace (which must then have the BACKWARD size) and insr_siren_backward on the same,
+                                   * untouched workspace skips recomputing them -- what autograd's saved activations are to
+                                   * the reference (base/baseModel.py:77).  Only where insr_siren_tape_supported() says 1;
+                                   * ignored by the H <= 32 family (its backward kernel recomputes inside registers). */
 
 int insr_version(void);
 const char *insr_last_error(void);
@@ -180,6 +185,10 @@ int insr_sample_boxes(int n_boxes, int dim, const int32_t *count, const float *l
 int insr_sample_mesh(const float *V, const int32_t *elem, const float *cdf, int n_elem, int verts_per_elem, int64_t n,
                      int dim_out, uint64_t seed, int64_t *counter, uint32_t *ticket, int64_t point_offset, float *out,
                      void *stream);
+
+/* 1 if a forward / backward pair with INSR_FLAG_KEEP_TAPE shares its tape for this shape and batch (the batch must be a
+ * single workspace chunk of the tiled family), 0 if the flag would be refused, negative = error */
+int insr_siren_tape_supported(const insr_siren_desc *desc, int64_t n_points, int order);
 
 /* introspection used by bench.py / tests: which kernel family a call would dispatch to.
  * returns 0 = generic, 1 = fused resident-weights kernels (H <= 32), 2 = tiled shared-memory GEMM

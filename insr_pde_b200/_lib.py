@@ -17,11 +17,12 @@ ORDER_VALUE, ORDER_JAC, ORDER_LAP, ORDER_HESS = 0, 1, 2, 3
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_TENSOR = 2
 FLAG_FFMA_BWD = 4
+FLAG_KEEP_TAPE = 8
 
 EXPORTS = [
     "insr_version", "insr_last_error", "insr_siren_theta_size", "insr_siren_workspace_bytes",
     "insr_siren_forward", "insr_siren_backward", "insr_siren_lsq_step", "insr_siren_kernel_family",
-    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes", "insr_sample_mesh",
+    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes", "insr_sample_mesh", "insr_siren_tape_supported",
 ]
 
 
@@ -61,6 +62,8 @@ class Library:
         c.insr_siren_lsq_step.restype = _i32
         c.insr_siren_lsq_step.argtypes = [_dp, _vp, _vp, _i64, _i32, _i32, ctypes.POINTER(ctypes.c_float),
                                           _vp, ctypes.c_float, _vp, _vp, _vp, _sz, _vp]
+        c.insr_siren_tape_supported.restype = _i32
+        c.insr_siren_tape_supported.argtypes = [_dp, _i64, _i32]
         c.insr_siren_kernel_family.restype = _i32
         c.insr_siren_kernel_family.argtypes = [_dp, _i32, _i32]
         _f = ctypes.c_float
@@ -91,6 +94,9 @@ class Library:
 
     def workspace_bytes(self, desc, n, order, backward):
         return int(self.cdll.insr_siren_workspace_bytes(ctypes.byref(desc), n, order, int(backward)))
+
+    def tape_supported(self, desc, n, order):
+        return int(self.cdll.insr_siren_tape_supported(ctypes.byref(desc), n, order)) == 1
 
     def kernel_family(self, desc, order, backward):
         return int(self.cdll.insr_siren_kernel_family(ctypes.byref(desc), order, int(backward)))

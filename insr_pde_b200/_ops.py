@@ -69,8 +69,16 @@ def out_shapes(desc, n, order):
     return shapes
 
 
-def siren_forward(desc, theta, x, order):
-    """theta: flat (P,), x: (N, D) -> tuple (y[, jac[, h2]])"""
+def _tape_desc(desc):
+    return _lib.make_desc(desc.in_features, desc.out_features, desc.hidden_features, desc.num_hidden_layers, desc.omega,
+                          desc.flags | _lib.FLAG_KEEP_TAPE)
+
+
+def siren_forward(desc, theta, x, order, keep_tape=False):
+    """theta: flat (P,), x: (N, D) -> tuple (y[, jac[, h2]]).
+    ``keep_tape=True`` (a forward whose backward will follow): returns ``(outs, tape)`` where ``tape`` is the workspace
+    holding the activations of every layer, to be handed to ``siren_backward(..., tape=tape)``, or None where the kernel
+    family keeps no tape (H <= 32: recomputed in registers; batches beyond one workspace chunk)."""
     lib = _lib.get_lib()
     _require_cuda(x)
     x = _check_input(x, "x")
@@ -82,20 +90,27 @@ def siren_forward(desc, theta, x, order):
         raise ValueError(f"theta has {theta.numel()} elements, expected {lib.theta_size(desc)}")
     outs = [torch.empty(s, dtype=torch.float32, device=x.device) for s in out_shapes(desc, n, order)]
     if n == 0:
-        return tuple(outs)
+        return (tuple(outs), None) if keep_tape else tuple(outs)
+    tape = None
     with _DeviceGuard(x.device):
-        ws, nb = _workspace(lib.workspace_bytes(desc, n, order, False), x.device)
+        taped = keep_tape and lib.tape_supported(desc, n, order)
+        if taped:
+            desc = _tape_desc(desc)
+        ws, nb = _workspace(lib.workspace_bytes(desc, n, order, taped), x.device)
         y = outs[0]
         jac = outs[1] if order >= ORDER_JAC else None
         h2 = outs[2] if order >= ORDER_LAP else None
         lib.forward(desc, theta.data_ptr(), x.data_ptr(), n, order, y.data_ptr(), _ptr(jac), _ptr(h2),
                     _ptr(ws), nb, _stream(x.device))
-    return tuple(outs)
+        if taped:
+            tape = (ws, nb)
+    return (tuple(outs), tape) if keep_tape else tuple(outs)
 
 
-def siren_backward(desc, theta, x, order, gy=None, gjac=None, gh2=None, need_gx=False, gtheta=None):
+def siren_backward(desc, theta, x, order, gy=None, gjac=None, gh2=None, need_gx=False, gtheta=None, tape=None):
     """returns (gtheta flat (P,), gx (N, D) or None).  If ``gtheta`` is given the parameter
-    gradient is accumulated into it (it must be a flat fp32 buffer of P elements)."""
+    gradient is accumulated into it (it must be a flat fp32 buffer of P elements).  ``tape``: what
+    ``siren_forward(..., keep_tape=True)`` returned for the same (desc, theta, x, order) -- skips the recomputation."""
     lib = _lib.get_lib()
     _require_cuda(x)
     x = _check_input(x, "x")
@@ -111,7 +126,11 @@ def siren_backward(desc, theta, x, order, gy=None, gjac=None, gh2=None, need_gx=
     if n == 0:
         return gtheta, gx
     with _DeviceGuard(x.device):
-        ws, nb = _workspace(lib.workspace_bytes(desc, n, order, True), x.device)
+        if tape is not None:
+            desc = _tape_desc(desc)
+            ws, nb = tape
+        else:
+            ws, nb = _workspace(lib.workspace_bytes(desc, n, order, True), x.device)
         lib.backward(desc, theta.data_ptr(), x.data_ptr(), n, order, _ptr(gy), _ptr(gjac), _ptr(gh2),
                      gtheta.data_ptr(), _ptr(gx), _ptr(ws), nb, _stream(x.device))
     return gtheta, gx

@@ -200,6 +200,15 @@ int insr_siren_kernel_family(const insr_siren_desc *desc, int order, int backwar
     return insr_tiled_supported(dm, order) ? 2 : 0;
 }
 
+int insr_siren_tape_supported(const insr_siren_desc *desc, int64_t n_points, int order) {
+    SirenDims dm;
+    int rc = validate(desc, n_points, order, &dm);
+    if (rc) return rc;
+    if (desc->flags & INSR_FLAG_FORCE_GENERIC) return 0;
+    if (insr_fused_supported(dm, order, 1) || !insr_tiled_supported(dm, order)) return 0;
+    return insr_tiled_tape_fits(dm, n_points, order) ? 1 : 0;
+}
+
 size_t insr_siren_workspace_bytes(const insr_siren_desc *desc, int64_t n_points, int order, int backward) {
     SirenDims dm;
     if (validate(desc, n_points, order, &dm)) return 0;
@@ -234,8 +243,16 @@ int insr_siren_forward(const insr_siren_desc *desc, const float *theta, const fl
         return check_cuda("fused forward");
     }
     if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_tiled_supported(dm, order)) {
+        const bool keep = (desc->flags & INSR_FLAG_KEEP_TAPE) != 0;
+        if (keep) {
+            if (!insr_tiled_tape_fits(dm, n_points, order))
+                return fail(INSR_ERR_UNSUPPORTED, "KEEP_TAPE: %lld points do not fit one workspace chunk", (long long)n_points);
+            const size_t need_b = insr_siren_workspace_bytes(desc, n_points, order, 1);
+            if (workspace_bytes < need_b)
+                return fail(INSR_ERR_WORKSPACE, "KEEP_TAPE forward needs the backward workspace (%zu bytes), got %zu", need_b, workspace_bytes);
+        }
         rc = insr_tiled_forward(dm, order, theta, x, n_points, y, jac, h2, (float *)workspace, stream, &g_launches,
-                                !(desc->flags & INSR_FLAG_NO_TENSOR));
+                                !(desc->flags & INSR_FLAG_NO_TENSOR), keep);
         if (rc) return fail(rc, "tiled forward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
         return check_cuda("tiled forward");
     }
@@ -266,8 +283,11 @@ int insr_siren_backward(const insr_siren_desc *desc, const float *theta, const f
         return check_cuda("fused backward");
     }
     if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_tiled_supported(dm, order)) {
+        const bool have_tape = (desc->flags & INSR_FLAG_KEEP_TAPE) != 0;
+        if (have_tape && !insr_tiled_tape_fits(dm, n_points, order))
+            return fail(INSR_ERR_UNSUPPORTED, "KEEP_TAPE: %lld points do not fit one workspace chunk", (long long)n_points);
         rc = insr_tiled_backward(dm, order, theta, x, n_points, gy, gjac, gh2, gtheta, gx, (float *)workspace, stream,
-                                 &g_launches, !(desc->flags & INSR_FLAG_NO_TENSOR));
+                                 &g_launches, !(desc->flags & INSR_FLAG_NO_TENSOR), have_tape);
         if (rc) return fail(rc, "tiled backward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
         return check_cuda("tiled backward");
     }

@@ -536,6 +536,8 @@ __global__ void __launch_bounds__(NT) k_tiled_wgrad(SirenDims dm, int HP, int S,
 //   gWo[o][j] += sum_p sum_s G[o][s][p] actL[s][p][j],                      gbo[o] += sum_p G[o][0][p]
 // One thread per neuron j (coalesced over j), each CTA reduces a slice of points, then red.global.
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int edge_lanes(int H) { const int w = (H + 31) & ~31; return w < 128 ? w : 128; }
+
 template <int D, int O, int ORDER>
 __global__ void __launch_bounds__(NT) k_tiled_edge(SirenDims dm, int HP, const float *__restrict__ x, int64_t n0,
                                                    int nv, int64_t NCp, const float *__restrict__ ZB0,
@@ -543,16 +545,19 @@ __global__ void __launch_bounds__(NT) k_tiled_edge(SirenDims dm, int HP, const f
                                                    int pslice, float *__restrict__ gtheta) {
     typedef StreamCfg<D, ORDER> C;
     constexpr int S = C::S;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    // JW lanes over the neurons, NT / JW groups of lanes striding through the CTA's slice of points
+    const int JW = edge_lanes(dm.H), nsub = NT / JW;
+    const int j = blockIdx.x * JW + (int)threadIdx.x % JW, sub = (int)threadIdx.x / JW;
     const int p_begin = blockIdx.y * pslice;
     const int p_end = (p_begin + pslice < nv) ? (p_begin + pslice) : nv;
-    if (j < dm.H) {
+    if (j < dm.H && sub < nsub) {
         float gw1[D], gb1 = 0.f, gwo[O];
         INSR_PRAGMA_UNROLL
         for (int d = 0; d < D; ++d) gw1[d] = 0.f;
         INSR_PRAGMA_UNROLL
         for (int o = 0; o < O; ++o) gwo[o] = 0.f;
-        for (int p = p_begin; p < p_end; ++p) {
+        INSR_PRAGMA_UNROLL_N(unroll 4)
+        for (int p = p_begin + sub; p < p_end; p += nsub) {
             const float z0 = ZB0[(int64_t)p * HP + j];
             gb1 += z0;
             INSR_PRAGMA_UNROLL
@@ -608,10 +613,74 @@ __global__ void __launch_bounds__(NT) k_tiled_gx(SirenDims dm, int HP, const flo
 
 // (host-side sizing helpers live in siren_tiled_api.h)
 
+// the forward sweep that leaves the tape (pre-activations and activations of every sine layer) in the backward
+// workspace layout: Zpre[l], Act[l] = [stream][NCp][HP] for l = 0..L
+template <int D, int ORDER>
+void taped_forward(const SirenDims &dm, const Geo &g, const float *theta, const float *x, int64_t n0, int nv, int64_t NCp,
+                   int64_t rows, size_t buf, float *Zpre, float *Act, void *stream, int64_t *launches, bool tensor) {
+    constexpr int S = StreamCfg<D, ORDER>::S;
+    (void)S;
+    const int64_t items = rows * (g.HP / 4);
+    const unsigned eg = (unsigned)((items + NT - 1) / NT);
+    const size_t smem = gemm_smem_floats(g) * sizeof(float);
+    auto kfwd = k_tiled_fwd<D, ORDER>;
+    auto k0 = k_tiled_layer0<D, ORDER>;
+    INSR_LAUNCH(k0, dim3(eg), dim3(NT), 0, stream, dm, g.HP, theta, x, n0, nv, NCp, Zpre, Act);
+    ++*launches;
+    for (int l = 1; l <= dm.L; ++l) {
+#ifndef INSR_CPU_EMU
+        if constexpr (S <= 4) {
+            if (tensor) {
+                insr_wide::launch_wide<D, ORDER, 0>(dm, theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l),
+                                                    Act + (size_t)(l - 1) * buf, NCp, rows, nullptr, Zpre + (size_t)l * buf,
+                                                    Act + (size_t)l * buf, stream, launches);
+                continue;
+            }
+        }
+#endif
+        INSR_LAUNCH(kfwd, dim3((unsigned)(rows / g.BP), g.panels), dim3(NT), smem, stream, dm, g,
+                    theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l), Act + (size_t)(l - 1) * buf, NCp,
+                    Zpre + (size_t)l * buf, Act + (size_t)l * buf);
+        ++*launches;
+    }
+}
+
+// forward that keeps its tape for a following run_backward(..., have_tape = true) on the SAME workspace (the backward
+// layout and size); only for batches of one workspace chunk (tape_fits)
+template <int D, int O, int ORDER>
+int run_forward_tape(const SirenDims &dm, const float *theta, const float *x, int64_t N, float *y, float *jac,
+                     float *h2, float *ws, void *stream, int64_t *launches, bool tensor) {
+    constexpr int S = StreamCfg<D, ORDER>::S;
+#ifdef INSR_CPU_EMU
+    tensor = false;
+#else
+    tensor = tensor && S <= 4;
+#endif
+    constexpr int TP = Tile<S>::TP;
+    const Geo g = make_geo(dm.H, S, TP);
+    const int64_t chunk = chunk_points(dm, S, true, N);
+    if (N > chunk) return -6;
+    const int64_t NCp = capacity(chunk);
+    const size_t buf = (size_t)S * NCp * g.HP;
+    float *Zpre = ws, *Act = ws + (size_t)(dm.L + 1) * buf;
+    const size_t smem = gemm_smem_floats(g) * sizeof(float);
+    auto kfwd = k_tiled_fwd<D, ORDER>;
+    cudaFuncSetAttribute(kfwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int nv = (int)N;
+    const int64_t rows = round_up(nv, tensor ? 128 : g.BP);
+    taped_forward<D, ORDER>(dm, g, theta, x, 0, nv, NCp, rows, buf, Zpre, Act, stream, launches, tensor);
+    auto ko = k_tiled_out_fwd<D, O, ORDER>;
+    INSR_LAUNCH(ko, dim3((unsigned)(((int64_t)nv * 32 + NT - 1) / NT)), dim3(NT), 0, stream, dm, g.HP, theta,
+                Act + (size_t)dm.L * buf, NCp, (int64_t)0, nv, y, jac, h2);
+    ++*launches;
+    return 0;
+}
+
 template <int D, int O, int ORDER>
 int run_forward(const SirenDims &dm, const float *theta, const float *x, int64_t N, float *y, float *jac,
-                float *h2, float *ws, void *stream, int64_t *launches, bool tensor) {
+                float *h2, float *ws, void *stream, int64_t *launches, bool tensor, bool tape) {
     constexpr int S = StreamCfg<D, ORDER>::S;
+    if (tape) return run_forward_tape<D, O, ORDER>(dm, theta, x, N, y, jac, h2, ws, stream, launches, tensor);
 #ifdef INSR_CPU_EMU
     tensor = false;
 #else
@@ -662,7 +731,7 @@ int run_forward(const SirenDims &dm, const float *theta, const float *x, int64_t
 template <int D, int O, int ORDER>
 int run_backward(const SirenDims &dm, const float *theta, const float *x, int64_t N, const float *gy,
                  const float *gjac, const float *gh2, float *gtheta, float *gx, float *ws, void *stream,
-                 int64_t *launches, bool tensor) {
+                 int64_t *launches, bool tensor, bool have_tape) {
     constexpr int S = StreamCfg<D, ORDER>::S;
 #ifdef INSR_CPU_EMU
     tensor = false;
@@ -688,31 +757,14 @@ int run_backward(const SirenDims &dm, const float *theta, const float *x, int64_
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
+    if (have_tape && N > chunk) return -6;
     for (int64_t n0 = 0; n0 < N; n0 += chunk) {
         const int nv = (int)((N - n0 < chunk) ? (N - n0) : chunk);
         const int64_t rows = round_up(nv, tensor ? 128 : g.BP);
         const int64_t items = rows * (g.HP / 4);
         const unsigned eg = (unsigned)((items + NT - 1) / NT);
-        // ---- forward with tape
-        auto k0 = k_tiled_layer0<D, ORDER>;
-        INSR_LAUNCH(k0, dim3(eg), dim3(NT), 0, stream, dm, g.HP, theta, x, n0, nv, NCp, Zpre, Act);
-        ++*launches;
-        for (int l = 1; l <= L; ++l) {
-#ifndef INSR_CPU_EMU
-            if constexpr (S <= 4) {
-                if (tensor) {
-                    insr_wide::launch_wide<D, ORDER, 0>(dm, theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l),
-                                                        Act + (size_t)(l - 1) * buf, NCp, rows, nullptr, Zpre + (size_t)l * buf,
-                                                        Act + (size_t)l * buf, stream, launches);
-                    continue;
-                }
-            }
-#endif
-            INSR_LAUNCH(kfwd, dim3((unsigned)(rows / g.BP), g.panels), dim3(NT), smem, stream, dm, g,
-                        theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l), Act + (size_t)(l - 1) * buf, NCp,
-                        Zpre + (size_t)l * buf, Act + (size_t)l * buf);
-            ++*launches;
-        }
+        // ---- forward with tape (skipped when the caller kept the tape of its forward call in this workspace)
+        if (!have_tape) taped_forward<D, ORDER>(dm, g, theta, x, n0, nv, NCp, rows, buf, Zpre, Act, stream, launches, tensor);
         // ---- output layer backward -> zbar_L
         auto kob = k_tiled_out_bwd<D, O, ORDER>;
         INSR_LAUNCH(kob, dim3(eg), dim3(NT), 0, stream, dm, g.HP, theta, gy, gjac, gh2, n0, nv, NCp,
@@ -758,10 +810,11 @@ int run_backward(const SirenDims &dm, const float *theta, const float *x, int64_
             float *t = zin; zin = zout; zout = t;
         }
         // ---- thin layers + gx  (zin now holds zbar_0)
-        int pslice = (nv + 2 * sms - 1) / (2 * sms);
-        if (pslice < 64) pslice = 64;
+        const int jw = edge_lanes(dm.H);
+        int pslice = (nv + 4 * sms - 1) / (4 * sms);
+        if (pslice < 8 * (NT / jw)) pslice = 8 * (NT / jw);
         auto ke = k_tiled_edge<D, O, ORDER>;
-        INSR_LAUNCH(ke, dim3((dm.H + NT - 1) / NT, (nv + pslice - 1) / pslice), dim3(NT), 0, stream, dm, g.HP, x, n0,
+        INSR_LAUNCH(ke, dim3((dm.H + jw - 1) / jw, (nv + pslice - 1) / pslice), dim3(NT), 0, stream, dm, g.HP, x, n0,
                     nv, NCp, zin, Act + (size_t)L * buf, G, pslice, gtheta);
         ++*launches;
         if (gx) {

@@ -34,10 +34,16 @@ inline size_t ws_bytes(const SirenDims &dm, int order, bool bwd, int64_t N) {
 // non-template entry points, defined in siren_tiled_inst.cuh (own translation unit under nvcc)
 // tensor = true: hidden-layer GEMMs (forward + data gradient) on tcgen05 where the shape allows (siren_wide_tc.cuh)
 int insr_tiled_forward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N, float *y,
-                       float *jac, float *h2, float *ws, void *stream, int64_t *launches, bool tensor = false);
+                       float *jac, float *h2, float *ws, void *stream, int64_t *launches, bool tensor = false,
+                       bool keep_tape = false);
 int insr_tiled_backward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
                         const float *gy, const float *gjac, const float *gh2, float *gtheta, float *gx, float *ws,
-                        void *stream, int64_t *launches, bool tensor = false);
+                        void *stream, int64_t *launches, bool tensor = false, bool have_tape = false);
+// keep_tape / have_tape: the forward leaves its tape in the (backward-sized) workspace and the backward call on the same
+// workspace skips the recomputation; possible when the batch is a single workspace chunk
+inline bool insr_tiled_tape_fits(const SirenDims &dm, int64_t N, int order) {
+    return N <= insr_tiled::chunk_points(dm, insr_nstreams(dm.D, order), true, N);
+}
 inline bool insr_tiled_supported(const SirenDims &dm, int order) { return dm.H > 32 && dm.H <= 512 && order <= 3; }
 inline size_t insr_tiled_ws_bytes(const SirenDims &dm, int64_t N, int order, int backward) {
     return insr_tiled::ws_bytes(dm, order, backward != 0, N);

@@ -7,14 +7,14 @@
 #define INSR_TILED_ALL(CALL) INSR_TILED_ORD(1, CALL) INSR_TILED_ORD(2, CALL) INSR_TILED_ORD(3, CALL)
 
 int insr_tiled_forward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N, float *y,
-                       float *jac, float *h2, float *ws, void *stream, int64_t *launches, bool tensor) {
-    INSR_TILED_ALL((insr_tiled::run_forward<D, O, ORDER>(dm, theta, x, N, y, jac, h2, ws, stream, launches, tensor)))
+                       float *jac, float *h2, float *ws, void *stream, int64_t *launches, bool tensor, bool keep_tape) {
+    INSR_TILED_ALL((insr_tiled::run_forward<D, O, ORDER>(dm, theta, x, N, y, jac, h2, ws, stream, launches, tensor, keep_tape)))
     return -6;
 }
 int insr_tiled_backward(const SirenDims &dm, int order, const float *theta, const float *x, int64_t N,
                         const float *gy, const float *gjac, const float *gh2, float *gtheta, float *gx, float *ws,
-                        void *stream, int64_t *launches, bool tensor) {
-    INSR_TILED_ALL((insr_tiled::run_backward<D, O, ORDER>(dm, theta, x, N, gy, gjac, gh2, gtheta, gx, ws, stream, launches, tensor)))
+                        void *stream, int64_t *launches, bool tensor, bool have_tape) {
+    INSR_TILED_ALL((insr_tiled::run_backward<D, O, ORDER>(dm, theta, x, N, gy, gjac, gh2, gtheta, gx, ws, stream, launches, tensor, have_tape)))
     return -6;
 }
 

@@ -479,30 +479,36 @@ __global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int
     __syncthreads();
     if (tid < 128 && tid < H && bsumS[tid] != 0.f) atomicAdd(gb + tid, dm.omega * bsumS[tid]);
     if (nstages > 0) {
-        float *tile = reinterpret_cast<float *>(sm);             // 64 x 64 floats (operand region is free)
-        const int m = 32 * (warp & 3) + lane;                    // accumulator row: level (m >> 6), neuron (m & 63)
+        // every (neuron j, input k) of a block has four partial sums -- (level of z) x (level of a) -- held by four
+        // different warps: each warp parks its 32 x 32 piece in its own padded slab (no atomics, no bank conflicts),
+        // then all threads add the four pieces and issue ONE global reduction per element.
+        float *piece = reinterpret_cast<float *>(sm);            // [8 warps][32 rows][33] floats (operand region is free)
         const int half = warp >> 2;                              // columns 64 half .. + 63: level of `a`
-        const uint32_t trow = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+        const uint32_t trow = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);   // rows: level of z (warp & 2), neurons 32 (warp & 1) ..
         for (int jb = 0; jb < NBJ; ++jb)
-            for (int kb = 0; kb < NBJ; ++kb) {
-                for (int idx = tid; idx < 64 * 64; idx += WGT) tile[idx] = 0.f;
-                __syncthreads();
-                INSR_PRAGMA_UNROLL
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    float v[8];
-                    insr_tc::tmem_ld8(trow + (uint32_t)((jb * NBJ + kb) * 128 + 64 * half + 8 * c8), v);
-                    insr_tc::tmem_ld_wait();
+            for (int kb = 0; kb < NBJ; ++kb)
+                for (int cc = 0; cc < 2; ++cc) {                 // 32 input columns at a time
                     INSR_PRAGMA_UNROLL
-                    for (int i = 0; i < 8; ++i) atomicAdd(tile + (m & 63) * 64 + 8 * c8 + i, v[i]);
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        float v[8];
+                        insr_tc::tmem_ld8(trow + (uint32_t)((jb * NBJ + kb) * 128 + 64 * half + 32 * cc + 8 * c8), v);
+                        insr_tc::tmem_ld_wait();
+                        INSR_PRAGMA_UNROLL
+                        for (int i = 0; i < 8; ++i) piece[(warp * 32 + lane) * 33 + 8 * c8 + i] = v[i];
+                    }
+                    __syncthreads();
+                    for (int idx = tid; idx < 64 * 32; idx += WGT) {
+                        const int jl = idx >> 5, kl = idx & 31;
+                        const int j = jb * 64 + jl, k = kb * 64 + 32 * cc + kl;
+                        if (j < H && k < H) {
+                            const int wq = jl >> 5, rr = (jl & 31) * 33 + kl;      // warp & 1, row inside the piece
+                            const float v = (piece[(wq + 0) * 32 * 33 + rr] + piece[(wq + 2) * 32 * 33 + rr]) +
+                                            (piece[(wq + 4) * 32 * 33 + rr] + piece[(wq + 6) * 32 * 33 + rr]);
+                            if (v != 0.f) atomicAdd(gW + (size_t)j * H + k, dm.omega * v);
+                        }
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
-                for (int idx = tid; idx < 64 * 64; idx += WGT) {
-                    const int j = jb * 64 + (idx >> 6), k = kb * 64 + (idx & 63);
-                    const float v = tile[idx];
-                    if (j < H && k < H && v != 0.f) atomicAdd(gW + (size_t)j * H + k, dm.omega * v);
-                }
-                __syncthreads();
-            }
     }
     insr_tc::tc_fence_before();
     __syncthreads();

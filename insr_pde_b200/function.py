@@ -33,7 +33,13 @@ class SirenFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, net, order, *params):
         theta = net.flat_theta()
-        outs = _ops.siren_forward(net.desc, theta, x, order)
+        # a forward that will be differentiated w.r.t. the parameters keeps its tape (the 32 < H <= 512 family would
+        # otherwise recompute every hidden layer in the reverse sweep); frozen nets and no_grad calls do not
+        want_tape = any(ctx.needs_input_grad[3:])
+        if want_tape:
+            outs, ctx.tape = _ops.siren_forward(net.desc, theta, x, order, keep_tape=True)
+        else:
+            outs, ctx.tape = _ops.siren_forward(net.desc, theta, x, order), None
         ctx.net, ctx.order, ctx.theta = net, order, theta
         ctx.save_for_backward(x, *params)
         ctx.set_materialize_grads(False)
@@ -71,7 +77,8 @@ class SirenFn(torch.autograd.Function):
 
         # ---- ordinary backward: one fused reverse kernel
         need_gx = ctx.needs_input_grad[0]
-        gtheta, gx = _ops.siren_backward(net.desc, ctx.theta, x, order, gy, gjac, gh2, need_gx=need_gx)
+        gtheta, gx = _ops.siren_backward(net.desc, ctx.theta, x, order, gy, gjac, gh2, need_gx=need_gx, tape=ctx.tape)
+        ctx.tape = None                                   # the reverse kernels overwrite parts of it
         grads = []
         for (off, numel, shape), need in zip(net.param_slices(), ctx.needs_input_grad[1 + n_extra:]):
             grads.append(gtheta[off:off + numel].view(shape) if need else None)

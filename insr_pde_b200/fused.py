@@ -193,19 +193,35 @@ def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_le
     reference's elementwise expressions."""
     from . import function, linalg
     samples = samples.detach().reshape(-1, deformation.in_features).contiguous()
-    q_prev = evaluate(prev, samples, ORDER_VALUE)[0] + samples
-    q_pp = evaluate(prev_prev, samples, ORDER_VALUE)[0] + samples
+    n = samples.shape[0]
     ra = ratio_arap if "arap" in energy else 0.0
     rv = ratio_volume if "volume" in energy else 0.0
+    # the clamped faces ride along with the interior batch (+1..2 % points) instead of costing two more forward /
+    # reverse kernel chains of their own: rows [n, n + n_left) and [n + n_left, ...) of the same evaluation
+    use_left = "constraint" in energy and torch.is_tensor(fixed_left)
+    use_right = ("constraint_right" in energy or "constraint_right_compress" in energy) and torch.is_tensor(fixed_right)
+    extra = ([fixed_left.detach()] if use_left else []) + ([fixed_right.detach()] if use_right else [])
+    x_all = torch.cat([samples] + [e.reshape(-1, samples.shape[1]).to(samples.dtype) for e in extra], dim=0) if extra else samples
+    n_left = extra[0].shape[0] if use_left else 0
+
     # value and Jacobian of the trainable field from ONE order-1 kernel (and one reverse kernel for both cotangents);
-    # jacobian(net(x) + x, x) = J + I, so the points themselves need no gradient and no NaN-status host sync happens
-    outs = function.evaluate(deformation, samples, ORDER_JAC if (ra or rv) else ORDER_VALUE)
-    q = outs[0] + samples
+    # jacobian(net(x) + x, x) = J + I, so the points need no gradient and no NaN-status host sync happens.  The two
+    # frozen previous-frame evaluations are independent of it: side streams (a fork / join under graph capture).
+    outs, y_prev, y_pp = parallel(samples,
+                                  lambda: function.evaluate(deformation, x_all, ORDER_JAC if (ra or rv) else ORDER_VALUE),
+                                  lambda: evaluate(prev, samples, ORDER_VALUE)[0],
+                                  lambda: evaluate(prev_prev, samples, ORDER_VALUE)[0])
+    if samples.is_cuda and not torch.cuda.is_current_stream_capturing():
+        for t in (y_prev, y_pp):
+            t.record_stream(torch.cuda.current_stream(samples.device))
+    q_prev, q_pp = y_prev + samples, y_pp + samples
+    y_all = outs[0]
+    q = y_all[:n] + samples
     qdot = (q - q_prev) / dt
     qdot_prev = (q_prev - q_pp) / dt
     loss = 0
     if ra or rv:
-        F = outs[1] + torch.eye(samples.shape[1], device=samples.device, dtype=samples.dtype)
+        F = outs[1][:n] + torch.eye(samples.shape[1], device=samples.device, dtype=samples.dtype)
         loss = loss + linalg.elastic_energy(F, ra, rv)
     for term in energy:
         if term in ("arap", "volume"):
@@ -216,10 +232,10 @@ def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_le
             if timestep <= external_force_timesteps:
                 loss = loss - dt * torch.sum(qdot * external_force.reshape(1, -1))
         elif term == "constraint":
-            loss = loss + ratio_constraint * torch.sum(deformation(fixed_left) ** 2)
+            loss = loss + ratio_constraint * torch.sum(y_all[n:n + n_left] ** 2)
         elif term in ("constraint_right", "constraint_right_compress"):
             sign = 1.0 if term == "constraint_right" else -1.0
-            loss = loss + ratio_constraint * torch.sum((deformation(fixed_right) - sign * constraint_offset_right.reshape(1, -1)) ** 2)
+            loss = loss + ratio_constraint * torch.sum((y_all[n + n_left:] - sign * constraint_offset_right.reshape(1, -1)) ** 2)
         elif term == "collision":                                  # elasticity/losses.py:10-20, masked instead of gathered
             hit = (q[:, -1] < plane_height).to(q.dtype)
             loss = loss - dt * ratio_collide * torch.sum(hit * qdot[:, -1] * (plane_height - q[:, -1]))

@@ -129,6 +129,47 @@ def test_tiled_family_under_emulation(emu_library, case):
     run_case(emu_library, *case)
 
 
+@pytest.mark.parametrize("case", [(2, 2, 68, 3, 150, 1), (3, 1, 40, 2, 70, 2), (2, 1, 130, 1, 33, 0)])
+def test_tiled_forward_keeps_tape_for_backward(emu_library, case):
+    """INSR_FLAG_KEEP_TAPE: the forward leaves the activations of every layer in the backward-sized workspace and the
+    backward on the same workspace skips the recomputation -- same outputs and the same gradients as the plain pair;
+    refused (tape_supported == 0) for the H <= 32 family"""
+    lib = emu_library
+    D, O, H, L, N, order = case
+    rng = np.random.default_rng(11)
+    theta = make_theta(rng, D, O, H, L)
+    x = rng.uniform(-1, 1, (N, D)).astype(np.float32)
+    gy = rng.standard_normal((N, O)).astype(np.float32)
+    gj = rng.standard_normal((N, O, D)).astype(np.float32)
+    gh = rng.standard_normal((N, O)).astype(np.float32)
+    res = {}
+    for keep in (False, True):
+        desc = _lib.make_desc(D, O, H, L, flags=_lib.FLAG_KEEP_TAPE if keep else 0)
+        assert lib.tape_supported(desc, N, order)
+        y = np.full((N, O), np.nan, np.float32); jac = np.full((N, O, D), np.nan, np.float32); h2 = np.full((N, O), np.nan, np.float32)
+        nb_b = lib.workspace_bytes(desc, N, order, True)
+        ws = np.zeros(nb_b // 4 + 8, np.float32)
+        nb_f = nb_b if keep else lib.workspace_bytes(desc, N, order, False)
+        lib.forward(desc, ptr(theta), ptr(x), N, order, ptr(y), ptr(jac) if order >= 1 else None, ptr(h2) if order >= 2 else None,
+                    ptr(ws), nb_f, None)
+        if not keep:
+            ws[:] = 0                                   # the plain backward recomputes: nothing of the forward is needed
+        gth = np.zeros(theta.size, np.float32); gx = np.full((N, D), np.nan, np.float32)
+        lib.backward(desc, ptr(theta), ptr(x), N, order, ptr(gy), ptr(gj) if order >= 1 else None, ptr(gh) if order >= 2 else None,
+                     ptr(gth), ptr(gx), ptr(ws), nb_b, None)
+        res[keep] = (y, jac if order >= 1 else None, h2 if order >= 2 else None, gth, gx)
+    for a, b in zip(res[False], res[True]):
+        if a is not None:
+            assert np.array_equal(a, b)
+    # a forward with the flag but only the forward-sized workspace is refused, loudly
+    desc = _lib.make_desc(D, O, H, L, flags=_lib.FLAG_KEEP_TAPE)
+    nb_f = lib.workspace_bytes(_lib.make_desc(D, O, H, L), N, order, False)
+    with pytest.raises(RuntimeError, match="KEEP_TAPE"):
+        lib.forward(desc, ptr(theta), ptr(x), N, order, ptr(res[True][0]), ptr(gj) if order >= 1 else None, ptr(gh) if order >= 2 else None,
+                    ptr(ws), nb_f, None)
+    assert not lib.tape_supported(_lib.make_desc(2, 1, 32, 3), N, 2)
+
+
 def test_family_dispatch_rules(emu_library):
     fam = emu_library.kernel_family
     assert fam(_lib.make_desc(2, 1, 32, 3), 2, True) == 1

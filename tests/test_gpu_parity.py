@@ -475,6 +475,54 @@ def test_box_sampler_on_device_and_under_graph_replay():
     assert int(s.counter) == 1 + 3
 
 
+@pytest.mark.parametrize("case", [(2, 2, 68, 3, 20400, 1), (3, 3, 66, 3, 999, 1), (2, 1, 128, 3, 5000, 2), (2, 1, 256, 2, 300, 2)])
+def test_autograd_forward_keeps_its_tape_for_the_reverse_sweep(case):
+    """32 < H <= 512 family: SirenFn.forward of a trainable net keeps the layer activations (INSR_FLAG_KEEP_TAPE) and the
+    reverse sweep starts from them -- fewer launches, the gradients of the recomputing path; frozen nets
+    and no_grad evaluations keep nothing"""
+    from insr_pde_b200 import function
+    D, O, H, L, N, order = case
+    torch.manual_seed(N)
+    net = ib.MLP(D, O, L, H, nonlinearity="sine").cuda()
+    x = torch.rand(N, D, device="cuda") * 2 - 1
+    lib = _lib.get_lib()
+    assert lib.tape_supported(net.desc, N, order)
+    cots = None
+    grads, launches = {}, {}
+    for keep in (True, False):
+        net.zero_grad()
+        if keep:
+            outs = function.evaluate(net, x, order)
+        else:                                   # the plain pair through _ops (what the Function did before)
+            outs = _ops.siren_forward(net.desc, net.flat_theta(), x, order)
+        if cots is None:
+            cots = [torch.randn_like(o) for o in outs]
+        lib.launch_count(reset=True)
+        if keep:
+            torch.autograd.backward(list(outs), cots)
+            launches[keep] = lib.launch_count()
+            grads[keep] = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
+        else:
+            g, _ = _ops.siren_backward(net.desc, net.flat_theta(), x, order, *cots)
+            launches[keep] = lib.launch_count()
+            grads[keep] = g
+    assert rel(grads[True], grads[False]) < 2e-5             # same arithmetic; the global reductions are unordered
+    # launch counts are per host thread (autograd's reverse sweep runs on its own): count through the direct calls
+    outs_t, tape = _ops.siren_forward(net.desc, net.flat_theta(), x, order, keep_tape=True)
+    assert tape is not None and all(torch.equal(a, b) for a, b in zip(outs_t, outs))
+    lib.launch_count(reset=True)
+    g_t, _ = _ops.siren_backward(net.desc, net.flat_theta(), x, order, *cots, tape=tape)
+    assert lib.launch_count() == launches[False] - (L + 1)      # layer 0 + L hidden layers not recomputed
+    assert rel(g_t, grads[False]) < 2e-5
+    frozen = ib.MLP(D, O, L, H, nonlinearity="sine").cuda()
+    for p in frozen.parameters():
+        p.requires_grad_(False)
+    node = function.evaluate(frozen, x, order)[0]
+    assert node.grad_fn is None
+    # beyond one workspace chunk the flag is not offered
+    assert not lib.tape_supported(_lib.make_desc(2, 1, 512, 5), 1 << 22, 2)
+
+
 def _elastic_nets(seed, dim, H):
     torch.manual_seed(seed)
     defo = ib.MLP(dim, dim, 3, H, nonlinearity="sine").cuda()

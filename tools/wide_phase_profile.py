@@ -1,5 +1,5 @@
 """Phase timing of k_wide_tc (library built with -DINSR_WIDE_PROFILE): cycles per phase of warp 1, per 128-point tile.
-usage: python tools/wide_phase_profile.py [workload] [points]"""
+usage: python tools/wide_phase_profile.py [workload] [points] [order]"""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,6 +10,8 @@ from insr_pde_b200 import _lib, _ops
 wl = sys.argv[1] if len(sys.argv) > 1 else "elasticity2Dstretch"
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
 D, O, H, L, order, _ = bench.WORKLOADS[wl]
+if len(sys.argv) > 3:
+    order = int(sys.argv[3])
 torch.manual_seed(0)
 net = ib.MLP(D, O, L, H, nonlinearity="sine").cuda()
 theta = net.flat_theta()
