@@ -162,6 +162,29 @@ int insr_elastic_energy(const float *F, int64_t n, int d, float ratio_arap, floa
                         float *gF, void *stream);
 
 /*
+ * The whole loss of ElasticityModel._solve_deformation (elasticity/model.py:127-189 with elasticity/losses.py:6-39) and
+ * its cotangents w.r.t. the trainable field's outputs, in one kernel.  Rows [0, n) are the interior samples (value y,
+ * Jacobian J of the field, points x, the two previous-frame fields' values); rows [n, n + n_left) the clamped left face
+ * (ratio_constraint |y|^2); rows [n + n_left, n + n_left + n_right) the right face (ratio_constraint |y - offset_right|^2,
+ * offset carrying the sign of 'constraint_right' / 'constraint_right_compress').  A ratio of zero switches a term off;
+ * external_force must be zeroed by the caller once timestep > external_force_timesteps (model.py:155).
+ * The sphere term is the 2-D form of losses.py:22-39 (force = ratio * (q - center)); the reference's 3-D form broadcasts
+ * (M,1,1) * (M,3) into an (M,M,3) product and is not offered here.
+ * loss: device scalar, ACCUMULATED.  gy (n_all, d), gJ (n_all, d, d; may be NULL when r_arap = r_volume = 0): overwritten.
+ */
+typedef struct insr_elastic_terms_desc {
+    int64_t n, n_left, n_right;
+    float dt;
+    float r_arap, r_volume, r_kinematics;
+    float r_left, r_right;
+    float r_plane, plane_height;
+    float r_sphere, radius;
+    float external_force[3], offset_right[3], center[3];
+} insr_elastic_terms_desc;
+int insr_elastic_terms(const insr_elastic_terms_desc *t, int d, const float *y, const float *J, const float *x,
+                       const float *y_prev, const float *y_pp, float *loss, float *gy, float *gJ, void *stream);
+
+/*
  * All collocation-point sets of one iteration in one kernel.  Replaces the torch.rand / scale / shift / cat sequences
  * of base/sampling.py:14-18 (sample_random) and :21-64 (sample_boundary, sample_boundary2D_separate): every set is
  * i.i.d. uniform in an axis-aligned box.  Box b holds count[b] points in [lo[b], hi[b])^dim (lo, hi: n_boxes x dim,

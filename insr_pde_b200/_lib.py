@@ -22,7 +22,7 @@ FLAG_KEEP_TAPE = 8
 EXPORTS = [
     "insr_version", "insr_last_error", "insr_siren_theta_size", "insr_siren_workspace_bytes",
     "insr_siren_forward", "insr_siren_backward", "insr_siren_lsq_step", "insr_siren_kernel_family",
-    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes", "insr_sample_mesh", "insr_siren_tape_supported",
+    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes", "insr_sample_mesh", "insr_siren_tape_supported", "insr_elastic_terms",
 ]
 
 
@@ -75,6 +75,8 @@ class Library:
         c.insr_svd_small.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp]
         c.insr_elastic_energy.restype = _i32
         c.insr_elastic_energy.argtypes = [_vp, _i64, _i32, _f, _f, _vp, _vp, _vp]
+        c.insr_elastic_terms.restype = _i32
+        c.insr_elastic_terms.argtypes = [ctypes.POINTER(ElasticTermsDesc), _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
         c.insr_sample_mesh.restype = _i32
         c.insr_sample_mesh.argtypes = [_vp, _vp, _vp, _i32, _i32, _i64, _i32, ctypes.c_uint64, _vp, _vp, _i64, _vp, _vp]
         c.insr_sample_boxes.restype = _i32
@@ -129,6 +131,9 @@ class Library:
         self.check(self.cdll.insr_sample_mesh(V, elem, cdf, n_elem, k, n, dim_out, seed, counter, ticket, point_offset,
                                               out, stream))
 
+    def elastic_terms(self, tdesc, d, y, J, x, y_prev, y_pp, loss, gy, gJ, stream):
+        self.check(self.cdll.insr_elastic_terms(ctypes.byref(tdesc), d, y, J, x, y_prev, y_pp, loss, gy, gJ, stream))
+
     def svd_small(self, F, n, d, U, S, V, stream):
         self.check(self.cdll.insr_svd_small(F, n, d, U, S, V, stream))
 
@@ -157,6 +162,14 @@ def get_lib() -> Library:
                     build.build_library()
                 _LIB = Library(LIB_PATH)
     return _LIB
+
+
+class ElasticTermsDesc(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int64), ("n_left", ctypes.c_int64), ("n_right", ctypes.c_int64), ("dt", ctypes.c_float),
+                ("r_arap", ctypes.c_float), ("r_volume", ctypes.c_float), ("r_kinematics", ctypes.c_float),
+                ("r_left", ctypes.c_float), ("r_right", ctypes.c_float), ("r_plane", ctypes.c_float),
+                ("plane_height", ctypes.c_float), ("r_sphere", ctypes.c_float), ("radius", ctypes.c_float),
+                ("external_force", ctypes.c_float * 3), ("offset_right", ctypes.c_float * 3), ("center", ctypes.c_float * 3)]
 
 
 def make_desc(in_features, out_features, hidden_features, num_hidden_layers, omega=30.0, flags=0):

@@ -221,3 +221,37 @@ def elastic_energy(F, ratio_arap, ratio_volume, need_grad=True):
             lib.elastic_energy(Fc.data_ptr(), n, d, float(ratio_arap), float(ratio_volume), E.data_ptr(), _ptr(gF),
                                _stream(F.device))
     return E, (gF.reshape(F.shape) if need_grad else None)
+
+
+def elastic_terms(y, J, x, y_prev, y_pp, n_left, n_right, *, dt, r_arap=0.0, r_volume=0.0, r_kinematics=0.0, r_left=0.0,
+                  r_right=0.0, r_plane=0.0, plane_height=0.0, r_sphere=0.0, radius=0.0, external_force=None,
+                  offset_right=None, center=None):
+    """every term of the elasticity closure and its cotangents in one kernel (include/insr_b200.h: insr_elastic_terms).
+    y (n + n_left + n_right, d), J (same rows, d, d) or None, x / y_prev / y_pp (n, d).  Returns (loss (1,), gy, gJ)."""
+    lib = _lib.get_lib()
+    _require_cuda(y)
+    d = y.shape[1]
+    n_all = y.shape[0]
+    n = n_all - n_left - n_right
+    y = _check_input(y, "y")
+    J = _check_input(J, "J", (n_all, d, d)) if J is not None else None
+    x = _check_input(x, "x", (n, d))
+    y_prev = _check_input(y_prev, "y_prev", (n, d))
+    y_pp = _check_input(y_pp, "y_pp", (n, d))
+    t = _lib.ElasticTermsDesc()
+    t.n, t.n_left, t.n_right, t.dt = n, n_left, n_right, float(dt)
+    t.r_arap, t.r_volume, t.r_kinematics = float(r_arap), float(r_volume), float(r_kinematics)
+    t.r_left, t.r_right, t.r_plane, t.plane_height = float(r_left), float(r_right), float(r_plane), float(plane_height)
+    t.r_sphere, t.radius = float(r_sphere), float(radius)
+    for name, vals in (("external_force", external_force), ("offset_right", offset_right), ("center", center)):
+        arr = getattr(t, name)
+        for i in range(3):
+            arr[i] = float(vals[i]) if vals is not None and i < len(vals) else 0.0
+    loss = torch.zeros(1, dtype=torch.float32, device=y.device)
+    gy = torch.empty_like(y)
+    gJ = torch.empty_like(J) if J is not None else None
+    if n_all:
+        with _DeviceGuard(y.device):
+            lib.elastic_terms(t, d, y.data_ptr(), _ptr(J), x.data_ptr(), y_prev.data_ptr(), y_pp.data_ptr(), loss.data_ptr(),
+                              gy.data_ptr(), _ptr(gJ), _stream(y.device))
+    return loss, gy, gJ

@@ -377,6 +377,34 @@ int insr_elastic_energy(const float *F, int64_t n, int d, float ratio_arap, floa
     return check_cuda("k_elastic_energy");
 }
 
+int insr_elastic_terms(const insr_elastic_terms_desc *t, int d, const float *y, const float *J, const float *x,
+                       const float *y_prev, const float *y_pp, float *loss, float *gy, float *gJ, void *stream) {
+    if (!t || !y || !loss || !gy) return fail(INSR_ERR_NULL, "elastic_terms: desc, y, loss and gy must not be NULL");
+    if (d != 2 && d != 3) return fail(INSR_ERR_SHAPE, "elastic_terms: d=%d (must be 2 or 3)", d);
+    if (t->n < 0 || t->n_left < 0 || t->n_right < 0) return fail(INSR_ERR_SHAPE, "elastic_terms: negative row count");
+    if (t->n > 0 && (!x || !y_prev || !y_pp)) return fail(INSR_ERR_NULL, "elastic_terms: interior rows need x, y_prev, y_pp");
+    if ((t->r_arap != 0.f || t->r_volume != 0.f) && (!J || !gJ))
+        return fail(INSR_ERR_NULL, "elastic_terms: arap / volume need J and gJ");
+    if (!(t->dt > 0.f)) return fail(INSR_ERR_SHAPE, "elastic_terms: dt must be positive");
+    int rc = check_device();
+    if (rc) return rc;
+    insr_elastic_terms_k k{};
+    k.n = t->n; k.n_left = t->n_left; k.n_right = t->n_right;
+    k.dt = t->dt; k.r_arap = t->r_arap; k.r_volume = t->r_volume; k.r_kin = t->r_kinematics; k.r_left = t->r_left;
+    k.r_right = t->r_right; k.r_plane = t->r_plane; k.plane_height = t->plane_height; k.r_sphere = t->r_sphere;
+    k.radius = t->radius;
+    for (int i = 0; i < 3; ++i) { k.ext[i] = t->external_force[i]; k.off[i] = t->offset_right[i]; k.center[i] = t->center[i]; }
+    const int64_t n_all = k.n + k.n_left + k.n_right;
+    if (n_all == 0) return 0;
+    const bool energy = (k.r_arap != 0.f || k.r_volume != 0.f);
+    int64_t blocks = (n_all + 127) / 128;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (d == 2) { auto kfn = k_elastic_terms<2>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, k, y, energy ? J : nullptr, x, y_prev, y_pp, loss, gy, energy ? gJ : nullptr); }
+    else        { auto kfn = k_elastic_terms<3>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, k, y, energy ? J : nullptr, x, y_prev, y_pp, loss, gy, energy ? gJ : nullptr); }
+    ++g_launches;
+    return check_cuda("k_elastic_terms");
+}
+
 int insr_sample_boxes(int n_boxes, int dim, const int32_t *count, const float *lo, const float *hi, uint64_t seed,
                       int64_t *counter, uint32_t *ticket, int64_t point_offset, float *out, void *stream) {
     if (!count || !lo || !hi || !out) return fail(INSR_ERR_NULL, "sample_boxes: NULL argument");

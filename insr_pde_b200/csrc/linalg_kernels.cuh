@@ -158,3 +158,116 @@ __global__ void k_elastic_energy(const float *__restrict__ F, int64_t n, float r
     for (int m = 16; m >= 1; m >>= 1) e_sum += __shfl_xor_sync(0xffffffffu, e_sum, m);
     if ((threadIdx.x & 31) == 0) atomicAdd(energy, e_sum);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Every term of ElasticityModel._solve_deformation (elasticity/model.py:127-189, elasticity/losses.py:6-39) in ONE kernel:
+// the loss and its cotangents w.r.t. the trainable field's value y and Jacobian J at every row of the batch
+//     rows [0, n)                    interior samples x:  q = y + x,  F = J + I,  qdot = (y - y_prev) / dt,
+//                                    qdot_prev = (y_prev - y_pp) / dt   (the x of q, q_prev, q_pp cancels)
+//         r_a sum_k (s_k - 1)^2 + r_v (prod s - 1)^2             arap / volume        (model.py:143-149)
+//         r_k |qdot - qdot_prev|^2                                kinematics           (:151-153)
+//         - dt qdot . f_ext                                       external             (:155-158)
+//         - dt r_c [q_last < h] qdot_last (h - q_last)            plane collision      (losses.py:10-20)
+//         - dt r_c [|q - c| < R] qdot . (q - c)                   sphere collision, 2-D form (losses.py:22-39; force =
+//                                                                 r_c * dist * dir = r_c (q - c))
+//     rows [n, n + n_left)           clamped left face:   r_l |y|^2                    (:160-162)
+//     rows [n + n_left, n_all)       right face:          r_r |y - off|^2              (:164-171; off carries the sign)
+// A ratio of zero switches a term off.  loss: device scalar, ACCUMULATED; gy (n_all, D), gJ (n_all, D, D; NULL when
+// r_a = r_v = 0) are overwritten.
+struct insr_elastic_terms_k {
+    int64_t n, n_left, n_right;
+    float dt, r_arap, r_volume, r_kin, r_left, r_right, r_plane, plane_height, r_sphere, radius;
+    float ext[3], off[3], center[3];
+};
+
+template <int D>
+__global__ void k_elastic_terms(insr_elastic_terms_k t, const float *__restrict__ y, const float *__restrict__ J,
+                                const float *__restrict__ x, const float *__restrict__ y_prev, const float *__restrict__ y_pp,
+                                float *__restrict__ loss, float *__restrict__ gy, float *__restrict__ gJ) {
+    const int64_t n_all = t.n + t.n_left + t.n_right;
+    const float inv_dt = 1.f / t.dt;
+    float e_sum = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_all; i += (int64_t)gridDim.x * blockDim.x) {
+        float yv[D], g[D];
+        INSR_PRAGMA_UNROLL
+        for (int d = 0; d < D; ++d) { yv[d] = y[i * D + d]; g[d] = 0.f; }
+        if (i < t.n) {
+            float qd[D], qdp[D], q[D];
+            INSR_PRAGMA_UNROLL
+            for (int d = 0; d < D; ++d) {
+                const float yp = y_prev[i * D + d], ypp = y_pp[i * D + d];
+                qd[d] = (yv[d] - yp) * inv_dt;
+                qdp[d] = (yp - ypp) * inv_dt;
+                q[d] = yv[d] + x[i * D + d];
+            }
+            if (J) {
+                float f[D][D], u[D][D], s[D], v[D][D];
+                INSR_PRAGMA_UNROLL
+                for (int r = 0; r < D; ++r)
+                    INSR_PRAGMA_UNROLL
+                    for (int c = 0; c < D; ++c) f[r][c] = J[i * D * D + r * D + c] + (r == c ? 1.f : 0.f);
+                insr_svd_small<D>(f, u, s, v);
+                float prod = 1.f, arap = 0.f, ds[D];
+                INSR_PRAGMA_UNROLL
+                for (int k = 0; k < D; ++k) { prod *= s[k]; arap = fmaf(s[k] - 1.f, s[k] - 1.f, arap); }
+                e_sum += t.r_arap * arap + t.r_volume * (prod - 1.f) * (prod - 1.f);
+                INSR_PRAGMA_UNROLL
+                for (int k = 0; k < D; ++k) {
+                    float others = 1.f;
+                    INSR_PRAGMA_UNROLL
+                    for (int j = 0; j < D; ++j) if (j != k) others *= s[j];
+                    ds[k] = 2.f * t.r_arap * (s[k] - 1.f) + 2.f * t.r_volume * (prod - 1.f) * others;
+                }
+                INSR_PRAGMA_UNROLL
+                for (int r = 0; r < D; ++r)
+                    INSR_PRAGMA_UNROLL
+                    for (int c = 0; c < D; ++c) {
+                        float acc = 0.f;
+                        INSR_PRAGMA_UNROLL
+                        for (int k = 0; k < D; ++k) acc = fmaf(u[r][k] * ds[k], v[c][k], acc);
+                        gJ[i * D * D + r * D + c] = acc;
+                    }
+            }
+            float dist2 = 0.f, qd_vec = 0.f;
+            INSR_PRAGMA_UNROLL
+            for (int d = 0; d < D; ++d) {
+                const float a = qd[d] - qdp[d];
+                e_sum = fmaf(t.r_kin * a, a, e_sum);
+                g[d] = fmaf(2.f * t.r_kin * inv_dt, a, g[d]);
+                e_sum = fmaf(-t.dt * qd[d], t.ext[d], e_sum);
+                g[d] -= t.ext[d];
+                const float vec = q[d] - t.center[d];
+                dist2 = fmaf(vec, vec, dist2);
+                qd_vec = fmaf(qd[d], vec, qd_vec);
+            }
+            if (t.r_plane != 0.f && q[D - 1] < t.plane_height) {
+                const float gap = t.plane_height - q[D - 1];
+                e_sum -= t.dt * t.r_plane * qd[D - 1] * gap;
+                g[D - 1] -= t.dt * t.r_plane * (gap * inv_dt - qd[D - 1]);
+            }
+            if (t.r_sphere != 0.f && sqrtf(dist2) < t.radius) {
+                e_sum -= t.dt * t.r_sphere * qd_vec;
+                INSR_PRAGMA_UNROLL
+                for (int d = 0; d < D; ++d) g[d] -= t.dt * t.r_sphere * ((q[d] - t.center[d]) * inv_dt + qd[d]);
+            }
+        } else {
+            const bool left = i < t.n + t.n_left;
+            const float r = left ? t.r_left : t.r_right;
+            INSR_PRAGMA_UNROLL
+            for (int d = 0; d < D; ++d) {
+                const float a = yv[d] - (left ? 0.f : t.off[d]);
+                e_sum = fmaf(r * a, a, e_sum);
+                g[d] = 2.f * r * a;
+            }
+            if (gJ) {
+                INSR_PRAGMA_UNROLL
+                for (int k = 0; k < D * D; ++k) gJ[i * D * D + k] = 0.f;
+            }
+        }
+        INSR_PRAGMA_UNROLL
+        for (int d = 0; d < D; ++d) gy[i * D + d] = g[d];
+    }
+    INSR_PRAGMA_UNROLL
+    for (int m = 16; m >= 1; m >>= 1) e_sum += __shfl_xor_sync(0xffffffffu, e_sum, m);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss, e_sum);
+}

@@ -46,6 +46,10 @@ def flat_grad(net):
             buf = torch.zeros_like(theta)
             net._flat_grad = buf
         for p, (off, numel, shape) in zip(net.parameters(), net.param_slices()):
+            if p.grad is None:                   # dropped by zero_grad(set_to_none=True): that means zero
+                buf[off:off + numel].zero_()
+            elif p.grad.data_ptr() != buf.data_ptr() + 4 * off:
+                buf[off:off + numel].copy_(p.grad.reshape(-1))
             p.grad = buf[off:off + numel].view(shape)
     return buf
 
@@ -184,13 +188,82 @@ def fluid_projection(velocity, velocity_prev, pressure, samples, bc_x, bc_y):
 # ------------------------------------------------------------------------------------------------
 # elasticity (elasticity/model.py:127-189, elasticity/losses.py): the deformation-gradient energies in one kernel
 # ------------------------------------------------------------------------------------------------
+def _host_vec(v):
+    """closure constants (forces, offsets, centres) as host floats, read back ONCE per tensor (they never change)"""
+    if not torch.is_tensor(v):
+        return [float(a) for a in v]
+    cached = getattr(v, "_insr_host", None)
+    if cached is None:
+        cached = [float(a) for a in v.detach().reshape(-1).cpu()]
+        try:
+            v._insr_host = cached
+        except AttributeError:
+            pass
+    return cached
+
+
 def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_left, fixed_right, *, dt, timestep, energy,
                                  ratio_arap, ratio_volume, ratio_kinematics, ratio_constraint, ratio_collide,
                                  external_force, external_force_timesteps, constraint_offset_right, plane_height,
                                  circle_center, circle_radius):
+    """ElasticityModel._solve_deformation (elasticity/model.py:127-189) without an autograd graph: one order-1 evaluation
+    of the trainable field over [interior | left face | right face] that keeps its tape, the two frozen fields on side
+    streams, ONE kernel for every loss term and its cotangents (insr_elastic_terms: Jacobi SVD energies, kinematics,
+    external force, constraints, collisions), and the reverse sweep from the tape straight into the flat gradient buffer.
+    Returns detached values, like the fluid closures.  The reference's 3-D sphere collision (an (M,M,3) broadcast) and
+    unknown terms fall back to ``elasticity_solve_deformation_autograd``."""
+    known = {"arap", "volume", "kinematics", "external", "constraint", "constraint_right", "constraint_right_compress",
+             "collision", "collision_sphere"}
+    dim = deformation.in_features
+    both_right = "constraint_right" in energy and "constraint_right_compress" in energy
+    if (not samples.is_cuda or not set(energy) <= known or both_right or ("collision_sphere" in energy and dim != 2)
+            or len(set(energy)) != len(list(energy))):
+        return elasticity_solve_deformation_autograd(
+            deformation, prev, prev_prev, samples, fixed_left, fixed_right, dt=dt, timestep=timestep, energy=energy,
+            ratio_arap=ratio_arap, ratio_volume=ratio_volume, ratio_kinematics=ratio_kinematics,
+            ratio_constraint=ratio_constraint, ratio_collide=ratio_collide, external_force=external_force,
+            external_force_timesteps=external_force_timesteps, constraint_offset_right=constraint_offset_right,
+            plane_height=plane_height, circle_center=circle_center, circle_radius=circle_radius)
+    samples = samples.detach().reshape(-1, dim).contiguous()
+    n = samples.shape[0]
+    ra = ratio_arap if "arap" in energy else 0.0
+    rv = ratio_volume if "volume" in energy else 0.0
+    use_left = "constraint" in energy and torch.is_tensor(fixed_left)
+    use_right = ("constraint_right" in energy or "constraint_right_compress" in energy) and torch.is_tensor(fixed_right)
+    extra = ([fixed_left.detach()] if use_left else []) + ([fixed_right.detach()] if use_right else [])
+    x_all = torch.cat([samples] + [e.reshape(-1, dim).to(samples.dtype) for e in extra], dim=0) if extra else samples
+    n_left = extra[0].shape[0] if use_left else 0
+    n_right = x_all.shape[0] - n - n_left
+    order = ORDER_JAC if (ra or rv) else ORDER_VALUE
+    theta = deformation.flat_theta()
+
+    (outs, tape), y_prev, y_pp = parallel(samples,
+                                          lambda: _ops.siren_forward(deformation.desc, theta, x_all, order, keep_tape=True),
+                                          lambda: evaluate(prev, samples, ORDER_VALUE)[0],
+                                          lambda: evaluate(prev_prev, samples, ORDER_VALUE)[0])
+    if not torch.cuda.is_current_stream_capturing():
+        for t in (y_prev, y_pp):
+            t.record_stream(torch.cuda.current_stream(samples.device))
+    sign = -1.0 if "constraint_right_compress" in energy else 1.0
+    forced = "external" in energy and timestep <= external_force_timesteps
+    loss, gy, gJ = _ops.elastic_terms(
+        outs[0], outs[1] if order == ORDER_JAC else None, samples, y_prev, y_pp, n_left, n_right, dt=dt, r_arap=ra, r_volume=rv,
+        r_kinematics=ratio_kinematics if "kinematics" in energy else 0.0, r_left=ratio_constraint if use_left else 0.0,
+        r_right=ratio_constraint if use_right else 0.0, r_plane=ratio_collide if "collision" in energy else 0.0,
+        plane_height=plane_height, r_sphere=ratio_collide if "collision_sphere" in energy else 0.0, radius=circle_radius,
+        external_force=_host_vec(external_force) if forced else None,
+        offset_right=[sign * a for a in _host_vec(constraint_offset_right)], center=_host_vec(circle_center))
+    _ops.siren_backward(deformation.desc, theta, x_all, order, gy, gJ, None, gtheta=flat_grad(deformation), tape=tape)
+    return {"main": loss[0]}
+
+
+def elasticity_solve_deformation_autograd(deformation, prev, prev_prev, samples, fixed_left, fixed_right, *, dt, timestep, energy,
+                                          ratio_arap, ratio_volume, ratio_kinematics, ratio_constraint, ratio_collide,
+                                          external_force, external_force_timesteps, constraint_offset_right, plane_height,
+                                          circle_center, circle_radius):
     """the reference closure with ``jacobian -> torch.svd -> (S - 1)^2, (prod S - 1)^2`` replaced by the field's
     order-1 kernel and ONE ``insr_elastic_energy`` kernel (energy + adjoint, no SVD graph); the remaining terms are the
-    reference's elementwise expressions."""
+    reference's elementwise expressions under autograd (the caller runs ``backward``)."""
     from . import function, linalg
     samples = samples.detach().reshape(-1, deformation.in_features).contiguous()
     n = samples.shape[0]

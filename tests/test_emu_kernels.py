@@ -360,3 +360,62 @@ def test_sample_mesh_under_emulation(emu_library):
     tri = s[big]
     assert ((tri[:, 0] - 2) + tri[:, 1] <= 2 + 1e-5).all() and (tri[:, 1] >= -1e-6).all()
     assert np.abs(tri.mean(0) - np.array([2 + 2 / 3, 2 / 3])).max() < 0.03     # centroid
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_elastic_terms_under_emulation(emu_library, d):
+    """insr_elastic_terms: every term of elasticity/model.py:127-189 + elasticity/losses.py:6-39 and its cotangents
+    against the same expressions under torch autograd in fp64 (svdvals energies, kinematics, external force, both
+    constraints, plane collision; the 2-D sphere collision for d = 2)"""
+    import torch
+    lib = emu_library
+    rng = np.random.default_rng(40 + d)
+    n, nl, nr = 300, 17, 23
+    na = n + nl + nr
+    y = (0.3 * rng.standard_normal((na, d))).astype(np.float32)
+    J = (0.25 * rng.standard_normal((na, d, d))).astype(np.float32)
+    x = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    yp = (y[:n] + 0.05 * rng.standard_normal((n, d))).astype(np.float32)
+    ypp = (yp + 0.05 * rng.standard_normal((n, d))).astype(np.float32)
+    t = _lib.ElasticTermsDesc()
+    t.n, t.n_left, t.n_right, t.dt = n, nl, nr, 0.05
+    t.r_arap, t.r_volume, t.r_kinematics, t.r_left, t.r_right = 2.0, 30.0, 1.5, 100.0, 80.0
+    t.r_plane, t.plane_height = 7.0, -0.2
+    t.r_sphere, t.radius = (5.0, 0.8) if d == 2 else (0.0, 0.0)
+    ext, off, cen = [0.3, -2.0, 0.7], [0.4, -0.1, 0.2], [0.1, -0.3, 0.0]
+    for i in range(3):
+        t.external_force[i], t.offset_right[i], t.center[i] = ext[i], off[i], cen[i]
+    loss = np.zeros(1, np.float32); gy = np.full((na, d), np.nan, np.float32); gJ = np.full((na, d, d), np.nan, np.float32)
+    lib.elastic_terms(t, d, ptr(y), ptr(J), ptr(x), ptr(yp), ptr(ypp), ptr(loss), ptr(gy), ptr(gJ), None)
+
+    Y = torch.tensor(y, dtype=torch.float64, requires_grad=True); Jt = torch.tensor(J, dtype=torch.float64, requires_grad=True)
+    X, YP, YPP = (torch.tensor(a, dtype=torch.float64) for a in (x, yp, ypp))
+    dt = 0.05
+    q, q_prev, q_pp = Y[:n] + X, YP + X, YPP + X
+    qdot, qdot_prev = (q - q_prev) / dt, (q_prev - q_pp) / dt
+    S = torch.linalg.svdvals(Jt[:n] + torch.eye(d, dtype=torch.float64))
+    E = 2.0 * ((S - 1) ** 2).sum() + 30.0 * ((S.prod(1) - 1) ** 2).sum()
+    E = E + 1.5 * ((qdot - qdot_prev) ** 2).sum() - dt * (qdot * torch.tensor(ext[:d], dtype=torch.float64)).sum()
+    E = E + 100.0 * (Y[n:n + nl] ** 2).sum() + 80.0 * ((Y[n + nl:] - torch.tensor(off[:d], dtype=torch.float64)) ** 2).sum()
+    hit = (q[:, -1] < -0.2).double()
+    assert 0 < hit.sum() < n
+    E = E - dt * 7.0 * (hit * qdot[:, -1] * (-0.2 - q[:, -1])).sum()
+    if d == 2:
+        vec = q - torch.tensor(cen[:2], dtype=torch.float64)
+        inside = (vec.norm(dim=1) < 0.8).double()
+        assert 0 < inside.sum() < n
+        E = E - dt * 5.0 * (inside[:, None] * qdot * vec).sum()
+    E.backward()
+    E = E.detach()
+    assert abs(loss[0] - float(E)) < 3e-5 * abs(float(E))
+    assert rel(gy, Y.grad.numpy()) < 3e-5
+    assert rel(gJ[:n], Jt.grad.numpy()[:n]) < 1e-4 and not gJ[n:].any()
+    # accumulation into the loss word, and the energy-free form (no J): gJ untouched
+    t.r_arap = t.r_volume = 0.0
+    before = float(loss[0])
+    lib.elastic_terms(t, d, ptr(y), None, ptr(x), ptr(yp), ptr(ypp), ptr(loss), ptr(gy), None, None)
+    E_s = 2.0 * ((S - 1) ** 2).sum() + 30.0 * ((S.prod(1) - 1) ** 2).sum()
+    assert abs((loss[0] - before) - float(E - E_s.detach())) < 1e-4 * abs(float(E))
+    with pytest.raises(RuntimeError, match="arap / volume need J"):
+        t.r_arap = 1.0
+        lib.elastic_terms(t, d, ptr(y), None, ptr(x), ptr(yp), ptr(ypp), ptr(loss), ptr(gy), None, None)

@@ -439,15 +439,20 @@ def test_closures_elasticity_with_device_svd_and_fused_energy(tag, monkeypatch):
     class _FusedOps:                      # elasticity_case calls closures.elasticity_solve_deformation(defo, prev, pp, ops, ...)
         pass
 
-    def fused_closure(defo, prev, pp, ops, samples, left, right, **kw):
-        return fused.elasticity_solve_deformation(defo, prev, pp, samples, left, right, **kw)
+    # (b) the one-kernel closure (insr_elastic_terms, no autograd graph) and (c) its autograd sibling (insr_elastic_energy +
+    # the reference's elementwise terms), which also serves the term combinations the kernel does not offer
+    for fn in (fused.elasticity_solve_deformation, fused.elasticity_solve_deformation_autograd):
+        def fused_closure(defo, prev, pp, ops, samples, left, right, **kw):
+            out = fn(defo, prev, pp, samples, left, right, **kw)
+            assert out["main"].requires_grad == (fn is fused.elasticity_solve_deformation_autograd)
+            return out
 
-    monkeypatch.setattr(closures, "elasticity_solve_deformation", fused_closure)
-    val2, grad2 = elasticity_case(tag, g, _mk, ib)
-    assert abs(val2 - ref) < 2e-4 * abs(ref)
-    assert rel(grad2, g["solve_deformation.grad.deformation"]) < 5e-3
-    # the fused energy avoids the SVD backward (1 / (s_i^2 - s_j^2) terms): it agrees with the reference at least as well
-    assert rel(grad2, grad) < 5e-3
+        monkeypatch.setattr(closures, "elasticity_solve_deformation", fused_closure)
+        val2, grad2 = elasticity_case(tag, g, _mk, ib)
+        assert abs(val2 - ref) < 2e-4 * abs(ref)
+        assert rel(grad2, g["solve_deformation.grad.deformation"]) < 5e-3
+        # the fused energy avoids the SVD backward (1 / (s_i^2 - s_j^2) terms): it agrees with the reference at least as well
+        assert rel(grad2, grad) < 5e-3
 
 
 def test_box_sampler_on_device_and_under_graph_replay():

@@ -174,7 +174,8 @@ def elasticity_case(tag, g, make_net, ops):
         external_force=torch.tensor(c["ext"][:dim], device=dev), external_force_timesteps=c["ext_T"],
         constraint_offset_right=torch.tensor(c["off"][:dim], device=dev), plane_height=c["plane"],
         circle_center=torch.tensor(c["center"][:dim], device=dev), circle_radius=c["radius"])
-    loss["main"].backward()
+    if loss["main"].requires_grad:                  # the fused CUDA closure accumulates its gradient itself
+        loss["main"].backward()
     return float(loss["main"]), _flat_grad(defo).detach().cpu().numpy()
 
 
