@@ -172,6 +172,48 @@ def fluid_timestep_ours(dev, iters, world=1):
                     "fluid2Dtlgn step on fused lsq closures + torch Adam + flat-gradient all-reduce, host sync per iteration"}
 
 
+ELASTIC_CASES = {
+    # scripts/elasticity2Dstretch.sh: 100^2 uniform + 100^2 random interior points, clamped faces, H = 68
+    "elasticity2Dstretch": dict(dim=2, H=68, sr=100, dt=0.05, energy=["arap", "constraint", "constraint_right", "volume"],
+                                ratio_volume=1e3, ratio_arap=1e0, ratio_constraint=1e4, ratio_kinematics=1e0, ratio_collide=1e0,
+                                ext=[0., 0., 0.], ext_T=5, off=[2.0, 0., 0.], plane=-2.0, center=[0., -2., 0.], radius=1.0),
+    # the 3-D bunny's network and point count (13 824 + 13 824 points, H = 66) on the cube (no mesh file offline)
+    "elasticity3D_bunny_sized": dict(dim=3, H=66, sr=24, dt=0.1, energy=["arap", "kinematics", "collision", "external", "volume"],
+                                     ratio_volume=1e3, ratio_arap=1e2, ratio_constraint=1e3, ratio_kinematics=1e0, ratio_collide=1e6,
+                                     ext=[0., 0., -1e2], ext_T=5, off=[1.0, 0., 0.], plane=-0.9, center=[0., -2., 0.], radius=1.0),
+}
+
+
+def elasticity_timestep_ours(dev, iters, case="elasticity2Dstretch"):
+    """seconds per elasticity time step (elasticity/model.py:119-189: one @_training_loop of `iters` Adam iterations) on
+    ElasticityStepper: the whole iteration -- Philox sampling, order-1 field kernels with the tape kept, the frozen
+    previous frames on side streams, insr_elastic_terms, reverse sweep, device Adam / plateau -- as one CUDA graph."""
+    import insr_pde_b200 as ib
+    from insr_pde_b200 import fused
+    c = ELASTIC_CASES[case]
+    dim = c["dim"]
+    kw = dict(energy=c["energy"], ratio_arap=c["ratio_arap"], ratio_volume=c["ratio_volume"], ratio_kinematics=c["ratio_kinematics"],
+              ratio_constraint=c["ratio_constraint"], ratio_collide=c["ratio_collide"],
+              external_force=torch.tensor(c["ext"][:dim], device=dev), external_force_timesteps=c["ext_T"],
+              constraint_offset_right=torch.tensor(c["off"][:dim], device=dev), plane_height=c["plane"],
+              circle_center=torch.tensor(c["center"][:dim], device=dev), circle_radius=c["radius"])
+    torch.manual_seed(0)
+    nets = [ib.MLP(dim, dim, 3, c["H"], nonlinearity="sine").to(dev) for _ in range(3)]
+    st = fused.ElasticityStepper(*nets, dim, dt=c["dt"], sample_resolution=c["sr"], graphed=True, **kw)
+    st.initialize(5)
+    st.step(5)                                          # warm-up: the graph is captured here
+    sec = float("inf")
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h = st.step(iters)
+        torch.cuda.synchronize()
+        sec = min(sec, time.perf_counter() - t0)
+    npts = 2 * c["sr"] ** dim
+    return {"case": case, "sec_per_timestep": round(sec, 4), "iters_per_loop": iters, "us_per_iteration": round(sec / iters * 1e6, 1),
+            "points_per_iteration": npts, "points_per_s": round(npts * iters / sec, 1), "final_loss": round(h[-1]["main"], 6)}
+
+
 def fluid_timestep_cpu(iters_measured=3, iters_per_loop=100):
     """the same time step with the reference algorithm (oracle port) on the host cores; a few
     iterations per loop are timed and scaled to `iters_per_loop`."""
@@ -455,6 +497,8 @@ def run_ours(args):
         timestep = fluid_timestep_ours(dev, args.timestep_iters, world)
         if rank == 0 and not args.no_cpu_baseline:
             timestep["cpu_reference"] = fluid_timestep_cpu(3, args.timestep_iters)
+        if world == 1:                                  # the 32 < H <= 512 family's closure, same metric
+            timestep["elasticity"] = [elasticity_timestep_ours(dev, args.timestep_iters, c) for c in ELASTIC_CASES]
 
     # ---- CPU baseline (oracle port of the reference algorithm), rank 0, bounded sample
     cpu, torch_gpu = None, None

@@ -10,14 +10,8 @@ from insr_pde_b200 import fused, sampling
 from oracle import closures, torch_port as tp
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 200
-CASES = {
-    "elasticity2Dstretch": dict(dim=2, H=68, sr=100, dt=0.05, energy=["arap", "constraint", "constraint_right", "volume"],
-                                ratio_volume=1e3, ratio_arap=1e0, ratio_constraint=1e4, ratio_kinematics=1e0, ratio_collide=1e0,
-                                ext=[0., 0., 0.], ext_T=5, off=[2.0, 0., 0.], plane=-2.0, center=[0., -2., 0.], radius=1.0),
-    "elasticity3D_bunny_sized": dict(dim=3, H=66, sr=24, dt=0.1, energy=["arap", "kinematics", "collision", "external", "volume"],
-                                     ratio_volume=1e3, ratio_arap=1e2, ratio_constraint=1e3, ratio_kinematics=1e0, ratio_collide=1e6,
-                                     ext=[0., 0., -1e2], ext_T=5, off=[1.0, 0., 0.], plane=-0.9, center=[0., -2., 0.], radius=1.0),
-}
+import bench
+CASES = bench.ELASTIC_CASES
 for name, c in CASES.items():
     dim = c["dim"]
     kw = dict(energy=c["energy"], ratio_arap=c["ratio_arap"], ratio_volume=c["ratio_volume"], ratio_kinematics=c["ratio_kinematics"],

@@ -18,3 +18,8 @@ if [ "$2" == "ncu" ]; then
       --csv --log-file gpurun_out/traffic_$TAG.csv python tools/prof_one.py --points 4194304 --reps 2 --lsq > gpurun_out/ncu_traffic_$TAG.log 2>&1
   tail -n 3 gpurun_out/ncu_list_$TAG.log; tail -n 3 gpurun_out/ncu_full_$TAG.log; tail -n 7 gpurun_out/traffic_$TAG.csv | cut -c1-300
 fi
+if [ "$3" == "elastic" ]; then
+  timeout 300 python tools/elastic_step_bench.py 200 2>&1 | grep -v "Warn\|return float" > gpurun_out/elastic_step_$TAG.txt; cat gpurun_out/elastic_step_$TAG.txt
+  (timeout 200 python tools/elastic_graph_profile.py 2d; timeout 200 python tools/elastic_graph_profile.py 3d) 2>&1 | grep -v "Warn\|_warn" > gpurun_out/elastic_kernels_$TAG.txt
+  (timeout 200 python tools/wide_scaling_probe.py 68 2 0; timeout 200 python tools/wide_scaling_probe.py 68 2 1) 2>&1 | grep tiles > gpurun_out/wide_scaling_$TAG.txt
+fi
