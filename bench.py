@@ -350,7 +350,7 @@ def run_ours(args):
     no_tensor = bool(desc.flags & _lib.FLAG_NO_TENSOR)
     tensor_pipe_txt = ("tcgen05: 3xTF32 forward / data gradient (hi operand in TMEM), 2-level bf16 weight gradient, FP32 accumulators in TMEM"
                        if tensor_path else
-                       ("tcgen05 hidden-layer GEMMs, layer by layer through HBM: 3xTF32 forward + data gradient, 2-level bf16 weight gradient (H <= 128; fp32 ffma above)"
+                       ("tcgen05 hidden-layer GEMMs, layer by layer through HBM: 3xTF32 forward + data gradient, 2-level bf16 weight gradient in 128 x 128 weight groups with TMEM-resident accumulators"
                         if fam_b == 2 and not no_tensor and len(shapes) <= 3 and order <= 2 else "fp32 ffma"))
     ach_bwd = 2 * f_fwd * N / (ms_bwd / 1e3) / 1e12
     ach_fwd = f_fwd * N / (ms_fwd / 1e3) / 1e12

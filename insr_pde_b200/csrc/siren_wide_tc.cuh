@@ -337,7 +337,7 @@ int launch_wide(const SirenDims &dm, const float *W, const float *bias, const fl
 }
 
 // =============================================================================================
-// weight gradient of a hidden layer of the tiled family, HP <= 128:
+// weight gradient of a hidden layer of the tiled family (HP <= 128: one 128 x 128 group; wider: one grid row per group):
 //     gW[j][k] += omega * sum_{s,p} zbar[s][p][j] * act[s][p][k],      gb[j] += omega * sum_p zbar[0][p][j]
 // The reduction runs over POINTS, i.e. over the rows of the [stream][point][HP] buffers: both operands are MN-major,
 // which kind::tf32 does not support (siren_tc.cuh), so -- as in the H <= 32 family -- the operands are split in two
@@ -362,7 +362,11 @@ __global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int
                                                       float *__restrict__ gW, float *__restrict__ gb) {
     extern __shared__ __align__(1024) unsigned char smraw_[];
     unsigned char *sm = smraw_ + ((1024u - (s32(smraw_) & 1023u)) & 1023u);
-    const int NBJ = (HP + 63) >> 6;                          // 1 or 2 blocks of 64 neurons
+    // blockIdx.y = 128 x 128 group of the weight matrix (H > 128): output neurons jz0.., input neurons ka0..
+    const int G1 = (HP + 127) >> 7;
+    const int jz0 = ((int)blockIdx.y / G1) * 128, ka0 = ((int)blockIdx.y % G1) * 128;
+    const int HPz = HP - jz0 < 128 ? HP - jz0 : 128, HPa = HP - ka0 < 128 ? HP - ka0 : 128;
+    const int NBZ = (HPz + 63) >> 6, NBA = (HPa + 63) >> 6;  // 1 or 2 blocks of 64 neurons on either side
     unsigned char *zt = sm, *at = sm + 4 * WG_ATOM;          // [block][level][64 x 128 B] each
     float *bsumS = reinterpret_cast<float *>(sm + 8 * WG_ATOM);                 // 128 floats
     const uint32_t mbar = s32(sm + 8 * WG_ATOM + 512), tslot = mbar + 16;
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int
 
     // staging: per operand 64 rows x 32 chunk slots (16 B of fp32 = 4 neurons); thread -> chunk slot (tid & 31), rows (tid >> 5) + 8 i
     const int ch = tid & 31, r0 = tid >> 5;
-    const bool ch_ok = 4 * ch < HP;
+    const bool z_ok = 4 * ch < HPz, a_ok = 4 * ch < HPa;
     float4 rz[8], ra[8];
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     const int ngroups = (nv + WG_PTS - 1) / WG_PTS;
@@ -400,10 +404,10 @@ __global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int
             const int64_t pnt = (int64_t)g * WG_PTS + r;
             rz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             ra[i] = rz[i];
-            if (ch_ok && pnt < nv) {
+            if (pnt < nv) {
                 const int64_t off = ((int64_t)s * NCp + pnt) * HP + 4 * ch;
-                rz[i] = __ldg(reinterpret_cast<const float4 *>(ZB + off));
-                ra[i] = __ldg(reinterpret_cast<const float4 *>(Act + off));
+                if (z_ok) rz[i] = __ldg(reinterpret_cast<const float4 *>(ZB + off + jz0));
+                if (a_ok) ra[i] = __ldg(reinterpret_cast<const float4 *>(Act + off + ka0));
             }
         }
     };
@@ -420,20 +424,23 @@ __global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int
     auto sstore = [&](int64_t st) {
         int g, s;
         stage_coords(st, g, s);
-        if (4 * ch < 64 * NBJ) {
-            const int jb = ch >> 4, jj = (4 * ch) & 63;          // block, neuron inside the block (multiple of 4)
-            INSR_PRAGMA_UNROLL
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 8 * i;
-                const int off = r * 128 + ((((jj >> 3) ^ r) & 7) << 4) + (jj & 7) * 2;
-                uint2 l1, l2;
+        const int jb = ch >> 4, jj = (4 * ch) & 63;              // block, neuron inside the block (multiple of 4)
+        const bool zs = 4 * ch < 64 * NBZ, as = 4 * ch < 64 * NBA;
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 8 * i;
+            const int off = r * 128 + ((((jj >> 3) ^ r) & 7) << 4) + (jj & 7) * 2;
+            uint2 l1, l2;
+            if (zs) {
                 split4(rz[i], l1, l2);
                 *reinterpret_cast<uint2 *>(zt + (jb * 2 + 0) * WG_ATOM + off) = l1;
                 *reinterpret_cast<uint2 *>(zt + (jb * 2 + 1) * WG_ATOM + off) = l2;
+                if (s == 0 && ka0 == 0) { bsum.x += rz[i].x; bsum.y += rz[i].y; bsum.z += rz[i].z; bsum.w += rz[i].w; }
+            }
+            if (as) {
                 split4(ra[i], l1, l2);
                 *reinterpret_cast<uint2 *>(at + (jb * 2 + 0) * WG_ATOM + off) = l1;
                 *reinterpret_cast<uint2 *>(at + (jb * 2 + 1) * WG_ATOM + off) = l2;
-                if (s == 0) { bsum.x += rz[i].x; bsum.y += rz[i].y; bsum.z += rz[i].z; bsum.w += rz[i].w; }
             }
         }
     };
@@ -449,9 +456,9 @@ __global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int
         if (warp == 0) {
             insr_tc::tc_fence_after();
             if (insr_tc::elect_one()) {
-                for (int jb = 0; jb < NBJ; ++jb)
-                    for (int kb = 0; kb < NBJ; ++kb) {
-                        const uint32_t d = tmem_base + (uint32_t)((jb * NBJ + kb) * 128);
+                for (int jb = 0; jb < NBZ; ++jb)
+                    for (int kb = 0; kb < NBA; ++kb) {
+                        const uint32_t d = tmem_base + (uint32_t)((jb * 2 + kb) * 128);
                         const uint32_t za = s32(zt + jb * 2 * WG_ATOM), aa = s32(at + kb * 2 * WG_ATOM);
                         INSR_PRAGMA_UNROLL
                         for (int q = 0; q < 4; ++q) {              // 16 points per instruction = two 1024-byte row groups
@@ -472,12 +479,12 @@ __global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int
     }
 
     // ---- flush: bias gradient, then the weight blocks (quadrants combined in shared memory)
-    if (ch_ok) {
+    if (z_ok && ka0 == 0) {
         atomicAdd(bsumS + 4 * ch + 0, bsum.x); atomicAdd(bsumS + 4 * ch + 1, bsum.y);
         atomicAdd(bsumS + 4 * ch + 2, bsum.z); atomicAdd(bsumS + 4 * ch + 3, bsum.w);
     }
     __syncthreads();
-    if (tid < 128 && tid < H && bsumS[tid] != 0.f) atomicAdd(gb + tid, dm.omega * bsumS[tid]);
+    if (tid < 128 && jz0 + tid < H && bsumS[tid] != 0.f) atomicAdd(gb + jz0 + tid, dm.omega * bsumS[tid]);
     if (nstages > 0) {
         // every (neuron j, input k) of a block has four partial sums -- (level of z) x (level of a) -- held by four
         // different warps: each warp parks its 32 x 32 piece in its own padded slab (no atomics, no bank conflicts),
@@ -485,13 +492,13 @@ __global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int
         float *piece = reinterpret_cast<float *>(sm);            // [8 warps][32 rows][33] floats (operand region is free)
         const int half = warp >> 2;                              // columns 64 half .. + 63: level of `a`
         const uint32_t trow = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);   // rows: level of z (warp & 2), neurons 32 (warp & 1) ..
-        for (int jb = 0; jb < NBJ; ++jb)
-            for (int kb = 0; kb < NBJ; ++kb)
+        for (int jb = 0; jb < NBZ; ++jb)
+            for (int kb = 0; kb < NBA; ++kb)
                 for (int cc = 0; cc < 2; ++cc) {                 // 32 input columns at a time
                     INSR_PRAGMA_UNROLL
                     for (int c8 = 0; c8 < 4; ++c8) {
                         float v[8];
-                        insr_tc::tmem_ld8(trow + (uint32_t)((jb * NBJ + kb) * 128 + 64 * half + 32 * cc + 8 * c8), v);
+                        insr_tc::tmem_ld8(trow + (uint32_t)((jb * 2 + kb) * 128 + 64 * half + 32 * cc + 8 * c8), v);
                         insr_tc::tmem_ld_wait();
                         INSR_PRAGMA_UNROLL
                         for (int i = 0; i < 8; ++i) piece[(warp * 32 + lane) * 33 + 8 * c8 + i] = v[i];
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int
                     __syncthreads();
                     for (int idx = tid; idx < 64 * 32; idx += WGT) {
                         const int jl = idx >> 5, kl = idx & 31;
-                        const int j = jb * 64 + jl, k = kb * 64 + 32 * cc + kl;
+                        const int j = jz0 + jb * 64 + jl, k = ka0 + kb * 64 + 32 * cc + kl;
                         if (j < H && k < H) {
                             const int wq = jl >> 5, rr = (jl & 31) * 33 + kl;      // warp & 1, row inside the piece
                             const float v = (piece[(wq + 0) * 32 * 33 + rr] + piece[(wq + 2) * 32 * 33 + rr]) +
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__(WGT, 1) k_wide_wgrad(SirenDims dm, int HP, int
     }
 }
 
-inline bool wide_wgrad_ok(int H) { return ((H + 7) & ~7) <= 128; }
+inline bool wide_wgrad_ok(int H) { return ((H + 7) & ~7) <= 512; }
 
 inline int launch_wide_wgrad(const SirenDims &dm, int S, const float *ZB, const float *Act, int64_t NCp, int nv, float *gW,
                              float *gb, void *stream, int64_t *launches) {
@@ -526,8 +533,11 @@ inline int launch_wide_wgrad(const SirenDims &dm, int S, const float *ZB, const 
     cudaFuncSetAttribute(k_wide_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int groups = (nv + WG_PTS - 1) / WG_PTS;
     const int sms = insr_fused::sm_count();
-    const int ctas = groups < sms ? groups : sms;
-    k_wide_wgrad<<<dim3((unsigned)ctas), dim3(WGT), smem, reinterpret_cast<cudaStream_t>(stream)>>>(dm, HP, S, ZB, Act, NCp, nv, gW, gb);
+    const int G1 = (HP + 127) >> 7, G = G1 * G1;             // 128 x 128 groups of the weight matrix, one grid row each
+    int ctas = sms / G;                                      // one CTA per SM (512 TMEM columns each)
+    if (ctas < 1) ctas = 1;
+    if (ctas > groups) ctas = groups;
+    k_wide_wgrad<<<dim3((unsigned)ctas, (unsigned)G), dim3(WGT), smem, reinterpret_cast<cudaStream_t>(stream)>>>(dm, HP, S, ZB, Act, NCp, nv, gW, gb);
     ++*launches;
     return 0;
 }
