@@ -617,7 +617,8 @@ __global__ void __launch_bounds__(NT) k_tiled_gx(SirenDims dm, int HP, const flo
 // workspace layout: Zpre[l], Act[l] = [stream][NCp][HP] for l = 0..L
 template <int D, int ORDER>
 void taped_forward(const SirenDims &dm, const Geo &g, const float *theta, const float *x, int64_t n0, int nv, int64_t NCp,
-                   int64_t rows, size_t buf, float *Zpre, float *Act, void *stream, int64_t *launches, bool tensor) {
+                   int64_t rows, size_t buf, float *Zpre, float *Act, void *stream, int64_t *launches, bool tensor,
+                   float *y = nullptr, float *jac = nullptr, float *h2 = nullptr, bool *fused_out = nullptr) {
     constexpr int S = StreamCfg<D, ORDER>::S;
     (void)S;
     const int64_t items = rows * (g.HP / 4);
@@ -631,6 +632,14 @@ void taped_forward(const SirenDims &dm, const Geo &g, const float *theta, const 
 #ifndef INSR_CPU_EMU
         if constexpr (S <= 4) {
             if (tensor) {
+                if (l == dm.L && y && insr_wide::wide_out_ok(dm.H)) {      // output layer rides on the last hidden layer
+                    insr_wide::WideOut wo{theta + insr_w_offset(dm, dm.L + 1), theta + insr_b_offset(dm, dm.L + 1), dm.O, nv, n0, y, jac, h2};
+                    insr_wide::launch_wide<D, ORDER, 0, true>(dm, theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l),
+                                                              Act + (size_t)(l - 1) * buf, NCp, rows, nullptr, Zpre + (size_t)l * buf,
+                                                              Act + (size_t)l * buf, stream, launches, wo);
+                    if (fused_out) *fused_out = true;
+                    continue;
+                }
                 insr_wide::launch_wide<D, ORDER, 0>(dm, theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l),
                                                     Act + (size_t)(l - 1) * buf, NCp, rows, nullptr, Zpre + (size_t)l * buf,
                                                     Act + (size_t)l * buf, stream, launches);
@@ -668,11 +677,14 @@ int run_forward_tape(const SirenDims &dm, const float *theta, const float *x, in
     cudaFuncSetAttribute(kfwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int nv = (int)N;
     const int64_t rows = round_up(nv, tensor ? 128 : g.BP);
-    taped_forward<D, ORDER>(dm, g, theta, x, 0, nv, NCp, rows, buf, Zpre, Act, stream, launches, tensor);
-    auto ko = k_tiled_out_fwd<D, O, ORDER>;
-    INSR_LAUNCH(ko, dim3((unsigned)(((int64_t)nv * 32 + NT - 1) / NT)), dim3(NT), 0, stream, dm, g.HP, theta,
-                Act + (size_t)dm.L * buf, NCp, (int64_t)0, nv, y, jac, h2);
-    ++*launches;
+    bool fused_out = false;
+    taped_forward<D, ORDER>(dm, g, theta, x, 0, nv, NCp, rows, buf, Zpre, Act, stream, launches, tensor, y, jac, h2, &fused_out);
+    if (!fused_out) {
+        auto ko = k_tiled_out_fwd<D, O, ORDER>;
+        INSR_LAUNCH(ko, dim3((unsigned)(((int64_t)nv * 32 + NT - 1) / NT)), dim3(NT), 0, stream, dm, g.HP, theta,
+                    Act + (size_t)dm.L * buf, NCp, (int64_t)0, nv, y, jac, h2);
+        ++*launches;
+    }
     return 0;
 }
 
@@ -704,10 +716,18 @@ int run_forward(const SirenDims &dm, const float *theta, const float *x, int64_t
                     NCp, (float *)nullptr, A0);
         ++*launches;
         float *in = A0, *out = A1;
+        bool fused_out = false;
         for (int l = 1; l <= dm.L; ++l) {
 #ifndef INSR_CPU_EMU
             if constexpr (S <= 4) {
                 if (tensor) {
+                    if (l == dm.L && insr_wide::wide_out_ok(dm.H)) {   // output layer in the epilogue; the last activations never reach HBM
+                        insr_wide::WideOut wo{theta + insr_w_offset(dm, dm.L + 1), theta + insr_b_offset(dm, dm.L + 1), dm.O, nv, n0, y, jac, h2};
+                        insr_wide::launch_wide<D, ORDER, 0, true>(dm, theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l), in, NCp, rows,
+                                                                  nullptr, nullptr, nullptr, stream, launches, wo);
+                        fused_out = true;
+                        continue;
+                    }
                     insr_wide::launch_wide<D, ORDER, 0>(dm, theta + insr_w_offset(dm, l), theta + insr_b_offset(dm, l), in, NCp, rows,
                                                         nullptr, nullptr, out, stream, launches);
                     float *t = in; in = out; out = t;
@@ -720,10 +740,12 @@ int run_forward(const SirenDims &dm, const float *theta, const float *x, int64_t
             ++*launches;
             float *t = in; in = out; out = t;
         }
-        auto ko = k_tiled_out_fwd<D, O, ORDER>;
-        INSR_LAUNCH(ko, dim3((unsigned)(((int64_t)nv * 32 + NT - 1) / NT)), dim3(NT), 0, stream, dm, g.HP, theta, in,
-                    NCp, n0, nv, y, jac, h2);
-        ++*launches;
+        if (!fused_out) {
+            auto ko = k_tiled_out_fwd<D, O, ORDER>;
+            INSR_LAUNCH(ko, dim3((unsigned)(((int64_t)nv * 32 + NT - 1) / NT)), dim3(NT), 0, stream, dm, g.HP, theta, in,
+                        NCp, n0, nv, y, jac, h2);
+            ++*launches;
+        }
     }
     return 0;
 }

@@ -72,12 +72,22 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
 __device__ unsigned long long g_wide_prof[16];
 #endif
 
-template <int D, int ORDER, int MODE>
+// OUT = true (last hidden layer of a forward, single column pass): the output layer  y = Wo act + bo  rides on the
+// epilogue's cooperative copy -- each thread dots its 4 staged activations of a row with Wo, 8 lanes reduce by shuffle --
+// so the (N, S, HP) activations are not read again by a separate kernel, and not even written when no tape is kept.
+struct WideOut {
+    const float *Wo, *bo;          // (O, H), (O)
+    int O, nv;                     // outputs, valid rows of this chunk
+    int64_t n0;                    // first point of the chunk in y / jac / h2
+    float *y, *jac, *h2;
+};
+
+template <int D, int ORDER, int MODE, bool OUT = false>
 __global__ void __launch_bounds__(WT, (StreamCfg<D, ORDER>::S <= 2) ? 2 : 1)
 k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__restrict__ W,
                                                    const float *__restrict__ bias, const float *__restrict__ Ain,
                                                    int64_t NCp, int64_t p_base, const float *__restrict__ Ztape,
-                                                   float *__restrict__ Zout, float *__restrict__ Aout) {
+                                                   float *__restrict__ Zout, float *__restrict__ Aout, WideOut wo) {
     typedef StreamCfg<D, ORDER> C;
     constexpr int S = C::S;
     static_assert(S <= 4, "S * NCOL must fit the 512 TMEM columns");
@@ -232,6 +242,13 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
         }
     };
     load_tape_chunk(j0);
+    float oacc[OUT ? CR : 1][OUT ? S : 1][3];
+    if (OUT) {
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < CR; ++i)
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) { oacc[OUT ? i : 0][OUT ? s : 0][0] = 0.f; oacc[OUT ? i : 0][OUT ? s : 0][1] = 0.f; oacc[OUT ? i : 0][OUT ? s : 0][2] = 0.f; }
+    }
     for (int cc = 0; cc < NCOL; cc += EC) {
         const int jc = j0 + cc;                                   // first output column of this chunk
         if (jc >= HP) break;
@@ -295,6 +312,17 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
             }
         }
         __syncthreads();
+        float4 wv[OUT ? 3 : 1];
+        if (OUT) {
+            const int j = jc + 4 * cch;
+            INSR_PRAGMA_UNROLL
+            for (int o = 0; o < 3; ++o) {
+                const float *wr = wo.Wo + (size_t)o * H + j;
+                const bool oo = o < wo.O;
+                wv[OUT ? o : 0] = make_float4(oo && j + 0 < H ? __ldg(wr + 0) : 0.f, oo && j + 1 < H ? __ldg(wr + 1) : 0.f,
+                                              oo && j + 2 < H ? __ldg(wr + 2) : 0.f, oo && j + 3 < H ? __ldg(wr + 3) : 0.f);
+            }
+        }
         INSR_PRAGMA_UNROLL
         for (int s = 0; s < S; ++s)
             INSR_PRAGMA_UNROLL
@@ -303,10 +331,49 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
                 if (j < HP) {
                     const int64_t g = ((int64_t)s * NCp + p0 + r) * HP + j;
                     if (MODE == 0 && Zout) *reinterpret_cast<float4 *>(Zout + g) = *reinterpret_cast<const float4 *>(tile_at(s, r, 4 * cch));
-                    *reinterpret_cast<float4 *>(Aout + g) = *reinterpret_cast<const float4 *>(tile_at(S + s, r, 4 * cch));
+                    const float4 av = *reinterpret_cast<const float4 *>(tile_at(S + s, r, 4 * cch));
+                    if (!OUT || Aout) *reinterpret_cast<float4 *>(Aout + g) = av;
+                    if (OUT) {
+                        INSR_PRAGMA_UNROLL
+                        for (int o = 0; o < 3; ++o) {
+                            const float4 wq = wv[OUT ? o : 0];
+                            float &t = oacc[OUT ? i : 0][OUT ? s : 0][o];
+                            t = fmaf(av.x, wq.x, fmaf(av.y, wq.y, fmaf(av.z, wq.z, fmaf(av.w, wq.w, t))));
+                        }
+                    }
                 }
             }
         __syncthreads();                                          // tiles are rewritten by the next chunk
+    }
+    if (OUT) {
+        typedef StreamCfg<D, ORDER> CO;
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < CR; ++i) {
+            const int64_t pr = p0 - p_base + crow + (WT / 8) * i;          // row inside the chunk
+            INSR_PRAGMA_UNROLL
+            for (int o = 0; o < 3; ++o) {
+                float out[S];
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s) {
+                    float v = oacc[OUT ? i : 0][OUT ? s : 0][o];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    out[s] = v;
+                }
+                if (cch == 0 && o < wo.O && pr < wo.nv) {
+                    const int64_t n = wo.n0 + pr;
+                    const int O = wo.O;
+                    wo.y[n * O + o] = out[0] + __ldg(wo.bo + o);
+                    INSR_PRAGMA_UNROLL
+                    for (int d = 0; d < CO::ND; ++d) wo.jac[(n * O + o) * D + d] = out[1 + d];
+                    if (ORDER == 2) wo.h2[n * O + o] = out[S - 1];
+                    if (ORDER == 3) {                                       // S <= 4 here means D = 1: one second derivative
+                        wo.h2[n * O + o] = out[S - 1];
+                    }
+                }
+            }
+        }
     }
     WTP(5);
 #ifdef INSR_WIDE_PROFILE
@@ -320,18 +387,20 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
 }
 
 // one hidden layer on the tensor cores; rows = number of point rows to process (multiple of 128, within the buffers)
-template <int D, int ORDER, int MODE>
+inline bool wide_out_ok(int H) { return make_wgeo(H).passes == 1; }      // the output layer can ride on the last hidden layer
+
+template <int D, int ORDER, int MODE, bool OUT = false>
 int launch_wide(const SirenDims &dm, const float *W, const float *bias, const float *Ain, int64_t NCp, int64_t rows,
-                const float *Ztape, float *Zout, float *Aout, void *stream, int64_t *launches) {
+                const float *Ztape, float *Zout, float *Aout, void *stream, int64_t *launches, WideOut wo = WideOut{}) {
     constexpr int S = StreamCfg<D, ORDER>::S;
     const WGeo g = make_wgeo(dm.H);
-    auto kfn = k_wide_tc<D, ORDER, MODE>;
+    auto kfn = k_wide_tc<D, ORDER, MODE, OUT>;
     const size_t smem = smem_bytes(S, g.NCOL);
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (S <= 2)      // room for two CTAs; otherwise leave the split to the driver: the weight loads like a large L1 (measured: 10 %)
         cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kfn<<<dim3((unsigned)(rows / TILE), (unsigned)g.passes), dim3(WT), smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dm, g.HP, g.NK, g.NCOL, insr_tc::pow2_cols(S * g.NCOL), W, bias, Ain, NCp, (int64_t)0, Ztape, Zout, Aout);
+        dm, g.HP, g.NK, g.NCOL, insr_tc::pow2_cols(S * g.NCOL), W, bias, Ain, NCp, (int64_t)0, Ztape, Zout, Aout, wo);
     ++*launches;
     return 0;
 }
