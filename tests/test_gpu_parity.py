@@ -573,6 +573,48 @@ def test_elasticity_stepper_graph_replay_matches_eager_loop():
     assert int(st._samplers[("box", 24)].counter) >= 6
 
 
+@pytest.mark.parametrize("dim,H,energy", [(2, 68, ["arap", "volume", "kinematics", "external", "constraint", "constraint_right", "collision_sphere"]),
+                                          (3, 66, ["arap", "volume", "kinematics", "external", "collision"])])
+def test_elasticity_time_step_follows_the_reference_algorithm(dim, H, energy):
+    """a short elasticity time step (elasticity/model.py:119-189 with base/baseModel.py:55-81): ElasticityStepper (one-kernel
+    closure, tape, torch Adam in the eager loop) against the reference algorithm restated in stock PyTorch -- autograd
+    jacobian, torch.svd, Adam -- from the same weights on the same ('uniform' pattern) samples: loss history and final
+    weights"""
+    from insr_pde_b200 import fused, sampling
+    kw = dict(energy=energy, ratio_arap=1.0, ratio_volume=20.0, ratio_kinematics=0.5, ratio_constraint=50.0, ratio_collide=4.0,
+              external_force=torch.tensor([0.0, -1.0, -2.0][-dim:] if dim == 2 else [0.0, 0.0, -2.0], device="cuda"),
+              external_force_timesteps=5, constraint_offset_right=torch.tensor([0.3, 0.0, 0.0][:dim], device="cuda"),
+              plane_height=-0.7, circle_center=torch.tensor([0.1, -0.8, 0.0][:dim], device="cuda"), circle_radius=0.6)
+    defo, prev, pp = _elastic_nets(21 + dim, dim, H)
+    ref = [tp.RefMLP(dim, dim, 3, H).cuda().load_flat_theta(n.flat_theta().detach().clone()) for n in (defo, prev, pp)]
+    sr, K, lr = (20, 8, 1e-4) if dim == 2 else (9, 8, 1e-4)
+    st = fused.ElasticityStepper(defo, prev, pp, dim, dt=0.05, sample_resolution=sr, lr=lr, sample_pattern=("uniform",),
+                                 graphed=False, **kw)
+    ours = [h["main"] for h in st.step(K)]
+    # the reference loop: hand-over of the previous frames, then K iterations of closure -> backward -> Adam
+    ref[2].load_state_dict(ref[1].state_dict()); ref[1].load_state_dict(ref[0].state_dict())
+    for n in ref[1:]:
+        for p_ in n.parameters():
+            p_.requires_grad_(False)
+    opt = torch.optim.Adam(ref[0].parameters(), lr=lr)
+    x = sampling.sample_uniform(sr, dim, device="cuda")
+    face = sampling.sample_uniform(sr, dim - 1, device="cuda")
+    one = torch.ones(face.shape[0], 1, device="cuda")
+    left, right = torch.cat((-one, face), 1), torch.cat((one, face), 1)
+    theirs = []
+    for _ in range(K):
+        opt.zero_grad()
+        loss = closures.elasticity_solve_deformation(ref[0], ref[1], ref[2], tp, x.clone().requires_grad_(True), left, right,
+                                                     dt=0.05, timestep=1, **kw)
+        loss["main"].backward()
+        opt.step()
+        theirs.append(float(loss["main"].detach()))
+    a, b = np.asarray(ours), np.asarray(theirs)
+    assert np.abs(a - b).max() <= 1e-3 * np.abs(b).max(), (a, b)
+    th_ref = torch.cat([p_.detach().reshape(-1) for p_ in ref[0].parameters()])
+    assert rel(defo.flat_theta(), th_ref) < 2e-3
+
+
 def test_elasticity_stepper_on_a_tetrahedron_mesh():
     """mesh branch of _sample_in_training (elasticity/model.py:198-207): volume samples from insr_sample_mesh plus the mesh
     vertices, 3-D field, graphed"""
