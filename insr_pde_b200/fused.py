@@ -216,7 +216,7 @@ def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_le
              "collision", "collision_sphere"}
     dim = deformation.in_features
     both_right = "constraint_right" in energy and "constraint_right_compress" in energy
-    if (not samples.is_cuda or not set(energy) <= known or both_right or ("collision_sphere" in energy and dim != 2)
+    if (not set(energy) <= known or both_right or ("collision_sphere" in energy and dim != 2)
             or len(set(energy)) != len(list(energy))):
         return elasticity_solve_deformation_autograd(
             deformation, prev, prev_prev, samples, fixed_left, fixed_right, dt=dt, timestep=timestep, energy=energy,
@@ -241,7 +241,7 @@ def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_le
                                           lambda: _ops.siren_forward(deformation.desc, theta, x_all, order, keep_tape=True),
                                           lambda: evaluate(prev, samples, ORDER_VALUE)[0],
                                           lambda: evaluate(prev_prev, samples, ORDER_VALUE)[0])
-    if not torch.cuda.is_current_stream_capturing():
+    if samples.is_cuda and not torch.cuda.is_current_stream_capturing():
         for t in (y_prev, y_pp):
             t.record_stream(torch.cuda.current_stream(samples.device))
     sign = -1.0 if "constraint_right_compress" in energy else 1.0

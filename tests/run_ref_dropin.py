@@ -1,7 +1,7 @@
 """Helper (run as a subprocess by test_reference_dropin.py): executes the reference's UNMODIFIED
 model classes for a few optimisation iterations, either as they are ("reference") or with the
-fused field/operator layer patched in ("fused"; C-ABI calls routed to the emulation build because
-the build container has no GPU).  Prints one JSON object with the per-iteration loss history."""
+fused field/operator layer patched in ("fused"; "fused_closures" additionally swaps the loss closures for the one-kernel ones; C-ABI calls routed to the
+emulation build because the build container has no GPU).  Prints one JSON object with the per-iteration loss history."""
 import json
 import os
 import sys
@@ -16,7 +16,7 @@ import torch  # noqa: E402
 from oracle import ref_loader  # noqa: E402
 
 torch.set_num_threads(1)
-if mode == "fused":
+if mode in ("fused", "fused_closures"):
     import build_emu
     from insr_pde_b200 import _lib, _ops, patch
     _lib._LIB = _lib.Library(build_emu.build_emu())
@@ -24,6 +24,8 @@ if mode == "fused":
     _ops._stream = lambda device: None
     patch.install(ref_loader.REF_ROOT)          # rebind BEFORE the PDE packages import the names
 ref = ref_loader.load(cpu=True)                 # stubs + cpu device proxy, then imports advection/fluid/elasticity
+if mode == "fused_closures":                    # second stage: the loss closures themselves (needs the PDE packages imported)
+    patch.install_fused_closures()
 
 hist = []
 
