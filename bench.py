@@ -151,9 +151,13 @@ def fluid_timestep_ours(dev, iters, world=1):
     from insr_pde_b200 import dist as idist, fused
     torch.manual_seed(0)
     vel, prev, pres = (ib.MLP(2, o, 3, 32, nonlinearity="sine").to(dev) for o in (2, 2, 1))
-    factory = (lambda nets: idist.GradAllReducer(nets)) if world > 1 else None
+    # world > 1: the iteration graph contains the ONE all-reduce of [gradients | loss values] (fused.SharedGradBuffer);
+    # INSR_GRAPH_NCCL=0 falls back to the eager loop (torch Adam, all-reduce and a host sync per iteration)
+    graph_dp = world == 1 or os.environ.get("INSR_GRAPH_NCCL", "1") != "0"
+    factory = (lambda nets: idist.GradAllReducer(nets)) if (world > 1 and not graph_dp) else None
     st = fused.FluidStepper(vel, prev, pres, dt=0.05, sample_resolution=128, lr=1e-4, reducer_factory=factory,
-                            graphed=(world == 1), device_sampler=True)
+                            graphed=graph_dp, device_sampler=True)
+    st.data_parallel = world > 1 and graph_dp
     st.initialize(fused.taylorgreen_velocity, 20, world)
     st.step(3, world)                                   # warm-up
     sec = float("inf")
@@ -163,12 +167,16 @@ def fluid_timestep_ours(dev, iters, world=1):
         h1, h2, h3 = st.step(iters, world)
         torch.cuda.synchronize()
         sec = min(sec, time.perf_counter() - t0)
+    for lp in getattr(st, "_loops", {}).values():       # release the captured graphs (and the NCCL work recorded in them) now
+        lp.graph = None
+    torch.cuda.synchronize()
     return {"sec_per_timestep": round(sec, 4), "iters_per_loop": iters, "loops": 3,
             "us_per_iteration": round(sec / (3 * iters) * 1e6, 1), "points_per_iteration": 128 * 128,
             "final_losses": [round(h[-1]["main"], 8) for h in (h1, h2, h3)],
             "note": ("fluid2Dtlgn step on fused lsq closures; one CUDA graph per iteration (one-kernel Philox sampling of the "
                      "three point sets, closures with interior / boundary terms on parallel branches, device Adam, device "
-                     "ReduceLROnPlateau), losses read back in bulk") if world == 1 else
+                     "ReduceLROnPlateau), losses read back in bulk" + ("; points sharded over the ranks, one NCCL all-reduce of [gradients | loss values] "
+                     "per iteration inside the graph" if world > 1 else "")) if graph_dp else
                     "fluid2Dtlgn step on fused lsq closures + torch Adam + flat-gradient all-reduce, host sync per iteration"}
 
 
@@ -529,7 +537,12 @@ def run_ours(args):
         }
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL kernels: tearing the communicator down under them can block forever (seen at N = 2).
+        # The line is out; leave together and skip the teardown -- this is a benchmark process, the driver only needs rc 0.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def cpu_reference(workload, budget_s=15.0, n_points=16384, threads=None, device="cpu"):
@@ -586,8 +599,9 @@ def run_reference(args):
     D, O, H, L, order, desc_txt = WORKLOADS[args.workload]
     n_points = 16384
     per_step_budget = 1.0
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every core this process may run on explicitly
     res = cpu_reference(args.workload, budget_s=max(5.0, min(120.0, per_step_budget * (args.steps + args.warmup))),
-                        n_points=n_points)
+                        n_points=n_points, threads=len(os.sched_getaffinity(0)))
     line = {
         "impl": "reference", "metric": "collocation points/s (SIREN fwd + grad + Laplacian + bwd)",
         "value": res["value"], "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -408,14 +408,49 @@ class DeviceOptimizer:
         return float(self.sched[0])          # host sync
 
 
+class SharedGradBuffer:
+    """[g_theta(net 0) | g_theta(net 1) | ... | loss slots] in ONE fp32 buffer: the nets' flat gradient
+    buffers ARE slices of it, so the fused kernels write there directly and the data-parallel exchange of an iteration --
+    parameter gradients and the loss values every rank must agree on for the LR schedule -- is a single all-reduce with
+    no flatten copy.  Graph-capturable (NCCL collectives record into CUDA graphs)."""
+
+    def __init__(self, nets, n_scalars=4, group=None):
+        sizes = [n.flat_theta().numel() for n in nets]
+        padded = [(sz + 3) // 4 * 4 for sz in sizes]            # every slice 16-byte aligned (C ABI requirement)
+        dev = nets[0].flat_theta().device
+        self.buf = torch.zeros(sum(padded) + n_scalars, dtype=torch.float32, device=dev)
+        off = 0
+        for n, sz, pd in zip(nets, sizes, padded):
+            n._flat_grad = self.buf[off:off + sz]
+            flat_grad(n)                                        # re-link the parameters' .grad views
+            off += pd
+        self.scalars = self.buf[off:]
+        self.group = group
+
+    def allreduce(self, values):
+        """values: list of 0-dim loss tensors of this rank -> list of their means over the ranks; the gradients are
+        averaged in place by the same collective"""
+        import torch.distributed as tdist
+        k = len(values)
+        if k > self.scalars.numel():
+            raise ValueError(f"{k} loss terms, {self.scalars.numel()} slots")
+        self.scalars[:k].copy_(torch.stack([v.reshape(()) for v in values]))
+        if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(self.group) > 1:
+            tdist.all_reduce(self.buf, group=self.group)
+            self.buf.div_(tdist.get_world_size(self.group))
+        return [self.scalars[i] for i in range(k)]
+
+
 class GraphedLoop:
     """One @_training_loop with the whole iteration -- sampling, fused closures, Adam, LR schedule, loss
     logging -- captured once as a CUDA graph and replayed: the per-iteration host work is one
     cudaGraphLaunch.  Loss values are written to a device ring and read back in bulk; the early-stop test
     (lr <= 1.1e-8, base/baseModel.py:132-134) is evaluated every ``check_every`` iterations."""
 
-    def __init__(self, nets, lr, closure, capacity=20000):
+    def __init__(self, nets, lr, closure, capacity=20000, data_parallel=False):
         self.nets, self.closure = list(nets), closure
+        # data_parallel: every rank runs the closure on its shard; ONE all-reduce per iteration inside the graph
+        self.shared = SharedGradBuffer(self.nets) if data_parallel else None
         self.opt = DeviceOptimizer(self.nets, lr)
         self.capacity = capacity
         self.hist = None
@@ -426,6 +461,9 @@ class GraphedLoop:
         zero_grads(*self.nets)
         loss_dict = self.closure()
         _backward_if_needed(loss_dict)
+        if self.shared is not None:
+            for k, v in zip(list(loss_dict), self.shared.allreduce([loss_dict[k] for k in loss_dict])):
+                loss_dict[k] = v
         vals = torch.stack([loss_dict[k].reshape(()) for k in loss_dict]).reshape(1, -1)
         if self.hist is None:
             self.hist = torch.zeros(self.capacity, vals.shape[1], device=vals.device)
@@ -482,7 +520,8 @@ class FluidStepper:
         self.vel, self.prev, self.pres = velocity, velocity_prev, pressure
         self.dt, self.sr, self.lr = dt, sample_resolution, lr
         self.reducer_factory = reducer_factory
-        self.graphed = graphed and reducer_factory is None
+        self.graphed = graphed
+        self.data_parallel = False                 # set by the caller for world > 1 with graphed=True
         self.device_sampler, self.seed, self._samplers = device_sampler, seed, {}
         for p in self.prev.parameters():
             p.requires_grad_(False)
@@ -510,7 +549,7 @@ class FluidStepper:
         if self.graphed:
             loops = self.__dict__.setdefault("_loops", {})
             if key not in loops:                       # capture once per closure kind, replay for every time step
-                loops[key] = GraphedLoop(nets, self.lr, lambda: closure(0))
+                loops[key] = GraphedLoop(nets, self.lr, lambda: closure(0), data_parallel=self.data_parallel)
             else:
                 loops[key].reset(self.lr)
             return loops[key].run(n_iters)

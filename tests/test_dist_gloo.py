@@ -94,3 +94,37 @@ def test_shard_partition_is_exact():
         parts = [shard(x, r, world) for r in range(world)]
         assert torch.equal(torch.cat(parts), x)
         assert max(p.shape[0] for p in parts) - min(p.shape[0] for p in parts) <= 1
+
+
+def _worker_shared(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import insr_pde_b200 as ib
+    from insr_pde_b200 import dist as idist, fused
+    torch.set_num_threads(1)
+    idist.init_from_env("gloo")
+    torch.manual_seed(0)
+    vel, pres = ib.MLP(2, 2, 3, 32, nonlinearity="sine"), ib.MLP(2, 1, 3, 32, nonlinearity="sine")   # 3330 / 3297 parameters
+    shared = fused.SharedGradBuffer([vel, pres])
+    gv, gp = fused.flat_grad(vel), fused.flat_grad(pres)
+    # the nets' gradient buffers are 16-byte aligned slices of the one buffer, and the parameters' .grad are views of them
+    assert gv.data_ptr() == shared.buf.data_ptr() and gp.data_ptr() == shared.buf.data_ptr() + 4 * 3332
+    assert gp.data_ptr() % 16 == 0 and shared.scalars.data_ptr() == shared.buf.data_ptr() + 4 * (3332 + 3300)
+    assert next(iter(pres.parameters())).grad.data_ptr() == gp.data_ptr()
+    gv.fill_(float(rank + 1)); gp.copy_(torch.arange(3297, dtype=torch.float32) * (rank + 1))
+    main, bc = shared.allreduce([torch.tensor(2.0 * rank), torch.tensor(10.0 + rank)])
+    np.savez(os.path.join(out_dir, f"shared{rank}.npz"), gv=gv.numpy(), gp=gp.numpy(), main=float(main), bc=float(bc),
+             pgrad=list(pres.parameters())[-1].grad.numpy())
+
+
+def test_shared_gradient_buffer_is_one_allreduce(tmp_path):
+    """fused.SharedGradBuffer (one flat buffer [gradients of all nets | loss values] per iteration): slices
+    aligned for the C ABI, parameters' .grad alias the buffer, one collective averages gradients and loss terms"""
+    world = 2
+    mp.spawn(_worker_shared, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"shared{k}.npz") for k in range(world)]
+    for k in range(world):
+        assert np.all(r[k]["gv"] == 1.5) and np.allclose(r[k]["gp"], np.arange(3297) * 1.5)
+        assert r[k]["main"] == 1.0 and r[k]["bc"] == 10.5
+        assert np.allclose(r[k]["pgrad"], r[k]["gp"][-1:])          # last parameter (output bias) = last element of the slice
