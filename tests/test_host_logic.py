@@ -260,6 +260,48 @@ def test_fused_training_loop_and_stepper_emulated(emu_backend):
     assert torch.equal(prev.flat_theta(), prev.flat_theta()) and not any(p.requires_grad for p in prev.parameters())
 
 
+def test_elasticity_stepper_follows_reference_algorithm_emulated(emu_backend):
+    """fused.ElasticityStepper (eager loop) under emulation: the reference's sample pattern (elasticity/model.py:198-253), the
+    one-kernel closure with its kept tape on the tiled family, torch Adam -- against the reference algorithm (autograd
+    jacobian + torch.svd + Adam, oracle port) from the same weights on the same 'uniform' samples"""
+    from insr_pde_b200 import fused, sampling
+    dim, H, sr, K, lr = 2, 40, 6, 3, 1e-3
+    kw = dict(energy=["arap", "volume", "kinematics", "external", "constraint", "constraint_right", "collision_sphere"],
+              ratio_arap=1.0, ratio_volume=20.0, ratio_kinematics=0.5, ratio_constraint=50.0, ratio_collide=4.0,
+              external_force=torch.tensor([0.0, -1.0]), external_force_timesteps=5,
+              constraint_offset_right=torch.tensor([0.3, 0.0]), plane_height=-0.7,
+              circle_center=torch.tensor([0.1, -0.8]), circle_radius=0.6)
+    torch.manual_seed(3)
+    nets = [ib.MLP(dim, dim, 3, H, nonlinearity="sine") for _ in range(3)]
+    ref = [tp.RefMLP(dim, dim, 3, H).load_flat_theta(n.flat_theta().detach().clone()) for n in nets]
+    st = fused.ElasticityStepper(*nets, dim, dt=0.05, sample_resolution=sr, lr=lr, sample_pattern=("random", "uniform"), **kw)
+    x = st._interior(sr)
+    left, right = st._fixed(sr)
+    assert x.shape == (2 * sr ** dim, dim) and x.requires_grad                  # random block, then the cell-centred grid
+    assert torch.equal(x[sr ** dim:].detach(), sampling.sample_uniform(sr, dim))
+    assert left.shape == (2 * sr, dim) and bool((left[:, 0] == -1).all()) and bool((right[:, 0] == 1).all())
+    st = fused.ElasticityStepper(*nets, dim, dt=0.05, sample_resolution=sr, lr=lr, sample_pattern=("uniform",), **kw)
+    ours = [h["main"] for h in st.step(K)]
+    ref[2].load_state_dict(ref[1].state_dict()); ref[1].load_state_dict(ref[0].state_dict())
+    for n in ref[1:]:
+        for p_ in n.parameters():
+            p_.requires_grad_(False)
+    opt = torch.optim.Adam(ref[0].parameters(), lr=lr)
+    xs = sampling.sample_uniform(sr, dim)
+    face = sampling.sample_uniform(sr, dim - 1)
+    one = torch.ones(face.shape[0], 1)
+    theirs = []
+    for _ in range(K):
+        opt.zero_grad()
+        loss = closures.elasticity_solve_deformation(ref[0], ref[1], ref[2], tp, xs.clone().requires_grad_(True),
+                                                     torch.cat((-one, face), 1), torch.cat((one, face), 1), dt=0.05, timestep=1, **kw)
+        loss["main"].backward()
+        opt.step()
+        theirs.append(float(loss["main"].detach()))
+    assert rel(ours, theirs) < 1e-3
+    assert rel(nets[0].flat_theta().detach().numpy(), torch.cat([p_.detach().reshape(-1) for p_ in ref[0].parameters()]).numpy()) < 2e-3
+
+
 def test_device_optimizer_matches_torch_adam_and_plateau(emu_backend):
     """insr_adam_step / insr_plateau_step reproduce torch.optim.Adam + ReduceLROnPlateau (base/baseModel.py:55-81)"""
     from insr_pde_b200 import _ops
