@@ -149,6 +149,19 @@ int insr_plateau_step(const float *loss, float *sched, float factor, int patienc
                       float min_lr, float eps, void *stream);
 
 /*
+ * The tail of one training iteration in one kernel: Adam for every trainable net (n_slots <= 8 flat vectors; host arrays of
+ * device pointers), the gradient buffers zeroed for the next iteration (optimizer.zero_grad, base/baseModel.py:76), the
+ * ReduceLROnPlateau step on losses[main_index] and the shared step counter (:79-81), and the iteration's n_losses loss
+ * values appended to the device log hist[hist_idx++] (the .item() logging of :116-118 without the host sync; hist may be
+ * NULL).  Same arithmetic as insr_adam_step + insr_plateau_step.  ticket: a zeroed device word (last-CTA detection).
+ */
+int insr_iteration_update(int n_slots, float *const *theta, float *const *grad, float *const *exp_avg,
+                          float *const *exp_avg_sq, const int64_t *n, float *sched, const float *losses, int n_losses,
+                          int main_index, float *hist, int64_t hist_capacity, int64_t *hist_idx, uint32_t *ticket, float beta1,
+                          float beta2, float eps, float factor, int patience, float threshold, float min_lr, float eps_lr,
+                          int zero_grad, void *stream);
+
+/*
  * Batched 2x2 / 3x3 singular value decomposition and the fused elasticity energy.
  * Replaces, in the elasticity closure (elasticity/model.py:143-149):
  *     U_x, S_x, V_x = torch.svd(jac_x)                                  -> insr_svd_small

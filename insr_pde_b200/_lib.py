@@ -22,7 +22,7 @@ FLAG_KEEP_TAPE = 8
 EXPORTS = [
     "insr_version", "insr_last_error", "insr_siren_theta_size", "insr_siren_workspace_bytes",
     "insr_siren_forward", "insr_siren_backward", "insr_siren_lsq_step", "insr_siren_kernel_family",
-    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes", "insr_sample_mesh", "insr_siren_tape_supported", "insr_elastic_terms",
+    "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes", "insr_sample_mesh", "insr_siren_tape_supported", "insr_elastic_terms", "insr_iteration_update",
 ]
 
 
@@ -75,6 +75,9 @@ class Library:
         c.insr_svd_small.argtypes = [_vp, _i64, _i32, _vp, _vp, _vp, _vp]
         c.insr_elastic_energy.restype = _i32
         c.insr_elastic_energy.argtypes = [_vp, _i64, _i32, _f, _f, _vp, _vp, _vp]
+        c.insr_iteration_update.restype = _i32
+        c.insr_iteration_update.argtypes = [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp] + \
+            [ctypes.c_float] * 4 + [_i32] + [ctypes.c_float] * 3 + [_i32, _vp]
         c.insr_elastic_terms.restype = _i32
         c.insr_elastic_terms.argtypes = [ctypes.POINTER(ElasticTermsDesc), _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
         c.insr_sample_mesh.restype = _i32
@@ -116,6 +119,15 @@ class Library:
 
     def adam_step(self, theta, grad, m, v, n, sched, beta1, beta2, eps, stream):
         self.check(self.cdll.insr_adam_step(theta, grad, m, v, n, sched, beta1, beta2, eps, stream))
+
+    def iteration_update(self, thetas, grads, ms, vs, sizes, sched, losses, n_losses, main_index, hist, hist_capacity,
+                         hist_idx, ticket, beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr, zero_grad, stream):
+        k = len(thetas)
+        arr = lambda ptrs: (ctypes.c_void_p * k)(*ptrs)
+        self.check(self.cdll.insr_iteration_update(k, arr(thetas), arr(grads), arr(ms), arr(vs), (ctypes.c_int64 * k)(*sizes),
+                                                   sched, losses, n_losses, main_index, hist, hist_capacity, hist_idx, ticket,
+                                                   beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr,
+                                                   int(zero_grad), stream))
 
     def plateau_step(self, loss, sched, factor, patience, threshold, min_lr, eps, stream):
         self.check(self.cdll.insr_plateau_step(loss, sched, factor, patience, threshold, min_lr, eps, stream))

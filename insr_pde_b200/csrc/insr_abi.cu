@@ -348,6 +348,39 @@ int insr_plateau_step(const float *loss, float *sched, float factor, int patienc
     return check_cuda("k_plateau_step");
 }
 
+int insr_iteration_update(int n_slots, float *const *theta, float *const *grad, float *const *exp_avg,
+                          float *const *exp_avg_sq, const int64_t *n, float *sched, const float *losses, int n_losses,
+                          int main_index, float *hist, int64_t hist_capacity, int64_t *hist_idx, uint32_t *ticket, float beta1,
+                          float beta2, float eps, float factor, int patience, float threshold, float min_lr, float eps_lr,
+                          int zero_grad, void *stream) {
+    if (!theta || !grad || !exp_avg || !exp_avg_sq || !n || !sched || !losses || !ticket)
+        return fail(INSR_ERR_NULL, "iteration_update: NULL argument");
+    if (n_slots < 1 || n_slots > INSR_MAX_OPT_SLOTS)
+        return fail(INSR_ERR_SHAPE, "iteration_update: n_slots=%d (1..%d)", n_slots, INSR_MAX_OPT_SLOTS);
+    if (n_losses < 1 || main_index < 0 || main_index >= n_losses)
+        return fail(INSR_ERR_SHAPE, "iteration_update: n_losses=%d main_index=%d", n_losses, main_index);
+    if (hist && (!hist_idx || hist_capacity < 1)) return fail(INSR_ERR_NULL, "iteration_update: a loss log needs its index word and a capacity");
+    insr_opt_slots sl{};
+    sl.n_slots = n_slots;
+    int64_t total = 0;
+    for (int k = 0; k < n_slots; ++k) {
+        if (!theta[k] || !grad[k] || !exp_avg[k] || !exp_avg_sq[k] || n[k] < 0)
+            return fail(INSR_ERR_NULL, "iteration_update: slot %d has a NULL buffer or a negative size", k);
+        sl.theta[k] = theta[k]; sl.grad[k] = grad[k]; sl.m[k] = exp_avg[k]; sl.v[k] = exp_avg_sq[k]; sl.n[k] = n[k];
+        total += n[k];
+    }
+    int rc = check_device();
+    if (rc) return rc;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1184) blocks = 1184;
+    auto kfn = k_iteration_update;
+    INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(256), 0, stream, sl, sched, losses, n_losses, main_index, hist, hist_capacity,
+                hist_idx, ticket, beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr, zero_grad);
+    ++g_launches;
+    return check_cuda("k_iteration_update");
+}
+
 int insr_svd_small(const float *F, int64_t n, int d, float *U, float *S, float *V, void *stream) {
     if (!F || !S) return fail(INSR_ERR_NULL, "svd_small: F and S must not be NULL");
     if (n < 0 || (d != 2 && d != 3)) return fail(INSR_ERR_SHAPE, "svd_small: n=%lld d=%d (d must be 2 or 3)", (long long)n, d);

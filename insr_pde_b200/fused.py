@@ -396,6 +396,26 @@ class DeviceOptimizer:
         _ops.plateau_step(main_loss.reshape(1), self.sched, self.factor, self.patience, self.threshold,
                           self.min_lr, 1e-8)
 
+    def update(self, losses, main_index, hist=None, hist_idx=None, zero_grad=True):
+        """the whole tail of an iteration in ONE kernel (insr_iteration_update): Adam for every net, gradients zeroed for
+        the next iteration, plateau schedule on ``losses[main_index]``, the loss values appended to ``hist[hist_idx++]``.
+        ``losses``: contiguous fp32 device vector of this iteration's loss terms."""
+        if not hasattr(self, "_ticket"):
+            self._ticket = torch.zeros(1, dtype=torch.int32, device=self.sched.device)
+        lib = _ops._lib.get_lib()
+        dev = self.sched.device
+        with _ops._DeviceGuard(dev):
+            lib.iteration_update([t.data_ptr() for _, t, _, _, _ in self.state], [g.data_ptr() for _, _, g, _, _ in self.state],
+                                 [m.data_ptr() for _, _, _, m, _ in self.state], [v.data_ptr() for _, _, _, _, v in self.state],
+                                 [t.numel() for _, t, _, _, _ in self.state], self.sched.data_ptr(), losses.data_ptr(),
+                                 losses.numel(), main_index, _ops._ptr(hist), 0 if hist is None else hist.shape[0],
+                                 _ops._ptr(hist_idx), self._ticket.data_ptr(), self.betas[0], self.betas[1], self.eps,
+                                 self.factor, self.patience, self.threshold, self.min_lr, 1e-8, zero_grad, _ops._stream(dev))
+
+    def zero_grads(self):
+        for _, _, grad, _, _ in self.state:
+            grad.zero_()
+
     def reset(self, lr):
         """fresh optimiser + scheduler state (the reference builds new ones per training loop)"""
         self.sched.copy_(torch.tensor([lr, float("inf"), 0.0, 0.0]))
@@ -458,19 +478,20 @@ class GraphedLoop:
         self.graph = None
 
     def _iteration(self):
-        zero_grads(*self.nets)
+        # the gradient buffers are zero here: zeroed by run() before the first iteration, then by every update kernel
         loss_dict = self.closure()
         _backward_if_needed(loss_dict)
+        keys = list(loss_dict)
         if self.shared is not None:
-            for k, v in zip(list(loss_dict), self.shared.allreduce([loss_dict[k] for k in loss_dict])):
-                loss_dict[k] = v
-        vals = torch.stack([loss_dict[k].reshape(()) for k in loss_dict]).reshape(1, -1)
+            self.shared.allreduce([loss_dict[k] for k in keys])
+            vals = self.shared.scalars[:len(keys)]             # averaged over the ranks, already contiguous
+        else:
+            vals = torch.stack([loss_dict[k].reshape(()) for k in keys])
         if self.hist is None:
-            self.hist = torch.zeros(self.capacity, vals.shape[1], device=vals.device)
-        self.hist.index_copy_(0, self.idx, vals)
-        self.idx += 1
-        self.opt.step(loss_dict["main"])
-        return list(loss_dict.keys())
+            self.hist = torch.zeros(self.capacity, len(keys), device=vals.device)
+        # Adam (all nets) + zero_grad + plateau + loss log: one kernel
+        self.opt.update(vals, keys.index("main"), self.hist, self.idx)
+        return keys
 
     def reset(self, lr):
         """reuse the captured graph for a new training loop: only the optimiser state and the log restart"""
@@ -478,6 +499,7 @@ class GraphedLoop:
         self.idx.zero_()
 
     def run(self, n_iters, early_stop=False, check_every=100):
+        self.opt.zero_grads()                          # whatever ran on these nets in between may have left gradients
         if self.graph is None:
             keys = self._iteration()                   # iteration 0 eagerly (also warms everything up)
             self.keys = keys

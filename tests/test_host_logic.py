@@ -325,3 +325,33 @@ def test_device_optimizer_matches_torch_adam_and_plateau(emu_backend):
         assert float((theta - ref_p.detach()).abs().max()) < 2e-6, it
     assert opt.param_groups[0]["lr"] < 1e-2          # the schedule actually fired
     assert float(sched[3]) == len(losses)
+
+
+def test_one_kernel_iteration_update_matches_torch(emu_backend):
+    """insr_iteration_update (DeviceOptimizer.update): Adam over TWO nets, gradients zeroed, ReduceLROnPlateau on the
+    main loss, step counter and the loss log -- against torch.optim.Adam + ReduceLROnPlateau (base/baseModel.py:55-81)"""
+    from insr_pde_b200 import fused
+    torch.manual_seed(1)
+    nets = [ib.MLP(2, 2, 3, 32, nonlinearity="sine"), ib.MLP(2, 1, 3, 32, nonlinearity="sine")]
+    refs = [torch.nn.Parameter(n.flat_theta().detach().clone()) for n in nets]
+    opt = torch.optim.Adam(refs, lr=1e-2)
+    sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=0.1, min_lr=1e-8, patience=3)
+    dev_opt = fused.DeviceOptimizer(nets, 1e-2, patience=3)
+    hist = torch.full((32, 2), -1.0)
+    idx = torch.zeros(1, dtype=torch.long)
+    losses = [1.0, 0.9, 0.95, 0.95, 0.96, 0.97, 0.98, 0.5, 0.6, 0.6, 0.6, 0.6, 0.6, 0.6]
+    for it, lv in enumerate(losses):
+        for n, r in zip(nets, refs):
+            g = torch.randn(r.numel()) * (1 + it)
+            fused.flat_grad(n).copy_(g)
+            r.grad = g.clone()
+        opt.step()
+        sch.step(lv)
+        dev_opt.update(torch.tensor([7.0 + it, lv]), 1, hist, idx)          # 'main' is the second entry here
+        assert abs(dev_opt.lr - opt.param_groups[0]["lr"]) < 1e-12 + 1e-6 * opt.param_groups[0]["lr"], it
+        for n, r in zip(nets, refs):
+            assert float((n.flat_theta() - r.detach()).abs().max()) < 2e-6, it
+            assert not fused.flat_grad(n).any()                              # zero_grad for the next iteration
+    assert opt.param_groups[0]["lr"] < 1e-2 and int(idx) == len(losses) and float(dev_opt.sched[3]) == len(losses)
+    assert torch.equal(hist[:len(losses), 1], torch.tensor(losses)) and torch.equal(hist[:len(losses), 0], 7.0 + torch.arange(len(losses)))
+    assert bool((hist[len(losses):] == -1).all()) and int(dev_opt._ticket) == 0
