@@ -59,16 +59,27 @@ def zero_grads(*nets):
         flat_grad(n).zero_()
 
 
-def lsq(net, x, order, cy, cj=None, cl=None, target=None, scale=None):
+class Losses(dict):
+    """a loss dict whose values are views of ONE small device vector (``.vector``, in key order): the kernels accumulate
+    their loss terms straight into its slots, and the consumers (loss log, all-reduce, LR schedule) take the vector as it
+    is -- no per-term zero fills, no ``bx + by``, no ``torch.stack`` in the iteration graph"""
+
+    def __init__(self, vector, keys):
+        super().__init__((k, vector[i]) for i, k in enumerate(keys))
+        self.vector = vector
+
+
+def lsq(net, x, order, cy, cj=None, cl=None, target=None, scale=None, out=None):
     """loss = scale * sum_{n,c} (sum_o cy[c,o] y + cj[c,o,:].J + cl[c,o] lap - target[n,c])^2 ;
-    d loss / d theta is ACCUMULATED into flat_grad(net); returns the loss (1-element tensor)."""
+    d loss / d theta is ACCUMULATED into flat_grad(net); returns the loss (1-element tensor).
+    ``out``: a 1-element view the loss is ACCUMULATED into instead of a fresh zero (several terms may share a slot)."""
     x = x.detach().reshape(-1, net.in_features).contiguous()
     rows = len(cy)
     if scale is None:
         scale = 1.0 / (x.shape[0] * rows)
     if target is not None:
         target = target.detach().reshape(x.shape[0], rows).contiguous().float()
-    loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+    loss = torch.zeros(1, dtype=torch.float32, device=x.device) if out is None else out
     _ops.siren_lsq_step(net.desc, net.flat_theta(), x, order, cy, cj, cl, target, scale,
                         loss_out=loss, gtheta=flat_grad(net))
     return loss[0]
@@ -129,17 +140,20 @@ def advect_step(field, field_prev, samples, boundary_samples, dt, vel):
     def interior():
         u_prev, j_prev = evaluate(field_prev, samples, ORDER_JAC)
         target = u_prev / dt - (0.5 * vel) * j_prev[:, :, 0]
-        return lsq(field, samples, ORDER_JAC, [[1.0 / dt]], cj=[[[0.5 * vel]]], target=target)
+        return lsq(field, samples, ORDER_JAC, [[1.0 / dt]], cj=[[[0.5 * vel]]], target=target, out=acc[0:1])
 
-    main, bc = parallel(samples, interior, lambda: lsq(field, boundary_samples, ORDER_VALUE, [[1.0]]))
-    return {"main": main, "bc": bc}
+    acc = torch.zeros(2, dtype=torch.float32, device=samples.device)
+    parallel(samples, interior, lambda: lsq(field, boundary_samples, ORDER_VALUE, [[1.0]], out=acc[1:2]))
+    return Losses(acc, ("main", "bc"))
 
 
 # ------------------------------------------------------------------------------------------------
 # fluid (2-D inviscid Euler, operator splitting)
 # ------------------------------------------------------------------------------------------------
-def _no_slip_terms(velocity, bc_x, bc_y):
-    return (lambda: lsq(velocity, bc_x, ORDER_VALUE, [[1.0, 0.0]]), lambda: lsq(velocity, bc_y, ORDER_VALUE, [[0.0, 1.0]]))
+def _no_slip_terms(velocity, bc_x, bc_y, out):
+    """mean(u_x^2) on the left / right bands + mean(u_y^2) on the bottom / top bands, both accumulated into ``out``"""
+    return (lambda: lsq(velocity, bc_x, ORDER_VALUE, [[1.0, 0.0]], out=out),
+            lambda: lsq(velocity, bc_y, ORDER_VALUE, [[0.0, 1.0]], out=out))
 
 
 def fluid_initialize(velocity, samples, init_values):
@@ -154,10 +168,11 @@ def fluid_advect_velocity(velocity, velocity_prev, samples, bc_x, bc_y, dt):
         (u_prev,) = evaluate(velocity_prev, x, ORDER_VALUE)
         back = torch.clamp(x - u_prev * dt, min=-1.0, max=1.0)
         (u_adv,) = evaluate(velocity_prev, back, ORDER_VALUE)
-        return lsq(velocity, x, ORDER_VALUE, _eye(2), target=u_adv)
+        return lsq(velocity, x, ORDER_VALUE, _eye(2), target=u_adv, out=acc[0:1])
 
-    main, bx, by = parallel(x, interior, *_no_slip_terms(velocity, bc_x, bc_y))
-    return {"main": main, "bc": bx + by}
+    acc = torch.zeros(2, dtype=torch.float32, device=x.device)
+    parallel(x, interior, *_no_slip_terms(velocity, bc_x, bc_y, acc[1:2]))
+    return Losses(acc, ("main", "bc"))
 
 
 def fluid_solve_pressure(velocity, pressure, samples, bc_x, bc_y):
@@ -165,12 +180,13 @@ def fluid_solve_pressure(velocity, pressure, samples, bc_x, bc_y):
     def interior():
         _, jac_u = evaluate(velocity, samples, ORDER_JAC)
         div_u = jac_u[:, 0, 0] + jac_u[:, 1, 1]
-        return lsq(pressure, samples, ORDER_LAP, [[0.0]], cl=[[1.0]], target=div_u)
+        return lsq(pressure, samples, ORDER_LAP, [[0.0]], cl=[[1.0]], target=div_u, out=acc[0:1])
 
-    main, bx, by = parallel(samples, interior,
-                            lambda: lsq(pressure, bc_x, ORDER_JAC, [[0.0]], cj=[[[1.0, 0.0]]]),
-                            lambda: lsq(pressure, bc_y, ORDER_JAC, [[0.0]], cj=[[[0.0, 1.0]]]))
-    return {"main": main, "bc": bx + by}
+    acc = torch.zeros(2, dtype=torch.float32, device=samples.device)
+    parallel(samples, interior,
+             lambda: lsq(pressure, bc_x, ORDER_JAC, [[0.0]], cj=[[[1.0, 0.0]]], out=acc[1:2]),
+             lambda: lsq(pressure, bc_y, ORDER_JAC, [[0.0]], cj=[[[0.0, 1.0]]], out=acc[1:2]))
+    return Losses(acc, ("main", "bc"))
 
 
 def fluid_projection(velocity, velocity_prev, pressure, samples, bc_x, bc_y):
@@ -179,10 +195,11 @@ def fluid_projection(velocity, velocity_prev, pressure, samples, bc_x, bc_y):
         (u_prev,) = evaluate(velocity_prev, samples, ORDER_VALUE)
         _, jac_p = evaluate(pressure, samples, ORDER_JAC)
         target = u_prev - jac_p[:, 0, :]
-        return lsq(velocity, samples, ORDER_VALUE, _eye(2), target=target)
+        return lsq(velocity, samples, ORDER_VALUE, _eye(2), target=target, out=acc[0:1])
 
-    main, bx, by = parallel(samples, interior, *_no_slip_terms(velocity, bc_x, bc_y))
-    return {"main": main, "bc": bx + by}
+    acc = torch.zeros(2, dtype=torch.float32, device=samples.device)
+    parallel(samples, interior, *_no_slip_terms(velocity, bc_x, bc_y, acc[1:2]))
+    return Losses(acc, ("main", "bc"))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -336,6 +353,8 @@ def _backward_if_needed(loss_dict):
     live = [v for v in loss_dict.values() if torch.is_tensor(v) and v.requires_grad]
     if live:
         sum(live).backward()
+    if isinstance(loss_dict, Losses):
+        return                                         # kernel-accumulated values: nothing to detach
     for k in loss_dict:
         if torch.is_tensor(loss_dict[k]):
             loss_dict[k] = loss_dict[k].detach()
@@ -454,7 +473,7 @@ class SharedGradBuffer:
         k = len(values)
         if k > self.scalars.numel():
             raise ValueError(f"{k} loss terms, {self.scalars.numel()} slots")
-        self.scalars[:k].copy_(torch.stack([v.reshape(()) for v in values]))
+        self.scalars[:k].copy_(values if torch.is_tensor(values) else torch.stack([v.reshape(()) for v in values]))
         if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(self.group) > 1:
             tdist.all_reduce(self.buf, group=self.group)
             self.buf.div_(tdist.get_world_size(self.group))
@@ -482,11 +501,12 @@ class GraphedLoop:
         loss_dict = self.closure()
         _backward_if_needed(loss_dict)
         keys = list(loss_dict)
+        vector = loss_dict.vector if isinstance(loss_dict, Losses) else None
         if self.shared is not None:
-            self.shared.allreduce([loss_dict[k] for k in keys])
+            self.shared.allreduce(vector if vector is not None else [loss_dict[k] for k in keys])
             vals = self.shared.scalars[:len(keys)]             # averaged over the ranks, already contiguous
         else:
-            vals = torch.stack([loss_dict[k].reshape(()) for k in keys])
+            vals = vector if vector is not None else torch.stack([loss_dict[k].reshape(()) for k in keys])
         if self.hist is None:
             self.hist = torch.zeros(self.capacity, len(keys), device=vals.device)
         # Adam (all nets) + zero_grad + plateau + loss log: one kernel
