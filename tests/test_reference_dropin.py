@@ -15,20 +15,34 @@ from oracle import ref_loader
 pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
 
 
+_PROCS = {}
 _CACHE = {}
+MODES, PDES = ("reference", "fused", "fused_closures"), ("advection", "fluid", "elasticity")
+
+
+def _start_all():
+    """all nine runs are independent single-threaded subprocesses (most of their time is importing torch): start them
+    together, collect on demand"""
+    if _PROCS:
+        return
+    if "fused" in MODES:                    # build the emulation library ONCE, before the parallel runs would race for it
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build_emu
+        build_emu.build_emu()
+    for mode in MODES:
+        for pde in PDES:
+            _PROCS[(mode, pde)] = subprocess.Popen(
+                [sys.executable, "-W", "ignore", os.path.join(ROOT, "tests", "run_ref_dropin.py"), mode, pde],
+                stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
 
 
 def run(mode, pde):
+    _start_all()
     if (mode, pde) not in _CACHE:
-        _CACHE[(mode, pde)] = _run(mode, pde)
+        out, err = _PROCS[(mode, pde)].communicate(timeout=900)
+        assert _PROCS[(mode, pde)].returncode == 0, err[-3000:]
+        _CACHE[(mode, pde)] = json.loads(out.strip().splitlines()[-1])
     return _CACHE[(mode, pde)]
-
-
-def _run(mode, pde):
-    res = subprocess.run([sys.executable, "-W", "ignore", os.path.join(ROOT, "tests", "run_ref_dropin.py"), mode, pde],
-                         capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stderr[-3000:]
-    return json.loads(res.stdout.strip().splitlines()[-1])
 
 
 @pytest.mark.parametrize("pde", ["advection", "fluid", "elasticity"])
