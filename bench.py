@@ -222,6 +222,27 @@ def elasticity_timestep_ours(dev, iters, case="elasticity2Dstretch"):
             "points_per_iteration": npts, "points_per_s": round(npts * iters / sec, 1), "final_loss": round(h[-1]["main"], 6)}
 
 
+def advection_timestep_ours(dev, iters):
+    """seconds per advect1D time step (advection/model.py:62-91: one loop of `iters` Adam iterations, 5000 points + 50
+    boundary points) on AdvectionStepper, one CUDA graph per iteration"""
+    import insr_pde_b200 as ib
+    from insr_pde_b200 import fused
+    torch.manual_seed(0)
+    field, prev = (ib.MLP(1, 1, 2, 20, nonlinearity="sine").to(dev) for _ in range(2))
+    st = fused.AdvectionStepper(field, prev, dt=0.05, vel=0.25, length=4.0, sample_resolution=5000, lr=1e-4, graphed=True)
+    st.initialize(fused.gaussian_like, 10)
+    st.step(5)
+    sec = float("inf")
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h = st.step(iters)
+        torch.cuda.synchronize()
+        sec = min(sec, time.perf_counter() - t0)
+    return {"case": "advect1D", "sec_per_timestep": round(sec, 4), "iters_per_loop": iters, "us_per_iteration": round(sec / iters * 1e6, 1),
+            "points_per_iteration": 5000, "final_loss": round(h[-1]["main"], 8)}
+
+
 def fluid_timestep_cpu(iters_measured=3, iters_per_loop=100):
     """the same time step with the reference algorithm (oracle port) on the host cores; a few
     iterations per loop are timed and scaled to `iters_per_loop`."""
@@ -506,7 +527,12 @@ def run_ours(args):
         if rank == 0 and not args.no_cpu_baseline:
             timestep["cpu_reference"] = fluid_timestep_cpu(3, args.timestep_iters)
         if world == 1:                                  # the 32 < H <= 512 family's closure, same metric
-            timestep["elasticity"] = [elasticity_timestep_ours(dev, args.timestep_iters, c) for c in ELASTIC_CASES]
+            for key, fn in (("elasticity", lambda: [elasticity_timestep_ours(dev, args.timestep_iters, c) for c in ELASTIC_CASES]),
+                            ("advection", lambda: advection_timestep_ours(dev, args.timestep_iters))):
+                try:                                    # secondary measurements must not take the headline line down
+                    timestep[key] = fn()
+                except Exception as e:
+                    timestep[key] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
     # ---- CPU baseline (oracle port of the reference algorithm), rank 0, bounded sample
     cpu, torch_gpu = None, None

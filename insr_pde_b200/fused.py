@@ -618,6 +618,56 @@ class FluidStepper:
         return h1, h2, h3
 
 
+class AdvectionStepper:
+    """Advection1DModel.initialize / step (advection/model.py:37-91): the Gaussian fit, then per time step the previous-frame
+    hand-over and one training loop of the midpoint-residual closure; points as the reference draws them
+    (``sample_random(sr, 1) * length / 2`` and the 2 x eps boundary bands) -- from one Philox kernel when ``graphed``."""
+
+    def __init__(self, field, field_prev, dt=0.05, vel=0.25, length=4.0, sample_resolution=5000, lr=1e-4, graphed=False, seed=0):
+        self.field, self.prev = field, field_prev
+        self.dt, self.vel, self.length, self.sr, self.lr = dt, vel, length, sample_resolution, lr
+        self.graphed, self.seed, self._sampler = graphed, seed, None
+        for p in self.prev.parameters():
+            p.requires_grad_(False)
+
+    def _samples(self):
+        from . import sampling
+        dev = next(self.field.parameters()).device
+        nb, half, eps = max(self.sr // 100, 10), self.length / 2, 1e-4
+        if self.graphed:
+            if self._sampler is None:       # base/sampling.py:21-37 scaled by length / 2: bands around -half and +half
+                sets = [[(self.sr, (-half,), (half,))],
+                        [(nb // 2, ((-1 - eps) * half,), ((-1 + eps) * half,)), (nb // 2, ((1 - eps) * half,), ((1 + eps) * half,))]]
+                self._sampler = sampling.BoxSampler(sets, 1, seed=self.seed, device=dev)
+            return tuple(self._sampler.sample())
+        return (sampling.sample_random(self.sr, 1, device=dev) * half, sampling.sample_boundary(nb, 1, device=dev) * half)
+
+    def _loop(self, closure, n_iters, key):
+        if self.graphed:
+            loops = self.__dict__.setdefault("_loops", {})
+            if key not in loops:
+                loops[key] = GraphedLoop([self.field], self.lr, lambda: closure(0))
+            else:
+                loops[key].reset(self.lr)
+            return loops[key].run(n_iters)
+        return TrainingLoop([self.field], self.lr).run(closure, n_iters)
+
+    def initialize(self, init_fn, n_iters):
+        def c(i):
+            x, _ = self._samples()
+            return advect_initialize(self.field, x, init_fn(x))
+        return self._loop(c, n_iters, "initialize")
+
+    def step(self, n_iters):
+        self.prev.load_state_dict(self.field.state_dict())
+        return self._loop(lambda i: advect_step(self.field, self.prev, *self._samples(), self.dt, self.vel), n_iters, "advect")
+
+
+def gaussian_like(x, mu=-1.5, sigma=0.1):
+    """advection/examples.py:14-16 with example1's mu"""
+    return torch.exp(-0.5 * (x - mu) ** 2 / (sigma ** 2))
+
+
 class ElasticityStepper:
     """ElasticityModel.initialize / step (elasticity/model.py:100-125) on the fused closure: previous-frame hand-over,
     the reference's sample pattern ('random' and / or 'uniform'; a mesh when ``mesh=(V, F)`` is given), one

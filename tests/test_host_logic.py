@@ -260,6 +260,23 @@ def test_fused_training_loop_and_stepper_emulated(emu_backend):
     assert torch.equal(prev.flat_theta(), prev.flat_theta()) and not any(p.requires_grad for p in prev.parameters())
 
 
+def test_advection_stepper_emulated(emu_backend):
+    """fused.AdvectionStepper (advection/model.py:37-91): Gaussian fit descends, the step hands the frame over and trains"""
+    from insr_pde_b200 import fused
+    torch.manual_seed(0)
+    field, prev = ib.MLP(1, 1, 2, 20, nonlinearity="sine"), ib.MLP(1, 1, 2, 20, nonlinearity="sine")
+    st = fused.AdvectionStepper(field, prev, dt=0.05, vel=0.25, length=4.0, sample_resolution=300, lr=1e-3)
+    x, xb = st._samples()
+    assert x.shape == (300, 1) and float(x.abs().max()) <= 2.0 and xb.shape == (10, 1)
+    assert float((xb.abs() - 2.0).abs().max()) <= 2.0001e-4            # the epsilon bands around -L/2 and +L/2
+    h0 = st.initialize(fused.gaussian_like, 8)
+    assert h0[-1]["main"] < h0[0]["main"]
+    before = field.flat_theta().clone()
+    h1 = st.step(3)
+    assert torch.equal(prev.flat_theta(), before) and not torch.equal(field.flat_theta(), before)
+    assert len(h1) == 3 and set(h1[0]) == {"main", "bc"} and all(np.isfinite(list(d.values())).all() for d in h1)
+
+
 def test_elasticity_stepper_follows_reference_algorithm_emulated(emu_backend):
     """fused.ElasticityStepper (eager loop) under emulation: the reference's sample pattern (elasticity/model.py:198-253), the
     one-kernel closure with its kept tape on the tiled family, torch Adam -- against the reference algorithm (autograd
