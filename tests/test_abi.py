@@ -67,3 +67,38 @@ def test_argument_validation_order(lib):
     assert lib.cdll.insr_siren_forward(ctypes.byref(d), p, p + 4, 1, 0, p, None, None, None, 0, None) == -4
     with pytest.raises(_lib.InsrError):
         lib.check(-4)
+
+
+def test_auxiliary_entry_points_validate_before_touching_the_device(lib):
+    """the closure / sampler / optimiser entry points reject bad arguments with their insr_status before any CUDA call
+    (this box has no GPU: reaching the device check would return a different code)"""
+    c = lib.cdll
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    p += (-p) % 16
+    t = _lib.ElasticTermsDesc()
+    t.n, t.n_left, t.n_right, t.dt = 4, 0, 0, 0.05
+    assert c.insr_elastic_terms(None, 2, p, None, p, p, p, p, p, None, None) == -1
+    assert c.insr_elastic_terms(ctypes.byref(t), 4, p, None, p, p, p, p, p, None, None) == -2          # d must be 2 or 3
+    t.r_arap = 1.0
+    assert c.insr_elastic_terms(ctypes.byref(t), 2, p, None, p, p, p, p, p, None, None) == -1          # arap needs J and gJ
+    assert b"arap / volume need J" in c.insr_last_error()
+    t.r_arap, t.dt = 0.0, 0.0
+    assert c.insr_elastic_terms(ctypes.byref(t), 2, p, None, p, p, p, p, p, None, None) == -2          # dt must be positive
+    assert c.insr_sample_mesh(p, p, p, 0, 4, 10, 3, 0, None, None, 0, p, None) == -2                   # no elements
+    assert c.insr_sample_mesh(p, p, p, 5, 5, 10, 3, 0, None, None, 0, p, None) == -2                   # neither triangles nor tets
+    assert c.insr_sample_mesh(p, p, p, 5, 4, 10, 3, 0, p, None, 0, p, None) == -1                      # counter without ticket
+    assert c.insr_sample_boxes(0, 2, p, p, p, 0, None, None, 0, p, None) == -2
+    assert c.insr_svd_small(p, 3, 4, None, p, None, None) == -2
+    arr = (ctypes.c_void_p * 1)(p)
+    sizes = (ctypes.c_int64 * 1)(8)
+    args = [ctypes.c_float(0.9), ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_float(0.1), 500,
+            ctypes.c_float(1e-4), ctypes.c_float(1e-8), ctypes.c_float(1e-8), 1, None]
+    assert c.insr_iteration_update(0, arr, arr, arr, arr, sizes, p, p, 1, 0, None, 0, None, p, *args) == -2    # no slots
+    assert c.insr_iteration_update(1, arr, arr, arr, arr, sizes, p, p, 2, 2, None, 0, None, p, *args) == -2    # main index out of range
+    assert c.insr_iteration_update(1, arr, arr, arr, arr, sizes, p, p, 1, 0, p, 0, None, p, *args) == -1       # log without index word
+    # tape: offered for the tiled family on one workspace chunk only, never for the H <= 32 family or forced-generic
+    assert lib.tape_supported(_lib.make_desc(2, 2, 68, 3), 20000, 1)
+    assert not lib.tape_supported(_lib.make_desc(2, 1, 32, 3), 20000, 2)
+    assert not lib.tape_supported(_lib.make_desc(2, 2, 68, 3, flags=_lib.FLAG_FORCE_GENERIC), 20000, 1)
+    assert not lib.tape_supported(_lib.make_desc(2, 1, 512, 5), 1 << 22, 2)
