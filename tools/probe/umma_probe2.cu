@@ -258,6 +258,11 @@ int main() {
     run_g("B MN-major SW128 lbo4096 sbo1024 off1024 (k-group 1)", {0, base | TB, 2, 4096, 1024, 1024, 0, 128});
     run_g("A MN-major SW128 lbo4096 sbo1024", {1, base | TA, 2, 4096, 1024, 0, 0, 128});
     run_g("A MN-major SW128 M=64 lbo4096 sbo1024", {1, idesc_tf32(64, 32) | TA, 2, 4096, 1024, 0, 0, 64});
+    // K-major 64-byte swizzle (16 fp32 per row, 8-row atoms of 512 B): what 16-wide K slabs of the wide family would use to
+    // halve its operand tiles (two CTAs per SM for S = 3) -- not yet run on hardware
+    run_g("B K-major SW64 sbo512 off0", {0, base, 4, 16, 512, 0, 0, 128});
+    run_g("B K-major SW64 sbo512 off32 (k-step 1)", {0, base, 4, 16, 512, 32, 0, 128});
+    run_g("A K-major SW64 sbo512 off0", {1, base, 4, 16, 512, 0, 0, 128});
     run_g("B MN-major SW64 lbo1024 sbo512", {0, base | TB, 4, 1024, 512, 0, 0, 128});
     run_g("B MN-major SW32 lbo1024 sbo256", {0, base | TB, 6, 1024, 256, 0, 0, 128});
     run_g("B MN-major none lbo1024 sbo128", {0, base | TB, 0, 1024, 128, 0, 0, 128});
