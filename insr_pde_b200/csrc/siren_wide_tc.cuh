@@ -20,6 +20,7 @@
 //
 // Only compiled by nvcc (inline PTX); the host-side SIMT emulation keeps using the FFMA kernels.
 #pragma once
+#include <cstdlib>
 #include "siren_tc.cuh"
 
 #ifndef INSR_CPU_EMU
@@ -44,9 +45,10 @@ inline WGeo make_wgeo(int H) {
     else { g.NCOL = 128; g.passes = (g.HP + 127) / 128; }
     return g;
 }
-inline size_t smem_bytes(int S, int NCOL) {
-    const size_t operands = (size_t)2 * S * A_TILE + (size_t)2 * NCOL * KS * 4 + 64;        // + mbarrier / TMEM slot
-    const size_t staging = (size_t)2 * S * TILE * 36 * 4;                                    // epilogue tiles (reuse the operand region)
+inline size_t smem_bytes(int S, int NCOL, bool k16 = false) {
+    const int ks = k16 ? 16 : KS, est = k16 ? 20 : 36;
+    const size_t operands = (size_t)2 * S * TILE * ks * 4 + (size_t)2 * NCOL * ks * 4 + 64;  // + mbarrier / TMEM slot
+    const size_t staging = (size_t)2 * S * TILE * est * 4;                                   // epilogue tiles (reuse the operand region)
     return (operands > staging ? operands : staging) + 1024;
 }
 
@@ -66,6 +68,20 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// byte offset of the 16-byte chunk `ch` of operand row `row`: 128-byte swizzle (rows of 128 B, chunk ^ (row & 7)) or, K16, the
+// 64-byte swizzle (rows of 64 B, 8-row atoms of 512 B, chunk ^ ((row >> 1) & 3); profiles/r1_tcgen05_probes.txt)
+template <bool K16>
+__device__ __forceinline__ int a_chunk_off(int row, int ch) {
+    if (K16) return (row >> 3) * 512 + (row & 7) * 64 + (((ch ^ (row >> 1)) & 3) << 4);
+    return (row >> 3) * 1024 + (row & 7) * 128 + (((ch ^ row) & 7) << 4);
+}
+template <bool K16>
+__device__ __forceinline__ uint64_t desc_k(uint32_t saddr) {
+    if (K16) return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+                    ((uint64_t)4 << 61);
+    return desc_sw128(saddr);
+}
+
 // S <= 2 (value-only evaluations of the frozen nets, 1-D fields): 2 CTAs per SM (<= 256 TMEM columns, <= 97 KB each), so one
 // CTA's MMAs and loads overlap the other's epilogue
 #ifdef INSR_WIDE_PROFILE
@@ -82,8 +98,8 @@ struct WideOut {
     float *y, *jac, *h2;
 };
 
-template <int D, int ORDER, int MODE, bool OUT = false>
-__global__ void __launch_bounds__(WT, (StreamCfg<D, ORDER>::S <= 2) ? 2 : 1)
+template <int D, int ORDER, int MODE, bool OUT = false, bool K16 = false>
+__global__ void __launch_bounds__(K16 ? 256 : WT, (K16 || StreamCfg<D, ORDER>::S <= 2) ? 2 : 1)
 k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__restrict__ W,
                                                    const float *__restrict__ bias, const float *__restrict__ Ain,
                                                    int64_t NCp, int64_t p_base, const float *__restrict__ Ztape,
@@ -91,11 +107,18 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
     typedef StreamCfg<D, ORDER> C;
     constexpr int S = C::S;
     static_assert(S <= 4, "S * NCOL must fit the 512 TMEM columns");
+    // K16 (opt-in, S >= 3): 16-wide K slabs in the 64-byte swizzle, 256 threads, 16-column epilogue stage -- half the
+    // shared memory, so that two CTAs share an SM (one CTA's loads and MMAs under the other's epilogue)
+    constexpr int KSL = K16 ? 16 : KS;                  // reduction slab
+    constexpr int NT_ = K16 ? 256 : WT;                 // threads
+    constexpr int ATL = TILE * KSL * 4;                 // one 128 x KSL fp32 operand tile
+    constexpr int CPR = KSL / 4;                        // 16-byte chunks per operand row
+    constexpr int LCPR = K16 ? 2 : 3;                   // log2(CPR)
     extern __shared__ __align__(1024) unsigned char smraw_[];
     unsigned char *sm = smraw_ + ((1024u - (s32(smraw_) & 1023u)) & 1023u);
-    unsigned char *a_hi = sm, *a_lo = sm + S * A_TILE;
-    unsigned char *b_hi = sm + 2 * S * A_TILE, *b_lo = b_hi + NCOL * KS * 4;
-    const uint32_t mbar = s32(b_lo + NCOL * KS * 4), tslot = mbar + 16;
+    unsigned char *a_hi = sm, *a_lo = sm + S * ATL;
+    unsigned char *b_hi = sm + 2 * S * ATL, *b_lo = b_hi + NCOL * KSL * 4;
+    const uint32_t mbar = s32(b_lo + NCOL * KSL * 4), tslot = mbar + 16;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = dm.H;
     const float w = dm.omega;
@@ -113,29 +136,29 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
     insr_tc::tc_fence_before();
     __syncthreads();
     insr_tc::tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(b_lo + NCOL * KS * 4 + 16);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(b_lo + NCOL * KSL * 4 + 16);
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((128u >> 4) << 24);
 
     // ---- staging assignment: A = S tiles of 128 rows x 8 chunks (16 B) -> 4 S chunks per thread; B = NCOL x 32 scalars
-    constexpr int NA = 1024 * S / WT;
-    constexpr int NB = 128 * KS / WT;
+    constexpr int NA = 128 * CPR * S / NT_;
+    constexpr int NB = 128 * KSL / NT_;
     float4 ra[NA];
     float rb[NB];
     auto gload = [&](int k0) {
         INSR_PRAGMA_UNROLL
         for (int i = 0; i < NA; ++i) {
-            const int c = tid + WT * i;                 // chunk index over (stream, row, chunk)
-            const int s = c >> 10, row = (c >> 3) & 127, ch = c & 7;
+            const int c = tid + NT_ * i;                // chunk index over (stream, row, chunk)
+            const int s = c >> (7 + LCPR), row = (c >> LCPR) & 127, ch = c & (CPR - 1);
             const int k = k0 + 4 * ch;
             ra[i] = (k < HP) ? __ldg(reinterpret_cast<const float4 *>(Ain + ((int64_t)s * NCp + p0 + row) * HP + k))
                              : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         INSR_PRAGMA_UNROLL
         for (int i = 0; i < NB; ++i) {                  // raw weights: omega is applied in sstore (no use of the value here, so the
-            const int e = tid + WT * i;                 // loads stay in flight while the tensor core works)
+            const int e = tid + NT_ * i;                // loads stay in flight while the tensor core works)
             float v = 0.f;
             if (MODE == 0) {                            // B[n][kk] = omega W[j0 + n][k0 + kk]
-                const int n = e >> 5, kk = e & 31;
+                const int n = e >> (LCPR + 2), kk = e & (KSL - 1);
                 const int j = j0 + n, k = k0 + kk;
                 if (n < NCOL && j < H && k < H) v = __ldg(W + (size_t)j * H + k);
             } else {                                    // B[n][kk] = omega W[k0 + kk][j0 + n]   (n = input neuron of the layer)
@@ -149,24 +172,24 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
     auto sstore = [&]() {
         INSR_PRAGMA_UNROLL
         for (int i = 0; i < NA; ++i) {
-            const int c = tid + WT * i;
-            const int s = c >> 10, row = (c >> 3) & 127, ch = c & 7;
+            const int c = tid + NT_ * i;
+            const int s = c >> (7 + LCPR), row = (c >> LCPR) & 127, ch = c & (CPR - 1);
             const float4 v = ra[i];
             const float4 h = make_float4(insr_tc::tf32_hi(v.x), insr_tc::tf32_hi(v.y), insr_tc::tf32_hi(v.z), insr_tc::tf32_hi(v.w));
-            const int off = s * A_TILE + (row >> 3) * 1024 + (row & 7) * 128 + (((ch ^ row) & 7) << 4);
+            const int off = s * ATL + a_chunk_off<K16>(row, ch);
             *reinterpret_cast<float4 *>(a_hi + off) = h;
             *reinterpret_cast<float4 *>(a_lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
         }
         INSR_PRAGMA_UNROLL
         for (int i = 0; i < NB; ++i) {
-            const int e = tid + WT * i;
+            const int e = tid + NT_ * i;
             int n, kk;
-            if (MODE == 0) { n = e >> 5; kk = e & 31; } else { n = e & 127; kk = e >> 7; }
+            if (MODE == 0) { n = e >> (LCPR + 2); kk = e & (KSL - 1); } else { n = e & 127; kk = e >> 7; }
             if (n < NCOL) {
                 const float v = w * rb[i];
                 const float h = insr_tc::tf32_hi(v);
-                *reinterpret_cast<float *>(b_hi + sw_off(n, kk)) = h;
-                *reinterpret_cast<float *>(b_lo + sw_off(n, kk)) = v - h;
+                *reinterpret_cast<float *>(b_hi + a_chunk_off<K16>(n, kk >> 2) + (kk & 3) * 4) = h;
+                *reinterpret_cast<float *>(b_lo + a_chunk_off<K16>(n, kk >> 2) + (kk & 3) * 4) = v - h;
             }
         }
     };
@@ -188,20 +211,20 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
         insr_tc::tc_fence_before();
         __syncthreads();
         WTP(2);
-        if (ks + 1 < NK) gload((ks + 1) * KS);          // in flight while the tensor core works on slab ks
+        if (ks + 1 < NK) gload((ks + 1) * KSL);          // in flight while the tensor core works on slab ks
         if (warp == 0) {
             insr_tc::tc_fence_after();
             if (insr_tc::elect_one()) {
                 const uint32_t bh = s32(b_hi), bl = s32(b_lo);
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s) {
-                    const uint32_t ah = s32(a_hi + s * A_TILE), al = s32(a_lo + s * A_TILE);
+                    const uint32_t ah = s32(a_hi + s * ATL), al = s32(a_lo + s * ATL);
                     const uint32_t d = tmem_base + (uint32_t)(s * NCOL);
                     INSR_PRAGMA_UNROLL
-                    for (int q = 0; q < 4; ++q) {       // K = 8 per instruction: 32 bytes inside the swizzled row
-                        mma_tf32(d, desc_sw128(ah + 32 * q), desc_sw128(bh + 32 * q), idesc, (ks > 0 || q > 0) ? 1u : 0u);
-                        mma_tf32(d, desc_sw128(al + 32 * q), desc_sw128(bh + 32 * q), idesc, 1u);
-                        mma_tf32(d, desc_sw128(ah + 32 * q), desc_sw128(bl + 32 * q), idesc, 1u);
+                    for (int q = 0; q < KSL / 8; ++q) { // K = 8 per instruction: 32 bytes inside the swizzled row
+                        mma_tf32(d, desc_k<K16>(ah + 32 * q), desc_k<K16>(bh + 32 * q), idesc, (ks > 0 || q > 0) ? 1u : 0u);
+                        mma_tf32(d, desc_k<K16>(al + 32 * q), desc_k<K16>(bh + 32 * q), idesc, 1u);
+                        mma_tf32(d, desc_k<K16>(ah + 32 * q), desc_k<K16>(bl + 32 * q), idesc, 1u);
                     }
                 }
                 insr_tc::mma_commit(mbar);
@@ -220,14 +243,15 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
     // row-per-lane store to [stream][point][HP] would touch 32 different lines per instruction (measured: 3x slower).
     //   staging tiles: [tile][128 rows][36 floats] (row stride 144 B = 16 mod 128: conflict-free 16-byte accesses),
     //   tiles 0..S-1 = tape (MODE 0: Zout, written; MODE 1: Ztape, read), tiles S..2S-1 = Aout
-    constexpr int EC = 32, EST = 36;
+    constexpr int EC = NT_ / 16, EST = EC + 4;         // 32 columns / row stride 36 floats (K16: 16 / 20)
     float *stage = reinterpret_cast<float *>(sm);
     auto tile_at = [&](int t, int r, int c) -> float * { return stage + ((size_t)t * TILE + r) * EST + c; };
     const int row = 32 * (warp & 3) + lane;
     const int quarter = warp >> 2;                                // 8 of the 32 columns of a chunk
     const uint32_t trow = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-    const int crow = tid >> 3, cch = tid & 7;                     // cooperative copies: 8 lanes per 128-byte row segment, 64 rows per sweep
-    constexpr int CR = TILE * 8 / WT;                             // row sweeps of a cooperative copy (2)
+    constexpr int LPR = EC / 4;                                   // lanes per staged row segment (8; K16: 4)
+    const int crow = tid >> (LCPR), cch = tid & (LPR - 1);                  // cooperative copies: LPR lanes per row segment, 64 rows per sweep
+    constexpr int CR = TILE * LPR / NT_;                          // row sweeps of a cooperative copy (2)
     float4 zpre[MODE == 1 ? S : 1][CR];                           // MODE 1: tape chunk in registers
     auto load_tape_chunk = [&](int jc_) {
         if (MODE == 1) {
@@ -235,7 +259,7 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
             for (int s = 0; s < S; ++s)
                 INSR_PRAGMA_UNROLL
                 for (int i = 0; i < CR; ++i) {
-                    const int r = crow + (WT / 8) * i, j = jc_ + 4 * cch;
+                    const int r = crow + (NT_ / LPR) * i, j = jc_ + 4 * cch;
                     zpre[MODE == 1 ? s : 0][i] = (j < HP) ? __ldg(reinterpret_cast<const float4 *>(Ztape + ((int64_t)s * NCp + p0 + r) * HP + j))
                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -257,7 +281,7 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
             for (int s = 0; s < S; ++s)
                 INSR_PRAGMA_UNROLL
                 for (int i = 0; i < CR; ++i)
-                    *reinterpret_cast<float4 *>(tile_at(s, crow + (WT / 8) * i, 4 * cch)) = zpre[MODE == 1 ? s : 0][i];
+                    *reinterpret_cast<float4 *>(tile_at(s, crow + (NT_ / LPR) * i, 4 * cch)) = zpre[MODE == 1 ? s : 0][i];
             __syncthreads();
             if (cc + EC < NCOL) load_tape_chunk(jc + EC);         // in flight during this chunk's arithmetic
         }
@@ -327,7 +351,7 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
         for (int s = 0; s < S; ++s)
             INSR_PRAGMA_UNROLL
             for (int i = 0; i < CR; ++i) {
-                const int r = crow + (WT / 8) * i, j = jc + 4 * cch;
+                const int r = crow + (NT_ / LPR) * i, j = jc + 4 * cch;
                 if (j < HP) {
                     const int64_t g = ((int64_t)s * NCp + p0 + r) * HP + j;
                     if (MODE == 0 && Zout) *reinterpret_cast<float4 *>(Zout + g) = *reinterpret_cast<const float4 *>(tile_at(s, r, 4 * cch));
@@ -349,7 +373,7 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
         typedef StreamCfg<D, ORDER> CO;
         INSR_PRAGMA_UNROLL
         for (int i = 0; i < CR; ++i) {
-            const int64_t pr = p0 - p_base + crow + (WT / 8) * i;          // row inside the chunk
+            const int64_t pr = p0 - p_base + crow + (NT_ / LPR) * i;          // row inside the chunk
             INSR_PRAGMA_UNROLL
             for (int o = 0; o < 3; ++o) {
                 float out[S];
@@ -358,7 +382,7 @@ k_wide_tc(SirenDims dm, int HP, int NK, int NCOL, int tmem_cols, const float *__
                     float v = oacc[OUT ? i : 0][OUT ? s : 0][o];
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    if (LPR == 8) v += __shfl_xor_sync(0xffffffffu, v, 4);
                     out[s] = v;
                 }
                 if (cch == 0 && o < wo.O && pr < wo.nv) {
@@ -394,6 +418,20 @@ int launch_wide(const SirenDims &dm, const float *W, const float *bias, const fl
                 const float *Ztape, float *Zout, float *Aout, void *stream, int64_t *launches, WideOut wo = WideOut{}) {
     constexpr int S = StreamCfg<D, ORDER>::S;
     const WGeo g = make_wgeo(dm.H);
+    if constexpr (S >= 3) {
+        // opt-in (INSR_WIDE_K16=1) until measured: 16-wide K slabs, two CTAs per SM where S * NCOL fits 256 TMEM columns
+        static const bool want_k16 = [] { const char *e = getenv("INSR_WIDE_K16"); return e && e[0] == '1'; }();
+        if (want_k16 && insr_tc::pow2_cols(S * g.NCOL) <= 256) {
+            auto k16 = k_wide_tc<D, ORDER, MODE, OUT, true>;
+            const size_t smem16 = smem_bytes(S, g.NCOL, true);
+            cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+            cudaFuncSetAttribute(k16, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            k16<<<dim3((unsigned)(rows / TILE), (unsigned)g.passes), dim3(256), smem16, reinterpret_cast<cudaStream_t>(stream)>>>(
+                dm, g.HP, (g.HP + 15) / 16, g.NCOL, insr_tc::pow2_cols(S * g.NCOL), W, bias, Ain, NCp, (int64_t)0, Ztape, Zout, Aout, wo);
+            ++*launches;
+            return 0;
+        }
+    }
     auto kfn = k_wide_tc<D, ORDER, MODE, OUT>;
     const size_t smem = smem_bytes(S, g.NCOL);
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
