@@ -23,7 +23,7 @@ def build_emu(force: bool = False):
     newest = max(os.path.getmtime(s) for s in srcs)
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
-    cmd = ["g++", "-std=c++20", "-O2", "-g", "-fPIC", "-shared", "-pthread", "-DINSR_CPU_EMU", "-DINSR_SINGLE_TU",
+    cmd = ["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-DINSR_CPU_EMU", "-DINSR_SINGLE_TU",
            "-Wno-unknown-pragmas", "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"),
            "-x", "c++", os.path.join(CSRC, "insr_abi.cu"), "-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -158,9 +158,12 @@ def test_tiled_forward_keeps_tape_for_backward(emu_library, case):
         lib.backward(desc, ptr(theta), ptr(x), N, order, ptr(gy), ptr(gj) if order >= 1 else None, ptr(gh) if order >= 2 else None,
                      ptr(gth), ptr(gx), ptr(ws), nb_b, None)
         res[keep] = (y, jac if order >= 1 else None, h2 if order >= 2 else None, gth, gx)
-    for a, b in zip(res[False], res[True]):
+    for i, (a, b) in enumerate(zip(res[False], res[True])):
         if a is not None:
-            assert np.array_equal(a, b)
+            if i == 3:          # parameter gradient: same arithmetic, but the global reductions are unordered atomics
+                assert rel(b, a) < 1e-5
+            else:
+                assert np.array_equal(a, b)
     # a forward with the flag but only the forward-sized workspace is refused, loudly
     desc = _lib.make_desc(D, O, H, L, flags=_lib.FLAG_KEEP_TAPE)
     nb_f = lib.workspace_bytes(_lib.make_desc(D, O, H, L), N, order, False)
