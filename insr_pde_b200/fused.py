@@ -595,6 +595,9 @@ class FluidStepper:
             else:
                 loops[key].reset(self.lr)
             return loops[key].run(n_iters)
+        if self.data_parallel and not self.reducer_factory:
+            raise RuntimeError("FluidStepper: data_parallel needs graphed=True (all-reduce inside the iteration graph) or a "
+                               "reducer_factory for the eager loop -- refusing to train unsynchronised replicas")
         red = self.reducer_factory(nets) if self.reducer_factory else None
         return TrainingLoop(nets, self.lr, reducer=red).run(closure, n_iters)
 
