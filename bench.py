@@ -222,6 +222,50 @@ def elasticity_timestep_ours(dev, iters, case="elasticity2Dstretch"):
             "points_per_iteration": npts, "points_per_s": round(npts * iters / sec, 1), "final_loss": round(h[-1]["main"], 6)}
 
 
+def elasticity_reference_baseline(device, case="elasticity2Dstretch", iters=20, sample_resolution=None):
+    """baseline leg (kind "port"): the reference's _solve_deformation iteration -- sampling, autograd jacobian, torch.svd,
+    energies, backward, Adam (elasticity/model.py:127-189, base/baseModel.py:73-81) -- restated in stock PyTorch
+    (oracle.closures / oracle.torch_port) on `device` ("cpu": the host cores; "cuda": the same B200).  Seconds per iteration."""
+    from insr_pde_b200 import sampling
+    from oracle import closures, torch_port as tp
+    c = ELASTIC_CASES[case]
+    dim, sr = c["dim"], sample_resolution or c["sr"]
+    kw = dict(energy=c["energy"], ratio_arap=c["ratio_arap"], ratio_volume=c["ratio_volume"], ratio_kinematics=c["ratio_kinematics"],
+              ratio_constraint=c["ratio_constraint"], ratio_collide=c["ratio_collide"],
+              external_force=torch.tensor(c["ext"][:dim], device=device), external_force_timesteps=c["ext_T"],
+              constraint_offset_right=torch.tensor(c["off"][:dim], device=device), plane_height=c["plane"],
+              circle_center=torch.tensor(c["center"][:dim], device=device), circle_radius=c["radius"])
+    on_gpu = str(device).startswith("cuda")
+    torch.manual_seed(0)
+    nets = [tp.RefMLP(dim, dim, 3, c["H"]).to(device) for _ in range(3)]
+    for n in nets[1:]:
+        for p in n.parameters():
+            p.requires_grad_(False)
+    opt = torch.optim.Adam(nets[0].parameters(), lr=1e-4)
+
+    def iteration():
+        x = torch.cat([sampling.sample_random(sr ** dim, dim, device=device), sampling.sample_uniform(sr, dim, device=device)]).requires_grad_(True)
+        one = torch.ones(sr, 1, device=device)
+        left = torch.cat((-one, sampling.sample_random(sr, dim - 1, device=device)), 1)
+        right = torch.cat((one, sampling.sample_random(sr, dim - 1, device=device)), 1)
+        opt.zero_grad()
+        loss = closures.elasticity_solve_deformation(nets[0], nets[1], nets[2], tp, x, left, right, dt=c["dt"], timestep=1, **kw)
+        loss["main"].backward()
+        opt.step()
+        return float(loss["main"].detach())
+
+    for _ in range(3):
+        iteration()
+    if on_gpu:
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        iteration()
+    if on_gpu:
+        torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / iters
+
+
 def advection_timestep_ours(dev, iters):
     """seconds per advect1D time step (advection/model.py:62-91: one loop of `iters` Adam iterations, 5000 points + 50
     boundary points) on AdvectionStepper, one CUDA graph per iteration"""

@@ -1,13 +1,12 @@
 """seconds per elasticity training iteration / time step on one B200 (elasticity2Dstretch and bunny-sized configs):
-ElasticityStepper eager and CUDA-graphed, beside the reference closure restated in stock PyTorch (oracle port) on the
-same GPU.  Usage: python tools/elastic_step_bench.py [iters]"""
+ElasticityStepper eager and CUDA-graphed, beside the reference closure restated in stock PyTorch on the same GPU
+(bench.elasticity_reference_baseline).  Usage: python tools/elastic_step_bench.py [iters]"""
 import os, sys, time
 sys.path.insert(0, os.getcwd())
 import numpy as np
 import torch
 import insr_pde_b200 as ib
-from insr_pde_b200 import fused, sampling
-from oracle import closures, torch_port as tp
+from insr_pde_b200 import fused
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 import bench
@@ -30,27 +29,8 @@ for name, c in CASES.items():
         h = st.step(K)
         torch.cuda.synchronize(); res[graphed] = (time.perf_counter() - t0) / K
         npts = st._interior(c["sr"]).shape[0]
-    # the reference closure in stock PyTorch on the same GPU (autograd jacobian + torch.svd + Adam), fixed samples
-    torch.manual_seed(0)
-    rn = [tp.RefMLP(dim, dim, 3, c["H"]).cuda() for _ in range(3)]
-    for n in rn[1:]:
-        for p in n.parameters():
-            p.requires_grad_(False)
-    opt = torch.optim.Adam(rn[0].parameters(), lr=1e-4)
-    def ref_iter():
-        x = torch.cat([sampling.sample_random(c["sr"] ** dim, dim, device="cuda"), sampling.sample_uniform(c["sr"], dim, device="cuda")]).requires_grad_(True)
-        one = torch.ones(c["sr"], 1, device="cuda")
-        l = torch.cat((-one, sampling.sample_random(c["sr"], dim - 1, device="cuda")), 1)
-        r = torch.cat((one, sampling.sample_random(c["sr"], dim - 1, device="cuda")), 1)
-        opt.zero_grad()
-        loss = closures.elasticity_solve_deformation(rn[0], rn[1], rn[2], tp, x, l, r, dt=c["dt"], timestep=1, **kw)
-        loss["main"].backward(); opt.step()
-        return float(loss["main"])
-    for _ in range(3): ref_iter()
-    kr = max(5, K // 10)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(kr): ref_iter()
-    torch.cuda.synchronize(); tref = (time.perf_counter() - t0) / kr
+    # the reference closure in stock PyTorch on the same GPU (bench.py's baseline leg: autograd jacobian + torch.svd + Adam)
+    tref = bench.elasticity_reference_baseline("cuda", name, iters=max(5, K // 10))
     print(f"{name}: {npts} points/iter  eager {res[False]*1e3:.3f} ms/iter  graphed {res[True]*1e3:.3f} ms/iter "
           f"({npts / res[True] / 1e6:.1f} Mpts/s)  stock PyTorch on the same GPU {tref*1e3:.2f} ms/iter  "
           f"-> {tref / res[True]:.1f}x", flush=True)
