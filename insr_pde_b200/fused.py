@@ -789,3 +789,24 @@ def taylorgreen_velocity(samples):
     px = (samples[..., 0] + 1) * math.pi
     py = (samples[..., 1] + 1) * math.pi
     return torch.stack([torch.sin(px) * torch.cos(py) / math.pi, -torch.cos(px) * torch.sin(py) / math.pi], dim=-1)
+
+
+def taylorgreen_multi_velocity(samples, scale=8, gap=0.05):
+    """fluid/examples.py:34-52 (init_cond 'taylorgreen_multi', scripts/fluid2DtlgnM.sh): a Taylor-Green vortex squeezed into
+    the lower-left quadrant and a small one into the upper-right corner, each faded out over a thin band.  Same values as
+    the reference's masked assignments, written with ``torch.where`` (fixed shapes: graph-capturable)."""
+    def tg(p):                                     # taylorgreen_velocity(..., rescale=False)
+        px, py = (p[..., 0] + 1) * math.pi, (p[..., 1] + 1) * math.pi
+        return torch.stack([torch.sin(px) * torch.cos(py), -torch.cos(px) * torch.sin(py)], dim=-1)
+
+    x, y = samples[..., 0], samples[..., 1]
+    in1 = torch.logical_and(x <= gap, y <= gap)
+    w1 = 1.0 - samples.clamp(min=0, max=gap).norm(dim=-1) / gap
+    v1 = tg(torch.clamp(samples * 2 + 1, min=-1, max=1)) * w1.unsqueeze(-1)
+    p = 1 - 2 / scale
+    gap2 = gap * 2 / scale
+    in2 = torch.logical_and(x > p - gap2, y > p - gap2)
+    w2 = 1.0 - (p - samples).clamp(min=0, max=gap2).norm(dim=-1) / gap2
+    v2 = tg(torch.clamp(samples * scale + (1 - scale), min=-1, max=1)) * w2.unsqueeze(-1)
+    vel = torch.where(in1.unsqueeze(-1), v1, torch.zeros_like(samples))
+    return torch.where(in2.unsqueeze(-1), v2, vel)

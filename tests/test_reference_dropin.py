@@ -78,3 +78,27 @@ def test_unmodified_reference_loop_with_fused_closures(pde):
         va, vb = np.array(a[1:]), np.array(b[1:])
         tol = 5e-3 if pde == "elasticity" else 5e-4
         assert np.all(np.abs(va - vb) <= tol * np.maximum(np.abs(vb), 1e-6)), (a, b)
+
+
+def test_initial_conditions_match_reference_examples():
+    """fused.taylorgreen_velocity / taylorgreen_multi_velocity / gaussian_like against fluid/examples.py and
+    advection/examples.py of the reference (imported directly: they are plain torch)"""
+    import importlib.util
+    import torch
+    from insr_pde_b200 import fused
+
+    def load(rel, name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ref_loader.REF_ROOT, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    fl, ad = load("fluid/examples.py", "_ref_fluid_examples"), load("advection/examples.py", "_ref_adv_examples")
+    torch.manual_seed(0)
+    s = torch.rand(20000, 2) * 2 - 1
+    s = torch.cat([s, torch.tensor([[0.05, 0.05], [0.0, 0.0], [0.74, 0.9], [0.7375, 0.7375], [1.0, 1.0], [-1.0, -1.0], [0.06, -0.5]])])
+    assert torch.allclose(fused.taylorgreen_velocity(s), fl.get_examples("taylorgreen")(s), atol=1e-7)
+    ours, ref = fused.taylorgreen_multi_velocity(s), fl.get_examples("taylorgreen_multi")(s)
+    assert float(ref.abs().max()) > 0.5 and float((ours - ref).abs().max()) < 1e-6
+    x = torch.rand(1000, 1) * 4 - 2
+    assert torch.allclose(fused.gaussian_like(x), ad.get_examples("example1")(x), atol=1e-7)
