@@ -44,6 +44,11 @@ WORKLOADS = {
     "sweep.h128": (2, 1, 128, 3, 2, "synthetic sweep 2->1 H=128 L=3: y+J+Laplacian fwd + bwd"),
     "sweep.h256": (2, 1, 256, 3, 2, "synthetic sweep 2->1 H=256 L=3: y+J+Laplacian fwd + bwd"),
     "sweep.h512": (2, 1, 512, 5, 2, "synthetic sweep 2->1 H=512 L=5: y+J+Laplacian fwd + bwd"),
+    # further points of SURVEY.md 8d's sweep (depth 4 / 5, the 3 -> 3 value + Jacobian mode); not yet measured
+    "sweep.h128.l5": (2, 1, 128, 5, 2, "synthetic sweep 2->1 H=128 L=5: y+J+Laplacian fwd + bwd"),
+    "sweep.h256.l4": (2, 1, 256, 4, 2, "synthetic sweep 2->1 H=256 L=4: y+J+Laplacian fwd + bwd"),
+    "sweep.3d.h128": (3, 3, 128, 3, 1, "synthetic sweep 3->3 H=128 L=3: y+J fwd + bwd (elasticity3Dlucy's network)"),
+    "sweep.3d.h256": (3, 3, 256, 3, 1, "synthetic sweep 3->3 H=256 L=3: y+J fwd + bwd"),
 }
 
 
