@@ -6,7 +6,7 @@ NG=${2:-1}
 : > gpurun_out/sweep_$TAG.jsonl
 for wl in ${WORKLOADS:-advect1D fluid2Dtlgn.velocity fluid2Dtlgn.pressure elasticity2Dstretch elasticity3Dbunny sweep.h64 sweep.h128 sweep.h256 sweep.h512}; do
   pts=1048576
-  case $wl in sweep.h256) pts=131072;; sweep.h512) pts=32768;; sweep.h128) pts=262144;; esac
+  case $wl in sweep.h256*|sweep.3d.h256) pts=131072;; sweep.h512) pts=32768;; sweep.h128*|sweep.3d.h128) pts=262144;; esac
   timeout 300 python bench.py --workload $wl --points $pts --steps 5 --warmup 3 --no-cpu-baseline >> gpurun_out/sweep_$TAG.jsonl 2>> gpurun_out/sweep_$TAG.err
 done
 if [ "$NG" -gt 1 ]; then
