@@ -114,6 +114,11 @@ def _worker_shared(rank, world, port, out_dir):
     assert next(iter(pres.parameters())).grad.data_ptr() == gp.data_ptr()
     gv.fill_(float(rank + 1)); gp.copy_(torch.arange(3297, dtype=torch.float32) * (rank + 1))
     main, bc = shared.allreduce([torch.tensor(2.0 * rank), torch.tensor(10.0 + rank)])
+    main, bc = float(main), float(bc)
+    # the fused closures hand their loss terms over as ONE vector (fused.Losses.vector): same collective, no stack
+    gv.fill_(float(rank + 1)); gp.copy_(torch.arange(3297, dtype=torch.float32) * (rank + 1))
+    vec = shared.allreduce(torch.tensor([4.0 * rank, 1.0]))
+    assert float(vec[0]) == 2.0 and float(vec[1]) == 1.0 and vec[0].data_ptr() == shared.scalars.data_ptr()
     np.savez(os.path.join(out_dir, f"shared{rank}.npz"), gv=gv.numpy(), gp=gp.numpy(), main=float(main), bc=float(bc),
              pgrad=list(pres.parameters())[-1].grad.numpy())
 
