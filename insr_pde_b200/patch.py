@@ -72,11 +72,29 @@ def _ensure_optional_modules():
         _stub_module("tensorboardX", SummaryWriter=_Sink)
     if not have("matplotlib"):
         mpl = _stub_module("matplotlib")
-        for sub in ("pyplot", "cm", "colors"):
+        for sub in ("pyplot", "colors"):
             setattr(mpl, sub, _stub_module(f"matplotlib.{sub}"))
-    for name in ("meshio", "open3d"):
-        if not have(name):
-            _stub_module(name)
+        # fluid/visualize.py:31-43 does arithmetic on ``cm.bwr(field)``: a colormap stand-in must return a real RGBA
+        # array (a grey ramp); the images it ends up in are plotting output, not part of the hot path
+        cm = _stub_module("matplotlib.cm")
+
+        def _colormap(name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+
+            def ramp(values, *a, **k):
+                import numpy as np
+                v = np.clip(np.asarray(values, dtype=np.float64), 0.0, 1.0)
+                return np.stack([v, v, v, np.ones_like(v)], axis=-1)
+            return ramp
+
+        cm.__getattr__ = _colormap
+        mpl.cm = cm
+    if not have("meshio"):                        # elasticity/model.py:77: meshio.read(cfg.mesh_path) of a MEDIT .mesh
+        from . import medit
+        _stub_module("meshio", read=medit.read)
+    if not have("open3d"):
+        _stub_module("open3d")
 
 
 def _shim_torch():

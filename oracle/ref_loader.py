@@ -1,10 +1,9 @@
-"""Import the REAL reference (read-only tree at /root/reference) on CPU.
+"""Import the REAL reference: the read-only tree at /root/reference in the build container, or
+the verbatim copy ``oracle/_ref`` that ``oracle/build_ref.py`` makes from it (git-ignored, shipped
+to the GPU box with the snapshot -- /root/reference does not exist there).
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Only usable in the build
-container: ``/root/reference`` does not exist on the GPU box, so nothing in the ``-m gpu``
-tests, ``smoke()`` or ``bench.py`` may call this at run time.  It is used by
-``oracle/make_goldens.py`` and by the CPU-side pinning tests (skipped when the tree is
-absent).
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``): used by ``oracle/make_goldens.py``, the
+pinning tests, the GPU drop-in tests and the baseline legs of ``bench.py``; never by the product.
 
 The reference cannot be imported unmodified here: ``pytorch3d``,
 ``tensorboardX``, ``matplotlib``, ``meshio``, ``open3d`` are missing, torch>=2.7 dropped
@@ -26,7 +25,18 @@ import sys
 import tempfile
 import types
 
-REF_ROOT = os.environ.get("INSR_REFERENCE_ROOT", "/root/reference")
+_SHIPPED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _resolve_root():
+    env = os.environ.get("INSR_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", _SHIPPED]:
+        if cand and os.path.isfile(os.path.join(cand, "base", "networks.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REF_ROOT = _resolve_root()
 
 
 def available() -> bool:
@@ -73,7 +83,10 @@ def _install_stubs():
         mpl.pyplot = _stub("matplotlib.pyplot")
         mpl.cm = _stub("matplotlib.cm")
         mpl.colors = _stub("matplotlib.colors")
-    for name in ("meshio", "open3d", "cupy", "cupyx"):
+    if "meshio" not in sys.modules:               # elasticity/model.py:77 reads MEDIT .mesh files through meshio.read
+        from insr_pde_b200 import medit
+        _stub("meshio", read=medit.read)
+    for name in ("open3d", "cupy", "cupyx"):
         if name not in sys.modules:
             _stub(name)
 

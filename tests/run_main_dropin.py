@@ -1,0 +1,58 @@
+"""Helper (run as a subprocess): the reference's UNMODIFIED main.py through ``insr_pde_b200.patch.run_main`` -- the
+launcher INTEGRATION.md describes -- with the given main.py arguments.  ``cuda`` as first argument: the real library on
+cuda:0 (GPU box); ``cpu``: C-ABI calls routed to the emulation build and the reference's hard-coded cuda:0 proxied to
+the CPU (build container).  Prints one JSON object: the files main.py wrote under <exp_dir>/results and the loss history."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+device, fused_closures, argv = sys.argv[1], sys.argv[2] == "1", sys.argv[3:]
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from insr_pde_b200 import patch  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+root = ref_loader.REF_ROOT
+if device == "cpu":
+    import build_emu
+    from insr_pde_b200 import _lib, _ops
+    torch.set_num_threads(1)
+    _lib._LIB = _lib.Library(build_emu.build_emu())
+    _ops._require_cuda = lambda t: None
+    _ops._stream = lambda dev: None
+    patch.install(root)
+    ref_loader._patch_torch(True)
+    import base.baseModel as bm
+    bm.torch = ref_loader._TorchCpuProxy(torch)
+
+patch.install(root)
+import base.baseModel as bm  # noqa: E402
+
+hist = []
+ref_update = None
+
+
+def spy(self, loss_dict, __orig=bm.BaseModel._update_network):
+    hist.append([float(v) for v in loss_dict.values()])
+    return __orig(self, loss_dict)
+
+
+if not fused_closures:
+    bm.BaseModel._update_network = spy
+torch.manual_seed(123)
+np.random.seed(123)
+patch.run_main(argv, root, fused_closures=fused_closures)
+proj = argv[argv.index("--proj_dir") + 1]
+tag = argv[argv.index("--tag") + 1]
+res = os.path.join(proj, tag, "results")
+files = sorted(os.listdir(res))
+out = {"files": files, "hist": hist, "ckpts": sorted(os.listdir(os.path.join(proj, tag, "model")))}
+for f in files:
+    if f.endswith(".npy"):
+        out.setdefault("npy", {})[f] = [float(np.abs(np.load(os.path.join(res, f))).max())]
+print(json.dumps(out))

@@ -23,7 +23,7 @@ target = torch.randn(a.points, 1, device="cuda")
 for _ in range(a.reps):
     outs = _ops.siren_forward(net.desc, theta, x, order)
     g, _ = _ops.siren_backward(net.desc, theta, x, order, *cots)
-    if a.lsq:
+    if a.lsq and _ops._lib.get_lib().kernel_family(net.desc, order, True) == 1:
         cy = [[0.0] * O]
         cl = [[1.0] * O] if order == 2 else None
         _ops.siren_lsq_step(net.desc, theta, x, order, cy if order == 2 else [[1.0] * O], None, cl, target, 1.0 / a.points)
