@@ -10,9 +10,11 @@ the per-step parameter gradient is all-reduced with NCCL.
 
 Workload (config.workload): the fluid2Dtlgn pressure network of scripts/fluid2Dtlgn.sh
 (2 -> 1, hidden 32, 3 hidden layers = the `_solve_pressure` closure's operator,
-fluid/model.py:103-125) on `--points` synthetic points per GPU per step (default 2^22, larger
-than L2 together with its outputs and cotangents; the script's own batch is 128^2 = 16384
-points, reported under "script_size").
+fluid/model.py:103-125) on a FIXED GLOBAL batch of `--points` synthetic points per step (default
+2^24, split over the ranks: strong scaling -- the north star's ">= 7x at 8 GPUs"; the per-GPU
+buffers exceed L2 at every N <= 8); "weak" in the line is the same step at 2^22 points per GPU,
+"sweep" the other BASELINE.json shapes on their own fixed global batches, "script_size" the script's
+own 128^2-point batch.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU)
@@ -44,7 +46,8 @@ WORKLOADS = {
     "sweep.h128": (2, 1, 128, 3, 2, "synthetic sweep 2->1 H=128 L=3: y+J+Laplacian fwd + bwd"),
     "sweep.h256": (2, 1, 256, 3, 2, "synthetic sweep 2->1 H=256 L=3: y+J+Laplacian fwd + bwd"),
     "sweep.h512": (2, 1, 512, 5, 2, "synthetic sweep 2->1 H=512 L=5: y+J+Laplacian fwd + bwd"),
-    # further points of SURVEY.md 8d's sweep (depth 4 / 5, the 3 -> 3 value + Jacobian mode); not yet measured
+    "sweep.h512.l3": (2, 1, 512, 3, 2, "synthetic sweep 2->1 H=512 L=3: y+J+Laplacian fwd + bwd"),
+    # further points of SURVEY.md 8d's sweep (depth 4 / 5, the 3 -> 3 value + Jacobian mode)
     "sweep.h128.l5": (2, 1, 128, 5, 2, "synthetic sweep 2->1 H=128 L=5: y+J+Laplacian fwd + bwd"),
     "sweep.h256.l4": (2, 1, 256, 4, 2, "synthetic sweep 2->1 H=256 L=4: y+J+Laplacian fwd + bwd"),
     "sweep.3d.h128": (3, 3, 128, 3, 1, "synthetic sweep 3->3 H=128 L=3: y+J fwd + bwd (elasticity3Dlucy's network)"),
@@ -77,6 +80,14 @@ def flops_fwd_per_point(D, O, H, L, order):
     return 2 * (D * H + S * (L * H * H + H * O))
 
 
+def sm_count():
+    """cudaDeviceProp.multiProcessorCount of the current device (148 on the B200)"""
+    try:
+        return int(torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count)
+    except Exception:
+        return 148
+
+
 def fp32_peak_tflops():
     sm_mhz, how = 1965.0, "fallback sm_max 1965 MHz"
     try:
@@ -84,7 +95,24 @@ def fp32_peak_tflops():
         sm_mhz, how = float(peaks["sm_max_mhz"]), "MEASURED_PEAKS.json sm_max_mhz"
     except Exception:
         pass
-    return 148 * 128 * 2 * sm_mhz * 1e6 / 1e12, how
+    return sm_count() * 128 * 2 * sm_mhz * 1e6 / 1e12, f"{sm_count()} SM (cudaDeviceProp) x 128 lanes x 2 x {how}"
+
+
+def bf16_peak_tflops():
+    """measured dense bf16 throughput: the sustained figure (a kernel timed inside a long step), else the recipe's fallback"""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained"
+    except Exception:
+        return 1384.0, "fallback 1384 TFLOP/s"
+
+
+def source_sha16(*rel):
+    """hash of kernel sources: committed ncu captures carry it, so a capture of an older kernel is never quoted"""
+    import hashlib
+    h = hashlib.sha256()
+    for r in rel:
+        h.update(open(os.path.join(ROOT, r), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def hbm_peak_gbs():
@@ -148,10 +176,10 @@ def synth_theta(net_shape, device, seed=0):
     return net
 
 
-def fluid_timestep_ours(dev, iters, world=1):
+def fluid_timestep_ours(dev, iters, world=1, sample_resolution=128):
     """seconds per PDE time step of fluid2Dtlgn (fluid/model.py:61-70: advect -> pressure -> projection,
-    `iters` Adam iterations per loop, 128^2 points + 2x162 boundary points per iteration, early stop off)
-    on the fused closures (insr_pde_b200.fused)."""
+    `iters` Adam iterations per loop, sample_resolution^2 points (the script: 128^2) + 2 x sr^2/100 boundary points per
+    iteration -- split over the ranks --, early stop off) on the fused closures (insr_pde_b200.fused)."""
     import insr_pde_b200 as ib
     from insr_pde_b200 import dist as idist, fused
     torch.manual_seed(0)
@@ -160,7 +188,7 @@ def fluid_timestep_ours(dev, iters, world=1):
     # INSR_GRAPH_NCCL=0 falls back to the eager loop (torch Adam, all-reduce and a host sync per iteration)
     graph_dp = world == 1 or os.environ.get("INSR_GRAPH_NCCL", "1") != "0"
     factory = (lambda nets: idist.GradAllReducer(nets)) if (world > 1 and not graph_dp) else None
-    st = fused.FluidStepper(vel, prev, pres, dt=0.05, sample_resolution=128, lr=1e-4, reducer_factory=factory,
+    st = fused.FluidStepper(vel, prev, pres, dt=0.05, sample_resolution=sample_resolution, lr=1e-4, reducer_factory=factory,
                             graphed=graph_dp, device_sampler=True)
     st.data_parallel = world > 1 and graph_dp
     st.initialize(fused.taylorgreen_velocity, 20, world)
@@ -172,11 +200,9 @@ def fluid_timestep_ours(dev, iters, world=1):
         h1, h2, h3 = st.step(iters, world)
         torch.cuda.synchronize()
         sec = min(sec, time.perf_counter() - t0)
-    for lp in getattr(st, "_loops", {}).values():       # release the captured graphs (and the NCCL work recorded in them) now
-        lp.graph = None
-    torch.cuda.synchronize()
+    st.close()                                          # release the captured graphs (and the NCCL work recorded in them) now
     return {"sec_per_timestep": round(sec, 4), "iters_per_loop": iters, "loops": 3,
-            "us_per_iteration": round(sec / (3 * iters) * 1e6, 1), "points_per_iteration": 128 * 128,
+            "us_per_iteration": round(sec / (3 * iters) * 1e6, 1), "points_per_iteration": sample_resolution ** 2,
             "final_losses": [round(h[-1]["main"], 8) for h in (h1, h2, h3)],
             "note": ("fluid2Dtlgn step on fused lsq closures; one CUDA graph per iteration (one-kernel Philox sampling of the "
                      "three point sets, closures with interior / boundary terms on parallel branches, device Adam, device "
@@ -190,11 +216,21 @@ ELASTIC_CASES = {
     "elasticity2Dstretch": dict(dim=2, H=68, sr=100, dt=0.05, energy=["arap", "constraint", "constraint_right", "volume"],
                                 ratio_volume=1e3, ratio_arap=1e0, ratio_constraint=1e4, ratio_kinematics=1e0, ratio_collide=1e0,
                                 ext=[0., 0., 0.], ext_T=5, off=[2.0, 0., 0.], plane=-2.0, center=[0., -2., 0.], radius=1.0),
-    # the 3-D bunny's network and point count (13 824 + 13 824 points, H = 66) on the cube (no mesh file offline)
-    "elasticity3D_bunny_sized": dict(dim=3, H=66, sr=24, dt=0.1, energy=["arap", "kinematics", "collision", "external", "volume"],
-                                     ratio_volume=1e3, ratio_arap=1e2, ratio_constraint=1e3, ratio_kinematics=1e0, ratio_collide=1e6,
-                                     ext=[0., 0., -1e2], ext_T=5, off=[1.0, 0., 0.], plane=-0.9, center=[0., -2., 0.], radius=1.0),
+    # scripts/elasticity3Dbunny.sh on the real mesh (elasticity/data/bunny.mesh: 18 592 vertices, 76 854 tetrahedra):
+    # 20^3 volume samples + every vertex = 26 592 points per iteration, H = 66
+    "elasticity3Dbunny": dict(dim=3, H=66, sr=20, dt=0.1, energy=["arap", "kinematics", "collision", "external", "volume"],
+                              ratio_volume=1e3, ratio_arap=1e2, ratio_constraint=1e3, ratio_kinematics=1e0, ratio_collide=1e6,
+                              ext=[0., 0., -1e2], ext_T=5, off=[1.0, 0., 0.], plane=-2.0, center=[0., -2., 0.], radius=1.0,
+                              mesh="bunny.mesh"),
 }
+
+
+def find_mesh(name):
+    """elasticity/data/<name> of the reference tree (data, not source): /root/reference here, the shipped copy on the GPU box"""
+    for root in (os.environ.get("INSR_REFERENCE_ROOT"), "/root/reference", os.path.join(ROOT, "oracle", "_ref")):
+        if root and os.path.isfile(os.path.join(root, "elasticity", "data", name)):
+            return os.path.join(root, "elasticity", "data", name)
+    return None
 
 
 def elasticity_timestep_ours(dev, iters, case="elasticity2Dstretch"):
@@ -212,7 +248,15 @@ def elasticity_timestep_ours(dev, iters, case="elasticity2Dstretch"):
               circle_center=torch.tensor(c["center"][:dim], device=dev), circle_radius=c["radius"])
     torch.manual_seed(0)
     nets = [ib.MLP(dim, dim, 3, c["H"], nonlinearity="sine").to(dev) for _ in range(3)]
-    st = fused.ElasticityStepper(*nets, dim, dt=c["dt"], sample_resolution=c["sr"], graphed=True, **kw)
+    mesh, n_vert = None, 0
+    if c.get("mesh"):
+        from insr_pde_b200 import medit
+        path = find_mesh(c["mesh"])
+        if path is None:
+            return {"case": case, "error": f"{c['mesh']} not found (neither /root/reference nor oracle/_ref)"}
+        mesh = medit.load_normalized(path, dim, device=dev)
+        n_vert = int(mesh[0].shape[0])
+    st = fused.ElasticityStepper(*nets, dim, dt=c["dt"], sample_resolution=c["sr"], graphed=True, mesh=mesh, **kw)
     st.initialize(5)
     st.step(5)                                          # warm-up: the graph is captured here
     sec = float("inf")
@@ -222,53 +266,10 @@ def elasticity_timestep_ours(dev, iters, case="elasticity2Dstretch"):
         h = st.step(iters)
         torch.cuda.synchronize()
         sec = min(sec, time.perf_counter() - t0)
-    npts = 2 * c["sr"] ** dim
+    npts = c["sr"] ** dim + (n_vert if mesh is not None else c["sr"] ** dim)
+    st.close()
     return {"case": case, "sec_per_timestep": round(sec, 4), "iters_per_loop": iters, "us_per_iteration": round(sec / iters * 1e6, 1),
             "points_per_iteration": npts, "points_per_s": round(npts * iters / sec, 1), "final_loss": round(h[-1]["main"], 6)}
-
-
-def elasticity_reference_baseline(device, case="elasticity2Dstretch", iters=20, sample_resolution=None):
-    """baseline leg (kind "port"): the reference's _solve_deformation iteration -- sampling, autograd jacobian, torch.svd,
-    energies, backward, Adam (elasticity/model.py:127-189, base/baseModel.py:73-81) -- restated in stock PyTorch
-    (oracle.closures / oracle.torch_port) on `device` ("cpu": the host cores; "cuda": the same B200).  Seconds per iteration."""
-    from insr_pde_b200 import sampling
-    from oracle import closures, torch_port as tp
-    c = ELASTIC_CASES[case]
-    dim, sr = c["dim"], sample_resolution or c["sr"]
-    kw = dict(energy=c["energy"], ratio_arap=c["ratio_arap"], ratio_volume=c["ratio_volume"], ratio_kinematics=c["ratio_kinematics"],
-              ratio_constraint=c["ratio_constraint"], ratio_collide=c["ratio_collide"],
-              external_force=torch.tensor(c["ext"][:dim], device=device), external_force_timesteps=c["ext_T"],
-              constraint_offset_right=torch.tensor(c["off"][:dim], device=device), plane_height=c["plane"],
-              circle_center=torch.tensor(c["center"][:dim], device=device), circle_radius=c["radius"])
-    on_gpu = str(device).startswith("cuda")
-    torch.manual_seed(0)
-    nets = [tp.RefMLP(dim, dim, 3, c["H"]).to(device) for _ in range(3)]
-    for n in nets[1:]:
-        for p in n.parameters():
-            p.requires_grad_(False)
-    opt = torch.optim.Adam(nets[0].parameters(), lr=1e-4)
-
-    def iteration():
-        x = torch.cat([sampling.sample_random(sr ** dim, dim, device=device), sampling.sample_uniform(sr, dim, device=device)]).requires_grad_(True)
-        one = torch.ones(sr, 1, device=device)
-        left = torch.cat((-one, sampling.sample_random(sr, dim - 1, device=device)), 1)
-        right = torch.cat((one, sampling.sample_random(sr, dim - 1, device=device)), 1)
-        opt.zero_grad()
-        loss = closures.elasticity_solve_deformation(nets[0], nets[1], nets[2], tp, x, left, right, dt=c["dt"], timestep=1, **kw)
-        loss["main"].backward()
-        opt.step()
-        return float(loss["main"].detach())
-
-    for _ in range(3):
-        iteration()
-    if on_gpu:
-        torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(iters):
-        iteration()
-    if on_gpu:
-        torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / iters
 
 
 def advection_timestep_ours(dev, iters):
@@ -288,39 +289,263 @@ def advection_timestep_ours(dev, iters):
         h = st.step(iters)
         torch.cuda.synchronize()
         sec = min(sec, time.perf_counter() - t0)
+    st.close()
     return {"case": "advect1D", "sec_per_timestep": round(sec, 4), "iters_per_loop": iters, "us_per_iteration": round(sec / iters * 1e6, 1),
             "points_per_iteration": 5000, "final_loss": round(h[-1]["main"], 8)}
 
 
-def fluid_timestep_cpu(iters_measured=3, iters_per_loop=100):
-    """the same time step with the reference algorithm (oracle port) on the host cores; a few
-    iterations per loop are timed and scaled to `iters_per_loop`."""
-    from oracle import closures, torch_port as tp, training
+# ------------------------------------------------------------------------------------------------
+# reference legs (run in a subprocess: ref_loader's CPU shims must not live in the process that drives the GPU kernels)
+# ------------------------------------------------------------------------------------------------
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def reference_operator(workload, n_points, steps, warmup, device="cpu", budget_s=120.0):
+    """the REAL reference (base/networks.py MLP + base/diff_ops.py jacobian / laplace + loss.backward(), imported from
+    /root/reference or the shipped copy oracle/_ref) on the workload's operator: y (+ J (+ Laplacian)) and the reverse
+    sweep for given output cotangents; `steps` timed steps of `n_points` points after `warmup` untimed ones"""
+    from oracle import ref_loader
+    D, O, H, L, order, _ = WORKLOADS[workload]
+    ns = ref_loader.load(cpu=(device == "cpu"))
     torch.manual_seed(0)
-    vel, prev, pres = (tp.RefMLP(2, o, 3, 32) for o in (2, 2, 1))
-    for p in prev.parameters():
-        p.requires_grad_(False)
+    on_gpu = str(device).startswith("cuda")
+    net = ns.base.MLP(D, O, L, H, nonlinearity="sine").to(device)
+    x = (torch.rand(n_points, D, device=device) * 2 - 1).requires_grad_(True)
+    gy = torch.randn(n_points, O, device=device) / n_points
+    gj = torch.randn(n_points, O, D, device=device) / n_points
+    gl = torch.randn(n_points, 1, device=device) / n_points
 
-    def samples():
-        return (tp.sample_random(128 * 128, 2).requires_grad_(True),
-                tp.sample_boundary2D_separate(163, "horizontal").requires_grad_(True),
-                tp.sample_boundary2D_separate(163, "vertical").requires_grad_(True))
+    def step():
+        net.zero_grad()
+        y = net(x)
+        loss = (gy * y).sum()
+        if order >= 1:
+            jac, _ = ns.base.jacobian(y, x)
+            loss = loss + (gj * jac).sum()
+        if order >= 2:
+            loss = loss + (gl * ns.base.laplace(y, x)).sum()
+        loss.backward()
 
-    loops = [lambda i: closures.fluid_advect_velocity(vel, prev, *samples(), 0.05),
-             lambda i: closures.fluid_solve_pressure(vel, pres, tp, *samples()),
-             lambda i: closures.fluid_projection(vel, prev, pres, tp, *samples())]
-    per_iter = []
-    for c in loops:
-        training.training_loop(c, [vel, pres], 1, 1e-4)
-        t0 = time.perf_counter()
-        training.training_loop(c, [vel, pres], iters_measured, 1e-4)
-        per_iter.append((time.perf_counter() - t0) / iters_measured)
-    return {"sec_per_timestep": round(sum(per_iter) * iters_per_loop, 3), "iters_per_loop": iters_per_loop,
-            "ms_per_iteration": [round(t * 1e3, 2) for t in per_iter], "cores": torch.get_num_threads(),
-            "kind": "port", "sample": f"{iters_measured} timed iterations per loop, scaled to {iters_per_loop}"}
+    for _ in range(max(warmup, 1)):
+        step()
+    if on_gpu:
+        torch.cuda.synchronize()
+    t0, n = time.perf_counter(), 0
+    while n < steps:
+        step()
+        n += 1
+        if on_gpu:
+            torch.cuda.synchronize()
+        if time.perf_counter() - t0 > budget_s:
+            break
+    el = time.perf_counter() - t0
+    where = f"stock PyTorch eager on {torch.cuda.get_device_name()}" if on_gpu else f"CPU ({cpu_model_name()})"
+    return {"value": round(n_points * n / el, 1), "unit": "points/s", "cores": torch.get_num_threads(), "kind": "reference",
+            "cpu_model": cpu_model_name(),
+            "sample": f"{n} timed steps of {n_points} points each (a bounded sample of the step's global batch) on the {workload} "
+                      f"operator; the reference's own base.networks.MLP + base.diff_ops + loss.backward() from {ref_loader.REF_ROOT}, "
+                      f"torch {torch.__version__}, {where}, fp32",
+            "ms_per_step": round(el / n * 1e3, 3), "points_per_step": n_points}
+
+
+def reference_fluid_timestep(device="cpu", iters_measured=3, iters_per_loop=100):
+    """seconds per fluid2Dtlgn time step of the REAL reference: Fluid2DModel(cfg).step() (fluid/model.py:61-70, its own
+    training loop, Adam, scheduler, sampling) with max_n_iters = iters_measured, scaled to iters_per_loop"""
+    from oracle import ref_loader
+    ns = ref_loader.load(cpu=(device == "cpu"))
+    torch.manual_seed(0)
+    cfg = ref_loader.make_cfg("fluid", sample_resolution=128, max_n_iters=iters_measured)
+    model = ns.fluid.Fluid2DModel(cfg)
+    model.initialize()
+    model.step()                                        # warm-up
+    if device != "cpu":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model.step()
+    if device != "cpu":
+        torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    return {"sec_per_timestep": round(sec / iters_measured * iters_per_loop, 3), "iters_per_loop": iters_per_loop,
+            "ms_per_iteration": round(sec / (3 * iters_measured) * 1e3, 2), "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"Fluid2DModel.step() with max_n_iters = {iters_measured} (3 loops, 128^2 + 2 x 162 points), scaled to {iters_per_loop}; "
+                      "includes the per-step checkpoint write"}
+
+
+def reference_elasticity_iteration(device="cpu", case="elasticity2Dstretch", iters=5):
+    """seconds per _solve_deformation iteration of the REAL reference ElasticityModel (elasticity/model.py:127-189 under
+    base/baseModel.py:104-134) at the script's sizes; the bunny case reads the real mesh"""
+    from oracle import ref_loader
+    ns = ref_loader.load(cpu=(device == "cpu"))
+    torch.manual_seed(0)
+    c = ELASTIC_CASES[case]
+    kw = dict(dim=c["dim"], hidden_features=c["H"], sample_resolution=c["sr"], dt=c["dt"], energy=c["energy"],
+              ratio_arap=c["ratio_arap"], ratio_volume=c["ratio_volume"], ratio_kinematics=c["ratio_kinematics"],
+              ratio_constraint=c["ratio_constraint"], ratio_collide=c["ratio_collide"], external_force_timesteps=c["ext_T"],
+              external_force_x=c["ext"][0], external_force_y=c["ext"][1], external_force_z=c["ext"][2],
+              constraint_right_offset_x=c["off"][0], plane_height=c["plane"], max_n_iters=iters, vis_resolution=50)
+    if c.get("mesh"):
+        kw.update(use_mesh=True, mesh_path=os.path.join(ref_loader.REF_ROOT, "elasticity", "data", c["mesh"]))
+    model = ns.elasticity.ElasticityModel(ref_loader.make_cfg("elasticity", **kw))
+    model.timestep = 1
+    model._create_tb("bench")
+    model._solve_deformation()                          # warm-up loop
+    if device != "cpu":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model._solve_deformation()
+    if device != "cpu":
+        torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / iters
+
+
+def run_reference(args):
+    """the reference arm: the reference's own implementation of the path (kind "reference": the tree itself, from
+    /root/reference here or from the shipped copy oracle/_ref on the GPU box) on the box's host cores with every thread
+    this process may use -- or, --device cuda (internal, the like-for-like leg), as stock PyTorch on the GPU"""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every core this process may run on explicitly
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    D, O, H, L, order, desc_txt = WORKLOADS[args.workload]
+    res = reference_operator(args.workload, args.ref_points, args.steps, args.warmup, device=args.device,
+                             budget_s=args.ref_budget)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(args, world),
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if args.ref_legs == "all":                          # the in-line legs of our arm: time step and elasticity iteration too
+        try:
+            line["timestep"] = reference_fluid_timestep(args.device, 3, args.timestep_iters or 100)
+        except Exception as e:
+            line["timestep"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        el = {}
+        for case in ELASTIC_CASES:
+            try:
+                el[case] = round(reference_elasticity_iteration(args.device, case, 3 if args.device == "cpu" else 10), 5)
+            except Exception as e:
+                el[case] = f"{type(e).__name__}: {str(e)[:200]}"
+        line["elasticity_sec_per_iteration"] = el
+    emit(line)
+
+
+def reference_subprocess(args, device, legs="all", steps=8, warmup=2, budget=14.0, points=None):
+    """run a reference leg in its own process (all host threads) and return its JSON line"""
+    cmd = [sys.executable, "-W", "ignore", os.path.abspath(__file__), "--impl", "reference", "--device", device, "--workload",
+           args.workload, "--steps", str(steps), "--warmup", str(warmup), "--ref-budget", str(budget), "--ref-legs", legs,
+           "--ref-points", str(points or args.ref_points), "--points", str(args.points), "--scaling", args.scaling,
+           "--timestep-iters", str(args.timestep_iters)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS")}
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+        lines = [l for l in res.stdout.strip().splitlines() if l.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"error": (res.stderr or "no output")[-300:]}
+        return json.loads(lines[-1])
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
+
+METRIC = "collocation points/s (SIREN fwd + grad + Laplacian + bwd)"
+
+
+def config_block(args, world):
+    """the same for both arms: what one step is"""
+    D, O, H, L, order, desc_txt = WORKLOADS[args.workload]
+    n_local = args.points // world if args.scaling == "strong" else args.points
+    return {"workload": f"{args.workload}: {desc_txt}", "global_points_per_step": n_local * world,
+            "points_per_step_per_gpu": n_local,
+            "parallelism": f"dp{world} (points sharded, weights replicated, one all-reduce of the flat gradient per step)",
+            "l2": "per-GPU inputs + outputs + cotangents of a step exceed the 126 MB L2 (40 B/point in, out and cotangents each)"
+                  if n_local >= (1 << 21) else "per-GPU working set may fit L2 at this size",
+            "init": "reference sine init, torch.manual_seed(0); points U[-1,1]^D seed 1234; cotangents randn/N seed 4321"}
+
+
+class OperatorCase:
+    """one workload at one per-rank batch: synthetic points, cotangents and buffers; step() = forward streams + reverse
+    sweep (+ the all-reduce of the flat gradient when world > 1)"""
+
+    def __init__(self, workload, n_local, dev, rank, world):
+        import torch.distributed as dist
+        from insr_pde_b200 import _ops
+        self.dist, self._ops = dist, _ops
+        self.workload, self.N, self.world, self.dev = workload, n_local, world, dev
+        self.D, self.O, self.H, self.L, self.order, self.text = WORKLOADS[workload]
+        self.net = synth_theta((self.D, self.O, self.H, self.L), dev)
+        self.theta, self.desc = self.net.flat_theta(), self.net.desc
+        self.P = self.theta.numel()
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.x = (torch.rand(n_local, self.D, generator=gen, device=dev) * 2 - 1).contiguous()
+        self.cg = torch.Generator(device=dev).manual_seed(4321 + rank)
+        self.shapes = _ops.out_shapes(self.desc, n_local, self.order)
+        self.cots = [torch.randn(sh, generator=self.cg, device=dev) / n_local for sh in self.shapes]
+        self.gtheta = torch.zeros(self.P, device=dev)
+        self.f_fwd = flops_fwd_per_point(self.D, self.O, self.H, self.L, self.order)
+
+    def step(self):
+        outs = self._ops.siren_forward(self.desc, self.theta, self.x, self.order)
+        self.gtheta.zero_()
+        self._ops.siren_backward(self.desc, self.theta, self.x, self.order, *self.cots, gtheta=self.gtheta)
+        if self.world > 1:
+            self.dist.all_reduce(self.gtheta)
+        return outs
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, steps, warmup):
+        """ms for `steps` steps: CUDA events on the launch stream, barrier + synchronize on both sides, max over ranks"""
+        for _ in range(warmup):
+            self.step()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        for _ in range(steps):
+            self.step()
+        ev1.record()
+        self.barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+# the other BASELINE.json shapes, each on its own fixed GLOBAL batch (split over the ranks like the headline)
+SWEEP = [("advect1D", 1 << 22), ("fluid2Dtlgn.velocity", 1 << 22), ("elasticity2Dstretch", 1 << 20), ("elasticity3Dbunny", 1 << 20),
+         ("sweep.h64", 1 << 20), ("sweep.h128", 1 << 20), ("sweep.h128.l5", 1 << 19), ("sweep.3d.h128", 1 << 19),
+         ("sweep.h256", 1 << 18), ("sweep.h256.l4", 1 << 18), ("sweep.h512.l3", 1 << 16), ("sweep.h512", 1 << 16)]
+
+
+def time_call(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
 
 
 def run_ours(args):
+    import gc
+    import math
+    import threading
     import torch.distributed as dist
     import insr_pde_b200 as ib
     from insr_pde_b200 import _lib, _ops
@@ -335,53 +560,24 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    D, O, H, L, order, desc_txt = WORKLOADS[args.workload]
     lib = _lib.get_lib()
-    net = synth_theta((D, O, H, L), dev)
-    theta = net.flat_theta()
-    desc = net.desc
-    P = theta.numel()
-    N = args.points if args.scaling == "weak" else args.points // world     # strong: the global batch is fixed
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = (torch.rand(N, D, generator=gen, device=dev) * 2 - 1).contiguous()
-    cg = torch.Generator(device=dev).manual_seed(4321 + rank)
-    shapes = _ops.out_shapes(desc, N, order)
-    cots = [torch.randn(s, generator=cg, device=dev) / N for s in shapes]
-    gtheta = torch.zeros(P, device=dev)
+    N = args.points // world if args.scaling == "strong" else args.points
+    case = OperatorCase(args.workload, N, dev, rank, world)
+    D, O, H, L, order, desc_txt = case.D, case.O, case.H, case.L, case.order, case.text
+    net, theta, desc, P, x, cots, gtheta, shapes = case.net, case.theta, case.desc, case.P, case.x, case.cots, case.gtheta, case.shapes
+    cg = case.cg
+    step, barrier = case.step, case.barrier
 
-    def step():
-        outs = _ops.siren_forward(desc, theta, x, order)
-        gtheta.zero_()
-        _ops.siren_backward(desc, theta, x, order, *cots, gtheta=gtheta)
-        if world > 1:
-            dist.all_reduce(gtheta)
-        return outs
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     lib.launch_count(True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms = case.timed(args.steps, 0)
     launches = lib.launch_count(True) + args.steps * (1 + (1 if world > 1 else 0))   # + zero-fill (+ NCCL)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     # sustain the load long enough for the clock sampler when the timed region is short.  The step
     # contains a collective for N > 1, so EVERY rank runs the same (deterministic) number of extra steps.
     n_extra = int(max(0.0, 1000.0 - ms) / max(ms / args.steps, 1e-3)) + 1
@@ -391,19 +587,16 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     pts_per_s = world * N * args.steps / (ms / 1e3)
 
-    # ---- dominant kernel alone (backward), CUDA events on the launch stream
-    def time_call(fn, reps):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
+    # ---- the same step with a fixed batch PER GPU (weak scaling), 2^22 points each
+    weak = None
+    if args.weak_points > 0:
+        wc = case if args.weak_points == N else OperatorCase(args.workload, args.weak_points, dev, rank, world)
+        wms = wc.timed(args.steps, 3)
+        weak = {"points_per_gpu": args.weak_points, "ms_per_step": round(wms / args.steps, 4),
+                "value": round(world * args.weak_points * args.steps / (wms / 1e3), 1), "unit": "points/s", "scaling": "weak"}
+        del wc
 
+    # ---- dominant kernel alone (backward), CUDA events on the launch stream
     ws_b = torch.empty(lib.workspace_bytes(desc, N, order, True) + 16, dtype=torch.uint8, device=dev)
     ws_f = torch.empty(lib.workspace_bytes(desc, N, order, False) + 16, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
@@ -421,71 +614,78 @@ def run_ours(args):
 
     reps = max(3, min(args.steps, 20))
     ms_bwd, ms_fwd = time_call(bwd_only, reps), time_call(fwd_only, reps)
-    f_fwd = flops_fwd_per_point(D, O, H, L, order)
+    del ws_b, ws_f, outs
+    f_fwd = case.f_fwd
     peak, peak_how = fp32_peak_tflops()
-    tensor_path = lib.kernel_family(desc, order, True) == 1 and not (desc.flags & (_lib.FLAG_NO_TENSOR | _lib.FLAG_FFMA_BWD))
+    bf16_peak, bf16_how = bf16_peak_tflops()
     fam_b = lib.kernel_family(desc, order, True)
+    tensor_path = fam_b == 1 and not (desc.flags & (_lib.FLAG_NO_TENSOR | _lib.FLAG_FFMA_BWD))
     no_tensor = bool(desc.flags & _lib.FLAG_NO_TENSOR)
+    wide_tensor = fam_b == 2 and not no_tensor and len(shapes) <= 3 and order <= 2
     tensor_pipe_txt = ("tcgen05: 3xTF32 forward / data gradient (hi operand in TMEM), 2-level bf16 weight gradient, FP32 accumulators in TMEM"
                        if tensor_path else
-                       ("tcgen05 hidden-layer GEMMs, layer by layer through HBM: 3xTF32 forward + data gradient, 2-level bf16 weight gradient in 128 x 128 weight groups with TMEM-resident accumulators"
-                        if fam_b == 2 and not no_tensor and len(shapes) <= 3 and order <= 2 else "fp32 ffma"))
+                       ("tcgen05 hidden-layer GEMMs: 3xTF32 forward + data gradient, 2-level bf16 weight gradient with TMEM-resident accumulators"
+                        if wide_tensor else "fp32 ffma"))
     ach_bwd = 2 * f_fwd * N / (ms_bwd / 1e3) / 1e12
     ach_fwd = f_fwd * N / (ms_fwd / 1e3) / 1e12
-    import math
     bytes_pt = 4 * (D + 2 * sum(math.prod(s[1:]) for s in shapes))   # x + outputs written + cotangents read
     hbm, hbm_how = hbm_peak_gbs()
+    step_frac = 3 * f_fwd * N * args.steps / (ms / 1e3) / 1e12 / peak
+    fp32_view = {"bound": "fp32", "achieved": round(ach_bwd, 3), "peak": round(peak, 2), "unit": "TFLOP/s",
+                 "frac": round(ach_bwd / peak, 4), "peak_source": peak_how, "step_frac": round(step_frac, 4),
+                 "fwd_kernel": {"achieved": round(ach_fwd, 3), "frac": round(ach_fwd / peak, 4)},
+                 "note": "algorithmic FP32 flops (SURVEY.md 8d: 2 MAC(S) per point forward, twice that backward) against the FP32 FFMA "
+                         "peak -- the north star's FP32 roofline; not a bound for a kernel that executes on the tensor pipe"}
     roofline = {
-        "bound": "fp32", "kernel": "siren backward (recompute + dgrad + wgrad)",
-        "bound_note": "achieved = algorithmic FP32 flops / time against the FP32 FFMA peak (north star's FP32 roofline); on the tcgen05 path the same algorithmic flops run on the tensor pipe, see 'tensor'",
-        "achieved": round(ach_bwd, 3), "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(ach_bwd / peak, 4),
-        "traffic": None, "peak_source": f"148 SM x 128 lanes x 2 x {peak_how}",
-        "algorithmic_flops_per_point": {"fwd": f_fwd, "bwd": 2 * f_fwd},
+        "kernel": "siren backward (recompute + dgrad + wgrad)",
+        "traffic": None, "algorithmic_flops_per_point": {"fwd": f_fwd, "bwd": 2 * f_fwd},
         "ms_per_launch": {"bwd": round(ms_bwd, 4), "fwd": round(ms_fwd, 4)},
-        "fwd_kernel": {"achieved": round(ach_fwd, 3), "frac": round(ach_fwd / peak, 4)},
-        "step_frac": round(3 * f_fwd * N * args.steps / (ms / 1e3) / 1e12 / peak, 4),
         "hbm": {"algorithmic_bytes_per_point": bytes_pt,
                 "achieved_gbs": round(bytes_pt * N / ((ms_bwd + ms_fwd) / 1e3) / 1e9, 1), "peak_gbs": hbm, "peak_source": hbm_how},
-        "kernel_family": {"fwd": lib.kernel_family(desc, order, False), "bwd": lib.kernel_family(desc, order, True),
-                          "pipe": tensor_pipe_txt},
+        "kernel_family": {"fwd": lib.kernel_family(desc, order, False), "bwd": fam_b, "pipe": tensor_pipe_txt},
+        "fp32": fp32_view, "step_frac": round(step_frac, 4),
     }
-    # DRAM traffic of the dominant kernel: one ncu capture at the bench size, committed under profiles/
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic_tcgen05_v5.json")))
-        want = "k_tc_bwd" if tensor_path else "k_fused_bwd"
-        ks = [k for k in tr["kernels"] if want in k["kernel"] and ", 0>" in k["kernel"]]       # LSQ = false instantiation
-        if ks and tr.get("points") == N and args.workload == "fluid2Dtlgn.pressure":
-            k = ks[-1]                                   # last (warm) launch
-            roofline["traffic"] = int(k["dram_read_bytes"] + k["dram_write_bytes"])
-            roofline["traffic_note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum of {k['kernel']} at {N} points "
-                                        f"({tr['source']}); algorithmic bytes of the backward = {4 * (D + sum(math.prod(sh[1:]) for sh in shapes)) * N}")
-    except Exception:
-        pass
     if tensor_path:
-        # executed tensor-pipe work of the backward kernel in bf16-equivalent flops (a TF32 flop costs two bf16
-        # flops of pipe time): forward recompute + data gradient = 2 x 3 TF32 products, weight gradient = 4 bf16
-        # products, each 2*S*L*H^2 flops per point; against the measured dense bf16 peak (sustained)
+        # the kernel executes on the tensor pipe: EXECUTED work of the backward kernel in bf16-equivalent flops (a TF32
+        # flop costs two bf16 flops of pipe time): forward recompute + data gradient = 2 x 3 TF32 products, weight
+        # gradient = 4 bf16 products, each 2 S L HP^2 flops per point (HP = 32: the padded width the MMAs run at)
         S_ = (f_fwd // 2 - D * H) // (L * H * H + H * O)
         hp = 32
         exec_bf16eq = (2 * (2 * 3) + 4) * 2 * S_ * L * hp * hp
-        try:
-            bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
-        except Exception:
-            bf16_peak = 1384.0
         ach_t = exec_bf16eq * N / (ms_bwd / 1e3) / 1e12
-        roofline["tensor"] = {"executed_bf16_equivalent_tflops": round(ach_t, 1), "peak_bf16_tflops": bf16_peak,
-                              "frac": round(ach_t / bf16_peak, 4),
-                              "note": "N = 32 MMAs: 16 cycles with A in TMEM, 40 with A in shared memory (tools/probe); the kernel is bound by the SIMT epilogues (sin/cos, stream algebra, operand splits), not by the tensor pipe"}
+        roofline.update({"bound": "tensor", "achieved": round(ach_t, 1), "peak": bf16_peak, "unit": "TFLOP/s",
+                         "frac": round(ach_t / bf16_peak, 4), "peak_source": bf16_how,
+                         "bound_note": "tensor pipe: executed bf16-equivalent flops of the backward kernel (3xTF32 = 6, 2-level bf16 weight "
+                                       "gradient = 4 bf16-equivalents per algorithmic flop) / its launch time against the measured dense bf16 "
+                                       "throughput; 'fp32' holds the same launch against the FP32 FFMA peak (algorithmic flops)"})
+    else:
+        roofline.update({k: fp32_view[k] for k in ("bound", "achieved", "peak", "unit", "frac", "peak_source")})
+    # DRAM traffic and pipe utilisation of the dominant kernel: one ncu capture at the bench size, committed under profiles/
+    # and keyed to a hash of the kernel source -- a capture of an older kernel is not quoted
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_k_tc_bwd.json")))
+        if tr.get("source_sha16") != source_sha16("insr_pde_b200/csrc/siren_tc.cuh"):
+            roofline["traffic_note"] = "committed ncu capture is of an older siren_tc.cuh: not quoted"
+        elif tensor_path and args.workload == "fluid2Dtlgn.pressure":
+            k = tr["kernel"]
+            per_point = (k["dram_read_bytes"] + k["dram_write_bytes"]) / tr["points"]
+            roofline["traffic"] = int(per_point * N)
+            roofline["traffic_note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum of {k['name']} measured at {tr['points']} points "
+                                        f"({tr['source']}), scaled per point to this launch; algorithmic bytes of the backward = "
+                                        f"{4 * (D + sum(math.prod(sh[1:]) for sh in shapes)) * N}")
+            if "pipe_tensor_pct" in k:
+                roofline["ncu"] = {"sm__pipe_tensor_cycles_active_pct": k["pipe_tensor_pct"], "issue_slots_pct": k.get("issue_pct"),
+                                   "warps_active_pct": k.get("warps_active_pct")}
+    except Exception:
+        pass
 
     # ---- fused closure step (insr_siren_lsq_step): forward streams + residual + loss + backward in ONE kernel
     fused_closure = None
-    if lib.kernel_family(desc, order, True) == 1:
-        from insr_pde_b200 import fused
+    if fam_b == 1:
         tgt = torch.randn(N, 1, generator=cg, device=dev)
         loss_buf = torch.zeros(1, device=dev)
-        O_ = desc.out_features
-        cyc = [[0.0] * O_] if order == 2 else [[1.0] * O_]
-        clc = [[1.0] * O_] if order == 2 else None
+        cyc = [[0.0] * O] if order == 2 else [[1.0] * O]
+        clc = [[1.0] * O] if order == 2 else None
 
         def lsq_only():
             _ops.siren_lsq_step(desc, theta, x, order, cyc, None, clc, tgt, 1.0 / N, loss_out=loss_buf, gtheta=gtheta)
@@ -493,15 +693,15 @@ def run_ours(args):
         ms_lsq = time_call(lsq_only, reps)
         fused_closure = {"ms_per_step": round(ms_lsq, 4), "points_per_s": round(world * N / (ms_lsq / 1e3), 1),
                          "achieved_tflops": round(3 * f_fwd * N / (ms_lsq / 1e3) / 1e12, 3),
-                         "frac": round(3 * f_fwd * N / (ms_lsq / 1e3) / 1e12 / peak, 4),
+                         "frac_fp32": round(3 * f_fwd * N / (ms_lsq / 1e3) / 1e12 / peak, 4),
                          "kernel": ("k_tc_bwd" if tensor_path else "k_fused_bwd") + "<..., LSQ=true>: loss = mean((lap - target)^2) and d loss/d theta in one kernel, no output round trip"}
+        del tgt
 
     # ---- end to end through the public API with HOST buffers (rank-local shard)
     Ne = args.e2e_points or N
     xh = (torch.rand(Ne, D) * 2 - 1).pin_memory()
     th = torch.randn(Ne, 1).pin_memory()
     grad_host = torch.empty(P).pin_memory()
-
     copy_stream = torch.cuda.Stream(device=dev)
 
     def fetch():
@@ -540,7 +740,6 @@ def run_ours(args):
         _, staged = e2e_step(staged, True)
     barrier()
     k_e = max(2, min(args.steps, 10))
-    t0 = time.perf_counter()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     staged = fetch()                                    # k_e copies inside the timed region: this one is exposed,
@@ -554,10 +753,12 @@ def run_ours(args):
     e2e = {"value": round(world * Ne * k_e / (float(ms_e.item()) / 1e3), 1), "unit": "points/s",
            "h2d_bytes_per_step": int(xh.numel() * 4 + th.numel() * 4), "d2h_bytes_per_step": int(P * 4 + 4),
            "points_per_step_per_gpu": Ne, "steps": k_e,
-           "api": "MLP.forward + diff_ops.laplace/gradient + loss.backward() (autograd boundary); inputs in pinned host buffers, each step's H2D copy issued on a copy stream one step ahead; gradient + loss read back every step"}
+           "api": "MLP.forward + diff_ops.laplace/gradient + loss.backward() (autograd boundary); inputs in pinned host buffers, each step's H2D copy issued on a copy stream one step ahead; gradient + loss read back every step",
+           "note": None if world == 1 else f"the {world} ranks share the host's PCIe / memory bandwidth for their H2D copies"}
+    del xh, th, staged
 
     # ---- the script's own batch size (128^2 points / iteration), launch-latency bound
-    Ns = 16384
+    Ns = min(16384, N)
     xs = x[:Ns].contiguous()
     cs = [c[:Ns].contiguous() for c in cots]
 
@@ -569,6 +770,25 @@ def run_ours(args):
     ms_small = time_call(small_step, 50)
     script = {"points": Ns, "us_per_step": round(ms_small * 1e3, 2), "points_per_s": round(Ns / (ms_small / 1e3), 1)}
 
+    # ---- the other BASELINE.json shapes: each a fixed global batch split over the ranks, gradient all-reduce included
+    sweep = None
+    if not args.no_sweep:
+        sweep = {}
+        for wl, g_pts in SWEEP:
+            try:
+                n_loc = g_pts // world
+                sc = OperatorCase(wl, n_loc, dev, rank, world)
+                k_s = 3
+                sms = sc.timed(k_s, 2)
+                v = world * n_loc * k_s / (sms / 1e3)
+                sweep[wl] = {"global_points": n_loc * world, "ms_per_step": round(sms / k_s, 4), "points_per_s": round(v, 1),
+                             "frac_fp32_step": round(3 * sc.f_fwd * v / 1e12 / (peak * world), 4),
+                             "family": lib.kernel_family(sc.desc, sc.order, True), "params": sc.P}
+                del sc
+            except Exception as e:                      # a secondary measurement must not take the headline line down
+                sweep[wl] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+            torch.cuda.empty_cache()
+
     # ---- seconds per PDE time step (second half of BASELINE.json's metric): fluid2Dtlgn, fixed iterations
     timestep = None
     if args.timestep_iters > 0:
@@ -576,8 +796,10 @@ def run_ours(args):
             timestep = fluid_timestep_ours(dev, args.timestep_iters, world)
         except Exception as e:                          # the second half of the metric must not take the first half down
             timestep = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
-        if rank == 0 and not args.no_cpu_baseline and "error" not in timestep:
-            timestep["cpu_reference"] = fluid_timestep_cpu(3, args.timestep_iters)
+        try:                                            # the same time step at a batch that CAN be sharded: 1024^2 points / iteration
+            timestep["large_batch"] = fluid_timestep_ours(dev, max(args.timestep_iters // 5, 5), world, sample_resolution=1024)
+        except Exception as e:
+            timestep["large_batch"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
         if world == 1:                                  # the 32 < H <= 512 family's closure, same metric
             for key, fn in (("elasticity", lambda: [elasticity_timestep_ours(dev, args.timestep_iters, c) for c in ELASTIC_CASES]),
                             ("advection", lambda: advection_timestep_ours(dev, args.timestep_iters))):
@@ -586,112 +808,55 @@ def run_ours(args):
                 except Exception as e:
                     timestep[key] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
-    # ---- CPU baseline (oracle port of the reference algorithm), rank 0, bounded sample
+    # ---- baselines: the reference itself, in its own process.  cpu_baseline: rank 0 at N = 1 only (the contract); the
+    # like-for-like leg (the same reference code as stock PyTorch on this GPU) likewise.
     cpu, torch_gpu = None, None
-    if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_reference(args.workload, budget_s=args.cpu_budget)
-        # like-for-like: the same algorithm as stock PyTorch on this GPU, at the largest size whose
-        # autograd graph fits comfortably
-        try:
-            torch_gpu = cpu_reference(args.workload, budget_s=5.0, n_points=min(N, 1 << 20), device=dev)
-        except Exception as e:                                  # e.g. out of memory on a wide net
-            torch_gpu = {"error": str(e)[:200]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.cuda.empty_cache()
+        ref_cpu = reference_subprocess(args, "cpu", legs="all", steps=16, warmup=2, budget=args.cpu_budget)
+        cpu = ref_cpu.get("cpu_baseline") or {"error": ref_cpu.get("error", "no line")}
+        if isinstance(timestep, dict) and "error" not in timestep:
+            timestep["cpu_reference"] = ref_cpu.get("timestep")
+            timestep["cpu_reference_elasticity_sec_per_iteration"] = ref_cpu.get("elasticity_sec_per_iteration")
+        ref_gpu = reference_subprocess(args, "cuda", legs="all", steps=10, warmup=3, budget=8.0, points=min(N, 1 << 20))
+        torch_gpu = ref_gpu.get("cpu_baseline") or {"error": ref_gpu.get("error", "no line")}
+        if isinstance(torch_gpu, dict) and "error" not in torch_gpu:
+            torch_gpu["timestep"] = ref_gpu.get("timestep")
+            torch_gpu["elasticity_sec_per_iteration"] = ref_gpu.get("elasticity_sec_per_iteration")
 
     if rank == 0:
+        cfg = config_block(args, world)
+        cfg["params"] = P
         line = {
-            "metric": "collocation points/s (SIREN fwd + grad + Laplacian + bwd)", "value": round(pts_per_s, 1),
-            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": round(pts_per_s, 1),
+            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc_txt}", "points_per_step_per_gpu": N,
-                       "global_points_per_step": world * N, "params": P,
-                       "parallelism": f"dp{world} (points sharded, weights replicated, NCCL all-reduce of the flat gradient)",
-                       "l2": "inputs + outputs + cotangents per step exceed the 126 MB L2" if N >= (1 << 22) else "flushed by size only if points >= 2^22",
-                       "init": "reference sine init, torch.manual_seed(0); points U[-1,1]^D seed 1234; cotangents randn/N seed 4321"},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "script_size": script, "timestep": timestep,
-            "fused_closure": fused_closure,
+            "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "weak": weak, "sweep": sweep, "script_size": script,
+            "timestep": timestep, "fused_closure": fused_closure,
+            "collective": None if world == 1 else "NCCL all-reduce (sum) of the flat fp32 gradient, one per step, on the compute stream",
         }
         emit(line)
     if world > 1:
-        # captured graphs hold NCCL kernels: tearing the communicator down under them can block forever (seen at N = 2).
-        # The line is out; leave together and skip the teardown -- this is a benchmark process, the driver only needs rc 0.
+        # Orderly teardown: every captured iteration graph (they hold NCCL kernels) has been dropped by the stepper
+        # helpers above; collect, drain the device, then destroy the communicator.  A watchdog turns a teardown that
+        # does not return (seen once at N = 2 in round 1, before the graphs were released first) into a clean exit.
+        gc.collect()
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush(); sys.stderr.flush()
-        os._exit(0)
+        done = threading.Event()
 
+        def watchdog():
+            if not done.wait(30.0):
+                sys.stderr.write("bench.py: destroy_process_group did not return within 30 s; leaving without it\n")
+                sys.stderr.flush()
+                os._exit(0)
 
-def cpu_reference(workload, budget_s=15.0, n_points=16384, threads=None, device="cpu"):
-    """the reference algorithm (oracle.torch_port: nn.Linear + sin(30x) + nested autograd.grad)
-    on the host cores -- or, device="cuda", as stock PyTorch on the same GPU -- on a bounded sample of the workload"""
-    from oracle import torch_port as tp
-    D, O, H, L, order, _ = WORKLOADS[workload]
-    if threads:
-        torch.set_num_threads(threads)
-    cores = torch.get_num_threads()
-    torch.manual_seed(0)
-    on_gpu = str(device).startswith("cuda")
-    net = tp.RefMLP(D, O, L, H).to(device)
-    x = (torch.rand(n_points, D, device=device) * 2 - 1).requires_grad_(True)
-    gy = torch.randn(n_points, O, device=device) / n_points
-    gj = torch.randn(n_points, O, D, device=device) / n_points
-    gl = torch.randn(n_points, 1, device=device) / n_points
-
-    def step():
-        net.zero_grad()
-        y = net(x)
-        loss = (gy * y).sum()
-        if order >= 1:
-            jac, _ = tp.jacobian(y, x)
-            loss = loss + (gj * jac).sum()
-        if order >= 2:
-            loss = loss + (gl * tp.laplace(y, x)).sum()
-        loss.backward()
-
-    step(); step()
-    if on_gpu:
-        torch.cuda.synchronize()
-    t0, n = time.perf_counter(), 0
-    while True:
-        step()
-        n += 1
-        if on_gpu:
-            torch.cuda.synchronize()
-        el = time.perf_counter() - t0
-        if el > budget_s or n >= 200:
-            break
-    where = f"stock PyTorch eager on {torch.cuda.get_device_name()}" if on_gpu else "CPU"
-    return {"value": round(n_points * n / el, 1), "unit": "points/s", "cores": cores, "kind": "port",
-            "sample": f"{n} steps of {n_points} points ({workload}); oracle.torch_port = the reference's algorithm "
-                      f"(nn.Linear + sin(30x) + nested autograd.grad) in torch {torch.__version__} {where} fp32",
-            "ms_per_step": round(el / n * 1e3, 2)}
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if rank != 0:
-        return
-    D, O, H, L, order, desc_txt = WORKLOADS[args.workload]
-    n_points = 16384
-    per_step_budget = 1.0
-    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every core this process may run on explicitly
-    res = cpu_reference(args.workload, budget_s=max(5.0, min(120.0, per_step_budget * (args.steps + args.warmup))),
-                        n_points=n_points, threads=len(os.sched_getaffinity(0)))
-    line = {
-        "impl": "reference", "metric": "collocation points/s (SIREN fwd + grad + Laplacian + bwd)",
-        "value": res["value"], "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc_txt}", "points_per_step": n_points,
-                   "note": "reference = Python/PyTorch; its tree cannot travel to the GPU box, so the oracle port of its "
-                           "algorithm is timed on the host cores (bounded sample)"},
-        "cpu_baseline": res,
-        "e2e": {"value": res["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit(line)
+        threading.Thread(target=watchdog, daemon=True).start()
+        dist.destroy_process_group()
+        done.set()
 
 
 def main():
@@ -701,13 +866,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="fluid2Dtlgn.pressure", choices=sorted(WORKLOADS))
-    ap.add_argument("--points", type=int, default=1 << 22, help="collocation points per GPU per step")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default, the driver's scaling run): --points per GPU; strong: --points in total, split over the GPUs")
+    ap.add_argument("--points", type=int, default=1 << 24,
+                    help="collocation points per step: in total (--scaling strong, the default) or per GPU (--scaling weak)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default, the driver's scaling run): --points in total, split over the GPUs; weak: --points per GPU")
+    ap.add_argument("--weak-points", type=int, default=1 << 22, help="per-GPU batch of the extra weak-scaling measurement (0 = skip)")
     ap.add_argument("--e2e-points", type=int, default=0)
-    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--cpu-budget", type=float, default=14.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--timestep-iters", type=int, default=100, help="Adam iterations per training loop of the fluid2Dtlgn time-step measurement (0 = skip)")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--timestep-iters", type=int, default=100, help="Adam iterations per training loop of the time-step measurements (0 = skip)")
+    # reference arm
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"], help="(--impl reference) cpu = the arm the driver runs; cuda = the like-for-like leg")
+    ap.add_argument("--ref-points", type=int, default=1 << 16, help="(--impl reference) points per timed step: a bounded sample of the global batch")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="(--impl reference) wall-clock cap of the timed steps, seconds")
+    ap.add_argument("--ref-legs", default="operator", choices=["operator", "all"])
     args = ap.parse_args()
     keep_stdout_clean()
     if args.impl == "reference":

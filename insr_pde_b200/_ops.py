@@ -52,6 +52,8 @@ def _check_input(t, name, shape=None):
         raise TypeError(f"{name} must be float32, got {t.dtype}")
     if not t.is_contiguous():
         t = t.contiguous()
+    if t.data_ptr() % 16:                 # the C ABI wants 16-byte aligned buffers: an offset view (a slice of a shard, a
+        t = t.clone()                     # torch.split piece, a narrow()ed gradient) is copied, not refused
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
     return t

@@ -77,11 +77,14 @@ int check_device() {
     return 0;
 }
 
+// streaming multiprocessors of the current device (cudaDevAttrMultiProcessorCount; 148 on the B200)
+int n_sm() { return insr_fused::sm_count(); }
+
 // number of workspace slots (= resident threads) of the generic kernels
 int generic_slots(int64_t N, size_t bytes_per_slot) {
     const size_t budget = (size_t)768 << 20;
     int64_t tmax = (int64_t)(budget / (bytes_per_slot ? bytes_per_slot : 1));
-    if (tmax > 148 * 512) tmax = 148 * 512;
+    if (tmax > n_sm() * 512) tmax = n_sm() * 512;
     if (tmax < 1024) tmax = 1024;
     int64_t t = ((N + INSR_GEN_THREADS - 1) / INSR_GEN_THREADS) * INSR_GEN_THREADS;
     if (t > tmax) t = (tmax / INSR_GEN_THREADS) * INSR_GEN_THREADS;
@@ -127,7 +130,7 @@ int launch_generic_bwd(const SirenDims &dm, const float *theta, const float *x, 
         ++g_launches;
         if (dm.L > 0) {
             const int tiles = (dm.H + 31) / 32;
-            int zsplit = (2 * 148 + tiles * tiles * dm.L - 1) / (tiles * tiles * dm.L);
+            int zsplit = (2 * n_sm() + tiles * tiles * dm.L - 1) / (tiles * tiles * dm.L);
             const int zmax = (nv + 255) / 256;
             if (zsplit > zmax) zsplit = zmax;
             if (zsplit < 1) zsplit = 1;
@@ -329,7 +332,7 @@ int insr_adam_step(float *theta, const float *grad, float *exp_avg, float *exp_a
     if (rc) return rc;
     if (n == 0) return 0;
     int64_t blocks = (n + 255) / 256;
-    if (blocks > 1184) blocks = 1184;
+    if (blocks > 8 * n_sm()) blocks = 8 * n_sm();
     auto kfn = k_adam_step;
     INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(256), 0, stream, theta, grad, exp_avg, exp_avg_sq, n, sched, beta1,
                 beta2, eps);
@@ -373,7 +376,7 @@ int insr_iteration_update(int n_slots, float *const *theta, float *const *grad, 
     if (rc) return rc;
     int64_t blocks = (total + 255) / 256;
     if (blocks < 1) blocks = 1;
-    if (blocks > 1184) blocks = 1184;
+    if (blocks > 8 * n_sm()) blocks = 8 * n_sm();
     auto kfn = k_iteration_update;
     INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(256), 0, stream, sl, sched, losses, n_losses, main_index, hist, hist_capacity,
                 hist_idx, ticket, beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr, zero_grad);
@@ -388,7 +391,7 @@ int insr_svd_small(const float *F, int64_t n, int d, float *U, float *S, float *
     if (rc) return rc;
     if (n == 0) return 0;
     int64_t blocks = (n + 127) / 128;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > n_sm() * 16) blocks = n_sm() * 16;
     if (d == 2) { auto kfn = k_svd_small<2>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, F, n, U, S, V); }
     else        { auto kfn = k_svd_small<3>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, F, n, U, S, V); }
     ++g_launches;
@@ -403,7 +406,7 @@ int insr_elastic_energy(const float *F, int64_t n, int d, float ratio_arap, floa
     if (rc) return rc;
     if (n == 0) return 0;
     int64_t blocks = (n + 127) / 128;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > n_sm() * 16) blocks = n_sm() * 16;
     if (d == 2) { auto kfn = k_elastic_energy<2>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, F, n, ratio_arap, ratio_volume, energy, gF); }
     else        { auto kfn = k_elastic_energy<3>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, F, n, ratio_arap, ratio_volume, energy, gF); }
     ++g_launches;
@@ -431,7 +434,7 @@ int insr_elastic_terms(const insr_elastic_terms_desc *t, int d, const float *y, 
     if (n_all == 0) return 0;
     const bool energy = (k.r_arap != 0.f || k.r_volume != 0.f);
     int64_t blocks = (n_all + 127) / 128;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > n_sm() * 16) blocks = n_sm() * 16;
     if (d == 2) { auto kfn = k_elastic_terms<2>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, k, y, energy ? J : nullptr, x, y_prev, y_pp, loss, gy, energy ? gJ : nullptr); }
     else        { auto kfn = k_elastic_terms<3>; INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(128), 0, stream, k, y, energy ? J : nullptr, x, y_prev, y_pp, loss, gy, energy ? gJ : nullptr); }
     ++g_launches;
@@ -456,7 +459,7 @@ int insr_sample_boxes(int n_boxes, int dim, const int32_t *count, const float *l
     if (rc) return rc;
     if (total == 0) return 0;
     int64_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > n_sm() * 8) blocks = n_sm() * 8;
     auto kfn = k_sample_boxes;
     INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(256), 0, stream, bs, seed, counter, ticket, point_offset, out);
     ++g_launches;
@@ -475,7 +478,7 @@ int insr_sample_mesh(const float *V, const int32_t *elem, const float *cdf, int 
     if (rc) return rc;
     if (n == 0) return 0;
     int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > n_sm() * 8) blocks = n_sm() * 8;
     if (verts_per_elem == 3) {
         auto kfn = k_sample_mesh<3>;
         INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(256), 0, stream, V, elem, cdf, n_elem, n, dim_out, seed, counter, ticket, point_offset, out);

@@ -109,11 +109,41 @@ class GradAllReducer:
 
 
 _GLOBAL_HANDLE = None
+_PLATEAU_ORIG = None
+
+
+def mean_over_ranks(value, group=None):
+    """the rank-averaged value of a loss scalar (tensor or float) as a 0-dim tensor on the value's device"""
+    t = value.detach().clone().float().reshape(1) if torch.is_tensor(value) else torch.tensor([float(value)])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if dist.get_backend(group) == "nccl" and not t.is_cuda:
+            t = t.cuda()
+        dist.all_reduce(t, group=group)
+        t /= dist.get_world_size(group)
+    return t[0]
+
+
+def sync_plateau_schedulers(group=None):
+    """``ReduceLROnPlateau.step(metric)`` sees the metric AVERAGED over the ranks.  The reference feeds the scheduler the
+    loss of its own batch (base/baseModel.py:81) and leaves the loop when the learning rate has decayed to min_lr
+    (:132-134); with sharded points every rank would otherwise cut its LR -- and stop iterating, i.e. stop entering the
+    all-reduce -- at a different iteration.  One extra 4-byte all-reduce per iteration keeps the replicas identical."""
+    global _PLATEAU_ORIG
+    cls = torch.optim.lr_scheduler.ReduceLROnPlateau
+    if _PLATEAU_ORIG is None:
+        _PLATEAU_ORIG = cls.step
+
+        def step(self, metrics, *args, **kwargs):
+            return _PLATEAU_ORIG(self, mean_over_ranks(metrics, step._insr_group), *args, **kwargs)
+
+        cls.step = step
+    cls.step._insr_group = group
 
 
 def install_global(nets_getter, group=None):
     """hook EVERY optimizer's step (the reference re-creates Adam per training loop,
-    base/baseModel.py:55-62).  ``nets_getter()`` returns the currently trainable modules."""
+    base/baseModel.py:55-62) and every plateau scheduler's step (``sync_plateau_schedulers``).
+    ``nets_getter()`` returns the currently trainable modules."""
     global _GLOBAL_HANDLE
     from torch.optim.optimizer import register_optimizer_step_pre_hook
 
@@ -123,4 +153,5 @@ def install_global(nets_getter, group=None):
     if _GLOBAL_HANDLE is not None:
         _GLOBAL_HANDLE.remove()
     _GLOBAL_HANDLE = register_optimizer_step_pre_hook(hook)
+    sync_plateau_schedulers(group)
     return _GLOBAL_HANDLE

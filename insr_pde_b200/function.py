@@ -18,8 +18,11 @@ modes:
   that actually received a cotangent.
 
 Limitations (none are exercised by the reference): gradients w.r.t. the parameters are not
-themselves differentiable (no create_graph w.r.t. theta), and third spatial derivatives
-through autograd are not available.
+themselves differentiable, and a backward under ``create_graph=True`` delivers gradients w.r.t.
+the POINTS only -- the direct parameter gradient of the node is not produced in that mode (it
+raises when the points need no gradient, i.e. when the parameter gradient is all that can be
+meant; with points that require grad use ``loss.backward()`` without create_graph, as
+base/baseModel.py:77 does); third spatial derivatives through autograd are not available.
 """
 from __future__ import annotations
 
@@ -58,6 +61,11 @@ class SirenFn(torch.autograd.Function):
 
         if torch.is_grad_enabled():
             # ---- differentiable backward: express dL/dx through higher-order outputs
+            if not ctx.needs_input_grad[0]:
+                # no gradient w.r.t. the points can be wanted, so this call is after d/d theta with create_graph=True
+                raise RuntimeError(
+                    "insr_pde_b200: parameter gradients under create_graph=True are not supported by the fused path "
+                    "(they would be silently missing); call backward() without create_graph, as base/baseModel.py:77 does")
             if gh2 is not None:
                 raise RuntimeError(
                     "insr_pde_b200: a differentiable (create_graph=True) backward through second "

@@ -80,8 +80,43 @@ def lsq(net, x, order, cy, cj=None, cl=None, target=None, scale=None, out=None):
     if target is not None:
         target = target.detach().reshape(x.shape[0], rows).contiguous().float()
     loss = torch.zeros(1, dtype=torch.float32, device=x.device) if out is None else out
+    if not lsq_kernel_available(net, order):
+        return _lsq_by_layers(net, x, order, cy, cj, cl, target, scale, loss)
     _ops.siren_lsq_step(net.desc, net.flat_theta(), x, order, cy, cj, cl, target, scale,
                         loss_out=loss, gtheta=flat_grad(net))
+    return loss[0]
+
+
+def lsq_kernel_available(net, order):
+    """insr_siren_lsq_step exists for the resident-weights family only (H <= 32, 1 <= L <= 3, (D, O) in {(1,1), (2,1), (2,2)})"""
+    return order <= ORDER_LAP and _ops._lib.get_lib().kernel_family(net.desc, order, True) == 1
+
+
+def _lsq_by_layers(net, x, order, cy, cj, cl, target, scale, loss):
+    """the same least-squares term for every other shape (the reference's default hidden_features = 64, deeper nets, 3-D):
+    one forward that keeps its tape, the residual / loss / cotangents as a few elementwise kernels, the reverse sweep from
+    the tape into the flat gradient buffer.  Same arguments and results as the one-kernel path."""
+    D, O = net.in_features, net.out_features
+    dev = x.device
+    cy_t = torch.as_tensor(cy, dtype=torch.float32, device=dev).reshape(-1, O)
+    R = cy_t.shape[0]
+    outs, tape = _ops.siren_forward(net.desc, net.flat_theta(), x, order, keep_tape=True)
+    r = outs[0] @ cy_t.t()
+    cj_t = cl_t = None
+    if order >= ORDER_JAC and cj is not None:
+        cj_t = torch.as_tensor(cj, dtype=torch.float32, device=dev).reshape(R, O, D)
+        r = r + torch.einsum("nod,cod->nc", outs[1], cj_t)
+    if order >= ORDER_LAP and cl is not None:
+        cl_t = torch.as_tensor(cl, dtype=torch.float32, device=dev).reshape(R, O)
+        r = r + outs[2] @ cl_t.t()
+    if target is not None:
+        r = r - target
+    loss += scale * torch.sum(r * r)
+    g = (2.0 * scale) * r
+    gy = g @ cy_t
+    gj = (torch.einsum("nc,cod->nod", g, cj_t) if cj_t is not None else torch.zeros_like(outs[1])) if order >= ORDER_JAC else None
+    gl = (g @ cl_t if cl_t is not None else torch.zeros_like(outs[2])) if order >= ORDER_LAP else None
+    _ops.siren_backward(net.desc, net.flat_theta(), x, order, gy, gj, gl, gtheta=flat_grad(net), tape=tape)
     return loss[0]
 
 
@@ -380,7 +415,12 @@ class TrainingLoop:
             loss_dict = closure(i)
             _backward_if_needed(loss_dict)
             if self.reducer is not None:
-                self.reducer.allreduce()
+                # gradients AND loss values in the one collective: every rank must feed the scheduler (and the
+                # early-stop test below) the same number, or the replicas' learning rates drift apart
+                keys = list(loss_dict)
+                red = self.reducer.allreduce(extra_scalars=torch.stack([loss_dict[k].detach().reshape(()).float() for k in keys]))
+                if red is not None:
+                    loss_dict = {k: red[j] for j, k in enumerate(keys)}
             self.opt.step()
             values = {k: float(v) for k, v in loss_dict.items()}        # host sync, as base/baseModel.py:116
             self.sched.step(values["main"])
@@ -518,6 +558,13 @@ class GraphedLoop:
         self.opt.reset(lr)
         self.idx.zero_()
 
+    def close(self):
+        """drop the captured graph NOW (it holds the kernels -- with data_parallel, the NCCL all-reduce -- of one iteration):
+        a process group must not be destroyed while a captured graph still references its communicator"""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph = None
+
     def run(self, n_iters, early_stop=False, check_every=100):
         self.opt.zero_grads()                          # whatever ran on these nets in between may have left gradients
         if self.graph is None:
@@ -553,7 +600,15 @@ class GraphedLoop:
         return [{k: float(h[i, j]) for j, k in enumerate(keys)} for i in range(done)]
 
 
-class FluidStepper:
+class _StepperBase:
+    def close(self):
+        """release every captured iteration graph of this stepper (see GraphedLoop.close)"""
+        for lp in self.__dict__.get("_loops", {}).values():
+            lp.close()
+        self.__dict__.pop("_loops", None)
+
+
+class FluidStepper(_StepperBase):
     """Fluid2DModel.step (fluid/model.py:61-70) on the fused closures, with the reference's sampling
     (base/sampling.py) and schedule; used for the seconds-per-timestep measurement."""
 
@@ -621,7 +676,7 @@ class FluidStepper:
         return h1, h2, h3
 
 
-class AdvectionStepper:
+class AdvectionStepper(_StepperBase):
     """Advection1DModel.initialize / step (advection/model.py:37-91): the Gaussian fit, then per time step the previous-frame
     hand-over and one training loop of the midpoint-residual closure; points as the reference draws them
     (``sample_random(sr, 1) * length / 2`` and the 2 x eps boundary bands) -- from one Philox kernel when ``graphed``."""
@@ -671,7 +726,7 @@ def gaussian_like(x, mu=-1.5, sigma=0.1):
     return torch.exp(-0.5 * (x - mu) ** 2 / (sigma ** 2))
 
 
-class ElasticityStepper:
+class ElasticityStepper(_StepperBase):
     """ElasticityModel.initialize / step (elasticity/model.py:100-125) on the fused closure: previous-frame hand-over,
     the reference's sample pattern ('random' and / or 'uniform'; a mesh when ``mesh=(V, F)`` is given), one
     @_training_loop per time step.  ``graphed=True`` captures the whole iteration (sampling kernel, field kernels, energy

@@ -6,7 +6,8 @@ I/O -- none is on the hot path), imports ``base`` and rebinds
 
     base.networks.get_network, base.baseModel.get_network, base.get_network, base.MLP
     base.diff_ops.{gradient,divergence,laplace,jacobian,hessian} and their re-exports in base
-    torch.svd  (dispatcher: batches of 2x2 / 3x3 fp32 CUDA matrices -> insr_svd_small, elasticity/model.py:144)
+    elasticity.model's ``torch.svd`` (a module-level proxy: batches of 2x2 / 3x3 fp32 CUDA matrices -> insr_svd_small,
+    elasticity/model.py:144; torch.svd itself is left alone)
 
 to this package *before* ``advection`` / ``fluid`` / ``elasticity`` bind them by name
 (``from base import gradient, ...``: fluid/model.py:5-6, advection/model.py:5,
@@ -112,19 +113,35 @@ def _shim_torch():
 
         sched.ReduceLROnPlateau = ReduceLROnPlateau
 
-    # elasticity/model.py:144 calls torch.svd on the (N, D, D) deformation gradients: route the small fp32 CUDA batches
-    # to the one-kernel SVD (insr_svd_small), everything else to torch's own
-    from . import linalg
-    if not getattr(torch.svd, "_insr_dispatch", False):
-        torch_svd = torch.svd
 
-        def svd(A, *args, **kwargs):
-            if linalg.supports(A) and not args and not kwargs:
-                return linalg.svd(A)
-            return torch_svd(A, *args, **kwargs)
 
-        svd._insr_dispatch = True
-        torch.svd = svd
+class _TorchWithDeviceSvd:
+    """stands in for the ``torch`` global of elasticity/model.py ONLY: ``torch.svd`` of the (N, D, D) deformation
+    gradients (elasticity/model.py:144) goes to the one-kernel SVD (insr_svd_small; differentiable through S, which is
+    all that file uses), everything else -- and every other module's ``torch.svd`` -- is torch's own."""
+
+    def __init__(self, torch_module):
+        self._t = torch_module
+
+    def svd(self, A, *args, **kwargs):
+        from . import linalg
+        if linalg.supports(A) and not args and not kwargs:
+            return linalg.svd(A)
+        return self._t.svd(A, *args, **kwargs)
+
+    def __getattr__(self, name):
+        return getattr(self._t, name)
+
+
+def _scope_device_svd():
+    """bind the proxy inside elasticity.model (imported here, after ``base`` has been rebound)"""
+    import torch
+    try:
+        ela = importlib.import_module("elasticity.model")
+    except Exception:                    # a tree without the elasticity package: nothing to scope
+        return
+    if not isinstance(ela.torch, _TorchWithDeviceSvd):
+        ela.torch = _TorchWithDeviceSvd(ela.torch if ela.torch is not None else torch)
 
 
 def install(reference_root: str):
@@ -150,6 +167,7 @@ def install(reference_root: str):
         setattr(ref_diff, name, fn)
         setattr(ref_networks, name, fn)     # networks.py does ``from .diff_ops import *``
         setattr(base, name, fn)
+    _scope_device_svd()
     return base
 
 

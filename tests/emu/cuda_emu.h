@@ -147,6 +147,11 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 #define __logf(x) logf(x)
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 static inline float fminf_(float a, float b) { return a < b ? a : b; }
 

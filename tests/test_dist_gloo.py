@@ -133,3 +133,48 @@ def test_shared_gradient_buffer_is_one_allreduce(tmp_path):
         assert np.all(r[k]["gv"] == 1.5) and np.allclose(r[k]["gp"], np.arange(3297) * 1.5)
         assert r[k]["main"] == 1.0 and r[k]["bc"] == 10.5
         assert np.allclose(r[k]["pgrad"], r[k]["gp"][-1:])          # last parameter (output bias) = last element of the slice
+
+
+def _worker_plateau(rank, world, port, out_dir):
+    """the INTEGRATION.md recipe (install_global + shard_points under a loop shaped like base/baseModel.py:73-81,104-134)
+    run PAST a ReduceLROnPlateau cut and the early-stop exit"""
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from insr_pde_b200 import dist as idist
+    from oracle import torch_port as tp
+    torch.set_num_threads(1)
+    idist.init_from_env("gloo")
+    torch.manual_seed(0)
+    net = tp.RefMLP(1, 1, 1, 8)
+    idist.install_global(lambda: [net])
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=0.1, min_lr=1e-5, patience=1)
+    g = torch.Generator().manual_seed(3)
+    lrs, n_iters = [], 0
+    for it in range(60):
+        x_all = torch.rand(64, 1, generator=g) * 2 - 1              # the same global set on every rank
+        x = idist.shard_points(x_all)
+        # shard-dependent noise: the LOCAL losses of the two ranks go up and down at different iterations
+        loss = torch.mean((net(x) - torch.sin(3 * x)) ** 2) * (1.0 + 0.5 * ((it + rank) % 2))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()                                                  # pre-hook: gradients averaged
+        sched.step(loss)                                            # patched: sees the rank-averaged loss
+        lrs.append(opt.param_groups[0]["lr"])
+        n_iters += 1
+        if opt.param_groups[0]["lr"] <= 1.1e-5:                     # early stop as base/baseModel.py:132-134
+            break
+    theta = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    np.savez(os.path.join(out_dir, f"plateau{rank}.npz"), theta=theta.numpy(), lrs=np.array(lrs), n_iters=n_iters)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replicas_stay_identical_through_plateau_cuts_and_early_stop(tmp_path):
+    world = 2
+    mp.spawn(_worker_plateau, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = np.load(tmp_path / "plateau0.npz"), np.load(tmp_path / "plateau1.npz")
+    assert int(a["n_iters"]) == int(b["n_iters"]) < 60              # both left the loop, at the same iteration
+    assert np.array_equal(a["lrs"], b["lrs"]) and a["lrs"][-1] < a["lrs"][0]      # same LR decisions, and cuts happened
+    assert np.array_equal(a["theta"], b["theta"])
