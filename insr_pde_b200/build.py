@@ -42,6 +42,7 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()):
         jobs.append((f"siren_fused_{d}{o}.o", [f"-DINSR_INST_D={d}", f"-DINSR_INST_O={o}",
                                                os.path.join(CSRC, "siren_fused_inst.cu")]))
     jobs.append(("siren_tiled.o", [os.path.join(CSRC, "siren_tiled_inst.cu")]))
+    jobs.append(("siren_mid.o", [os.path.join(CSRC, "siren_mid_inst.cu")]))
     procs = []
     for obj, args in jobs:
         cmd = [nvcc, *NVCC_FLAGS, *extra_flags, *inc, "-c", *args, "-o", os.path.join(OBJ_DIR, obj)]

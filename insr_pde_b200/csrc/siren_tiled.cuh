@@ -25,6 +25,7 @@
 #pragma once
 #include "siren_tiled_api.h"
 #include "siren_wide_tc.cuh"
+#include "siren_mid_api.h"
 
 namespace insr_tiled {
 
@@ -621,6 +622,18 @@ void taped_forward(const SirenDims &dm, const Geo &g, const float *theta, const 
                    float *y = nullptr, float *jac = nullptr, float *h2 = nullptr, bool *fused_out = nullptr) {
     constexpr int S = StreamCfg<D, ORDER>::S;
     (void)S;
+#ifndef INSR_CPU_EMU
+    // widths of the elasticity scripts with <= 3 streams: the whole network in ONE kernel that also leaves the tape
+    if (tensor && insr_mid_supported(dm, ORDER)) {     // (the caller has laid Zpre / Act out for the fused kernels' tape)
+        const int rc = insr_mid_forward(dm, ORDER, theta, x + n0 * D, nv, y ? y + n0 * dm.O : nullptr,
+                                        jac ? jac + n0 * dm.O * D : nullptr,
+                                        h2 ? h2 + n0 * dm.O * (ORDER == 3 ? D * D : 1) : nullptr, Zpre, Act, buf, stream, launches);
+        if (rc == 0) {
+            if (fused_out) *fused_out = true;
+            return;
+        }
+    }
+#endif
     const int64_t items = rows * (g.HP / 4);
     const unsigned eg = (unsigned)((items + NT - 1) / NT);
     const size_t smem = gemm_smem_floats(g) * sizeof(float);
@@ -670,7 +683,10 @@ int run_forward_tape(const SirenDims &dm, const float *theta, const float *x, in
     const int64_t chunk = chunk_points(dm, S, true, N);
     if (N > chunk) return -6;
     const int64_t NCp = capacity(chunk);
-    const size_t buf = (size_t)S * NCp * g.HP;
+    size_t buf = (size_t)S * NCp * g.HP;
+#ifndef INSR_CPU_EMU
+    if (tensor && insr_mid_supported(dm, ORDER)) buf = (size_t)S * NCp * insr_mid_width(dm);      // the fused kernels' tape
+#endif
     float *Zpre = ws, *Act = ws + (size_t)(dm.L + 1) * buf;
     const size_t smem = gemm_smem_floats(g) * sizeof(float);
     auto kfwd = k_tiled_fwd<D, ORDER>;
@@ -697,6 +713,9 @@ int run_forward(const SirenDims &dm, const float *theta, const float *x, int64_t
     tensor = false;
 #else
     tensor = tensor && S <= 4;                              // S * NCOL TMEM columns
+    if (tensor && insr_mid_supported(dm, ORDER) &&         // one kernel, no workspace, any batch
+        insr_mid_forward(dm, ORDER, theta, x, N, y, jac, h2, nullptr, nullptr, 0, stream, launches) == 0)
+        return 0;
 #endif
     constexpr int TP = Tile<S>::TP;
     const Geo g = make_geo(dm.H, S, TP);
@@ -765,6 +784,28 @@ int run_backward(const SirenDims &dm, const float *theta, const float *x, int64_
     const int L = dm.L;
     const int64_t chunk = chunk_points(dm, S, true, N);
     const int64_t NCp = capacity(chunk);
+#ifndef INSR_CPU_EMU
+    if (tensor && insr_mid_supported(dm, ORDER)) {
+        // widths of the elasticity scripts, <= 3 streams: (taped forward +) data-gradient chain + weight gradients of all
+        // layers + thin layers = 3-4 kernels per chunk on the fused kernels' private tape layout
+        if (have_tape && N > chunk) return -6;
+        const size_t mbuf = (size_t)S * NCp * insr_mid_width(dm);
+        float *Zp = ws, *Ac = ws + (size_t)(L + 1) * mbuf;
+        for (int64_t n0 = 0; n0 < N; n0 += chunk) {
+            const int64_t nv = (N - n0 < chunk) ? (N - n0) : chunk;
+            int rc = 0;
+            if (!have_tape)
+                rc = insr_mid_forward(dm, ORDER, theta, x + n0 * D, nv, nullptr, nullptr, nullptr, Zp, Ac, mbuf, stream, launches);
+            if (rc == 0)
+                rc = insr_mid_backward(dm, ORDER, theta, x + n0 * D, nv, gy ? gy + n0 * dm.O : nullptr,
+                                       gjac ? gjac + n0 * dm.O * D : nullptr,
+                                       gh2 ? gh2 + n0 * dm.O * (ORDER == 3 ? D * D : 1) : nullptr, gtheta,
+                                       gx ? gx + n0 * D : nullptr, Zp, Ac, mbuf, stream, launches);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+#endif
     const size_t buf = (size_t)S * NCp * g.HP;
     float *Zpre = ws;                               // [L+1] buffers
     float *Act = ws + (size_t)(L + 1) * buf;        // [L+1] buffers

@@ -6,9 +6,17 @@
 namespace insr_tiled {
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+// row width the workspace is sized for: H rounded up to 8, or -- for the widths the fused mid-width kernels serve
+// (siren_mid_tc.cuh: 32 < H <= 80) -- the kernel width 64 / 80 of their private tape layout
+inline int hp_alloc(const SirenDims &dm) {
+    const int hp = (dm.H + 7) & ~7, h16 = (dm.H + 15) & ~15;
+    if (dm.H > 32 && h16 <= 80) return h16 <= 64 ? 64 : 80;
+    return hp;
+}
+
 // points per chunk: bound the workspace to ~1.5 GB
 inline int64_t chunk_points(const SirenDims &dm, int S, bool bwd, int64_t N) {
-    const int HP = (dm.H + 7) & ~7;
+    const int HP = hp_alloc(dm);
     const size_t per_point = (size_t)S * HP * sizeof(float) * (bwd ? (2 * (dm.L + 1) + 2) : 2) + (bwd ? 16 * 4 * 4 : 0);
     int64_t nc = (int64_t)(((size_t)1536 << 20) / per_point);
     nc = nc / 1024 * 1024;
@@ -22,7 +30,7 @@ inline int64_t capacity(int64_t chunk) { return chunk + 256; }
 
 inline size_t ws_bytes(const SirenDims &dm, int order, bool bwd, int64_t N) {
     const int S = insr_nstreams(dm.D, order);
-    const int HP = (dm.H + 7) & ~7;
+    const int HP = hp_alloc(dm);
     const int64_t NCp = capacity(chunk_points(dm, S, bwd, N));
     const size_t buf = (size_t)S * NCp * HP;
     size_t floats = bwd ? buf * (2 * (dm.L + 1) + 2) + (size_t)dm.O * S * NCp : buf * 2;

@@ -517,7 +517,9 @@ def test_autograd_forward_keeps_its_tape_for_the_reverse_sweep(case):
     assert tape is not None and all(torch.equal(a, b) for a, b in zip(outs_t, outs))
     lib.launch_count(reset=True)
     g_t, _ = _ops.siren_backward(net.desc, net.flat_theta(), x, order, *cots, tape=tape)
-    assert lib.launch_count() == launches[False] - (L + 1)      # layer 0 + L hidden layers not recomputed
+    S = 1 + (D if order >= 1 else 0) + (1 if order == 2 else 0)
+    fused_mid = 32 < H <= 80 and S <= 3                          # siren_mid_tc.cuh: the whole forward is ONE kernel
+    assert lib.launch_count() == launches[False] - (1 if fused_mid else L + 1)      # the forward is not recomputed
     assert rel(g_t, grads[False]) < 2e-5
     frozen = ib.MLP(D, O, L, H, nonlinearity="sine").cuda()
     for p in frozen.parameters():
@@ -715,3 +717,98 @@ def test_wide_tcgen05_layers_against_fp64_oracle(case):
     for flags in res:
         assert rel(res[flags][0], gref) < TOL, flags
         assert rel(res[flags][1], gxref) < TOL, flags
+
+
+# ------------------------------------------------------------------------------------------------
+# fused mid-width family (siren_mid_tc.cuh): 32 < H <= 80, at most 3 streams -- the whole network in one kernel
+# ------------------------------------------------------------------------------------------------
+MID_CASES = [
+    # D, O, H, L, N, order                              what it exercises
+    (2, 2, 68, 3, 20400, 1),        # elasticity2Dstretch at its own batch (interior + faces): 160 tiles on 148 CTAs, ragged tail
+    (2, 2, 68, 3, 1, 1),            # a single point
+    (3, 3, 66, 3, 26592, 0),        # the bunny's frozen fields (value only, S = 1)
+    (2, 2, 64, 3, 4097, 0),         # width 64 instantiation, S = 1
+    (2, 1, 64, 2, 3000, 1),         # width 64, S = 3, O = 1
+    (1, 1, 40, 2, 1500, 3),         # H padded 40 -> 64, 1-D full Hessian (S = 3)
+    (1, 2, 80, 1, 700, 2),          # H = 80 exactly, one hidden layer, S = 3 (value, tangent, Laplacian)
+    (1, 3, 72, 4, 129, 1),          # S = 2, O = 3, L = 4
+    (3, 1, 33, 5, 513, 0),          # narrowest width of the family
+]
+
+
+def _mid_problem(case):
+    D, O, H, L, N, order = case
+    rng = np.random.default_rng(7 * N + H)
+    parts = []
+    for li, (o, i) in enumerate(fm.layer_shapes(D, O, H, L)):
+        b = 1.0 / i if li == 0 else np.sqrt(6.0 / i) / 30.0
+        parts += [rng.uniform(-b, b, o * i), rng.uniform(-1, 1, o) / np.sqrt(i)]
+    theta = np.concatenate(parts).astype(np.float32)
+    x = rng.uniform(-1, 1, (N, D)).astype(np.float32)
+    return rng, theta, x
+
+
+def _check_outputs(outs, ref, order):
+    assert rel(outs[0], ref["y"]) < TOL
+    if order >= 1:
+        assert rel(outs[1], ref["jac"]) < TOL
+    if order == 2:
+        assert rel(outs[2], ref["lap"]) < TOL
+    if order == 3:
+        assert rel(outs[2], ref["hess"]) < TOL
+
+
+@pytest.mark.parametrize("case", MID_CASES)
+def test_mid_width_fused_forward_and_taped_backward(case):
+    """k_mid_fwd against the fp64 oracle: plain evaluation, and the taped evaluation followed by the reverse sweep from
+    that tape (what SirenFn does for a trainable net); the layer-by-layer kernels (INSR_MID off is a process-wide switch,
+    so the FFMA family stands in) must agree with it too"""
+    D, O, H, L, N, order = case
+    rng, theta, x = _mid_problem(case)
+    desc = _lib.make_desc(D, O, H, L)
+    assert _lib.get_lib().kernel_family(desc, order, True) == 2
+    td, xd = dev(theta), dev(x).reshape(N, D)
+    ref = fm.forward(theta.astype(np.float64), x.astype(np.float64), D, O, H, L, order)
+    outs = _ops.siren_forward(desc, td, xd, order)
+    _check_outputs(outs, ref, order)
+    outs_ffma = _ops.siren_forward(_lib.make_desc(D, O, H, L, flags=_lib.FLAG_NO_TENSOR), td, xd, order)
+    for a, b in zip(outs, outs_ffma):
+        assert rel(a, b) < TOL
+    # taped forward -> backward from the tape
+    outs_t, tape = _ops.siren_forward(desc, td, xd, order, keep_tape=True)
+    assert tape is not None
+    _check_outputs(outs_t, ref, order)
+    cot = [rng.standard_normal(tuple(o.shape)).astype(np.float32) for o in outs]
+    gth, gx = _ops.siren_backward(desc, td, xd, order, *[dev(c) for c in cot], need_gx=True, tape=tape)
+    kw = dict(gy=cot[0])
+    if order >= 1:
+        kw["gjac"] = cot[1]
+    if order == 2:
+        kw["glap"] = cot[2]
+    if order == 3:
+        kw["ghess"] = cot[2]
+    gref, gxref = fm.backward(theta.astype(np.float64), x.astype(np.float64), D, O, H, L, order, **kw)
+    assert rel(gth, gref) < TOL and rel(gx, gxref) < TOL
+    # backward that recomputes its own tape
+    gth2, gx2 = _ops.siren_backward(desc, td, xd, order, *[dev(c) for c in cot], need_gx=True)
+    assert rel(gth2, gref) < TOL and rel(gx2, gxref) < TOL
+
+
+def test_mid_width_large_batch_properties():
+    """2^20 points through the fused kernels (several tiles per persistent CTA, several workspace chunks in the backward):
+    additivity over point shards and a sampled fp64 check"""
+    D, O, H, L, order, N = 2, 2, 68, 3, 1, 1 << 20
+    rng, theta, x = _mid_problem((D, O, H, L, N, order))
+    desc = _lib.make_desc(D, O, H, L)
+    td, xd = dev(theta), dev(x)
+    y, jac = _ops.siren_forward(desc, td, xd, order)
+    idx = rng.choice(N, 4096, replace=False)
+    idx[:3] = [0, N - 1, N // 2]
+    ref = fm.forward(theta.astype(np.float64), x[idx].astype(np.float64), D, O, H, L, order)
+    assert rel(y[idx], ref["y"]) < TOL and rel(jac[idx], ref["jac"]) < TOL
+    gy, gj = torch.randn_like(y) / N, torch.randn_like(jac) / N
+    g_all, _ = _ops.siren_backward(desc, td, xd, order, gy, gj)
+    half = N // 2 + 77
+    g_a, _ = _ops.siren_backward(desc, td, xd[:half], order, gy[:half], gj[:half])
+    g_b, _ = _ops.siren_backward(desc, td, xd[half:], order, gy[half:], gj[half:])
+    assert rel(g_a + g_b, g_all) < TOL
