@@ -8,10 +8,10 @@ bool insr_mid_supported(const SirenDims &dm, int order) { return insr_mid::mid_s
     if (dm.D == D_ && dm.O == O_ && order == ORD_) { constexpr int D = D_, O = O_, ORDER = ORD_; \
         (void)D; (void)O; (void)ORDER; return CALL; }
 #define INSR_MID_O(D_, ORD_, CALL) INSR_MID_CASE(D_, 1, ORD_, CALL) INSR_MID_CASE(D_, 2, ORD_, CALL) INSR_MID_CASE(D_, 3, ORD_, CALL)
-// (D, order) pairs with at most 3 forward-mode streams
+// (D, order) pairs with at most 4 forward-mode streams
 #define INSR_MID_ALL(CALL) \
     INSR_MID_O(1, 0, CALL) INSR_MID_O(1, 1, CALL) INSR_MID_O(1, 2, CALL) INSR_MID_O(1, 3, CALL) \
-    INSR_MID_O(2, 0, CALL) INSR_MID_O(2, 1, CALL) INSR_MID_O(3, 0, CALL)
+    INSR_MID_O(2, 0, CALL) INSR_MID_O(2, 1, CALL) INSR_MID_O(2, 2, CALL) INSR_MID_O(3, 0, CALL) INSR_MID_O(3, 1, CALL)
 
 int insr_mid_width(const SirenDims &dm) { return insr_mid::hp16_of(dm.H) <= 64 ? 64 : 80; }
 

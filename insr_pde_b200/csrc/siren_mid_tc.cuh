@@ -37,7 +37,7 @@ using insr_tc::s32;
 constexpr int MT = 512;                 // threads: 4 per point
 constexpr int TILE = 128;               // points per CTA tile
 constexpr int MAX_HP16 = 80;
-constexpr int MAX_S = 3;
+constexpr int MAX_S = 4;
 
 // tape element: the 4 neurons 16 i + 4 q .. + 3 of (tile T, stream s, row r); index in float4 units inside one layer buffer
 __host__ __device__ inline size_t tape_f4(int64_t T, int s, int i, int q, int r, int S, int NQ) {
@@ -59,6 +59,12 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
         :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -71,6 +77,11 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
     v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
 }
+// tcgen05.ld is asynchronous: values may only be consumed after tcgen05.wait::ld.  This empty volatile asm, placed after
+// the wait, makes every later use of the four registers depend on it (volatile asms keep their order).
+__device__ __forceinline__ void tmem_ld_ready4(float (&v)[4]) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory");
+}
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
                  :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
@@ -82,8 +93,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return w;
 }
 
+// streams whose hi operand lives in TMEM (beside the S HP16 accumulator columns); the others keep it in shared memory
+// (fp32, K-major canonical) and pay the operand fetch: 32 + N/4 instead of N/2 cycles per MMA
+__host__ __device__ constexpr int nht_of(int HP16, int S) { return (512 - S * HP16) / HP16 < S ? (512 - S * HP16) / HP16 : S; }
+
 struct MidSmem {
-    int w_hi, w_lo, w_hb, a_lo, bias, w1, wo, bo, part, mbar, tmem, total;
+    int w_hi, w_lo, w_hb, a_lo, a_hi, bias, w1, wo, bo, part, mbar, tmem, total;
 };
 __host__ __device__ inline MidSmem mid_smem(int HP16, int S, int L, int PS) {
     MidSmem m;
@@ -92,11 +107,12 @@ __host__ __device__ inline MidSmem mid_smem(int HP16, int S, int L, int PS) {
     m.w_lo = o; o += HP16 * HP16 * 4;
     m.w_hb = o; o += HP16 * HP16 * 2;
     m.a_lo = o; o += S * TILE * HP16 * 2;
+    m.a_hi = o; o += (S - nht_of(HP16, S)) * TILE * HP16 * 4;
     m.bias = o; o += L * HP16 * 4;
     m.w1 = o; o += HP16 * 16;
     m.wo = o; o += 3 * HP16 * 4;
     m.bo = o; o += 16;
-    m.part = o; o += 4 * TILE * PS * 4;
+    m.part = m.w_hi; (void)PS;                 // [4][128][PS] partials alias the weight buffer (idle between the tiles' contractions)
     m.mbar = o; o += 16;
     m.tmem = o; o += 16;
     m.total = o;
@@ -118,28 +134,37 @@ struct MidParams {
     float *gtheta;
 };
 
-// one layer's weights, raw from global memory (L2): element pairs along the reduction index
+// one layer's weights, raw from global memory (L2).  A warp handles one 8 x 8 block (n8, k8) of the operand B per
+// iteration: the lane's element pair (n, k), (n, k + 1) lands in the K-major canonical layout such that the 32 lanes
+// cover two full 128-byte core-matrix rows (tf32 operands) or one (bf16): conflict-free shared-memory stores, and every
+// global load touches 8 sectors of 32 bytes.
 template <int HP16, bool TRANSPOSED>
 struct WRegs {
-    static constexpr int NPAIR = HP16 * HP16 / 2;
-    static constexpr int NI = (NPAIR + MT - 1) / MT;
+    static constexpr int NB8 = HP16 / 8;
+    static constexpr int NU = NB8 * NB8;                 // 8 x 8 blocks
+    static constexpr int NI = (NU + MT / 32 - 1) / (MT / 32);
     float2 v[NI];
+    __device__ __forceinline__ static void coords(int unit, int lane, int &n, int &k) {
+        const int n8 = unit / NB8, k8 = unit % NB8;
+        const int nl = TRANSPOSED ? (lane & 7) : (lane >> 2), kp = TRANSPOSED ? (lane >> 3) : (lane & 3);
+        n = 8 * n8 + nl;
+        k = 8 * k8 + 2 * kp;
+    }
     // B[n][k] = W[n][k] (forward: n = output neuron) or W[k][n] (data gradient: n = input neuron)
     __device__ __forceinline__ void load(const float *__restrict__ W, int H, int tid) {
+        const int warp = tid >> 5, lane = tid & 31;
         INSR_PRAGMA_UNROLL
         for (int i = 0; i < NI; ++i) {
-            const int idx = tid + MT * i;
+            const int unit = warp + (MT / 32) * i;
             float a = 0.f, b = 0.f;
-            if (idx < NPAIR) {
-                if (!TRANSPOSED) {
-                    const int n = idx / (HP16 / 2), k = 2 * (idx % (HP16 / 2));
-                    if (n < H) {
+            if (NU % (MT / 32) == 0 || unit < NU) {
+                int n, k;
+                coords(unit, lane, n, k);
+                if (n < H) {
+                    if (!TRANSPOSED) {
                         if (k < H) a = __ldg(W + (size_t)n * H + k);
                         if (k + 1 < H) b = __ldg(W + (size_t)n * H + k + 1);
-                    }
-                } else {
-                    const int n = idx % HP16, k = 2 * (idx / HP16);
-                    if (n < H) {
+                    } else {
                         if (k < H) a = __ldg(W + (size_t)k * H + n);
                         if (k + 1 < H) b = __ldg(W + (size_t)(k + 1) * H + n);
                     }
@@ -150,13 +175,13 @@ struct WRegs {
     }
     __device__ __forceinline__ void store(unsigned char *whi, unsigned char *wlo, unsigned char *whb, float omega, int tid) const {
         constexpr int SBO32 = 32 * HP16, SBO16 = 16 * HP16;
+        const int warp = tid >> 5, lane = tid & 31;
         INSR_PRAGMA_UNROLL
         for (int i = 0; i < NI; ++i) {
-            const int idx = tid + MT * i;
-            if (idx < NPAIR) {
+            const int unit = warp + (MT / 32) * i;
+            if (NU % (MT / 32) == 0 || unit < NU) {
                 int n, k;
-                if (!TRANSPOSED) { n = idx / (HP16 / 2); k = 2 * (idx % (HP16 / 2)); }
-                else { n = idx % HP16; k = 2 * (idx / HP16); }
+                coords(unit, lane, n, k);
                 const float a = omega * v[i].x, b = omega * v[i].y;
                 const float ah = insr_tc::tf32_hi(a), bh = insr_tc::tf32_hi(b);
                 *reinterpret_cast<float2 *>(whi + off32(n, k, SBO32)) = make_float2(ah, bh);
@@ -169,22 +194,37 @@ struct WRegs {
 
 // the MMAs of one hidden-layer contraction (all streams), issued by one elected lane
 template <int HP16, int S>
-__device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t whi, uint32_t wlo, uint32_t whb, uint32_t alo) {
+__device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t whi, uint32_t wlo, uint32_t whb, uint32_t alo, uint32_t ahi_sm, int H) {
+    const int nk8 = (H + 7) >> 3, nk16 = (H + 15) >> 4;      // k-steps that hold data (the padding beyond H is zero on both sides)
+    constexpr int NHT = nht_of(HP16, S);
     constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HP16 >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HP16 >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t SBO32 = 32 * HP16, SBO16 = 16 * HP16;
     INSR_PRAGMA_UNROLL
     for (int s = 0; s < S; ++s) {
         const uint32_t d = tmem_base + (uint32_t)(s * HP16);
-        const uint32_t ahi = tmem_base + (uint32_t)((S + s) * HP16);
-        INSR_PRAGMA_UNROLL
-        for (int ks = 0; ks < HP16 / 8; ++ks) {        // K = 8 per tf32 instruction: 8 TMEM columns / two core matrices
-            mma_tf32_ts(d, ahi + 8 * ks, desc_kmajor(whi + 256 * ks, SBO32), IDESC_TF32, ks > 0 ? 1u : 0u);
-            mma_tf32_ts(d, ahi + 8 * ks, desc_kmajor(wlo + 256 * ks, SBO32), IDESC_TF32, 1u);
+        if (s < NHT) {
+            const uint32_t ahi = tmem_base + (uint32_t)((S + s) * HP16);
+            INSR_PRAGMA_UNROLL
+            for (int ks = 0; ks < HP16 / 8; ++ks) {    // K = 8 per tf32 instruction: 8 TMEM columns / two core matrices
+                if (ks < nk8) {
+                    mma_tf32_ts(d, ahi + 8 * ks, desc_kmajor(whi + 256 * ks, SBO32), IDESC_TF32, ks > 0 ? 1u : 0u);
+                    mma_tf32_ts(d, ahi + 8 * ks, desc_kmajor(wlo + 256 * ks, SBO32), IDESC_TF32, 1u);
+                }
+            }
+        } else {
+            const uint32_t ahi = ahi_sm + (uint32_t)((s - NHT) * TILE * HP16 * 4);
+            INSR_PRAGMA_UNROLL
+            for (int ks = 0; ks < HP16 / 8; ++ks) {
+                if (ks < nk8) {
+                    mma_tf32_ss(d, desc_kmajor(ahi + 256 * ks, SBO32), desc_kmajor(whi + 256 * ks, SBO32), IDESC_TF32, ks > 0 ? 1u : 0u);
+                    mma_tf32_ss(d, desc_kmajor(ahi + 256 * ks, SBO32), desc_kmajor(wlo + 256 * ks, SBO32), IDESC_TF32, 1u);
+                }
+            }
         }
         INSR_PRAGMA_UNROLL
         for (int kb = 0; kb < HP16 / 16; ++kb)         // K = 16 per bf16 instruction: two core matrices
-            mma_bf16_ss(d, desc_kmajor(alo + (uint32_t)(s * TILE * HP16 * 2) + 256 * kb, SBO16), desc_kmajor(whb + 256 * kb, SBO16),
+            if (kb < nk16) mma_bf16_ss(d, desc_kmajor(alo + (uint32_t)(s * TILE * HP16 * 2) + 256 * kb, SBO16), desc_kmajor(whb + 256 * kb, SBO16),
                         IDESC_BF16, 1u);
     }
 }
@@ -192,11 +232,12 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t whi, ui
 // 4 consecutive neurons j0 .. j0 + 3 of one stream of row `row` become the operand of the next contraction:
 // hi part -> TMEM, lo part -> bf16 shared-memory operand
 template <int HP16>
-__device__ __forceinline__ void store_operand4(uint32_t hi_tmem, unsigned char *alo_s, int row, int j0, const float (&a)[4]) {
+__device__ __forceinline__ void store_operand4(uint32_t hi_tmem, unsigned char *ahi_s, unsigned char *alo_s, int row, int j0, const float (&a)[4]) {
     float h[4];
     INSR_PRAGMA_UNROLL
     for (int c = 0; c < 4; ++c) h[c] = insr_tc::tf32_hi(a[c]);
-    tmem_st4(hi_tmem + j0, h);
+    if (ahi_s == nullptr) tmem_st4(hi_tmem + j0, h);
+    else *reinterpret_cast<float4 *>(ahi_s + off32(row, j0, 32 * HP16)) = make_float4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint2 *>(alo_s + off16(row, j0, 16 * HP16)) =
         make_uint2(pack_bf16x2(a[0] - h[0], a[1] - h[1]), pack_bf16x2(a[2] - h[2], a[3] - h[3]));
 }
@@ -211,7 +252,8 @@ __global__ void __launch_bounds__(MT, 1) k_mid_fwd(MidParams p, int tmem_cols) {
     constexpr int S = C::S;
     constexpr int NQ = HP16 / 16;                        // 16-column rounds = quads per thread
     constexpr int PS = O * S;
-    static_assert(S <= MAX_S && HP16 <= MAX_HP16 && 2 * S * HP16 <= 512, "TMEM budget");
+    constexpr int NHT = nht_of(HP16, S);
+    static_assert(S <= MAX_S && HP16 <= MAX_HP16 && NHT >= 1 && (S + NHT) * HP16 <= 512, "TMEM budget");
     extern __shared__ __align__(1024) unsigned char smraw_[];
     unsigned char *sm = smraw_ + ((128u - (s32(smraw_) & 127u)) & 127u);
     const SirenDims dm = p.dm;
@@ -299,7 +341,7 @@ __global__ void __launch_bounds__(MT, 1) k_mid_fwd(MidParams p, int tmem_cols) {
             }
             INSR_PRAGMA_UNROLL
             for (int s = 0; s < S; ++s) {
-                store_operand4<HP16>(tmem_row + (uint32_t)((S + s) * HP16), sm + M.a_lo + s * TILE * HP16 * 2, row, j0, aq[s]);
+                store_operand4<HP16>(tmem_row + (uint32_t)((S + s) * HP16), s < NHT ? nullptr : sm + M.a_hi + (s - NHT) * TILE * HP16 * 4, sm + M.a_lo + s * TILE * HP16 * 2, row, j0, aq[s]);
                 if (TAPE) {
                     const size_t t4 = tape_f4(tile, s, i, quarter, row, S, NQ);
                     reinterpret_cast<float4 *>(p.Zpre)[t4] = make_float4(zq[s][0], zq[s][1], zq[s][2], zq[s][3]);
@@ -323,7 +365,7 @@ __global__ void __launch_bounds__(MT, 1) k_mid_fwd(MidParams p, int tmem_cols) {
             if (warp == 0) {
                 insr_tc::tc_fence_after();
                 if (insr_tc::elect_one()) {
-                    issue_layer<HP16, S>(tmem_base, s32(sm + M.w_hi), s32(sm + M.w_lo), s32(sm + M.w_hb), s32(sm + M.a_lo));
+                    issue_layer<HP16, S>(tmem_base, s32(sm + M.w_hi), s32(sm + M.w_lo), s32(sm + M.w_hb), s32(sm + M.a_lo), s32(sm + M.a_hi), H);
                     insr_tc::mma_commit(mbar);
                 }
                 __syncwarp();
@@ -337,13 +379,25 @@ __global__ void __launch_bounds__(MT, 1) k_mid_fwd(MidParams p, int tmem_cols) {
             phase ^= 1;
             insr_tc::tc_fence_after();
             const bool last = (l == L);
+            // accumulators of round i + 1 are requested before round i is processed (tcgen05.ld latency under the arithmetic)
+            float znext[S][4];
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) tmem_ld4(tmem_row + (uint32_t)(s * HP16 + 4 * quarter), znext[s]);
             INSR_PRAGMA_UNROLL
             for (int i = 0; i < NQ; ++i) {
                 const int j0 = 16 * i + 4 * quarter;
                 float zz[S][4], aq[S][4];
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) tmem_ld4(tmem_row + (uint32_t)(s * HP16 + j0), zz[s]);
                 insr_tc::tmem_ld_wait();
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s) {
+                    tmem_ld_ready4(znext[s]);
+                    INSR_PRAGMA_UNROLL
+                    for (int c = 0; c < 4; ++c) zz[s][c] = znext[s][c];
+                }
+                if (i + 1 < NQ) {
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s) tmem_ld4(tmem_row + (uint32_t)(s * HP16 + j0 + 16), znext[s]);
+                }
                 const float4 bv = *reinterpret_cast<const float4 *>(biasS + (l - 1) * HP16 + j0);
                 INSR_PRAGMA_UNROLL
                 for (int c = 0; c < 4; ++c) {
@@ -368,7 +422,7 @@ __global__ void __launch_bounds__(MT, 1) k_mid_fwd(MidParams p, int tmem_cols) {
                 } else {
                     INSR_PRAGMA_UNROLL
                     for (int s = 0; s < S; ++s)
-                        store_operand4<HP16>(tmem_row + (uint32_t)((S + s) * HP16), sm + M.a_lo + s * TILE * HP16 * 2, row, j0, aq[s]);
+                        store_operand4<HP16>(tmem_row + (uint32_t)((S + s) * HP16), s < NHT ? nullptr : sm + M.a_hi + (s - NHT) * TILE * HP16 * 4, sm + M.a_lo + s * TILE * HP16 * 2, row, j0, aq[s]);
                 }
                 if (TAPE) {
                     INSR_PRAGMA_UNROLL
@@ -426,6 +480,7 @@ __global__ void __launch_bounds__(MT, 1) k_mid_dgrad(MidParams p, int tmem_cols)
     constexpr int S = C::S;
     constexpr int NQ = HP16 / 16;
     constexpr int PS = D;
+    constexpr int NHT = nht_of(HP16, S);
     extern __shared__ __align__(1024) unsigned char smraw_[];
     unsigned char *sm = smraw_ + ((128u - (s32(smraw_) & 127u)) & 127u);
     const SirenDims dm = p.dm;
@@ -510,7 +565,7 @@ __global__ void __launch_bounds__(MT, 1) k_mid_dgrad(MidParams p, int tmem_cols)
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s) {
                     zt[tape_f4(tile, s, i, quarter, row, S, NQ)] = make_float4(zbq[s][0], zbq[s][1], zbq[s][2], zbq[s][3]);
-                    store_operand4<HP16>(tmem_row + (uint32_t)((S + s) * HP16), sm + M.a_lo + s * TILE * HP16 * 2, row, j0, zbq[s]);
+                    store_operand4<HP16>(tmem_row + (uint32_t)((S + s) * HP16), s < NHT ? nullptr : sm + M.a_hi + (s - NHT) * TILE * HP16 * 4, sm + M.a_lo + s * TILE * HP16 * 2, row, j0, zbq[s]);
                 }
             }
         }
@@ -527,7 +582,7 @@ __global__ void __launch_bounds__(MT, 1) k_mid_dgrad(MidParams p, int tmem_cols)
             if (warp == 0) {
                 insr_tc::tc_fence_after();
                 if (insr_tc::elect_one()) {
-                    issue_layer<HP16, S>(tmem_base, s32(sm + M.w_hi), s32(sm + M.w_lo), s32(sm + M.w_hb), s32(sm + M.a_lo));
+                    issue_layer<HP16, S>(tmem_base, s32(sm + M.w_hi), s32(sm + M.w_lo), s32(sm + M.w_hb), s32(sm + M.a_lo), s32(sm + M.a_hi), H);
                     insr_tc::mma_commit(mbar);
                 }
                 __syncwarp();
@@ -554,6 +609,8 @@ __global__ void __launch_bounds__(MT, 1) k_mid_dgrad(MidParams p, int tmem_cols)
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s) z4[s] = (i == 0) ? zfirst[s] : zt[tape_f4(tile, s, i, quarter, row, S, NQ)];
                 insr_tc::tmem_ld_wait();
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s) tmem_ld_ready4(acc[s]);
                 float zbq[S][4];
                 INSR_PRAGMA_UNROLL
                 for (int c = 0; c < 4; ++c) {
@@ -567,7 +624,7 @@ __global__ void __launch_bounds__(MT, 1) k_mid_dgrad(MidParams p, int tmem_cols)
                 INSR_PRAGMA_UNROLL
                 for (int s = 0; s < S; ++s) {
                     zt[tape_f4(tile, s, i, quarter, row, S, NQ)] = make_float4(zbq[s][0], zbq[s][1], zbq[s][2], zbq[s][3]);
-                    if (l > 1) store_operand4<HP16>(tmem_row + (uint32_t)((S + s) * HP16), sm + M.a_lo + s * TILE * HP16 * 2, row, j0, zbq[s]);
+                    if (l > 1) store_operand4<HP16>(tmem_row + (uint32_t)((S + s) * HP16), s < NHT ? nullptr : sm + M.a_hi + (s - NHT) * TILE * HP16 * 4, sm + M.a_lo + s * TILE * HP16 * 2, row, j0, zbq[s]);
                 }
                 if (l == 1 && p.gx) {                      // d loss / d x = (omega W1)^T zbar_0 (value stream)
                     INSR_PRAGMA_UNROLL
@@ -897,7 +954,9 @@ inline bool mid_enabled() {
 // shapes the fused kernels serve: the widths of the elasticity scripts with at most 3 streams
 inline bool mid_supported(const SirenDims &dm, int order) {
     const int S = insr_nstreams(dm.D, order);
-    return mid_enabled() && dm.H > 32 && hp16_of(dm.H) <= MAX_HP16 && S <= MAX_S && dm.L >= 1 && dm.L <= 8;
+    if (!(mid_enabled() && dm.H > 32 && hp16_of(dm.H) <= MAX_HP16 && S <= MAX_S && dm.L >= 1 && dm.L <= 8)) return false;
+    const int hp = hp16_of(dm.H) <= 64 ? 64 : 80;
+    return mid_smem(hp, S, dm.L, 0).total + 128 <= 232448;      // 227 KB of shared memory per CTA
 }
 
 template <int D, int O, int ORDER, int HP16, bool TAPE>
@@ -912,7 +971,7 @@ int launch_mid_fwd_hp(MidParams &p, void *stream, int64_t *launches) {
         const int64_t tiles = (p.N + TILE - 1) / TILE;
         const int64_t sms = insr_fused::sm_count();
         const int64_t ctas = tiles < sms ? tiles : sms;
-        kfn<<<dim3((unsigned)ctas), dim3(MT), M.total + 128, reinterpret_cast<cudaStream_t>(stream)>>>(p, insr_tc::pow2_cols(2 * S * HP16));
+        kfn<<<dim3((unsigned)ctas), dim3(MT), M.total + 128, reinterpret_cast<cudaStream_t>(stream)>>>(p, insr_tc::pow2_cols((S + nht_of(HP16, S)) * HP16));
         ++*launches;
         return 0;
     }
@@ -939,7 +998,7 @@ int launch_mid_bwd_hp(MidParams &p, void *stream, int64_t *launches) {
             auto kfn = k_mid_dgrad<D, O, ORDER, HP16>;
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, M.total + 128);
             const int64_t ctas = tiles < sms ? tiles : sms;
-            kfn<<<dim3((unsigned)ctas), dim3(MT), M.total + 128, st>>>(p, insr_tc::pow2_cols(2 * S * HP16));
+            kfn<<<dim3((unsigned)ctas), dim3(MT), M.total + 128, st>>>(p, insr_tc::pow2_cols((S + nht_of(HP16, S)) * HP16));
             ++*launches;
         }
         {   // hidden-layer weight gradients, all layers in one launch

@@ -518,7 +518,7 @@ def test_autograd_forward_keeps_its_tape_for_the_reverse_sweep(case):
     lib.launch_count(reset=True)
     g_t, _ = _ops.siren_backward(net.desc, net.flat_theta(), x, order, *cots, tape=tape)
     S = 1 + (D if order >= 1 else 0) + (1 if order == 2 else 0)
-    fused_mid = 32 < H <= 80 and S <= 3                          # siren_mid_tc.cuh: the whole forward is ONE kernel
+    fused_mid = 32 < H <= 80 and S <= 4                          # siren_mid_tc.cuh: the whole forward is ONE kernel
     assert lib.launch_count() == launches[False] - (1 if fused_mid else L + 1)      # the forward is not recomputed
     assert rel(g_t, grads[False]) < 2e-5
     frozen = ib.MLP(D, O, L, H, nonlinearity="sine").cuda()
@@ -720,7 +720,7 @@ def test_wide_tcgen05_layers_against_fp64_oracle(case):
 
 
 # ------------------------------------------------------------------------------------------------
-# fused mid-width family (siren_mid_tc.cuh): 32 < H <= 80, at most 3 streams -- the whole network in one kernel
+# fused mid-width family (siren_mid_tc.cuh): 32 < H <= 80, at most 4 streams -- the whole network in one kernel
 # ------------------------------------------------------------------------------------------------
 MID_CASES = [
     # D, O, H, L, N, order                              what it exercises
@@ -733,6 +733,10 @@ MID_CASES = [
     (1, 2, 80, 1, 700, 2),          # H = 80 exactly, one hidden layer, S = 3 (value, tangent, Laplacian)
     (1, 3, 72, 4, 129, 1),          # S = 2, O = 3, L = 4
     (3, 1, 33, 5, 513, 0),          # narrowest width of the family
+    (3, 3, 66, 3, 26592, 1),        # elasticity3Dbunny's trainable field: S = 4 at width 80 (two hi operands in TMEM, two in shared memory)
+    (2, 1, 64, 3, 5000, 2),         # sweep.h64: S = 4 at width 64 (all hi operands in TMEM)
+    (2, 2, 80, 2, 1000, 2),         # S = 4, O = 2, H = 80
+    (3, 2, 48, 1, 300, 1),          # S = 4, H padded 48 -> 64, one hidden layer
 ]
 
 
