@@ -148,6 +148,9 @@ def load(cpu: bool = True):
     ns.fluid = importlib.import_module("fluid")
     try:
         ns.elasticity = importlib.import_module("elasticity")
+        if cpu:     # torchgp/per_vertex_areas.py:14 picks "cuda" whenever a GPU is visible (the CPU legs also run on the GPU box)
+            pva = importlib.import_module("elasticity.torchgp.per_vertex_areas")
+            pva.torch = _TorchCpuProxy(torch)
     except Exception as exc:  # pragma: no cover - optional (needs numpy-only torchgp bits)
         ns.elasticity = None
         ns.elasticity_error = exc
