@@ -537,6 +537,16 @@ __global__ void __launch_bounds__(MT, 1) k_mid_dgrad(MidParams p, int tmem_cols)
                 for (int s = 0; s < S; ++s) g[o][s] = 0.f;
             }
         }
+        // DRAM latency of the tape is taken off the critical path: the layers that are needed later are pulled into L2 now
+        for (int l = L - 1; l >= 0; --l) {
+            const float4 *zt = reinterpret_cast<const float4 *>(p.Zpre + (size_t)l * p.buf);
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s)
+                INSR_PRAGMA_UNROLL
+                for (int i = 0; i < NQ; ++i)
+                    if ((lane & 1) == 0)        // one prefetch per 32-byte sector
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(zt + tape_f4(tile, s, i, quarter, row, S, NQ)));
+        }
         // ---- adjoint of the last sine layer: abar_L = Wo^T g  ->  zbar_L
         {
             float4 *zt = reinterpret_cast<float4 *>(p.Zpre + (size_t)L * p.buf);
@@ -592,25 +602,37 @@ __global__ void __launch_bounds__(MT, 1) k_mid_dgrad(MidParams p, int tmem_cols)
                 wr.load(p.theta + insr_w_offset(dm, ln), H, tid);
             }
             float4 *zt = reinterpret_cast<float4 *>(p.Zpre + (size_t)(l - 1) * p.buf);
-            // the tape of the previous layer travels while the tensor core works: first rounds' pre-activations now
-            float4 zfirst[S];
+            // the tape of the previous layer travels while the tensor core works: the first round's pre-activations are
+            // requested now, every later round one round ahead of its use
+            float4 znext[S];
             INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s) zfirst[s] = zt[tape_f4(tile, s, 0, quarter, row, S, NQ)];
+            for (int s = 0; s < S; ++s) znext[s] = zt[tape_f4(tile, s, 0, quarter, row, S, NQ)];
             insr_tc::mbar_wait(mbar, phase);
             phase ^= 1;
             insr_tc::tc_fence_after();
+            float accn[S][4];
+            INSR_PRAGMA_UNROLL
+            for (int s = 0; s < S; ++s) tmem_ld4(tmem_row + (uint32_t)(s * HP16 + 4 * quarter), accn[s]);
             INSR_PRAGMA_UNROLL
             for (int i = 0; i < NQ; ++i) {
                 const int j0 = 16 * i + 4 * quarter;
                 float acc[S][4];
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) tmem_ld4(tmem_row + (uint32_t)(s * HP16 + j0), acc[s]);
                 float4 z4[S];
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) z4[s] = (i == 0) ? zfirst[s] : zt[tape_f4(tile, s, i, quarter, row, S, NQ)];
                 insr_tc::tmem_ld_wait();
                 INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s) tmem_ld_ready4(acc[s]);
+                for (int s = 0; s < S; ++s) {
+                    tmem_ld_ready4(accn[s]);
+                    INSR_PRAGMA_UNROLL
+                    for (int c = 0; c < 4; ++c) acc[s][c] = accn[s][c];
+                    z4[s] = znext[s];
+                }
+                if (i + 1 < NQ) {
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s) {
+                        tmem_ld4(tmem_row + (uint32_t)(s * HP16 + j0 + 16), accn[s]);
+                        znext[s] = zt[tape_f4(tile, s, i + 1, quarter, row, S, NQ)];
+                    }
+                }
                 float zbq[S][4];
                 INSR_PRAGMA_UNROLL
                 for (int c = 0; c < 4; ++c) {
@@ -676,19 +698,31 @@ __device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr, uint32_t lbo) {
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-template <int HP16>
-__global__ void __launch_bounds__(WGT, 1) k_mid_wgrad(SirenDims dm, int S, const float *__restrict__ Zpre, const float *__restrict__ Act,
-                                                     int64_t buf, int nv, float *__restrict__ gtheta) {
+// thin layers (first / output layer gradients): see k_mid_edge_role below
+template <int D, int O, int ORDER, int HP16>
+__device__ __forceinline__ void mid_edge_role(const MidParams &p, int cta, int nctas);
+
+template <int D, int O, int ORDER, int HP16>
+__global__ void __launch_bounds__(WGT, 2) k_mid_wgrad(MidParams p) {
+    typedef StreamCfg<D, ORDER> C;
+    constexpr int S = C::S;
     constexpr int NQ = HP16 / 16;
     constexpr int NCH = HP16 / 4;                            // float4 chunks per row
     constexpr int NI = NCH / 4;                              // chunks per thread
     constexpr int NB = (HP16 + 63) / 64;                     // blocks of 64 neurons on either side
+    const SirenDims dm = p.dm;
+    if ((int)blockIdx.y == dm.L) {                           // the extra grid row: thin layers, beside the tensor-core CTAs
+        mid_edge_role<D, O, ORDER, HP16>(p, (int)blockIdx.x, (int)gridDim.x);
+        return;
+    }
     extern __shared__ __align__(1024) unsigned char smraw_[];
     unsigned char *sm = smraw_ + ((1024u - (s32(smraw_) & 1023u)) & 1023u);
     const int layer = 1 + (int)blockIdx.y;
-    const float4 *ZB = reinterpret_cast<const float4 *>(Zpre + (size_t)layer * buf);
-    const float4 *AC = reinterpret_cast<const float4 *>(Act + (size_t)(layer - 1) * buf);
-    float *gW = gtheta + insr_w_offset(dm, layer), *gb = gtheta + insr_b_offset(dm, layer);
+    const int64_t buf = p.buf;
+    const int nv = (int)p.N;
+    const float4 *ZB = reinterpret_cast<const float4 *>(p.Zpre + (size_t)layer * buf);
+    const float4 *AC = reinterpret_cast<const float4 *>(p.Act + (size_t)(layer - 1) * buf);
+    float *gW = p.gtheta + insr_w_offset(dm, layer), *gb = p.gtheta + insr_b_offset(dm, layer);
     unsigned char *zt = sm, *at = sm + 4 * WG_ATOM;          // [block][level][64 x 128 B] each
     float *bsumS = reinterpret_cast<float *>(sm + 8 * WG_ATOM);
     const uint32_t mbar = s32(sm + 8 * WG_ATOM + 512), tslot = mbar + 16;
@@ -710,24 +744,28 @@ __global__ void __launch_bounds__(WGT, 1) k_mid_wgrad(SirenDims dm, int S, const
     insr_tc::tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + 8 * WG_ATOM + 512 + 16);
 
-    const int rr = tid & 63, cg = tid >> 6;                   // row inside the 64-point group; chunks cg, cg + 4, ...
-    float4 rz[NI], ra[NI], bsum[NI];
+    // thread -> (row rr of the 64-point group, chunks ch(t)): a warp covers 16 rows x 2 adjacent chunks, so that its
+    // 8-byte operand stores touch every bank pair exactly twice (two wavefronts: the minimum) and every global load is
+    // two contiguous 256-byte runs
+    const int rr = 16 * (warp & 3) + (lane & 7) + 8 * (lane >> 4);
+    const int ch0 = 2 * (warp >> 2) + ((lane >> 3) & 1);      // chunks ch0 + 4 t
+    float4 rz[2][NI], ra[2][NI], bsum[NI];
     INSR_PRAGMA_UNROLL
     for (int t = 0; t < NI; ++t) bsum[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int ngroups = (nv + WG_PTS - 1) / WG_PTS;
     const int64_t nstages = (int64_t)((ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * S;
     auto stage_coords = [&](int64_t st, int &g, int &s) { g = (int)blockIdx.x + (int)(st / S) * (int)gridDim.x; s = (int)(st % S); };
-    auto gload = [&](int64_t st) {
+    auto gload = [&](int64_t st, float4 (&z)[NI], float4 (&a)[NI]) {
         int g, s;
         stage_coords(st, g, s);
         const int64_t T = g >> 1;
         const int r = 64 * (g & 1) + rr;
         INSR_PRAGMA_UNROLL
         for (int t = 0; t < NI; ++t) {
-            const int ch = cg + 4 * t;                        // neurons 4 ch .. = round ch / 4, quarter ch % 4
+            const int ch = ch0 + 4 * t;                       // neurons 4 ch .. = round ch / 4, quarter ch % 4
             const size_t idx = tape_f4(T, s, ch >> 2, ch & 3, r, S, NQ);
-            rz[t] = __ldg(ZB + idx);
-            ra[t] = __ldg(AC + idx);
+            z[t] = __ldg(ZB + idx);
+            a[t] = __ldg(AC + idx);
         }
     };
     auto split4 = [&](const float4 &v, uint2 &l1, uint2 &l2) {
@@ -737,20 +775,20 @@ __global__ void __launch_bounds__(WGT, 1) k_mid_wgrad(SirenDims dm, int S, const
         l1 = make_uint2(a, b);
         l2 = make_uint2(pack_bf16x2(r0_, r1_), pack_bf16x2(r2_, r3_));
     };
-    auto sstore = [&](int64_t st) {
+    auto sstore = [&](int64_t st, const float4 (&z)[NI], const float4 (&a)[NI]) {
         int g, s;
         stage_coords(st, g, s);
         INSR_PRAGMA_UNROLL
         for (int t = 0; t < NI; ++t) {
-            const int j = 4 * (cg + 4 * t);
+            const int j = 4 * (ch0 + 4 * t);
             const int jb = j >> 6, jj = j & 63;
             const int off = rr * 128 + ((((jj >> 3) ^ rr) & 7) << 4) + (jj & 7) * 2;
             uint2 l1, l2;
-            split4(rz[t], l1, l2);
+            split4(z[t], l1, l2);
             *reinterpret_cast<uint2 *>(zt + (jb * 2 + 0) * WG_ATOM + off) = l1;
             *reinterpret_cast<uint2 *>(zt + (jb * 2 + 1) * WG_ATOM + off) = l2;
-            if (s == 0) { bsum[t].x += rz[t].x; bsum[t].y += rz[t].y; bsum[t].z += rz[t].z; bsum[t].w += rz[t].w; }
-            split4(ra[t], l1, l2);
+            if (s == 0) { bsum[t].x += z[t].x; bsum[t].y += z[t].y; bsum[t].z += z[t].z; bsum[t].w += z[t].w; }
+            split4(a[t], l1, l2);
             *reinterpret_cast<uint2 *>(at + (jb * 2 + 0) * WG_ATOM + off) = l1;
             *reinterpret_cast<uint2 *>(at + (jb * 2 + 1) * WG_ATOM + off) = l2;
         }
@@ -760,14 +798,16 @@ __global__ void __launch_bounds__(WGT, 1) k_mid_wgrad(SirenDims dm, int S, const
         __syncthreads();
     }
 
+    // two stages in flight in registers (the loads of stage st + 2 are issued while stage st is in the tensor core)
     uint32_t phase = 0;
-    if (nstages > 0) gload(0);
+    if (nstages > 0) gload(0, rz[0], ra[0]);
+    if (nstages > 1) gload(1, rz[1], ra[1]);
     for (int64_t st = 0; st < nstages; ++st) {
-        sstore(st);
+        if (st & 1) sstore(st, rz[1], ra[1]); else sstore(st, rz[0], ra[0]);
         insr_tc::fence_async_smem();
         insr_tc::tc_fence_before();
         __syncthreads();
-        if (st + 1 < nstages) gload(st + 1);
+        if (st + 2 < nstages) { if (st & 1) gload(st + 2, rz[1], ra[1]); else gload(st + 2, rz[0], ra[0]); }
         if (warp == 0) {
             insr_tc::tc_fence_after();
             if (insr_tc::elect_one()) {
@@ -798,14 +838,16 @@ __global__ void __launch_bounds__(WGT, 1) k_mid_wgrad(SirenDims dm, int S, const
     // ---- flush: bias gradient, then the weight blocks (the four level-products of a weight are held by four warps)
     INSR_PRAGMA_UNROLL
     for (int t = 0; t < NI; ++t) {
-        const int j = 4 * (cg + 4 * t);
+        const int j = 4 * (ch0 + 4 * t);
         float v[4] = {bsum[t].x, bsum[t].y, bsum[t].z, bsum[t].w};
         INSR_PRAGMA_UNROLL
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; ++c) {                           // lanes with the same chunk: bit 3 of the lane index is the chunk
             float a = v[c];
-            INSR_PRAGMA_UNROLL
-            for (int m = 16; m >= 1; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
-            if (lane == 0 && j + c < 128) atomicAdd(bsumS + j + c, a);
+            a += __shfl_xor_sync(0xffffffffu, a, 16);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            if ((lane & 23) == 0 && j + c < 128) atomicAdd(bsumS + j + c, a);
         }
     }
     __syncthreads();
@@ -853,96 +895,106 @@ __global__ void __launch_bounds__(WGT, 1) k_mid_wgrad(SirenDims dm, int S, const
 // Replaces k_tiled_edge.
 // =============================================================================================
 template <int D, int O, int ORDER, int HP16>
-__global__ void __launch_bounds__(32 * (HP16 / 4)) k_mid_edge(MidParams p) {
+__device__ __forceinline__ void mid_edge_role(const MidParams &p, int cta, int nctas) {
     typedef StreamCfg<D, ORDER> C;
     constexpr int S = C::S;
     constexpr int NQ = HP16 / 16;
+    constexpr int NCH = HP16 / 4;
     const SirenDims dm = p.dm;
     const int L = dm.L, H = dm.H;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ch = warp;                                     // neurons 4 ch .. 4 ch + 3
-    const int i = ch >> 2, q = ch & 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const float4 *ZB0 = reinterpret_cast<const float4 *>(p.Zpre);
     const float4 *ACL = reinterpret_cast<const float4 *>(p.Act + (size_t)L * p.buf);
-    float gb1[4], gw1[D][4], gwo[O][4], gbo[O];
-    INSR_PRAGMA_UNROLL
-    for (int c = 0; c < 4; ++c) {
-        gb1[c] = 0.f;
-        INSR_PRAGMA_UNROLL
-        for (int d = 0; d < D; ++d) gw1[d][c] = 0.f;
-        INSR_PRAGMA_UNROLL
-        for (int o = 0; o < O; ++o) gwo[o][c] = 0.f;
-    }
-    INSR_PRAGMA_UNROLL
-    for (int o = 0; o < O; ++o) gbo[o] = 0.f;
     const int64_t ntiles = (p.N + TILE - 1) / TILE;
-    for (int64_t T = blockIdx.x; T < ntiles; T += gridDim.x) {
-        INSR_PRAGMA_UNROLL
-        for (int rq = 0; rq < 4; ++rq) {
-            const int r = 32 * rq + lane;
-            const int64_t n = T * TILE + r;
-            if (n >= p.N) continue;                            // zbar of the rows beyond the batch is zero anyway
-            float xv[D];
-            INSR_PRAGMA_UNROLL
-            for (int d = 0; d < D; ++d) xv[d] = __ldg(p.x + n * D + d);
-            const float4 z0 = __ldg(ZB0 + tape_f4(T, 0, i, q, r, S, NQ));
-            INSR_PRAGMA_UNROLL
-            for (int c = 0; c < 4; ++c) {
-                const float zc = insr_fused::f4get(z0, c);
-                gb1[c] += zc;
-                INSR_PRAGMA_UNROLL
-                for (int d = 0; d < D; ++d) gw1[d][c] = fmaf(zc, xv[d], gw1[d][c]);
-            }
-            INSR_PRAGMA_UNROLL
-            for (int d = 0; d < C::ND; ++d) {
-                const float4 zd = __ldg(ZB0 + tape_f4(T, 1 + d, i, q, r, S, NQ));
-                INSR_PRAGMA_UNROLL
-                for (int c = 0; c < 4; ++c) gw1[d][c] += insr_fused::f4get(zd, c);
-            }
-            float g[O][S];
-            INSR_PRAGMA_UNROLL
-            for (int o = 0; o < O; ++o) insr_load_cotangents<D, O, ORDER>(n, o, p.gy, p.gjac, p.gh2, g[o]);
-            INSR_PRAGMA_UNROLL
-            for (int s = 0; s < S; ++s) {
-                const float4 a4 = __ldg(ACL + tape_f4(T, s, i, q, r, S, NQ));
-                INSR_PRAGMA_UNROLL
-                for (int o = 0; o < O; ++o)
-                    INSR_PRAGMA_UNROLL
-                    for (int c = 0; c < 4; ++c) gwo[o][c] = fmaf(g[o][s], insr_fused::f4get(a4, c), gwo[o][c]);
-            }
-            if (ch == 0) {
-                INSR_PRAGMA_UNROLL
-                for (int o = 0; o < O; ++o) gbo[o] += g[o][0];
-            }
-        }
-    }
     auto wsum = [](float v) {
         INSR_PRAGMA_UNROLL
         for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
         return v;
     };
-    INSR_PRAGMA_UNROLL
-    for (int c = 0; c < 4; ++c) {
-        const int j = 4 * ch + c;
-        const float b1 = wsum(gb1[c]);
-        float w1[D], wo[O];
+    for (int ch = warp; ch < NCH; ch += nwarps) {           // neurons 4 ch .. 4 ch + 3
+        const int i = ch >> 2, q = ch & 3;
+        float gb1[4], gw1[D][4], gwo[O][4], gbo[O];
         INSR_PRAGMA_UNROLL
-        for (int d = 0; d < D; ++d) w1[d] = wsum(gw1[d][c]);
-        INSR_PRAGMA_UNROLL
-        for (int o = 0; o < O; ++o) wo[o] = wsum(gwo[o][c]);
-        if (lane == 0 && j < H) {
-            atomicAdd(p.gtheta + insr_b_offset(dm, 0) + j, dm.omega * b1);
+        for (int c = 0; c < 4; ++c) {
+            gb1[c] = 0.f;
             INSR_PRAGMA_UNROLL
-            for (int d = 0; d < D; ++d) atomicAdd(p.gtheta + insr_w_offset(dm, 0) + j * D + d, dm.omega * w1[d]);
+            for (int d = 0; d < D; ++d) gw1[d][c] = 0.f;
             INSR_PRAGMA_UNROLL
-            for (int o = 0; o < O; ++o) atomicAdd(p.gtheta + insr_w_offset(dm, L + 1) + o * H + j, wo[o]);
+            for (int o = 0; o < O; ++o) gwo[o][c] = 0.f;
         }
-    }
-    if (ch == 0) {
         INSR_PRAGMA_UNROLL
-        for (int o = 0; o < O; ++o) {
-            const float v = wsum(gbo[o]);
-            if (lane == 0) atomicAdd(p.gtheta + insr_b_offset(dm, L + 1) + o, v);
+        for (int o = 0; o < O; ++o) gbo[o] = 0.f;
+        for (int64_t T = cta; T < ntiles; T += nctas) {
+            INSR_PRAGMA_UNROLL
+            for (int rq = 0; rq < 4; ++rq) {
+                const int r = 32 * rq + lane;
+                const int64_t n = T * TILE + r;
+                const bool valid = n < p.N;                    // (zbar of the rows beyond the batch is zero anyway)
+                const int64_t nc = valid ? n : 0;
+                float xv[D];
+                INSR_PRAGMA_UNROLL
+                for (int d = 0; d < D; ++d) xv[d] = __ldg(p.x + nc * D + d);
+                const float4 z0 = __ldg(ZB0 + tape_f4(T, 0, i, q, r, S, NQ));
+                float4 zd[C::ND > 0 ? C::ND : 1], a4[S];
+                INSR_PRAGMA_UNROLL
+                for (int d = 0; d < C::ND; ++d) zd[d] = __ldg(ZB0 + tape_f4(T, 1 + d, i, q, r, S, NQ));
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s) a4[s] = __ldg(ACL + tape_f4(T, s, i, q, r, S, NQ));
+                float g[O][S];
+                INSR_PRAGMA_UNROLL
+                for (int o = 0; o < O; ++o) {
+                    insr_load_cotangents<D, O, ORDER>(nc, o, p.gy, p.gjac, p.gh2, g[o]);
+                    if (!valid) {
+                        INSR_PRAGMA_UNROLL
+                        for (int s = 0; s < S; ++s) g[o][s] = 0.f;
+                    }
+                }
+                INSR_PRAGMA_UNROLL
+                for (int c = 0; c < 4; ++c) {
+                    const float zc = valid ? insr_fused::f4get(z0, c) : 0.f;
+                    gb1[c] += zc;
+                    INSR_PRAGMA_UNROLL
+                    for (int d = 0; d < D; ++d) gw1[d][c] = fmaf(zc, xv[d], gw1[d][c]);
+                }
+                INSR_PRAGMA_UNROLL
+                for (int d = 0; d < C::ND; ++d)
+                    INSR_PRAGMA_UNROLL
+                    for (int c = 0; c < 4; ++c) gw1[d][c] += valid ? insr_fused::f4get(zd[d], c) : 0.f;
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s)
+                    INSR_PRAGMA_UNROLL
+                    for (int o = 0; o < O; ++o)
+                        INSR_PRAGMA_UNROLL
+                        for (int c = 0; c < 4; ++c) gwo[o][c] = fmaf(g[o][s], insr_fused::f4get(a4[s], c), gwo[o][c]);
+                if (ch == 0) {
+                    INSR_PRAGMA_UNROLL
+                    for (int o = 0; o < O; ++o) gbo[o] += g[o][0];
+                }
+            }
+        }
+        INSR_PRAGMA_UNROLL
+        for (int c = 0; c < 4; ++c) {
+            const int j = 4 * ch + c;
+            const float b1 = wsum(gb1[c]);
+            float w1[D], wo[O];
+            INSR_PRAGMA_UNROLL
+            for (int d = 0; d < D; ++d) w1[d] = wsum(gw1[d][c]);
+            INSR_PRAGMA_UNROLL
+            for (int o = 0; o < O; ++o) wo[o] = wsum(gwo[o][c]);
+            if (lane == 0 && j < H) {
+                atomicAdd(p.gtheta + insr_b_offset(dm, 0) + j, dm.omega * b1);
+                INSR_PRAGMA_UNROLL
+                for (int d = 0; d < D; ++d) atomicAdd(p.gtheta + insr_w_offset(dm, 0) + j * D + d, dm.omega * w1[d]);
+                INSR_PRAGMA_UNROLL
+                for (int o = 0; o < O; ++o) atomicAdd(p.gtheta + insr_w_offset(dm, L + 1) + o * H + j, wo[o]);
+            }
+        }
+        if (ch == 0) {
+            INSR_PRAGMA_UNROLL
+            for (int o = 0; o < O; ++o) {
+                const float v = wsum(gbo[o]);
+                if (lane == 0) atomicAdd(p.gtheta + insr_b_offset(dm, L + 1) + o, v);
+            }
         }
     }
 }
@@ -1001,21 +1053,15 @@ int launch_mid_bwd_hp(MidParams &p, void *stream, int64_t *launches) {
             kfn<<<dim3((unsigned)ctas), dim3(MT), M.total + 128, st>>>(p, insr_tc::pow2_cols((S + nht_of(HP16, S)) * HP16));
             ++*launches;
         }
-        {   // hidden-layer weight gradients, all layers in one launch
+        {   // hidden-layer weight gradients of all layers (grid rows 0 .. L-1) and, beside them, the thin layers (row L)
             const size_t smem = (size_t)8 * WG_ATOM + 512 + 64 + 1024;
-            auto kfn = k_mid_wgrad<HP16>;
+            auto kfn = k_mid_wgrad<D, O, ORDER, HP16>;
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             const int groups = (int)((p.N + WG_PTS - 1) / WG_PTS);
             int ctas = (int)(sms / p.dm.L);
             if (ctas < 1) ctas = 1;
             if (ctas > groups) ctas = groups;
-            kfn<<<dim3((unsigned)ctas, (unsigned)p.dm.L), dim3(WGT), smem, st>>>(p.dm, S, p.Zpre, p.Act, p.buf, (int)p.N, p.gtheta);
-            ++*launches;
-        }
-        {   // first / output layer
-            auto kfn = k_mid_edge<D, O, ORDER, HP16>;
-            int64_t ctas = tiles < 2 * sms ? tiles : 2 * sms;
-            kfn<<<dim3((unsigned)ctas), dim3(32 * (HP16 / 4)), 0, st>>>(p);
+            kfn<<<dim3((unsigned)ctas, (unsigned)p.dm.L + 1), dim3(WGT), smem, st>>>(p);
             ++*launches;
         }
         return 0;

@@ -1,7 +1,9 @@
 """Helper (run as a subprocess): the reference's UNMODIFIED main.py through ``insr_pde_b200.patch.run_main`` -- the
 launcher INTEGRATION.md describes -- with the given main.py arguments.  ``cuda`` as first argument: the real library on
 cuda:0 (GPU box); ``cpu``: C-ABI calls routed to the emulation build and the reference's hard-coded cuda:0 proxied to
-the CPU (build container).  Prints one JSON object: the files main.py wrote under <exp_dir>/results and the loss history."""
+the CPU (build container); ``cuda-reference`` / ``cuda-reference64``: the reference alone (no patch), stock PyTorch on
+cuda:0 in fp32 / fp64 -- the other side of the trajectory comparisons.  Prints one JSON object: the files main.py wrote
+under <exp_dir>/results and the loss history."""
 import json
 import os
 import sys
@@ -30,8 +32,18 @@ if device == "cpu":
     import base.baseModel as bm
     bm.torch = ref_loader._TorchCpuProxy(torch)
 
-patch.install(root)
+reference_only = device.startswith("cuda-reference")
+if reference_only:
+    if device.endswith("64"):
+        torch.set_default_dtype(torch.float64)
+    ref_loader.load(cpu=False)               # stubs + scheduler shim only; base / fluid / ... stay the reference's own
+else:
+    patch.install(root)
 import base.baseModel as bm  # noqa: E402
+import elasticity.model as _ela  # noqa: E402
+
+# elasticity writes its frames through open3d (absent here): keep the sampled deformation field as .npy instead
+_ela.write_pointcloud_to_file = lambda path, values: np.save(path + ".npy", np.asarray(values))
 
 hist = []
 ref_update = None
@@ -46,12 +58,23 @@ if not fused_closures:
     bm.BaseModel._update_network = spy
 torch.manual_seed(123)
 np.random.seed(123)
-patch.run_main(argv, root, fused_closures=fused_closures)
+if reference_only:
+    import runpy
+    old_argv, old_cwd = sys.argv, os.getcwd()
+    sys.argv = [os.path.join(root, "main.py"), *argv]
+    os.chdir(root)
+    try:
+        runpy.run_path(sys.argv[0], run_name="__main__")
+    finally:
+        sys.argv = old_argv
+        os.chdir(old_cwd)
+else:
+    patch.run_main(argv, root, fused_closures=fused_closures)
 proj = argv[argv.index("--proj_dir") + 1]
 tag = argv[argv.index("--tag") + 1]
 res = os.path.join(proj, tag, "results")
 files = sorted(os.listdir(res))
-out = {"files": files, "hist": hist, "ckpts": sorted(os.listdir(os.path.join(proj, tag, "model")))}
+out = {"files": files, "hist": hist, "ckpts": sorted(os.listdir(os.path.join(proj, tag, "model"))), "results_dir": res}
 for f in files:
     if f.endswith(".npy"):
         out.setdefault("npy", {})[f] = [float(np.abs(np.load(os.path.join(res, f))).max())]
