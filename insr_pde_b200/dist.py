@@ -140,7 +140,7 @@ def sync_plateau_schedulers(group=None):
     cls.step._insr_group = group
 
 
-def install_global(nets_getter, group=None):
+def install_global(nets_getter, group=None, average=True):
     """hook EVERY optimizer's step (the reference re-creates Adam per training loop,
     base/baseModel.py:55-62) and every plateau scheduler's step (``sync_plateau_schedulers``).
     ``nets_getter()`` returns the currently trainable modules."""
@@ -148,7 +148,7 @@ def install_global(nets_getter, group=None):
     from torch.optim.optimizer import register_optimizer_step_pre_hook
 
     def hook(opt, args, kwargs):
-        GradAllReducer(nets_getter(), group=group).allreduce()
+        GradAllReducer(nets_getter(), group=group, average=average).allreduce()
 
     if _GLOBAL_HANDLE is not None:
         _GLOBAL_HANDLE.remove()

@@ -277,14 +277,139 @@ def install_fused_closures():
     loop(ela, "_solve_deformation", ela_solve)
 
 
-def run_main(argv, reference_root: str, fused_closures: bool = None):
+def install_graphed_loops(data_parallel: bool = False):
+    """third stage, after ``install`` (implies ``install_fused_closures``): the BODY of the reference's training loop
+    (base/baseModel.py:104-134: closure -> _update_network -> .item() logging, once per iteration from Python) is replaced
+    by ``fused.GraphedLoop`` -- the whole iteration (the model's own sampling, the one-kernel closures, Adam of every
+    trainable net, ReduceLROnPlateau, loss log; with ``data_parallel`` also the ONE all-reduce of [gradients | losses]) is
+    captured once per (model, loop) as a CUDA graph and replayed ``max_n_iters`` times; the loss history is read back in
+    bulk and handed to tensorboard, early stop (lr <= 1.1e-8, :132-134) is tested every 100 iterations.  main.py, time
+    stepping, checkpoints and output writing stay the reference's code."""
+    import torch
+    from . import fused
+    install_fused_closures()
+    base_model = importlib.import_module("base.baseModel")
+    BaseModel = base_model.BaseModel
+    if getattr(BaseModel, "_insr_graphed", False):
+        return
+    BaseModel._insr_graphed = True
+
+    def graphed(cls, name):
+        method = getattr(cls, name)
+        body = next(c.cell_contents for c in method.__closure__ if callable(c.cell_contents))     # the fused closure
+        widths_ok = getattr(body, "_insr_graph_ok", True)
+
+        def loop(self):
+            nets = list(self._trainable_networks.values())
+            if not widths_ok or not all(p.is_cuda for n in nets for p in n.parameters()):
+                return method(self)                              # CPU tensors: the reference's own loop
+            loops = self.__dict__.setdefault("_insr_loops", {})
+            if name not in loops:
+                loops[name] = fused.GraphedLoop(nets, self.cfg.lr, lambda: body(self), capacity=max(int(self.max_n_iters), 1),
+                                                data_parallel=data_parallel)
+            else:
+                loops[name].reset(self.cfg.lr)
+            hist = loops[name].run(int(self.max_n_iters), early_stop=bool(self.cfg.early_stop))
+            self.train_step = len(hist)
+            for i, values in enumerate(hist):                   # the .item() logging of :116-118, in bulk
+                self.tb.add_scalars(name, values, global_step=i)
+            if hasattr(self, f"_vis{name}"):
+                getattr(self, f"_vis{name}")()
+            self._insr_last_hist = hist
+        loop.__name__ = name
+        setattr(cls, name, loop)
+
+    adv = importlib.import_module("advection.model").Advection1DModel
+    flu = importlib.import_module("fluid.model").Fluid2DModel
+    ela = importlib.import_module("elasticity.model").ElasticityModel
+    for cls, names in ((adv, ("_initialize", "_advect")), (flu, ("_initialize", "_advect_velocity", "_solve_pressure", "_projection")),
+                       (ela, ("_solve_deformation",))):
+        for name in names:
+            graphed(cls, name)
+
+
+def install_data_parallel(pde: str):
+    """one process per GPU (torchrun): every rank draws the SAME global sample sets (same seed, same generator state) and
+    keeps its contiguous shard of the interior points; gradients -- and the scheduler's loss -- are
+    all-reduced before every optimizer step (``dist.install_global``).  advection / fluid losses are means over points
+    (average over the ranks); elasticity's are sums over points: every point set is sharded and the reduction is a sum.
+    Returns (rank, world)."""
+    from . import dist as idist
+    rank, world = idist.init_from_env()
+    if world == 1:
+        return rank, world
+    module = {"advection": "advection.model", "fluid": "fluid.model", "elasticity": "elasticity.model"}[pde]
+    cls_name = {"advection": "Advection1DModel", "fluid": "Fluid2DModel", "elasticity": "ElasticityModel"}[pde]
+    cls = getattr(importlib.import_module(module), cls_name)
+    trainable = []
+
+    def shard_method(name):
+        orig = getattr(cls, name)
+
+        def sharded(self, *a, **k):
+            if self not in trainable:
+                trainable.append(self)
+            out = orig(self, *a, **k)
+            if isinstance(out, tuple):
+                return tuple(idist.shard_points(o) if hasattr(o, "shape") else o for o in out)
+            return idist.shard_points(out)
+        sharded.__name__ = name
+        setattr(cls, name, sharded)
+
+    shard_method("_sample_in_training")
+    if pde == "elasticity":
+        shard_method("_sample_fixed_in_training")
+    idist.install_global(lambda: [n for m in trainable for n in m._trainable_networks.values()], average=(pde != "elasticity"))
+    return rank, world
+
+
+def _silence_non_zero_rank(pde: str):
+    """rank > 0 of a data-parallel run: no frame output, no checkpoints (rank 0 writes them; the replicas are identical)"""
+    module = {"advection": "advection.model", "fluid": "fluid.model", "elasticity": "elasticity.model"}[pde]
+    cls_name = {"advection": "Advection1DModel", "fluid": "Fluid2DModel", "elasticity": "ElasticityModel"}[pde]
+    cls = getattr(importlib.import_module(module), cls_name)
+    cls.write_output = lambda self, folder: None
+    cls.save_ckpt = lambda self, *a, **k: None
+
+
+def run_main(argv, reference_root: str, fused_closures: bool = None, graphed: bool = False, data_parallel: bool = False,
+             seed: int = None):
     """python main.py <argv>  of the reference, unchanged, on the fused kernels.  ``fused_closures`` (default: the
-    environment variable INSR_FUSED_CLOSURES=1) additionally swaps the loss closures for the one-kernel ones."""
+    environment variable INSR_FUSED_CLOSURES=1) additionally swaps the loss closures for the one-kernel ones,
+    ``graphed`` the loop body for the CUDA-graphed iteration; ``data_parallel`` is the torchrun twin of main.py
+    (one process per GPU, RANK / LOCAL_RANK / WORLD_SIZE from the environment)."""
+    argv = list(argv)
+    rank, world = 0, 1
+    if data_parallel:
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        local = os.environ.get("LOCAL_RANK", "0")
+        # the reference hard-codes cuda:0 (base/baseModel.py:25) and config.py:28-29 exports CUDA_VISIBLE_DEVICES from -g:
+        # give every rank its own GPU as device 0, before CUDA is initialised
+        os.environ["CUDA_VISIBLE_DEVICES"] = local
+        argv += ["-g", local]
+        os.environ["LOCAL_RANK"] = "0"
+        if rank > 0 and "--proj_dir" in argv:                    # config.py creates / wipes the experiment directory
+            k = argv.index("--proj_dir") + 1
+            argv[k] = os.path.join(argv[k], f".rank{rank}")
+        elif rank > 0:
+            argv += ["--proj_dir", os.path.join("checkpoints", f".rank{rank}")]
     install(reference_root)
     if fused_closures is None:
         fused_closures = os.environ.get("INSR_FUSED_CLOSURES", "0") == "1"
-    if fused_closures:
+    pde = next((a for a in argv if a in ("advection", "fluid", "elasticity")), None)
+    if data_parallel and pde:
+        install_data_parallel(pde)
+        if rank > 0:
+            _silence_non_zero_rank(pde)
+    if graphed:
+        install_graphed_loops(data_parallel=data_parallel and world > 1)
+    elif fused_closures:
         install_fused_closures()
+    if seed is not None:
+        import numpy as np
+        import torch
+        torch.manual_seed(seed)
+        np.random.seed(seed)
     old_argv, old_cwd = sys.argv, os.getcwd()
     sys.argv = [os.path.join(reference_root, "main.py"), *argv]
     os.chdir(reference_root)     # config.py:55-57 copies *.py relative to cwd; mesh paths are relative
@@ -299,5 +424,18 @@ if __name__ == "__main__":
     root = os.environ.get("INSR_REFERENCE_ROOT")
     if not root:
         raise SystemExit("set INSR_REFERENCE_ROOT to the INSR-PDE checkout; usage: "
-                         "python -m insr_pde_b200.patch fluid --tag ... (main.py arguments)")
-    run_main(sys.argv[1:], root)
+                         "python -m insr_pde_b200.patch [--insr-closures] [--insr-graphed] [--insr-dp] [--insr-seed S] "
+                         "fluid --tag ... (main.py arguments);  data-parallel: torchrun --nproc-per-node G -m insr_pde_b200.patch --insr-dp ...")
+    args = sys.argv[1:]
+    flags = {"--insr-closures": False, "--insr-graphed": False, "--insr-dp": False}
+    for f in list(flags):
+        if f in args:
+            flags[f] = True
+            args.remove(f)
+    seed = None
+    if "--insr-seed" in args:
+        k = args.index("--insr-seed")
+        seed = int(args[k + 1])
+        del args[k:k + 2]
+    run_main(args, root, fused_closures=flags["--insr-closures"] or None, graphed=flags["--insr-graphed"],
+             data_parallel=flags["--insr-dp"], seed=seed)

@@ -81,8 +81,22 @@ def _install_stubs():
     if "matplotlib" not in sys.modules:
         mpl = _stub("matplotlib")
         mpl.pyplot = _stub("matplotlib.pyplot")
-        mpl.cm = _stub("matplotlib.cm")
         mpl.colors = _stub("matplotlib.colors")
+        # fluid/visualize.py:31-43 does arithmetic on ``cm.bwr(field)``: the colormap stand-in returns a real RGBA array
+        cm = _stub("matplotlib.cm")
+
+        def _colormap(name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+
+            def ramp(values, *a, **k):
+                import numpy as np
+                v = np.clip(np.asarray(values, dtype=np.float64), 0.0, 1.0)
+                return np.stack([v, v, v, np.ones_like(v)], axis=-1)
+            return ramp
+
+        cm.__getattr__ = _colormap  # type: ignore[attr-defined]
+        mpl.cm = cm
     if "meshio" not in sys.modules:               # elasticity/model.py:77 reads MEDIT .mesh files through meshio.read
         from insr_pde_b200 import medit
         _stub("meshio", read=medit.read)

@@ -32,11 +32,11 @@ if device == "cpu":
     import base.baseModel as bm
     bm.torch = ref_loader._TorchCpuProxy(torch)
 
-reference_only = device.startswith("cuda-reference")
+reference_only = "reference" in device       # cuda-reference, cuda-reference64; cpu-reference (build container)
 if reference_only:
     if device.endswith("64"):
         torch.set_default_dtype(torch.float64)
-    ref_loader.load(cpu=False)               # stubs + scheduler shim only; base / fluid / ... stay the reference's own
+    ref_loader.load(cpu=device.startswith("cpu"))    # stubs + scheduler shim only; base / fluid / ... stay the reference's own
 else:
     patch.install(root)
 import base.baseModel as bm  # noqa: E402
