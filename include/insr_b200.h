@@ -135,6 +135,28 @@ int insr_siren_lsq_step(const insr_siren_desc *desc, const float *theta, const f
                         void *workspace, size_t workspace_bytes, void *stream);
 
 /*
+ * The frozen-network side of a least-squares closure in one kernel: the target that insr_siren_lsq_step compares the
+ * trainable field with.  One or two frozen fields of the H <= 32 family are evaluated at the points x and a fixed
+ * linear combination of their outputs is written to target (n, n_res), n_res <= 2:
+ *     target[n,c] = sum_{o} ( cy_A[c,o] y_A + cj_A[c,o,:] . J_A + cl_A[c,o] lap_A )  +  the same for B
+ *   mode 0  field A at x                                fluid/model.py:108-109  div u  (cj = trace pattern)
+ *                                                       advection/model.py:78-84  u_prev / dt - vel/2 du_prev/dx
+ *   mode 1  backtrace: A (value, D -> D) at x, then A again at clamp(x - dt y_A(x), lo, hi); b's coefficients apply to
+ *           the second evaluation (b->desc / theta are ignored)   fluid/model.py:78-87  semi-Lagrangian advection
+ *   mode 2  A and B, both at x                          fluid/model.py:131-137  u_prev - grad p
+ * coef_* are HOST arrays (nullable = zeros): cy (n_res x O), cj (n_res x O x D), cl (n_res x O).
+ * Returns INSR_ERR_UNSUPPORTED for shapes outside the resident-weights family or combinations not instantiated.
+ */
+typedef struct insr_target_eval {
+    insr_siren_desc desc;
+    const float *theta;      /* device */
+    int32_t order;           /* INSR_ORDER_VALUE .. INSR_ORDER_JAC */
+    const float *coef_y, *coef_jac, *coef_lap;
+} insr_target_eval;
+int insr_siren_target(const insr_target_eval *a, const insr_target_eval *b, int mode, float dt, float lo, float hi,
+                      const float *x, int64_t n_points, int n_res, float *target, void *stream);
+
+/*
  * Optimiser side of one iteration, on the device (so a whole iteration can be one CUDA graph):
  * `sched` is 4 device floats {lr, best, num_bad_epochs, step}.
  *   insr_adam_step     torch.optim.Adam(amsgrad=False, weight_decay=0) on a flat vector, reading lr and the

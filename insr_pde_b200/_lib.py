@@ -23,6 +23,7 @@ EXPORTS = [
     "insr_version", "insr_last_error", "insr_siren_theta_size", "insr_siren_workspace_bytes",
     "insr_siren_forward", "insr_siren_backward", "insr_siren_lsq_step", "insr_siren_kernel_family",
     "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes", "insr_sample_mesh", "insr_siren_tape_supported", "insr_elastic_terms", "insr_iteration_update",
+    "insr_siren_target",
 ]
 
 
@@ -30,6 +31,13 @@ class SirenDesc(ctypes.Structure):
     _fields_ = [("in_features", ctypes.c_int32), ("out_features", ctypes.c_int32),
                 ("hidden_features", ctypes.c_int32), ("num_hidden_layers", ctypes.c_int32),
                 ("omega", ctypes.c_float), ("flags", ctypes.c_int32)]
+
+
+class TargetEval(ctypes.Structure):
+    """insr_target_eval: one frozen field of insr_siren_target with its host coefficient arrays"""
+    _fields_ = [("desc", SirenDesc), ("theta", ctypes.c_void_p), ("order", ctypes.c_int32),
+                ("coef_y", ctypes.POINTER(ctypes.c_float)), ("coef_jac", ctypes.POINTER(ctypes.c_float)),
+                ("coef_lap", ctypes.POINTER(ctypes.c_float))]
 
 
 class InsrError(RuntimeError):
@@ -86,6 +94,9 @@ class Library:
         c.insr_sample_boxes.argtypes = [_i32, _i32, _vp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _i64, _vp, _vp]
         c.insr_launch_count.restype = _i64
         c.insr_launch_count.argtypes = [_i32]
+        c.insr_siren_target.restype = _i32
+        c.insr_siren_target.argtypes = [ctypes.POINTER(TargetEval), ctypes.POINTER(TargetEval), _i32, ctypes.c_float, ctypes.c_float,
+                                        ctypes.c_float, _vp, _i64, _i32, _vp, _vp]
 
     def check(self, rc):
         if rc != 0:
@@ -159,8 +170,30 @@ class Library:
                                                  scale, loss_out, gtheta, ws, ws_bytes, stream))
 
 
-_LIB = None
+    def target(self, a, b, mode, dt, lo, hi, x, n, n_res, target, stream):
+        """a, b: (desc, theta_ptr, order, cy, cj, cl) with flat python lists (or None) as coefficients; b may be None"""
+        keep = []
+
+        def ev(t):
+            if t is None:
+                return None
+            desc, theta, order, cy, cj, cl = t
+            e = TargetEval()
+            e.desc, e.theta, e.order = desc, theta, int(order)
+            for name, vals in (("coef_y", cy), ("coef_jac", cj), ("coef_lap", cl)):
+                if vals is not None:
+                    arr = (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+                    keep.append(arr)
+                    setattr(e, name, ctypes.cast(arr, ctypes.POINTER(ctypes.c_float)))
+            keep.append(e)
+            return ctypes.byref(e)
+
+        self.check(self.cdll.insr_siren_target(ev(a), ev(b), int(mode), float(dt), float(lo), float(hi), x, n, int(n_res),
+                                               target, stream))
+
+
 _LOCK = threading.Lock()
+_LIB = None
 
 
 def get_lib() -> Library:

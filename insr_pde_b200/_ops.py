@@ -167,6 +167,34 @@ def siren_lsq_step(desc, theta, x, order, coef_y, coef_jac, coef_lap, target, sc
     return loss_out, gtheta
 
 
+def siren_target(x, n_res, a, b=None, mode=0, dt=0.0, lo=-1.0, hi=1.0):
+    """target (N, n_res) of a least-squares closure from one or two frozen fields in ONE kernel (include/insr_b200.h:
+    insr_siren_target).  a, b: dicts with ``net`` (an MLP of the H <= 32 family), ``order`` and the coefficient lists
+    ``cy`` (n_res x O), ``cj`` (n_res x O x D), ``cl`` (nested lists or None).  mode 0: a at x; 1: backtrace through a
+    (b carries the coefficients of the second evaluation); 2: a and b at x.  Raises InsrError(-6) where no kernel exists."""
+    lib = _lib.get_lib()
+    _require_cuda(x)
+    x = _check_input(x, "x")
+    n = x.shape[0]
+
+    def flat(v):
+        if v is None:
+            return None
+        return torch.as_tensor(v, dtype=torch.float32).reshape(-1).tolist()
+
+    def pack(t):
+        if t is None:
+            return None
+        net = t["net"]
+        return (net.desc, net.flat_theta().data_ptr(), t.get("order", 0), flat(t.get("cy")), flat(t.get("cj")), flat(t.get("cl")))
+
+    out = torch.empty(n, n_res, dtype=torch.float32, device=x.device)
+    if n:
+        with _DeviceGuard(x.device):
+            lib.target(pack(a), pack(b), mode, dt, lo, hi, x.data_ptr(), n, n_res, out.data_ptr(), _stream(x.device))
+    return out
+
+
 def adam_step(theta, grad, exp_avg, exp_avg_sq, sched, beta1=0.9, beta2=0.999, eps=1e-8):
     """torch.optim.Adam semantics on a flat fp32 vector; lr and step index are read from the device
     tensor ``sched`` = [lr, best, num_bad_epochs, step] (include/insr_b200.h: insr_adam_step)"""

@@ -13,6 +13,7 @@
 #include "optim_kernels.cuh"
 #include "linalg_kernels.cuh"
 #include "sampling_kernels.cuh"
+#include "siren_tc_target.cuh"
 #ifdef INSR_SINGLE_TU
 #include "siren_tiled.cuh"   // emulation build: everything in one translation unit
 #define INSR_INST_D 1
@@ -322,6 +323,69 @@ int insr_siren_lsq_step(const insr_siren_desc *desc, const float *theta, const f
         return fail(rc, "lsq_step: no fused kernel for D=%d O=%d H=%d L=%d order=%d", dm.D, dm.O, dm.H, dm.L, order);
     if (rc) return rc;
     return check_cuda("fused lsq_step");
+}
+
+#ifndef INSR_CPU_EMU
+namespace {
+// pack cy / cj / cl (host, nullable) into [c][o][s] with the stream order value, tangents, (Laplacian)
+void pack_coef(const insr_target_eval *e, int n_res, float *dst) {
+    const int D = e->desc.in_features, O = e->desc.out_features, S = insr_nstreams(D, e->order);
+    for (int c = 0; c < n_res; ++c)
+        for (int o = 0; o < O; ++o) {
+            float *q = dst + (c * O + o) * S;
+            q[0] = e->coef_y ? e->coef_y[c * O + o] : 0.f;
+            if (e->order >= 1)
+                for (int d = 0; d < D; ++d) q[1 + d] = e->coef_jac ? e->coef_jac[(c * O + o) * D + d] : 0.f;
+            if (e->order == 2) q[1 + D] = e->coef_lap ? e->coef_lap[c * O + o] : 0.f;
+        }
+}
+}  // namespace
+#endif
+
+int insr_siren_target(const insr_target_eval *a, const insr_target_eval *b, int mode, float dt, float lo, float hi,
+                      const float *x, int64_t n_points, int n_res, float *target, void *stream) {
+#ifdef INSR_CPU_EMU
+    return fail(INSR_ERR_UNSUPPORTED, "siren_target: tcgen05 kernels only");
+#else
+    if (!a || !x || !target || !a->theta) return fail(INSR_ERR_NULL, "siren_target: a, a->theta, x and target must not be NULL");
+    if (mode < 0 || mode > 2) return fail(INSR_ERR_SHAPE, "siren_target: mode=%d (0, 1 or 2)", mode);
+    if (mode != 0 && !b) return fail(INSR_ERR_NULL, "siren_target: mode %d needs b", mode);
+    if (mode == 2 && !b->theta) return fail(INSR_ERR_NULL, "siren_target: b->theta must not be NULL in mode 2");
+    if (n_res < 1 || n_res > 2) return fail(INSR_ERR_SHAPE, "siren_target: n_res=%d outside [1,2]", n_res);
+    SirenDims dA, dB;
+    int rc = validate(&a->desc, n_points, a->order, &dA);
+    if (rc) return rc;
+    dB = dA;
+    if (mode == 2 && (rc = validate(&b->desc, n_points, b->order, &dB))) return rc;
+    if (!insr_fused_supported(dA, a->order, 0) || !insr_fused_supported(dB, mode == 2 ? b->order : 0, 0) || dA.D != dB.D ||
+        a->order > 1 || (mode != 0 && b->order > 1))
+        return fail(INSR_ERR_UNSUPPORTED, "siren_target: both fields must belong to the H <= 32 resident-weights family, orders 0..1");
+    if ((rc = check_device())) return rc;
+    if (n_points == 0) return 0;
+    insr_tc::TargetParams p{};
+    p.dmA = dA; p.dmB = dB; p.thetaA = a->theta; p.thetaB = mode == 2 ? b->theta : a->theta;
+    p.x = x; p.N = n_points; p.target = target; p.n_res = n_res; p.dt = dt; p.lo = lo; p.hi = hi;
+    pack_coef(a, n_res, p.coefA);
+    if (mode == 1) {
+        insr_target_eval second = *b;
+        second.desc = a->desc;
+        pack_coef(&second, n_res, p.coefB);
+    } else if (mode == 2) {
+        pack_coef(b, n_res, p.coefB);
+    }
+    const int D = dA.D, OA = dA.O, OB = dB.O, oa = a->order, ob = mode == 0 ? 0 : b->order;
+#define INSR_TGT(D_, OA_, ORDA_, OB_, ORDB_, MODE_)                                                          \
+    if (D == D_ && OA == OA_ && oa == ORDA_ && mode == MODE_ && (MODE_ == 0 || (OB == OB_ && ob == ORDB_))) { \
+        insr_tc::launch_tc_target<D_, OA_, ORDA_, OB_, ORDB_, MODE_>(p, stream, &g_launches);                 \
+        return check_cuda("k_tc_target");                                                                     \
+    }
+    INSR_TGT(1, 1, 0, 1, 0, 0) INSR_TGT(1, 1, 1, 1, 0, 0) INSR_TGT(2, 1, 0, 1, 0, 0) INSR_TGT(2, 1, 1, 1, 0, 0)
+    INSR_TGT(2, 2, 0, 2, 0, 0) INSR_TGT(2, 2, 1, 2, 0, 0)
+    INSR_TGT(1, 1, 0, 1, 0, 1) INSR_TGT(2, 2, 0, 2, 0, 1)
+    INSR_TGT(2, 2, 0, 1, 1, 2) INSR_TGT(2, 2, 0, 1, 0, 2) INSR_TGT(2, 2, 1, 1, 1, 2) INSR_TGT(1, 1, 0, 1, 1, 2) INSR_TGT(1, 1, 1, 1, 1, 2)
+#undef INSR_TGT
+    return fail(INSR_ERR_UNSUPPORTED, "siren_target: no kernel for D=%d O_a=%d order_a=%d O_b=%d order_b=%d mode=%d", D, OA, oa, OB, ob, mode);
+#endif
 }
 
 int insr_adam_step(float *theta, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,

@@ -126,6 +126,26 @@ def evaluate(net, x, order):
     return _ops.siren_forward(net.desc, net.flat_theta(), x, order)
 
 
+_TARGET_OFF = set()          # (mode, shapes) for which insr_siren_target has no kernel: fall back to separate evaluations
+
+
+def _target(x, n_res, a, b=None, mode=0, dt=0.0):
+    """the frozen-net side of a closure in one kernel where insr_siren_target serves the shapes; None otherwise"""
+    def shape(t):
+        n = t["net"]
+        return (n.in_features, n.out_features, n.hidden_features, n.num_hidden_layers, t.get("order", 0))
+    key = (mode, shape(a), shape(b) if (b is not None and mode == 2) else None)
+    if key in _TARGET_OFF or not x.is_cuda:
+        return None
+    try:
+        return _ops.siren_target(x, n_res, a, b, mode=mode, dt=dt)
+    except _ops._lib.InsrError as e:
+        if e.code != -6:
+            raise
+        _TARGET_OFF.add(key)
+        return None
+
+
 def _eye(n):
     return [[1.0 if i == j else 0.0 for j in range(n)] for i in range(n)]
 
@@ -173,8 +193,10 @@ def advect_initialize(field, samples, init_values):
 def advect_step(field, field_prev, samples, boundary_samples, dt, vel):
     """midpoint residual  (u - u_prev)/dt + vel (u_x + u_prev_x)/2  and Dirichlet band"""
     def interior():
-        u_prev, j_prev = evaluate(field_prev, samples, ORDER_JAC)
-        target = u_prev / dt - (0.5 * vel) * j_prev[:, :, 0]
+        target = _target(samples.detach().reshape(-1, 1), 1, dict(net=field_prev, order=ORDER_JAC, cy=[[1.0 / dt]], cj=[[[-0.5 * vel]]]))
+        if target is None:
+            u_prev, j_prev = evaluate(field_prev, samples, ORDER_JAC)
+            target = u_prev / dt - (0.5 * vel) * j_prev[:, :, 0]
         return lsq(field, samples, ORDER_JAC, [[1.0 / dt]], cj=[[[0.5 * vel]]], target=target, out=acc[0:1])
 
     acc = torch.zeros(2, dtype=torch.float32, device=samples.device)
@@ -200,9 +222,13 @@ def fluid_advect_velocity(velocity, velocity_prev, samples, bc_x, bc_y, dt):
     x = samples.detach().reshape(-1, 2)
 
     def interior():
-        (u_prev,) = evaluate(velocity_prev, x, ORDER_VALUE)
-        back = torch.clamp(x - u_prev * dt, min=-1.0, max=1.0)
-        (u_adv,) = evaluate(velocity_prev, back, ORDER_VALUE)
+        # u_prev(clamp(x - u_prev(x) dt)): both evaluations, the clamp and nothing else in one kernel
+        u_adv = _target(x, 2, dict(net=velocity_prev, order=ORDER_VALUE), dict(net=velocity_prev, order=ORDER_VALUE, cy=_eye(2)),
+                        mode=1, dt=dt)
+        if u_adv is None:
+            (u_prev,) = evaluate(velocity_prev, x, ORDER_VALUE)
+            back = torch.clamp(x - u_prev * dt, min=-1.0, max=1.0)
+            (u_adv,) = evaluate(velocity_prev, back, ORDER_VALUE)
         return lsq(velocity, x, ORDER_VALUE, _eye(2), target=u_adv, out=acc[0:1])
 
     acc = torch.zeros(2, dtype=torch.float32, device=x.device)
@@ -213,8 +239,10 @@ def fluid_advect_velocity(velocity, velocity_prev, samples, bc_x, bc_y, dt):
 def fluid_solve_pressure(velocity, pressure, samples, bc_x, bc_y):
     """lap p = div u, Neumann band"""
     def interior():
-        _, jac_u = evaluate(velocity, samples, ORDER_JAC)
-        div_u = jac_u[:, 0, 0] + jac_u[:, 1, 1]
+        div_u = _target(samples.detach().reshape(-1, 2), 1, dict(net=velocity, order=ORDER_JAC, cj=[[[1.0, 0.0], [0.0, 1.0]]]))
+        if div_u is None:
+            _, jac_u = evaluate(velocity, samples, ORDER_JAC)
+            div_u = jac_u[:, 0, 0] + jac_u[:, 1, 1]
         return lsq(pressure, samples, ORDER_LAP, [[0.0]], cl=[[1.0]], target=div_u, out=acc[0:1])
 
     acc = torch.zeros(2, dtype=torch.float32, device=samples.device)
@@ -227,9 +255,12 @@ def fluid_solve_pressure(velocity, pressure, samples, bc_x, bc_y):
 def fluid_projection(velocity, velocity_prev, pressure, samples, bc_x, bc_y):
     """u <- u_prev - grad p"""
     def interior():
-        (u_prev,) = evaluate(velocity_prev, samples, ORDER_VALUE)
-        _, jac_p = evaluate(pressure, samples, ORDER_JAC)
-        target = u_prev - jac_p[:, 0, :]
+        target = _target(samples.detach().reshape(-1, 2), 2, dict(net=velocity_prev, order=ORDER_VALUE, cy=_eye(2)),
+                         dict(net=pressure, order=ORDER_JAC, cj=[[[-1.0, 0.0]], [[0.0, -1.0]]]), mode=2)
+        if target is None:
+            (u_prev,) = evaluate(velocity_prev, samples, ORDER_VALUE)
+            _, jac_p = evaluate(pressure, samples, ORDER_JAC)
+            target = u_prev - jac_p[:, 0, :]
         return lsq(velocity, samples, ORDER_VALUE, _eye(2), target=target, out=acc[0:1])
 
     acc = torch.zeros(2, dtype=torch.float32, device=samples.device)

@@ -186,24 +186,27 @@ def closures_fluid(ref):
     np.savez_compressed(os.path.join(OUT, "closure_fluid.npz"), **rec)
 
 
+ELASTICITY_CASES = (
+    ("stretch2d", dict(dim=2, energy=["arap", "constraint", "constraint_right", "volume"],
+                       ratio_volume=1e3, ratio_arap=1e0, ratio_constraint=1e4,
+                       constraint_right_offset_x=2.0, sample_resolution=10, hidden_features=68)),
+    ("collide2d", dict(dim=2, energy=["arap", "kinematics", "collision_sphere", "external", "volume"],
+                       ratio_volume=1e3, ratio_arap=2e1, ratio_collide=1e4, ratio_kinematics=1e1,
+                       external_force_y=-2e2, external_force_timesteps=2, dt=0.1,
+                       collide_circle_y=-0.5, sample_resolution=10, hidden_features=68)),
+    ("plane3d", dict(dim=3, energy=["arap", "kinematics", "collision", "external", "volume"],
+                     ratio_volume=1e3, ratio_arap=1e2, ratio_collide=1e6, ratio_kinematics=1e0,
+                     external_force_z=-1e2, external_force_timesteps=5, dt=0.1,
+                     plane_height=-0.9, sample_resolution=5, hidden_features=66)),
+)
+
+
 def closures_elasticity(ref):
     if ref.elasticity is None:
         print("elasticity import failed:", ref.elasticity_error)
         return
     import elasticity.model as mod
-    for tag, over in (
-        ("stretch2d", dict(dim=2, energy=["arap", "constraint", "constraint_right", "volume"],
-                           ratio_volume=1e3, ratio_arap=1e0, ratio_constraint=1e4,
-                           constraint_right_offset_x=2.0, sample_resolution=10, hidden_features=68)),
-        ("collide2d", dict(dim=2, energy=["arap", "kinematics", "collision_sphere", "external", "volume"],
-                           ratio_volume=1e3, ratio_arap=2e1, ratio_collide=1e4, ratio_kinematics=1e1,
-                           external_force_y=-2e2, external_force_timesteps=2, dt=0.1,
-                           collide_circle_y=-0.5, sample_resolution=10, hidden_features=68)),
-        ("plane3d", dict(dim=3, energy=["arap", "kinematics", "collision", "external", "volume"],
-                         ratio_volume=1e3, ratio_arap=1e2, ratio_collide=1e6, ratio_kinematics=1e0,
-                         external_force_z=-1e2, external_force_timesteps=5, dt=0.1,
-                         plane_height=-0.9, sample_resolution=5, hidden_features=66)),
-    ):
+    for tag, over in ELASTICITY_CASES:
         torch.manual_seed(13)
         cfg = ref_loader.make_cfg("elasticity", **over)
         m = ref.elasticity.ElasticityModel(cfg)
