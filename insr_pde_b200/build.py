@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libinsr_b200.so")
 FUSED_SHAPES = [(1, 1), (2, 1), (2, 2)]          # (D, O) pairs of the fused family, one object each
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-    "--use_fast_math", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+    "--use_fast_math", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", *(["-DINSR_TC_DEBUG_FLUSH"] if os.environ.get("INSR_BUILD_DEBUG_FLUSH") else []),
 ]
 OBJ_DIR = os.path.join(HERE, "build")
 

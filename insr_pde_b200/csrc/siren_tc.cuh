@@ -32,6 +32,7 @@
 //
 // Only compiled by nvcc (inline PTX); the host-side SIMT emulation does not cover this file.
 #pragma once
+#include <cstdlib>
 #include "siren_fused.cuh"
 
 #ifndef INSR_CPU_EMU
@@ -1025,12 +1026,22 @@ __global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__
     if (pendW) { mbar_wait(mbarW, phW); phW ^= 1; pendW = false; }
     tc_fence_after();
     const float wsc = dm.omega;
+#ifdef INSR_TC_DEBUG_FLUSH
+    if (p.nwarps & 1) wacc_mask = 0;                    // timing experiment: no hidden-layer weight-gradient atomics
+#endif
     // hidden-layer weight gradients.  M = 64 accumulator layout: row r of D sits in TMEM lane 32 (r >> 4) + (r & 15),
     // so lanes 0..15 of warp quadrant q hold rows 16 q .. 16 q + 15 = level (q >> 1), neurons 16 (q & 1) + lane;
     // the four warps of a quadrant split the 32 input neurons; columns k (x a1) and 32 + k (x a2) are added.
+    // Every CTA of a one-wave launch reaches this point at the same time and would walk the SAME addresses in the same
+    // order: same-address reductions serialise in L2 (measured: 39 of 58 us of a 128-tile launch).  So the CTAs start at
+    // different layers / halves (blockIdx-rotated order) and each thread reduces 4 consecutive weights per instruction
+    // (red.global.add.v4.f32) where the row is 16-byte aligned.
     {
         const int j = 16 * (warp & 1) + lane;
-        for (int l = 1; l <= L; ++l) {
+        const bool vec = (H & 3) == 0 && (reinterpret_cast<uintptr_t>(p.gtheta) & 15u) == 0;
+        const int rot = (int)blockIdx.x;
+        for (int ll = 0; ll < L; ++ll) {
+            const int l = 1 + (ll + rot) % L;
             if (!((wacc_mask >> (l - 1)) & 1u)) continue;
             float *gW = p.gtheta + insr_w_offset(dm, l);
             float v1[8], v2[8];
@@ -1039,9 +1050,21 @@ __global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__
             tmem_ld_wait();
             if (lane < 16 && j < H) {
                 INSR_PRAGMA_UNROLL
-                for (int i = 0; i < 8; ++i) {
-                    const int k = 8 * part + i;
-                    if (k < H) atomicAdd(gW + (size_t)j * H + k, wsc * (v1[i] + v2[i]));
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int h4 = (hh + (rot / L)) & 1;          // which half of the 8 weights first
+                    const int k0 = 8 * part + 4 * h4;
+                    float q[4];
+                    INSR_PRAGMA_UNROLL
+                    for (int i = 0; i < 4; ++i) q[i] = h4 ? wsc * (v1[4 + i] + v2[4 + i]) : wsc * (v1[i] + v2[i]);
+                    float *dst = gW + (size_t)j * H + k0;
+                    if (vec && k0 + 3 < H) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                                     :: "l"(dst), "f"(q[0]), "f"(q[1]), "f"(q[2]), "f"(q[3]) : "memory");
+                    } else {
+                        INSR_PRAGMA_UNROLL
+                        for (int i = 0; i < 4; ++i)
+                            if (k0 + i < H) atomicAdd(dst + i, q[i]);
+                    }
                 }
             }
         }
@@ -1087,6 +1110,9 @@ int launch_tc_bwd(Params &p, float *ws, void *stream, int64_t *launches) {
     const int64_t tiles = (p.N + TILE_M - 1) / TILE_M;
     int64_t ctas = tiles < insr_fused::sm_count() ? tiles : insr_fused::sm_count();
     float4 *tape = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(ws) + 15) & ~uintptr_t(15));
+#ifdef INSR_TC_DEBUG_FLUSH
+    { const char *e = getenv("INSR_TC_DEBUG"); p.nwarps = e ? atoi(e) : 0; }
+#endif
     kfn<<<dim3((unsigned)ctas), dim3(BT), M.total + 1024, reinterpret_cast<cudaStream_t>(stream)>>>(p, tape);
     ++*launches;
     return 0;

@@ -7,7 +7,7 @@ Tolerances (relative to the frame's max |value|; Adam divides by sqrt(v), so rou
 amplified over the hundreds of iterations of a frame, and every frame starts from the previous one):
     fluid2Dtlgn velocity field      frame 0 (after initialize): 1e-4; frames 1, 2: 5e-4
     advect1D field                  every frame: 2e-4
-    elasticity2Dstretch deformation frame 0: 1e-5; frame 1: 5e-2 (a stiff minimisation: see the test)
+    elasticity2Dstretch deformation frame 0: 1e-5; frame 1: 3x the reference's own run-to-run spread (see the test)
 The measured errors are printed; they are recorded in DESIGN.md."""
 import json
 import os
@@ -36,10 +36,10 @@ CASES = {
 _RUNS = {}
 
 
-def run(case, device, tmp):
-    key = (case, device)
+def run(case, device, tmp, repeat=0):
+    key = (case, device, repeat)
     if key not in _RUNS:
-        argv = CASES[case] + ["--proj_dir", str(tmp), "--tag", f"{case}_{device}"]
+        argv = CASES[case] + ["--proj_dir", str(tmp), "--tag", f"{case}_{device}_{repeat}"]
         res = subprocess.run([sys.executable, "-W", "ignore", os.path.join(ROOT, "tests", "run_main_dropin.py"), device, "0", *argv],
                              capture_output=True, text=True, timeout=1500)
         assert res.returncode == 0, res.stderr[-3000:]
@@ -85,12 +85,17 @@ def test_advect1d_frames(tmp_path_factory):
 def test_elasticity2dstretch_frames(tmp_path_factory):
     """frame 0 = the zero-deformation fit (500^2 points per iteration), frame 1 = the first stretch step.  The stretch step
     is a stiff, ill-conditioned minimisation (ratio_constraint 1e4 against ratio_arap 1): 200 Adam iterations amplify
-    rounding-level gradient differences far more than the fluid's loops do, so the per-frame tolerance is 5e-2 here, while
-    the closure itself is pinned to 1e-4 against the reference in fp32 AND fp64 (test_gpu_parity.py, closure goldens)"""
+    rounding-level gradient differences -- the reference does not even reproduce ITSELF from run to run (its backward
+    kernels reduce with atomics).  So the yardstick for frame 1 is the reference's own run-to-run spread (same seed, two
+    runs): ours may sit at most 3x that far from it (floor 1e-3).  The closure itself is pinned to 1e-4 against the
+    reference in fp32 AND fp64 (test_gpu_parity.py, closure goldens)."""
     tmp = tmp_path_factory.mktemp("traj_ela")
-    ours, ref32 = run("elasticity2Dstretch", "cuda", tmp), run("elasticity2Dstretch", "cuda-reference", tmp)
-    (fa, a), (fb, b) = frames(ours, ".ply.npy"), frames(ref32, ".ply.npy")
-    assert fa == fb and len(fa) == 2
+    ours = run("elasticity2Dstretch", "cuda", tmp)
+    ref_a, ref_b = run("elasticity2Dstretch", "cuda-reference", tmp), run("elasticity2Dstretch", "cuda-reference", tmp, repeat=1)
+    (fa, a), (fb, b), (fc, c) = frames(ours, ".ply.npy"), frames(ref_a, ".ply.npy"), frames(ref_b, ".ply.npy")
+    assert fa == fb == fc and len(fa) == 2
     errs = [rel(x, y) for x, y in zip(a, b)]
-    print("elasticity2Dstretch per-frame max relative deformation error:", errs)
-    assert errs[0] < 1e-5 and errs[1] < 5e-2, errs
+    spread = [rel(x, y) for x, y in zip(c, b)]
+    print("elasticity2Dstretch per-frame max relative deformation error: ours vs reference", errs, " reference vs reference (same seed)", spread)
+    assert errs[0] < 1e-5, errs
+    assert errs[1] < max(3 * spread[1], 1e-3), (errs, spread)
