@@ -76,8 +76,9 @@ def _tape_desc(desc):
                           desc.flags | _lib.FLAG_KEEP_TAPE)
 
 
-def siren_forward(desc, theta, x, order, keep_tape=False):
-    """theta: flat (P,), x: (N, D) -> tuple (y[, jac[, h2]]).
+def siren_forward(desc, theta, x, order, keep_tape=False, out=None):
+    """theta: flat (P,), x: (N, D) -> tuple (y[, jac[, h2]]).  ``out``: preallocated contiguous, 16-byte aligned fp32
+    tensors to write the outputs into (e.g. row ranges of persistent buffers) instead of fresh ones.
     ``keep_tape=True`` (a forward whose backward will follow): returns ``(outs, tape)`` where ``tape`` is the workspace
     holding the activations of every layer, to be handed to ``siren_backward(..., tape=tape)``, or None where the kernel
     family keeps no tape (H <= 32: recomputed in registers; batches beyond one workspace chunk)."""
@@ -90,7 +91,13 @@ def siren_forward(desc, theta, x, order, keep_tape=False):
         raise ValueError(f"x must be (N, {desc.in_features}), got {tuple(x.shape)}")
     if theta.numel() != lib.theta_size(desc):
         raise ValueError(f"theta has {theta.numel()} elements, expected {lib.theta_size(desc)}")
-    outs = [torch.empty(s, dtype=torch.float32, device=x.device) for s in out_shapes(desc, n, order)]
+    if out is None:
+        outs = [torch.empty(s, dtype=torch.float32, device=x.device) for s in out_shapes(desc, n, order)]
+    else:
+        outs = list(out)
+        for t, s in zip(outs, out_shapes(desc, n, order)):
+            if tuple(t.shape) != tuple(s) or not t.is_contiguous() or t.dtype != torch.float32 or t.data_ptr() % 16:
+                raise ValueError(f"siren_forward: out must be contiguous, 16-byte aligned fp32 of shape {tuple(s)}")
     if n == 0:
         return (tuple(outs), None) if keep_tape else tuple(outs)
     tape = None

@@ -288,7 +288,7 @@ def _host_vec(v):
 def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_left, fixed_right, *, dt, timestep, energy,
                                  ratio_arap, ratio_volume, ratio_kinematics, ratio_constraint, ratio_collide,
                                  external_force, external_force_timesteps, constraint_offset_right, plane_height,
-                                 circle_center, circle_radius):
+                                 circle_center, circle_radius, batch=None):
     """ElasticityModel._solve_deformation (elasticity/model.py:127-189) without an autograd graph: one order-1 evaluation
     of the trainable field over [interior | left face | right face] that keeps its tape, the two frozen fields on side
     streams, ONE kernel for every loss term and its cotangents (insr_elastic_terms: Jacobi SVD energies, kinematics,
@@ -307,24 +307,36 @@ def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_le
             ratio_constraint=ratio_constraint, ratio_collide=ratio_collide, external_force=external_force,
             external_force_timesteps=external_force_timesteps, constraint_offset_right=constraint_offset_right,
             plane_height=plane_height, circle_center=circle_center, circle_radius=circle_radius)
-    samples = samples.detach().reshape(-1, dim).contiguous()
-    n = samples.shape[0]
     ra = ratio_arap if "arap" in energy else 0.0
     rv = ratio_volume if "volume" in energy else 0.0
-    use_left = "constraint" in energy and torch.is_tensor(fixed_left)
-    use_right = ("constraint_right" in energy or "constraint_right_compress" in energy) and torch.is_tensor(fixed_right)
-    extra = ([fixed_left.detach()] if use_left else []) + ([fixed_right.detach()] if use_right else [])
-    x_all = torch.cat([samples] + [e.reshape(-1, dim).to(samples.dtype) for e in extra], dim=0) if extra else samples
-    n_left = extra[0].shape[0] if use_left else 0
-    n_right = x_all.shape[0] - n - n_left
     order = ORDER_JAC if (ra or rv) else ORDER_VALUE
     theta = deformation.flat_theta()
-
-    (outs, tape), y_prev, y_pp = parallel(samples,
-                                          lambda: _ops.siren_forward(deformation.desc, theta, x_all, order, keep_tape=True),
-                                          lambda: evaluate(prev, samples, ORDER_VALUE)[0],
-                                          lambda: evaluate(prev_prev, samples, ORDER_VALUE)[0])
-    if samples.is_cuda and not torch.cuda.is_current_stream_capturing():
+    if batch is not None:
+        # a prepared batch (ElasticityBatch): [interior | left face | right face] already sits in ONE persistent buffer (no cat
+        # kernels), and the previous-frame fields are only evaluated on the rows that change between iterations -- their
+        # values on the constant rows (the uniform grid / the mesh vertices) were computed once for this time step
+        x_all, samples, n, n_left, n_right = batch.x_all, batch.x_all[:batch.n], batch.n, batch.n_left, batch.n_right
+        use_left, use_right = n_left > 0, n_right > 0
+        x_var = batch.x_all[batch.n_const:batch.n]
+        (outs, tape), _, _ = parallel(samples,
+                                      lambda: _ops.siren_forward(deformation.desc, theta, x_all, order, keep_tape=True),
+                                      lambda: _ops.siren_forward(prev.desc, prev.flat_theta(), x_var, ORDER_VALUE, out=[batch.y_prev[batch.n_const:]]),
+                                      lambda: _ops.siren_forward(prev_prev.desc, prev_prev.flat_theta(), x_var, ORDER_VALUE, out=[batch.y_pp[batch.n_const:]]))
+        y_prev, y_pp = batch.y_prev, batch.y_pp
+    else:
+        samples = samples.detach().reshape(-1, dim).contiguous()
+        n = samples.shape[0]
+        use_left = "constraint" in energy and torch.is_tensor(fixed_left)
+        use_right = ("constraint_right" in energy or "constraint_right_compress" in energy) and torch.is_tensor(fixed_right)
+        extra = ([fixed_left.detach()] if use_left else []) + ([fixed_right.detach()] if use_right else [])
+        x_all = torch.cat([samples] + [e.reshape(-1, dim).to(samples.dtype) for e in extra], dim=0) if extra else samples
+        n_left = extra[0].shape[0] if use_left else 0
+        n_right = x_all.shape[0] - n - n_left
+        (outs, tape), y_prev, y_pp = parallel(samples,
+                                              lambda: _ops.siren_forward(deformation.desc, theta, x_all, order, keep_tape=True),
+                                              lambda: evaluate(prev, samples, ORDER_VALUE)[0],
+                                              lambda: evaluate(prev_prev, samples, ORDER_VALUE)[0])
+    if batch is None and samples.is_cuda and not torch.cuda.is_current_stream_capturing():
         for t in (y_prev, y_pp):
             t.record_stream(torch.cuda.current_stream(samples.device))
     sign = -1.0 if "constraint_right_compress" in energy else 1.0
@@ -757,6 +769,92 @@ def gaussian_like(x, mu=-1.5, sigma=0.1):
     return torch.exp(-0.5 * (x - mu) ** 2 / (sigma ** 2))
 
 
+class ElasticityBatch:
+    """The point batch of one elasticity iteration in ONE persistent buffer (graphed stepper):
+
+        x_all = [ constant interior | random interior | uniform left | random left | random right | uniform right ]
+
+    The constant part (the reference's 'uniform' grid, or every mesh vertex: elasticity/model.py:203-211) is written once;
+    the random parts are drawn in place by the Philox samplers every iteration (no torch.cat in the iteration graph).
+    ``y_prev`` / ``y_pp`` hold the two previous-frame fields on the interior rows: the constant rows are evaluated once
+    per time step (``refresh``), the random rows every iteration."""
+
+    def __init__(self, stepper, resolution, use_left, use_right):
+        from . import sampling
+        st, dev, dim = stepper, stepper._device(), stepper.dim
+        self.dim = dim
+        const, n_rand = [], 0
+        for kind in st.pattern:
+            if kind == "uniform":
+                const.append(st.mesh[0][:, :dim].to(dev).float() if st.mesh is not None else sampling.sample_uniform(resolution, dim, device=dev))
+            elif kind == "random":
+                n_rand += resolution ** dim
+            else:
+                raise NotImplementedError(kind)
+        self.n_const = sum(c.shape[0] for c in const)
+        self.n = self.n_const + n_rand
+        faces = st.mesh is None
+        lu = ru = lr = rr = 0
+        if faces:
+            for kind in st.pattern:
+                if kind == "uniform":
+                    lu = ru = resolution ** (dim - 1)
+                elif kind == "random":
+                    lr = rr = resolution
+        if not use_left:
+            lu = lr = 0
+        if not use_right:
+            ru = rr = 0
+        self.n_left, self.n_right = lu + lr, rr + ru
+        self.x_all = torch.zeros(self.n + self.n_left + self.n_right, dim, dtype=torch.float32, device=dev)
+        if const:
+            self.x_all[:self.n_const] = torch.cat(const, dim=0)
+        o = self.n
+        if lu:
+            face = sampling.sample_uniform(resolution, dim - 1, device=dev)
+            self.x_all[o:o + lu] = torch.cat((-torch.ones(lu, 1, device=dev), face), dim=1)
+        self._rand_faces = (o + lu, o + lu + lr + rr)
+        if ru:
+            face = sampling.sample_uniform(resolution, dim - 1, device=dev)
+            self.x_all[o + lu + lr + rr:] = torch.cat((torch.ones(ru, 1, device=dev), face), dim=1)
+        self.y_prev = torch.zeros(self.n, dim, dtype=torch.float32, device=dev)
+        self.y_pp = torch.zeros(self.n, dim, dtype=torch.float32, device=dev)
+        # samplers (one kernel for the interior, one for both faces)
+        self._interior = None
+        if n_rand:
+            if st.mesh is not None:
+                ms = sampling.MeshSampler(st.mesh[0].to(dev), st.mesh[1].to(dev), dim, st.seed)
+                self._interior = lambda out: ms.sample(n_rand, out=out)
+            else:
+                bs = sampling.BoxSampler([[(n_rand, (-1.0,) * dim, (1.0,) * dim)]], dim, seed=st.seed, device=dev)
+                self._interior = lambda out: bs.sample(out=out)
+        self._faces = None
+        if lr + rr:
+            lo, hi = (-1.0,) * (dim - 1), (1.0,) * (dim - 1)
+            boxes = ([[(lr, (-1.0,) + lo, (-1.0,) + hi)]] if lr else []) + ([[(rr, (1.0,) + lo, (1.0,) + hi)]] if rr else [])
+            fs = sampling.BoxSampler(boxes, dim, seed=st.seed + 1, device=dev)
+            self._faces = lambda out: fs.sample(out=out)
+
+    @property
+    def aligned(self):
+        """the row ranges handed to the kernels start on 16-byte boundaries"""
+        return (self.n_const * self.dim * 4) % 16 == 0
+
+    def draw(self):
+        if self._interior is not None:
+            self._interior(self.x_all[self.n_const:self.n])
+        if self._faces is not None:
+            a, b = self._rand_faces
+            self._faces(self.x_all[a:b])
+
+    def refresh(self, prev, pp):
+        """previous-frame fields on the constant rows: once per time step (they change only with the hand-over)"""
+        if self.n_const:
+            xc = self.x_all[:self.n_const]
+            self.y_prev[:self.n_const] = evaluate(prev, xc, ORDER_VALUE)[0]
+            self.y_pp[:self.n_const] = evaluate(pp, xc, ORDER_VALUE)[0]
+
+
 class ElasticityStepper(_StepperBase):
     """ElasticityModel.initialize / step (elasticity/model.py:100-125) on the fused closure: previous-frame hand-over,
     the reference's sample pattern ('random' and / or 'uniform'; a mesh when ``mesh=(V, F)`` is given), one
@@ -834,6 +932,23 @@ class ElasticityStepper(_StepperBase):
                 left.append(self._const[key][0]); right.append(self._const[key][1])
         return torch.cat(left, dim=0), torch.cat(right, dim=0)
 
+    def _batch(self):
+        """the persistent batch of the graphed iteration, or None where the one-kernel closure does not apply"""
+        if "_ebatch" not in self.__dict__:
+            energy = list(self.kw.get("energy", ()))
+            known = {"arap", "volume", "kinematics", "external", "constraint", "constraint_right", "constraint_right_compress",
+                     "collision", "collision_sphere"}
+            ok = (set(energy) <= known and len(set(energy)) == len(energy) and not ("collision_sphere" in energy and self.dim != 2)
+                  and not ("constraint_right" in energy and "constraint_right_compress" in energy))
+            b = None
+            if ok:
+                b = ElasticityBatch(self, self.sr, "constraint" in energy,
+                                    "constraint_right" in energy or "constraint_right_compress" in energy)
+                if not b.aligned:
+                    b = None
+            self._ebatch = b
+        return self._ebatch
+
     # --- the two training loops -----------------------------------------------------------------
     def _loop(self, closure, n_iters, key):
         if self.graphed:
@@ -861,8 +976,15 @@ class ElasticityStepper(_StepperBase):
         self.pp.load_state_dict(self.prev.state_dict())
         self.prev.load_state_dict(self.defo.state_dict())
         forced = self.timestep <= self.kw.get("external_force_timesteps", 0)
+        batch = self._batch() if self.graphed else None
+        if batch is not None:
+            batch.refresh(self.prev, self.pp)
 
         def c(i):
+            if batch is not None:
+                batch.draw()
+                return elasticity_solve_deformation(self.defo, self.prev, self.pp, None, None, None, dt=self.dt,
+                                                    timestep=self.timestep, batch=batch, **self.kw)
             left, right = self._fixed(self.sr)
             return elasticity_solve_deformation(self.defo, self.prev, self.pp, self._interior(self.sr), left, right,
                                                 dt=self.dt, timestep=self.timestep, **self.kw)

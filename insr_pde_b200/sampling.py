@@ -76,9 +76,13 @@ class BoxSampler:
         self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._lib = _lib
 
-    def sample(self):
+    def sample(self, out=None):
+        """``out``: a contiguous (sum of counts, dim) fp32 view to draw into (e.g. a slice of a persistent batch buffer)"""
         lib = self._lib.get_lib()
-        out = torch.empty(sum(self.sizes), self.dim, dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty(sum(self.sizes), self.dim, dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != (sum(self.sizes), self.dim) or not out.is_contiguous() or out.dtype != torch.float32:
+            raise ValueError("BoxSampler.sample: out must be a contiguous fp32 tensor of shape (sum of counts, dim)")
         with torch.cuda.device(self.device):
             lib.sample_boxes(self.counts, self.lo, self.hi, self.dim, self.seed, self.counter.data_ptr(), self.ticket.data_ptr(),
                              self.point_offset, out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
@@ -119,9 +123,12 @@ class MeshSampler:
         self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._lib = _lib
 
-    def sample(self, n):
+    def sample(self, n, out=None):
         lib = self._lib.get_lib()
-        out = torch.empty(n, self.dim_out, dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty(n, self.dim_out, dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != (n, self.dim_out) or not out.is_contiguous() or out.dtype != torch.float32:
+            raise ValueError("MeshSampler.sample: out must be a contiguous fp32 tensor of shape (n, dim_out)")
         with torch.cuda.device(self.device):
             lib.sample_mesh(self.V.data_ptr(), self.F.data_ptr(), self.cdf.data_ptr(), self.F.shape[0], self.F.shape[1], n,
                             self.dim_out, self.seed, self.counter.data_ptr(), self.ticket.data_ptr(), self.point_offset,

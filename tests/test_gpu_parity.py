@@ -575,7 +575,20 @@ def test_elasticity_stepper_graph_replay_matches_eager_loop():
     left, right = st._fixed(24)
     assert left.shape == (48, 2) and bool((left[:, 0] == -1).all()) and bool((right[:, 0] == 1).all())
     assert float(left[:24, 1].abs().max()) <= 1 and float(left[:24, 1].std()) > 0.3
-    assert int(st._samplers[("box", 24)].counter) >= 6
+    # the graphed step draws in place into ONE persistent batch buffer [const | random | faces] (fused.ElasticityBatch) and
+    # evaluates the previous-frame fields on the constant rows once per time step
+    b = st._batch()
+    assert b is not None and b.n_const == 576 and b.n == 1152 and b.n_left == 48 and b.n_right == 0
+    lf = b.x_all[b.n:b.n + b.n_left]
+    assert bool((lf[:, 0] == -1).all()) and float(lf[24:, 1].std()) > 0.3          # [uniform left | random left]
+    grid = ib.sample_uniform(24, 2, device="cuda")
+    assert torch.equal(b.x_all[:576], grid)
+    x_before = b.x_all.clone()
+    yp_before = b.y_prev.clone()
+    st.step(2)
+    assert torch.equal(b.x_all[:576], x_before[:576]) and not torch.equal(b.x_all[576:1152], x_before[576:1152])
+    (ref_prev,) = fused.evaluate(st.prev, b.x_all[:b.n], 0)
+    assert rel(b.y_prev, ref_prev) < 1e-6 and not torch.equal(b.y_prev, yp_before)     # cache refreshed after the hand-over
 
 
 @pytest.mark.parametrize("dim,H,energy", [(2, 68, ["arap", "volume", "kinematics", "external", "constraint", "constraint_right", "collision_sphere"]),
