@@ -58,6 +58,8 @@ if not fused_closures:
     bm.BaseModel._update_network = spy
 torch.manual_seed(123)
 np.random.seed(123)
+import time  # noqa: E402
+_t0 = time.perf_counter()
 if reference_only:
     import runpy
     old_argv, old_cwd = sys.argv, os.getcwd()
@@ -70,11 +72,14 @@ if reference_only:
         os.chdir(old_cwd)
 else:
     patch.run_main(argv, root, fused_closures=fused_closures)
+if torch.cuda.is_available():
+    torch.cuda.synchronize()
+_elapsed = time.perf_counter() - _t0
 proj = argv[argv.index("--proj_dir") + 1]
 tag = argv[argv.index("--tag") + 1]
 res = os.path.join(proj, tag, "results")
 files = sorted(os.listdir(res))
-out = {"files": files, "hist": hist, "ckpts": sorted(os.listdir(os.path.join(proj, tag, "model"))), "results_dir": res}
+out = {"seconds": round(_elapsed, 3), "files": files, "hist": hist, "ckpts": sorted(os.listdir(os.path.join(proj, tag, "model"))), "results_dir": res}
 for f in files:
     if f.endswith(".npy"):
         out.setdefault("npy", {})[f] = [float(np.abs(np.load(os.path.join(res, f))).max())]

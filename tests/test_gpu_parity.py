@@ -4,6 +4,8 @@ Tolerance: the north star asks for 1e-4 relative (max-abs error / max-abs refere
 for values, derivatives, losses and parameter gradients.  Tests assert a tighter 3e-5 against
 the fp64 reference outputs where the fp32 reference itself sits at ~5e-6.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -875,3 +877,81 @@ def test_target_kernel_matches_separate_evaluations(N):
     wide = ib.MLP(2, 2, 3, 68, nonlinearity="sine").cuda()
     with pytest.raises(_lib.InsrError):
         _ops.siren_target(x, 2, dict(net=wide, order=0, cy=eye))
+
+
+# ------------------------------------------------------------------------------------------------
+# the wide end of the sweep at sizes with many 128-point tiles (several workspace chunks, grid-row weight gradient)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [(2, 1, 512, 5, 1 << 16, 2), (2, 1, 256, 4, 1 << 16, 2), (3, 3, 128, 3, 1 << 17, 1), (2, 1, 128, 5, 70000, 2)])
+def test_wide_shapes_at_bench_sizes_sampled_fp64(case):
+    """sweep.h512 (L = 5), sweep.h256.l4, the 3 -> 3 value + Jacobian mode at H = 128 and H = 128 / L = 5 at >= 2^16 points:
+    outputs against the fp64 oracle on a sample of the points, the parameter gradient through additivity over point
+    shards (the sum of the gradients of two halves = the gradient of the whole) and against the fp64 oracle on a subset
+    whose cotangents are the only non-zero ones"""
+    D, O, H, L, N, order = case
+    # the deepest / widest point of the sweep accumulates 3xTF32 rounding over 5 x 512-wide layers: measured 1e-5 on the
+    # values and 3.1e-5 on the Jacobian, so it is held to the north star's 1e-4 instead of this file's 3e-5
+    TOL = 1e-4 if H * L >= 2048 else 3e-5
+    rng, theta, x = _mid_problem(case)
+    desc = _lib.make_desc(D, O, H, L)
+    td, xd = dev(theta), dev(x)
+    outs = _ops.siren_forward(desc, td, xd, order)
+    idx = np.sort(rng.choice(N, 384, replace=False))
+    idx[:2] = [0, N - 1]
+    idx = np.unique(idx)
+    ref = fm.forward(theta.astype(np.float64), x[idx].astype(np.float64), D, O, H, L, order)
+    assert rel(outs[0][idx], ref["y"]) < TOL and rel(outs[1][idx], ref["jac"]) < TOL
+    if order == 2:
+        assert rel(outs[2][idx], ref["lap"]) < TOL
+    # cotangents that vanish outside the sampled points: the full-batch backward must equal the fp64 backward on the sample
+    cots = [torch.zeros_like(o) for o in outs]
+    cs = [rng.standard_normal((len(idx),) + tuple(o.shape[1:])).astype(np.float32) for o in outs]
+    for c, v in zip(cots, cs):
+        c[torch.from_numpy(idx).cuda()] = dev(v)
+    g_all, _ = _ops.siren_backward(desc, td, xd, order, *cots)
+    kw = dict(gy=cs[0], gjac=cs[1])
+    if order == 2:
+        kw["glap"] = cs[2]
+    gref, _ = fm.backward(theta.astype(np.float64), x[idx].astype(np.float64), D, O, H, L, order, **kw)
+    assert rel(g_all, gref) < TOL
+    half = N // 2 + 33
+    dense = [torch.randn_like(o) / N for o in outs]
+    g_full, _ = _ops.siren_backward(desc, td, xd, order, *dense)
+    g_a, _ = _ops.siren_backward(desc, td, xd[:half], order, *[c[:half] for c in dense])
+    g_b, _ = _ops.siren_backward(desc, td, xd[half:], order, *[c[half:] for c in dense])
+    assert rel(g_a + g_b, g_full) < TOL
+
+
+def test_wide_k16_variant_parity():
+    """k_wide_tc<..., K16 = true> (INSR_WIDE_K16=1: 16-wide K slabs, two CTAs per SM) is an opt-in variant selected when the
+    library is first used, so it runs in a fresh process: outputs and gradient at H = 128 (S = 3 and S = 4) against the
+    default variant's in this process"""
+    import subprocess
+    import sys
+    import tempfile
+    from conftest import ROOT
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from insr_pde_b200 import _lib, _ops
+torch.manual_seed(3)
+out = {}
+for tag, (D, O, order) in {"s3": (2, 2, 1), "s4": (2, 1, 2)}.items():
+    desc = _lib.make_desc(D, O, 128, 3)
+    theta = (torch.rand(_lib.get_lib().theta_size(desc), device="cuda") - 0.5) * 0.1
+    x = torch.rand(5000, D, device="cuda") * 2 - 1
+    outs = _ops.siren_forward(desc, theta, x, order)
+    g, _ = _ops.siren_backward(desc, theta, x, order, *[torch.ones_like(o) / 5000 for o in outs])
+    out[tag + "_y"] = outs[0].cpu().numpy(); out[tag + "_j"] = outs[1].cpu().numpy(); out[tag + "_g"] = g.cpu().numpy()
+np.savez(sys.argv[1], **out)
+''' % ROOT
+    res = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for k16 in ("0", "1"):
+            path = os.path.join(tmp, f"k16_{k16}.npz")
+            r = subprocess.run([sys.executable, "-W", "ignore", "-c", code, path], env=dict(os.environ, INSR_WIDE_K16=k16),
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            res[k16] = dict(np.load(path))
+    for key in res["0"]:
+        assert rel(res["1"][key], res["0"][key]) < TOL, key
