@@ -175,6 +175,20 @@ int generic_backward(const SirenDims &dm, int order, const float *theta, const f
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// the 32 < H <= 512 family serves this call (H <= 32 only through its tensor-core kernels: no FFMA variant at those widths)
+bool tiled_ok(const insr_siren_desc *d, const SirenDims &dm, int order) {
+    if (d->flags & INSR_FLAG_FORCE_GENERIC) return false;
+    if (!insr_tiled_supported(dm, order)) return false;
+    return dm.H > 32 || !(d->flags & INSR_FLAG_NO_TENSOR);
+}
+// the resident-weights family (H <= 32) serves this forward call -- unless the call keeps its tape for a backward that only
+// the other family can run (e.g. L = 5: forward instantiated, backward not)
+bool fused_fwd_ok(const insr_siren_desc *d, const SirenDims &dm, int order) {
+    if ((d->flags & INSR_FLAG_FORCE_GENERIC) || !insr_fused_supported(dm, order, 0)) return false;
+    if ((d->flags & INSR_FLAG_KEEP_TAPE) && !insr_fused_supported(dm, order, 1) && tiled_ok(d, dm, order)) return false;
+    return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -200,8 +214,8 @@ int insr_siren_kernel_family(const insr_siren_desc *desc, int order, int backwar
     int rc = validate(desc, 0, order, &dm);
     if (rc) return rc;
     if (desc->flags & INSR_FLAG_FORCE_GENERIC) return 0;
-    if (insr_fused_supported(dm, order, backward)) return 1;
-    return insr_tiled_supported(dm, order) ? 2 : 0;
+    if (backward ? insr_fused_supported(dm, order, 1) : fused_fwd_ok(desc, dm, order)) return 1;
+    return tiled_ok(desc, dm, order) ? 2 : 0;
 }
 
 int insr_siren_tape_supported(const insr_siren_desc *desc, int64_t n_points, int order) {
@@ -209,7 +223,7 @@ int insr_siren_tape_supported(const insr_siren_desc *desc, int64_t n_points, int
     int rc = validate(desc, n_points, order, &dm);
     if (rc) return rc;
     if (desc->flags & INSR_FLAG_FORCE_GENERIC) return 0;
-    if (insr_fused_supported(dm, order, 1) || !insr_tiled_supported(dm, order)) return 0;
+    if (insr_fused_supported(dm, order, 1) || !tiled_ok(desc, dm, order)) return 0;
     return insr_tiled_tape_fits(dm, n_points, order) ? 1 : 0;
 }
 
@@ -217,8 +231,8 @@ size_t insr_siren_workspace_bytes(const insr_siren_desc *desc, int64_t n_points,
     SirenDims dm;
     if (validate(desc, n_points, order, &dm)) return 0;
     if (!(desc->flags & INSR_FLAG_FORCE_GENERIC)) {
-        if (insr_fused_supported(dm, order, backward)) return insr_fused_ws_bytes(dm, n_points, order, backward);
-        if (insr_tiled_supported(dm, order)) return insr_tiled_ws_bytes(dm, n_points, order, backward);
+        if (backward ? insr_fused_supported(dm, order, 1) : fused_fwd_ok(desc, dm, order)) return insr_fused_ws_bytes(dm, n_points, order, backward);
+        if (tiled_ok(desc, dm, order)) return insr_tiled_ws_bytes(dm, n_points, order, backward);
     }
     return generic_ws_bytes(dm, n_points, order, backward);
 }
@@ -239,14 +253,14 @@ int insr_siren_forward(const insr_siren_desc *desc, const float *theta, const fl
     const size_t need = insr_siren_workspace_bytes(desc, n_points, order, 0);
     if (need && (!workspace || workspace_bytes < need))
         return fail(INSR_ERR_WORKSPACE, "forward needs %zu workspace bytes, got %zu", need, workspace_bytes);
-    if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_fused_supported(dm, order, 0)) {
+    if (fused_fwd_ok(desc, dm, order)) {
         rc = insr_fused_forward(dm, order, theta, x, n_points, y, jac, h2, (float *)workspace, stream, &g_launches,
                                 (desc->flags & INSR_FLAG_NO_TENSOR) == 0);
         if (rc == INSR_ERR_UNSUPPORTED) return fail(rc, "fused forward dispatch failed for D=%d O=%d H=%d", dm.D, dm.O, dm.H);
         if (rc) return rc;
         return check_cuda("fused forward");
     }
-    if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_tiled_supported(dm, order)) {
+    if (tiled_ok(desc, dm, order)) {
         const bool keep = (desc->flags & INSR_FLAG_KEEP_TAPE) != 0;
         if (keep) {
             if (!insr_tiled_tape_fits(dm, n_points, order))
@@ -286,7 +300,7 @@ int insr_siren_backward(const insr_siren_desc *desc, const float *theta, const f
         if (rc) return rc;
         return check_cuda("fused backward");
     }
-    if (!(desc->flags & INSR_FLAG_FORCE_GENERIC) && insr_tiled_supported(dm, order)) {
+    if (tiled_ok(desc, dm, order)) {
         const bool have_tape = (desc->flags & INSR_FLAG_KEEP_TAPE) != 0;
         if (have_tape && !insr_tiled_tape_fits(dm, n_points, order))
             return fail(INSR_ERR_UNSUPPORTED, "KEEP_TAPE: %lld points do not fit one workspace chunk", (long long)n_points);

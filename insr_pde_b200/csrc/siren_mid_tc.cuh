@@ -1003,10 +1003,11 @@ inline bool mid_enabled() {
     static const bool on = [] { const char *e = getenv("INSR_MID"); return !(e && e[0] == '0'); }();
     return on;
 }
-// shapes the fused kernels serve: the widths of the elasticity scripts with at most 3 streams
+// shapes the fused kernels serve: widths up to 80 (the elasticity scripts; H <= 32 nets that the resident-weights family does not
+// instantiate -- D = 3, deeper than 3 hidden layers -- run at the padded width 64) with at most 4 streams
 inline bool mid_supported(const SirenDims &dm, int order) {
     const int S = insr_nstreams(dm.D, order);
-    if (!(mid_enabled() && dm.H > 32 && hp16_of(dm.H) <= MAX_HP16 && S <= MAX_S && dm.L >= 1 && dm.L <= 8)) return false;
+    if (!(mid_enabled() && dm.H >= 1 && hp16_of(dm.H) <= MAX_HP16 && S <= MAX_S && dm.L >= 1 && dm.L <= 8)) return false;
     const int hp = hp16_of(dm.H) <= 64 ? 64 : 80;
     return mid_smem(hp, S, dm.L, 0).total + 128 <= 232448;      // 227 KB of shared memory per CTA
 }

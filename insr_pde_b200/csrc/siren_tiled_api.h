@@ -10,7 +10,7 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 // (siren_mid_tc.cuh: 32 < H <= 80) -- the kernel width 64 / 80 of their private tape layout
 inline int hp_alloc(const SirenDims &dm) {
     const int hp = (dm.H + 7) & ~7, h16 = (dm.H + 15) & ~15;
-    if (dm.H > 32 && h16 <= 80) return h16 <= 64 ? 64 : 80;
+    if (h16 <= 80) return h16 <= 64 ? 64 : 80;
     return hp;
 }
 
@@ -52,7 +52,20 @@ int insr_tiled_backward(const SirenDims &dm, int order, const float *theta, cons
 inline bool insr_tiled_tape_fits(const SirenDims &dm, int64_t N, int order) {
     return N <= insr_tiled::chunk_points(dm, insr_nstreams(dm.D, order), true, N);
 }
-inline bool insr_tiled_supported(const SirenDims &dm, int order) { return dm.H > 32 && dm.H <= 512 && order <= 3; }
+#ifndef INSR_CPU_EMU
+bool insr_mid_supported(const SirenDims &dm, int order);      // siren_mid_api.h
+#endif
+// 32 < H <= 512; and those H <= 32 shapes outside the resident-weights family (D = 3, more than 3 hidden layers in the
+// backward) that the fused mid-width kernels serve at the padded width 64 instead of the generic thread-per-point kernels
+inline bool insr_tiled_supported(const SirenDims &dm, int order) {
+    if (order > 3) return false;
+    if (dm.H > 32) return dm.H <= 512;
+#ifndef INSR_CPU_EMU
+    return insr_mid_supported(dm, order);
+#else
+    return false;
+#endif
+}
 inline size_t insr_tiled_ws_bytes(const SirenDims &dm, int64_t N, int order, int backward) {
     return insr_tiled::ws_bytes(dm, order, backward != 0, N);
 }

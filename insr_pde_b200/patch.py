@@ -225,13 +225,15 @@ def install_fused_closures():
     loop(adv, "_initialize", adv_initialize)
     loop(adv, "_advect", adv_advect)
 
-    flu = importlib.import_module("fluid.model").Fluid2DModel
+    flu_mod = importlib.import_module("fluid.model")
+    flu = flu_mod.Fluid2DModel
 
     def flu_sets(self):
         samples = self._sample_in_training()
         n_bc = samples.shape[0] // 100
-        bc_x = sampling_ref.sample_boundary2D_separate(n_bc, side='horizontal', device=self.device)
-        bc_y = sampling_ref.sample_boundary2D_separate(n_bc, side='vertical', device=self.device)
+        # through the name fluid/model.py itself uses (the data-parallel twin rebinds it there)
+        bc_x = flu_mod.sample_boundary2D_separate(n_bc, side='horizontal', device=self.device)
+        bc_y = flu_mod.sample_boundary2D_separate(n_bc, side='vertical', device=self.device)
         return samples, bc_x, bc_y
 
     def flu_initialize(self):
@@ -328,6 +330,20 @@ def install_graphed_loops(data_parallel: bool = False):
             graphed(cls, name)
 
 
+_DP_MODELS = []          # lists of the models the data-parallel twin has seen (their captured graphs must go before NCCL does)
+
+
+def close_graphed_loops():
+    """drop every captured iteration graph of the models run so far (``GraphedLoop.close``): a process group must not be
+    destroyed -- and a process must not exit -- while a captured graph still references its communicator"""
+    for models in _DP_MODELS:
+        for m in models:
+            for lp in m.__dict__.get("_insr_loops", {}).values():
+                lp.close()
+            m.__dict__.pop("_insr_loops", None)
+        del models[:]
+
+
 def install_data_parallel(pde: str):
     """one process per GPU (torchrun): every rank draws the SAME global sample sets (same seed, same generator state) and
     keeps its contiguous shard of the interior points; gradients -- and the scheduler's loss -- are
@@ -359,7 +375,18 @@ def install_data_parallel(pde: str):
     shard_method("_sample_in_training")
     if pde == "elasticity":
         shard_method("_sample_fixed_in_training")
+    if pde == "fluid":
+        # fluid/model.py:94-95 etc. size the boundary sets from the (now sharded) interior batch: samples.shape[0] // 100.
+        # Scale the request back so that every rank draws the single-GPU boundary sets (same count, same random stream);
+        # they are evaluated redundantly on every rank, which the averaging all-reduce leaves unchanged.
+        mod = importlib.import_module(module)
+        orig_bc = mod.sample_boundary2D_separate
+
+        def sample_boundary2D_separate(N, *a, **k):
+            return orig_bc(N * world, *a, **k)
+        mod.sample_boundary2D_separate = sample_boundary2D_separate
     idist.install_global(lambda: [n for m in trainable for n in m._trainable_networks.values()], average=(pde != "elasticity"))
+    _DP_MODELS.append(trainable)
     return rank, world
 
 
@@ -380,6 +407,13 @@ def run_main(argv, reference_root: str, fused_closures: bool = None, graphed: bo
     (one process per GPU, RANK / LOCAL_RANK / WORLD_SIZE from the environment)."""
     argv = list(argv)
     rank, world = 0, 1
+    import time
+    t_start = time.perf_counter()
+
+    def note(msg):
+        if os.environ.get("INSR_PATCH_VERBOSE", "0") == "1":
+            sys.stderr.write(f"[insr-dp rank {os.environ.get('RANK', '0')}] {time.perf_counter() - t_start:7.1f} s  {msg}\n")
+            sys.stderr.flush()
     if data_parallel:
         rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
         local = os.environ.get("LOCAL_RANK", "0")
@@ -397,8 +431,10 @@ def run_main(argv, reference_root: str, fused_closures: bool = None, graphed: bo
     if fused_closures is None:
         fused_closures = os.environ.get("INSR_FUSED_CLOSURES", "0") == "1"
     pde = next((a for a in argv if a in ("advection", "fluid", "elasticity")), None)
+    note("field / operator layer installed")
     if data_parallel and pde:
         install_data_parallel(pde)
+        note("process group up")
         if rank > 0:
             _silence_non_zero_rank(pde)
     if graphed:
@@ -414,10 +450,24 @@ def run_main(argv, reference_root: str, fused_closures: bool = None, graphed: bo
     sys.argv = [os.path.join(reference_root, "main.py"), *argv]
     os.chdir(reference_root)     # config.py:55-57 copies *.py relative to cwd; mesh paths are relative
     try:
+        note("starting main.py")
         runpy.run_path(sys.argv[0], run_name="__main__")
+        note("main.py done")
     finally:
         sys.argv = old_argv
         os.chdir(old_cwd)
+    if data_parallel and world > 1:
+        # orderly teardown: captured iteration graphs hold NCCL kernels -- drop them before the communicator goes
+        import gc
+        import torch
+        import torch.distributed as tdist
+        close_graphed_loops()
+        gc.collect()
+        torch.cuda.synchronize()
+        if tdist.is_initialized():
+            tdist.barrier()
+            tdist.destroy_process_group()
+        note("process group destroyed")
 
 
 if __name__ == "__main__":

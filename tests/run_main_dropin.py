@@ -32,7 +32,7 @@ if device == "cpu":
     import base.baseModel as bm
     bm.torch = ref_loader._TorchCpuProxy(torch)
 
-reference_only = "reference" in device       # cuda-reference, cuda-reference64; cpu-reference (build container)
+reference_only = "reference" in device       # cuda-reference[64|-perturbed]; cpu-reference (build container)
 if reference_only:
     if device.endswith("64"):
         torch.set_default_dtype(torch.float64)
@@ -41,6 +41,20 @@ else:
     patch.install(root)
 import base.baseModel as bm  # noqa: E402
 import elasticity.model as _ela  # noqa: E402
+
+if device.endswith("-perturbed"):
+    # sensitivity yardstick of a trajectory: the same run with every initial weight moved by ~1e-7 relative (about one
+    # fp32 ulp) -- how far apart two runs end up that differ by rounding only
+    _orig_create = bm.BaseModel._create_network
+
+    def _create_network(self, *a, **k):
+        net = _orig_create(self, *a, **k)
+        g = torch.Generator(device="cpu").manual_seed(99)
+        with torch.no_grad():
+            for p_ in net.parameters():
+                p_.mul_(1.0 + 1e-7 * torch.randn(p_.shape, generator=g).to(p_.device))
+        return net
+    bm.BaseModel._create_network = _create_network
 
 # elasticity writes its frames through open3d (absent here): keep the sampled deformation field as .npy instead
 _ela.write_pointcloud_to_file = lambda path, values: np.save(path + ".npy", np.asarray(values))

@@ -24,7 +24,7 @@ ARGS = ["fluid", "--init_cond", "taylorgreen", "--num_hidden_layers", "3", "--hi
 def _run(tmp, tag, launcher, extra):
     env = dict(os.environ, INSR_REFERENCE_ROOT=ref_loader.REF_ROOT, PYTHONPATH=ROOT)
     cmd = launcher + ["-m", "insr_pde_b200.patch", *extra, "--insr-seed", "5", *ARGS, "--proj_dir", str(tmp), "--tag", tag]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-3000:]
     d = os.path.join(str(tmp), tag, "results")
     return [np.load(os.path.join(d, f)) for f in ("t000.npy", "t001.npy")]
@@ -38,4 +38,6 @@ def test_two_rank_run_reproduces_single_gpu_frames(tmp_path, graphed):
                                    "--master-addr", "127.0.0.1", "--master-port", "29533"], mode + ["--insr-dp"])
     errs = [float(np.abs(a - b).max() / np.abs(b).max()) for a, b in zip(twin, single)]
     print("2-rank vs 1-rank per-frame max relative field error (graphed =", graphed, "):", errs)
-    assert max(errs) < 5e-4, errs
+    # frame 0 (the initial-condition fit, 100 iterations) isolates the mechanics -- shards, all-reduce, identical Adam steps:
+    # a reordered sum, nothing else; frame 1 adds three loops of 100 iterations each on top of it
+    assert errs[0] < 1e-5 and errs[1] < 5e-4, errs

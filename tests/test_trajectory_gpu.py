@@ -7,7 +7,8 @@ Tolerances (relative to the frame's max |value|; Adam divides by sqrt(v), so rou
 amplified over the hundreds of iterations of a frame, and every frame starts from the previous one):
     fluid2Dtlgn velocity field      frame 0 (after initialize): 1e-4; frames 1, 2: 5e-4
     advect1D field                  every frame: 2e-4
-    elasticity2Dstretch deformation frame 0: 1e-5; frame 1: 3x the reference's own run-to-run spread (see the test)
+    elasticity2Dstretch deformation frame 0: 1e-5; frame 1: 3x the reference's own sensitivity to a 1-ulp perturbation of its
+                                    initial weights (see the test)
 The measured errors are printed; they are recorded in DESIGN.md."""
 import json
 import os
@@ -87,17 +88,18 @@ def test_advect1d_frames(tmp_path_factory):
 def test_elasticity2dstretch_frames(tmp_path_factory):
     """frame 0 = the zero-deformation fit (500^2 points per iteration), frame 1 = the first stretch step.  The stretch step
     is a stiff, ill-conditioned minimisation (ratio_constraint 1e4 against ratio_arap 1): 200 Adam iterations amplify
-    rounding-level gradient differences -- the reference does not even reproduce ITSELF from run to run (its backward
-    kernels reduce with atomics).  So the yardstick for frame 1 is the reference's own run-to-run spread (same seed, two
-    runs): ours may sit at most 3x that far from it (floor 1e-3).  The closure itself is pinned to 1e-4 against the
-    reference in fp32 AND fp64 (test_gpu_parity.py, closure goldens)."""
+    rounding-level differences by orders of magnitude.  The yardstick for frame 1 is therefore measured, not guessed: the
+    reference against ITSELF with every initial weight moved by 1e-7 relative (one fp32 ulp).  Ours may sit at most 3x
+    that far from the reference (floor 1e-3).  The closure itself is pinned to 1e-4 against the reference in fp32 AND fp64
+    (test_gpu_parity.py, closure goldens)."""
     tmp = tmp_path_factory.mktemp("traj_ela")
     ours = run("elasticity2Dstretch", "cuda", tmp)
-    ref_a, ref_b = run("elasticity2Dstretch", "cuda-reference", tmp), run("elasticity2Dstretch", "cuda-reference", tmp, repeat=1)
+    ref_a, ref_b = run("elasticity2Dstretch", "cuda-reference", tmp), run("elasticity2Dstretch", "cuda-reference-perturbed", tmp)
     (fa, a), (fb, b), (fc, c) = frames(ours, ".ply.npy"), frames(ref_a, ".ply.npy"), frames(ref_b, ".ply.npy")
     assert fa == fb == fc and len(fa) == 2
     errs = [rel(x, y) for x, y in zip(a, b)]
     spread = [rel(x, y) for x, y in zip(c, b)]
-    print("elasticity2Dstretch per-frame max relative deformation error: ours vs reference", errs, " reference vs reference (same seed)", spread)
+    print("elasticity2Dstretch per-frame max relative deformation error: ours vs reference", errs,
+          " reference vs reference with initial weights perturbed by 1e-7", spread)
     assert errs[0] < 1e-5, errs
     assert errs[1] < max(3 * spread[1], 1e-3), (errs, spread)
