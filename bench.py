@@ -200,14 +200,18 @@ def fluid_timestep_ours(dev, iters, world=1, sample_resolution=128):
         h1, h2, h3 = st.step(iters, world)
         torch.cuda.synchronize()
         sec = min(sec, time.perf_counter() - t0)
-    st.close()                                          # release the captured graphs (and the NCCL work recorded in them) now
+    peer_exchange = world > 1 and graph_dp and all(lp.shared is not None and lp.shared.peer is not None
+                                                   for lp in st.__dict__.get("_loops", {}).values())
+    st.close()                                          # release the captured graphs (and the exchange recorded in them) now
     return {"sec_per_timestep": round(sec, 4), "iters_per_loop": iters, "loops": 3,
             "us_per_iteration": round(sec / (3 * iters) * 1e6, 1), "points_per_iteration": sample_resolution ** 2,
             "final_losses": [round(h[-1]["main"], 8) for h in (h1, h2, h3)],
             "note": ("fluid2Dtlgn step on fused lsq closures; one CUDA graph per iteration (one-kernel Philox sampling of the "
                      "three point sets, closures with interior / boundary terms on parallel branches, device Adam, device "
-                     "ReduceLROnPlateau), losses read back in bulk" + ("; points sharded over the ranks, one NCCL all-reduce of [gradients | loss values] "
-                     "per iteration inside the graph" if world > 1 else "")) if graph_dp else
+                     "ReduceLROnPlateau), losses read back in bulk" + (("; points sharded over the ranks, the exchange of [gradients | loss values] "
+                     "fused into the update kernel over NVLink peer memory (insr_iteration_update_peer; no NCCL in the graph)" if peer_exchange else
+                     "; points sharded over the ranks, one NCCL all-reduce of [gradients | loss values] per iteration inside the graph")
+                     if world > 1 else "")) if graph_dp else
                     "fluid2Dtlgn step on fused lsq closures + torch Adam + flat-gradient all-reduce, host sync per iteration"}
 
 
@@ -490,16 +494,62 @@ class OperatorCase:
         self.cg = torch.Generator(device=dev).manual_seed(4321 + rank)
         self.shapes = _ops.out_shapes(self.desc, n_local, self.order)
         self.cots = [torch.randn(sh, generator=self.cg, device=dev) / n_local for sh in self.shapes]
-        self.gtheta = torch.zeros(self.P, device=dev)
         self.f_fwd = flops_fwd_per_point(self.D, self.O, self.H, self.L, self.order)
+        # the exchange of a step.  Where the ranks can map each other's memory the flat gradient lives in PEER memory and
+        # is reduced by the library's own one-shot kernel over NVLink (insr_peer_allreduce: every rank reads all copies
+        # and adds them in rank order) into gsum; otherwise -- or if the self-check below fails -- NCCL all-reduces it in
+        # place.  The choice is made collectively: every rank takes the same path.
+        self.peer, self.collective = None, None
+        if world > 1:
+            from insr_pde_b200 import peer as _peer
+            self.peer = _peer.PeerBuffer.create(self.P, dev)
+            self.collective = "nccl all-reduce of the flat gradient"
+        self.gtheta = self.peer.data if self.peer is not None else torch.zeros(self.P, device=dev)
+        self.gsum = torch.empty(self.P, device=dev) if self.peer is not None else self.gtheta
+        if self.peer is not None:
+            self._check_peer()
+
+    def _check_peer(self):
+        """one exchange of a known pattern against NCCL's result, plus the kernels' own time-out flag; any rank's failure
+        sends every rank to the NCCL path"""
+        dist = self.dist
+        rank = dist.get_rank()
+        pattern = torch.arange(self.P, device=self.dev, dtype=torch.float32) * 1e-3 + (rank + 1)
+        self.gtheta.copy_(pattern)
+        want = pattern.clone()
+        dist.all_reduce(want)
+        dist.barrier()
+        for _ in range(3):
+            self.peer.allreduce_into(self.gsum)
+        torch.cuda.synchronize()
+        ok = self.peer.healthy() and bool(torch.allclose(self.gsum, want, rtol=1e-6, atol=1e-6))
+        flag = torch.tensor([1.0 if ok else 0.0], device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag.item()) < 0.5:
+            self.peer.close()
+            self.peer = None
+            self.gtheta = torch.zeros(self.P, device=self.dev)
+            self.gsum = self.gtheta
+        else:
+            self.collective = ("one-shot all-reduce over NVLink peer memory (own kernel k_peer_allreduce: flag barrier, every rank "
+                               "reads all ranks' gradient buffers and adds them in rank order; no NCCL on the step)")
+        self.gtheta.zero_()
 
     def step(self):
         outs = self._ops.siren_forward(self.desc, self.theta, self.x, self.order)
         self.gtheta.zero_()
         self._ops.siren_backward(self.desc, self.theta, self.x, self.order, *self.cots, gtheta=self.gtheta)
-        if self.world > 1:
+        if self.peer is not None:
+            self.peer.allreduce_into(self.gsum)
+        elif self.world > 1:
             self.dist.all_reduce(self.gtheta)
         return outs
+
+    def close(self):
+        """collective: release the peer allocation"""
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
     def barrier(self):
         if self.world > 1:
@@ -577,7 +627,7 @@ def run_ours(args):
         sampler.start()
     lib.launch_count(True)
     ms = case.timed(args.steps, 0)
-    launches = lib.launch_count(True) + args.steps * (1 + (1 if world > 1 else 0))   # + zero-fill (+ NCCL)
+    launches = lib.launch_count(True) + args.steps * (1 + (1 if (world > 1 and case.peer is None) else 0))   # + zero-fill (+ NCCL; the peer-memory all-reduce is one of ours and counted by the library)
     # sustain the load long enough for the clock sampler when the timed region is short.  The step
     # contains a collective for N > 1, so EVERY rank runs the same (deterministic) number of extra steps.
     n_extra = int(max(0.0, 1000.0 - ms) / max(ms / args.steps, 1e-3)) + 1
@@ -594,6 +644,8 @@ def run_ours(args):
         wms = wc.timed(args.steps, 3)
         weak = {"points_per_gpu": args.weak_points, "ms_per_step": round(wms / args.steps, 4),
                 "value": round(world * args.weak_points * args.steps / (wms / 1e3), 1), "unit": "points/s", "scaling": "weak"}
+        if wc is not case:
+            wc.close()
         del wc
 
     # ---- dominant kernel alone (backward), CUDA events on the launch stream
@@ -784,6 +836,7 @@ def run_ours(args):
                 sweep[wl] = {"global_points": n_loc * world, "ms_per_step": round(sms / k_s, 4), "points_per_s": round(v, 1),
                              "frac_fp32_step": round(3 * sc.f_fwd * v / 1e12 / (peak * world), 4),
                              "family": lib.kernel_family(sc.desc, sc.order, True), "params": sc.P}
+                sc.close()
                 del sc
             except Exception as e:                      # a secondary measurement must not take the headline line down
                 sweep[wl] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
@@ -835,9 +888,10 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "weak": weak, "sweep": sweep, "script_size": script,
             "timestep": timestep, "fused_closure": fused_closure,
-            "collective": None if world == 1 else "NCCL all-reduce (sum) of the flat fp32 gradient, one per step, on the compute stream",
+            "collective": None if world == 1 else f"{case.collective} (sum of the flat fp32 gradient, one per step, on the compute stream)",
         }
         emit(line)
+    case.close()
     if world > 1:
         # Orderly teardown: every captured iteration graph (they hold NCCL kernels) has been dropped by the stepper
         # helpers above; collect, drain the device, then destroy the communicator.  A watchdog turns a teardown that

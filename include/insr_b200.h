@@ -176,12 +176,53 @@ int insr_plateau_step(const float *loss, float *sched, float factor, int patienc
  * ReduceLROnPlateau step on losses[main_index] and the shared step counter (:79-81), and the iteration's n_losses loss
  * values appended to the device log hist[hist_idx++] (the .item() logging of :116-118 without the host sync; hist may be
  * NULL).  Same arithmetic as insr_adam_step + insr_plateau_step.  ticket: a zeroed device word (last-CTA detection).
+ * clear_losses != 0: the loss slots -- accumulators of the closures' kernels -- are zeroed once they have been consumed.
  */
 int insr_iteration_update(int n_slots, float *const *theta, float *const *grad, float *const *exp_avg,
-                          float *const *exp_avg_sq, const int64_t *n, float *sched, const float *losses, int n_losses,
+                          float *const *exp_avg_sq, const int64_t *n, float *sched, float *losses, int n_losses,
                           int main_index, float *hist, int64_t hist_capacity, int64_t *hist_idx, uint32_t *ticket, float beta1,
                           float beta2, float eps, float factor, int patience, float threshold, float min_lr, float eps_lr,
-                          int zero_grad, void *stream);
+                          int zero_grad, int clear_losses, void *stream);
+
+/*
+ * Data parallelism over the GPUs of one box without a communication library on the path (the reference
+ * itself is single-GPU: base/baseModel.py:25 hard-codes cuda:0, and :73-81 is where a reduced gradient must meet the
+ * optimiser).  PEER MEMORY is the one exception to "the library allocates nothing": a buffer that other processes map
+ * must come from a plain cudaMalloc (cudaIpcGetMemHandle), which a caching allocator does not guarantee.
+ *
+ *   insr_peer_alloc   one allocation  [4096-byte header | data_bytes]  on the current device, zeroed; *base = its address,
+ *                     handle64 = the 64-byte cudaIpcMemHandle_t to hand to the other ranks (any host-side channel)
+ *   insr_peer_open    map another rank's allocation into this process (cudaIpcOpenMemHandle, lazy peer access)
+ *   insr_peer_close / insr_peer_free   unmap a peer's / release the own allocation (after all ranks have stopped using it)
+ *   insr_peer_status  1 if a barrier of a kernel below gave up after 60 s without its peers (results are then invalid),
+ *                     0 otherwise; synchronises the device; reset != 0 clears the flag
+ *
+ * Layout contract: every rank allocates the same size and keeps the same quantities at the same offsets.  bases[r] is THIS
+ * process's mapping of rank r's allocation (bases[rank] = the own one).  Every rank must issue the same sequence of the two
+ * calls below on the same allocation set, with the same sizes (they contain a flag barrier across the ranks).
+ *
+ *   insr_peer_allreduce         out[i] = scale * sum_r data_r[offset_floats + i], i < n, summed in rank order on every rank
+ *                               (bit-identical results); out is ordinary device memory, NOT part of a peer allocation;
+ *                               offset_floats counts from the allocation's base (>= 1024: behind the header), multiple of 4
+ *   insr_iteration_update_peer  insr_iteration_update with that reduction folded in: grad[k] and losses point INTO the own
+ *                               peer allocation (peer_bytes = its total size); the kernel reads every rank's gradients and
+ *                               loss slots, applies `scale`, runs Adam / the plateau schedule / the loss log on the reduced
+ *                               values (losses_red: n_losses floats of ordinary device memory) and leaves the own
+ *                               gradient (zero_grad) and loss slots (clear_losses) zeroed once no peer reads them any more
+ */
+int insr_peer_alloc(int64_t data_bytes, void **base, unsigned char *handle64);
+int insr_peer_open(const unsigned char *handle64, void **base);
+int insr_peer_close(void *base);
+int insr_peer_free(void *base);
+int insr_peer_status(void *base, int reset);
+int insr_peer_allreduce(int world, int rank, void *const *bases, int64_t offset_floats, int64_t n, float scale, float *out,
+                        void *stream);
+int insr_iteration_update_peer(int world, int rank, void *const *bases, int64_t peer_bytes, float scale, int n_slots,
+                               float *const *theta, float *const *grad, float *const *exp_avg, float *const *exp_avg_sq,
+                               const int64_t *n, float *sched, float *losses, int n_losses, int main_index, float *losses_red,
+                               float *hist, int64_t hist_capacity, int64_t *hist_idx, float beta1, float beta2, float eps,
+                               float factor, int patience, float threshold, float min_lr, float eps_lr, int zero_grad,
+                               int clear_losses, void *stream);
 
 /*
  * Batched 2x2 / 3x3 singular value decomposition and the fused elasticity energy.

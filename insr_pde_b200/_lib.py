@@ -24,6 +24,8 @@ EXPORTS = [
     "insr_siren_forward", "insr_siren_backward", "insr_siren_lsq_step", "insr_siren_kernel_family",
     "insr_launch_count", "insr_adam_step", "insr_plateau_step", "insr_svd_small", "insr_elastic_energy", "insr_sample_boxes", "insr_sample_mesh", "insr_siren_tape_supported", "insr_elastic_terms", "insr_iteration_update",
     "insr_siren_target",
+    "insr_peer_alloc", "insr_peer_open", "insr_peer_close", "insr_peer_free", "insr_peer_status", "insr_peer_allreduce",
+    "insr_iteration_update_peer",
 ]
 
 
@@ -85,7 +87,23 @@ class Library:
         c.insr_elastic_energy.argtypes = [_vp, _i64, _i32, _f, _f, _vp, _vp, _vp]
         c.insr_iteration_update.restype = _i32
         c.insr_iteration_update.argtypes = [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp] + \
-            [ctypes.c_float] * 4 + [_i32] + [ctypes.c_float] * 3 + [_i32, _vp]
+            [ctypes.c_float] * 4 + [_i32] + [ctypes.c_float] * 3 + [_i32, _i32, _vp]
+        c.insr_peer_alloc.restype = _i32
+        c.insr_peer_alloc.argtypes = [_i64, ctypes.POINTER(_vp), ctypes.c_char_p]
+        c.insr_peer_open.restype = _i32
+        c.insr_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(_vp)]
+        c.insr_peer_close.restype = _i32
+        c.insr_peer_close.argtypes = [_vp]
+        c.insr_peer_free.restype = _i32
+        c.insr_peer_free.argtypes = [_vp]
+        c.insr_peer_status.restype = _i32
+        c.insr_peer_status.argtypes = [_vp, _i32]
+        c.insr_peer_allreduce.restype = _i32
+        c.insr_peer_allreduce.argtypes = [_i32, _i32, _vp, _i64, _i64, ctypes.c_float, _vp, _vp]
+        c.insr_iteration_update_peer.restype = _i32
+        c.insr_iteration_update_peer.argtypes = [_i32, _i32, _vp, _i64, ctypes.c_float, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                                                 _vp, _vp, _i64, _vp] + [ctypes.c_float] * 4 + [_i32] + [ctypes.c_float] * 3 + \
+            [_i32, _i32, _vp]
         c.insr_elastic_terms.restype = _i32
         c.insr_elastic_terms.argtypes = [ctypes.POINTER(ElasticTermsDesc), _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
         c.insr_sample_mesh.restype = _i32
@@ -132,13 +150,53 @@ class Library:
         self.check(self.cdll.insr_adam_step(theta, grad, m, v, n, sched, beta1, beta2, eps, stream))
 
     def iteration_update(self, thetas, grads, ms, vs, sizes, sched, losses, n_losses, main_index, hist, hist_capacity,
-                         hist_idx, ticket, beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr, zero_grad, stream):
+                         hist_idx, ticket, beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr, zero_grad, stream,
+                         clear_losses=False):
         k = len(thetas)
         arr = lambda ptrs: (ctypes.c_void_p * k)(*ptrs)
         self.check(self.cdll.insr_iteration_update(k, arr(thetas), arr(grads), arr(ms), arr(vs), (ctypes.c_int64 * k)(*sizes),
                                                    sched, losses, n_losses, main_index, hist, hist_capacity, hist_idx, ticket,
                                                    beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr,
-                                                   int(zero_grad), stream))
+                                                   int(zero_grad), int(clear_losses), stream))
+
+    # ---- peer memory (one box, one process per GPU): see include/insr_b200.h
+    def peer_alloc(self, data_bytes):
+        """-> (base address, 64-byte IPC handle)"""
+        base = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        self.check(self.cdll.insr_peer_alloc(int(data_bytes), ctypes.byref(base), handle))
+        return int(base.value), handle.raw
+
+    def peer_open(self, handle):
+        base = ctypes.c_void_p()
+        self.check(self.cdll.insr_peer_open(ctypes.create_string_buffer(bytes(handle), 64), ctypes.byref(base)))
+        return int(base.value)
+
+    def peer_close(self, base):
+        self.check(self.cdll.insr_peer_close(base))
+
+    def peer_free(self, base):
+        self.check(self.cdll.insr_peer_free(base))
+
+    def peer_status(self, base, reset=False):
+        rc = self.cdll.insr_peer_status(base, int(reset))
+        if rc < 0 or rc > 1:
+            self.check(rc)
+        return rc
+
+    def peer_allreduce(self, world, rank, bases, offset_floats, n, scale, out, stream):
+        self.check(self.cdll.insr_peer_allreduce(world, rank, (ctypes.c_void_p * world)(*bases), offset_floats, n, scale, out, stream))
+
+    def iteration_update_peer(self, world, rank, bases, peer_bytes, scale, thetas, grads, ms, vs, sizes, sched, losses, n_losses,
+                              main_index, losses_red, hist, hist_capacity, hist_idx, beta1, beta2, eps, factor, patience,
+                              threshold, min_lr, eps_lr, zero_grad, clear_losses, stream):
+        k = len(thetas)
+        arr = lambda ptrs: (ctypes.c_void_p * k)(*ptrs)
+        self.check(self.cdll.insr_iteration_update_peer(world, rank, (ctypes.c_void_p * world)(*bases), peer_bytes, scale, k,
+                                                        arr(thetas), arr(grads), arr(ms), arr(vs), (ctypes.c_int64 * k)(*sizes),
+                                                        sched, losses, n_losses, main_index, losses_red, hist, hist_capacity,
+                                                        hist_idx, beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr,
+                                                        int(zero_grad), int(clear_losses), stream))
 
     def plateau_step(self, loss, sched, factor, patience, threshold, min_lr, eps, stream):
         self.check(self.cdll.insr_plateau_step(loss, sched, factor, patience, threshold, min_lr, eps, stream))

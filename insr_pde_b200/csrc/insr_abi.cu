@@ -11,6 +11,7 @@
 #include "siren_fused.cuh"
 #include "siren_tiled_api.h"
 #include "optim_kernels.cuh"
+#include "peer_kernels.cuh"
 #include "linalg_kernels.cuh"
 #include "sampling_kernels.cuh"
 #include "siren_tc_target.cuh"
@@ -430,10 +431,10 @@ int insr_plateau_step(const float *loss, float *sched, float factor, int patienc
 }
 
 int insr_iteration_update(int n_slots, float *const *theta, float *const *grad, float *const *exp_avg,
-                          float *const *exp_avg_sq, const int64_t *n, float *sched, const float *losses, int n_losses,
+                          float *const *exp_avg_sq, const int64_t *n, float *sched, float *losses, int n_losses,
                           int main_index, float *hist, int64_t hist_capacity, int64_t *hist_idx, uint32_t *ticket, float beta1,
                           float beta2, float eps, float factor, int patience, float threshold, float min_lr, float eps_lr,
-                          int zero_grad, void *stream) {
+                          int zero_grad, int clear_losses, void *stream) {
     if (!theta || !grad || !exp_avg || !exp_avg_sq || !n || !sched || !losses || !ticket)
         return fail(INSR_ERR_NULL, "iteration_update: NULL argument");
     if (n_slots < 1 || n_slots > INSR_MAX_OPT_SLOTS)
@@ -457,10 +458,161 @@ int insr_iteration_update(int n_slots, float *const *theta, float *const *grad, 
     if (blocks > 8 * n_sm()) blocks = 8 * n_sm();
     auto kfn = k_iteration_update;
     INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(256), 0, stream, sl, sched, losses, n_losses, main_index, hist, hist_capacity,
-                hist_idx, ticket, beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr, zero_grad);
+                hist_idx, ticket, beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr, zero_grad, clear_losses);
     ++g_launches;
     return check_cuda("k_iteration_update");
 }
+
+// ---------------------------------------------------------------- peer memory (one box, one process per GPU)
+#ifdef INSR_CPU_EMU
+int insr_peer_alloc(int64_t, void **, unsigned char *) { return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build"); }
+int insr_peer_open(const unsigned char *, void **) { return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build"); }
+int insr_peer_close(void *) { return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build"); }
+int insr_peer_free(void *) { return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build"); }
+int insr_peer_status(void *, int) { return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build"); }
+int insr_peer_allreduce(int, int, void *const *, int64_t, int64_t, float, float *, void *) {
+    return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build");
+}
+int insr_iteration_update_peer(int, int, void *const *, int64_t, float, int, float *const *, float *const *, float *const *,
+                               float *const *, const int64_t *, float *, float *, int, int, float *, float *, int64_t, int64_t *,
+                               float, float, float, float, int, float, float, float, int, int, void *) {
+    return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build");
+}
+#else
+namespace {
+int peer_set(int world, int rank, void *const *bases, insr_peer_set *ps) {
+    if (!bases) return fail(INSR_ERR_NULL, "peer: bases is NULL");
+    if (world < 1 || world > INSR_PEER_MAX_WORLD || rank < 0 || rank >= world)
+        return fail(INSR_ERR_SHAPE, "peer: world=%d rank=%d (world 1..%d)", world, rank, INSR_PEER_MAX_WORLD);
+    ps->world = world; ps->rank = rank;
+    for (int r = 0; r < INSR_PEER_MAX_WORLD; ++r) ps->base[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        if (!bases[r]) return fail(INSR_ERR_NULL, "peer: mapping of rank %d is NULL", r);
+        if (reinterpret_cast<uintptr_t>(bases[r]) & 15u) return fail(INSR_ERR_ALIGN, "peer: mapping of rank %d is not 16-byte aligned", r);
+        ps->base[r] = static_cast<unsigned char *>(bases[r]);
+    }
+    return 0;
+}
+}  // namespace
+
+int insr_peer_alloc(int64_t data_bytes, void **base, unsigned char *handle64) {
+    if (!base || !handle64) return fail(INSR_ERR_NULL, "peer_alloc: NULL argument");
+    if (data_bytes < 0) return fail(INSR_ERR_SHAPE, "peer_alloc: data_bytes=%lld", (long long)data_bytes);
+    int rc = check_device();
+    if (rc) return rc;
+    void *p = nullptr;
+    const size_t bytes = (size_t)INSR_PEER_HEADER_BYTES + (((size_t)data_bytes + 255) & ~(size_t)255);
+    cudaError_t e = cudaMalloc(&p, bytes);              // a plain cudaMalloc: the only kind of allocation cudaIpcGetMemHandle exports
+    if (e != cudaSuccess) return fail((int)e, "peer_alloc: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    const uint32_t one = 1u;
+    if ((e = cudaMemset(p, 0, bytes)) != cudaSuccess ||
+        (e = cudaMemcpy(static_cast<uint32_t *>(p) + INSR_PEER_EPOCH_WORD, &one, 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), p)) != cudaSuccess) {
+        cudaFree(p);
+        cudaGetLastError();
+        return fail((int)e, "peer_alloc: %s", cudaGetErrorString(e));
+    }
+    *base = p;
+    return 0;
+}
+
+int insr_peer_open(const unsigned char *handle64, void **base) {
+    if (!handle64 || !base) return fail(INSR_ERR_NULL, "peer_open: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); }
+    *base = p;
+    return 0;
+}
+
+int insr_peer_close(void *base) {
+    if (!base) return 0;
+    cudaError_t e = cudaIpcCloseMemHandle(base);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "peer_close: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+int insr_peer_free(void *base) {
+    if (!base) return 0;
+    cudaError_t e = cudaFree(base);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "peer_free: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+int insr_peer_status(void *base, int reset) {
+    if (!base) return fail(INSR_ERR_NULL, "peer_status: NULL argument");
+    uint32_t v = 0;
+    uint32_t *w = static_cast<uint32_t *>(base) + INSR_PEER_STATUS_WORD;
+    cudaError_t e = cudaMemcpy(&v, w, 4, cudaMemcpyDeviceToHost);           // synchronises: a host-side health check, never in a loop
+    if (e == cudaSuccess && reset && v) { const uint32_t z = 0; e = cudaMemcpy(w, &z, 4, cudaMemcpyHostToDevice); }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "peer_status: %s", cudaGetErrorString(e)); }
+    return (int)v;                                      // 0 healthy, 1 a barrier timed out since the last reset
+}
+
+int insr_peer_allreduce(int world, int rank, void *const *bases, int64_t offset_floats, int64_t n, float scale, float *out,
+                        void *stream) {
+    insr_peer_set ps;
+    int rc = peer_set(world, rank, bases, &ps);
+    if (rc) return rc;
+    if (!out) return fail(INSR_ERR_NULL, "peer_allreduce: out is NULL");
+    if (n < 0 || offset_floats < INSR_PEER_HEADER_BYTES / 4 || (offset_floats & 3))
+        return fail(INSR_ERR_SHAPE, "peer_allreduce: n=%lld offset=%lld floats (offset must lie behind the %d-byte header, 16-byte aligned)",
+                    (long long)n, (long long)offset_floats, INSR_PEER_HEADER_BYTES);
+    if ((rc = check_device())) return rc;
+    int64_t blocks = (n / 4 + 511) / 512;
+    if (blocks < 1) blocks = 1;
+    if (blocks > INSR_PEER_MAX_CTAS) blocks = INSR_PEER_MAX_CTAS;
+    auto kfn = insr_peer::k_peer_allreduce;
+    INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(512), 0, stream, ps, offset_floats, n, scale, out);
+    ++g_launches;
+    return check_cuda("k_peer_allreduce");
+}
+
+int insr_iteration_update_peer(int world, int rank, void *const *bases, int64_t peer_bytes, float scale, int n_slots,
+                               float *const *theta, float *const *grad, float *const *exp_avg, float *const *exp_avg_sq,
+                               const int64_t *n, float *sched, float *losses, int n_losses, int main_index, float *losses_red,
+                               float *hist, int64_t hist_capacity, int64_t *hist_idx, float beta1, float beta2, float eps,
+                               float factor, int patience, float threshold, float min_lr, float eps_lr, int zero_grad,
+                               int clear_losses, void *stream) {
+    insr_peer_set ps;
+    int rc = peer_set(world, rank, bases, &ps);
+    if (rc) return rc;
+    if (!theta || !grad || !exp_avg || !exp_avg_sq || !n || !sched || !losses || !losses_red)
+        return fail(INSR_ERR_NULL, "iteration_update_peer: NULL argument");
+    if (n_slots < 1 || n_slots > INSR_MAX_OPT_SLOTS)
+        return fail(INSR_ERR_SHAPE, "iteration_update_peer: n_slots=%d (1..%d)", n_slots, INSR_MAX_OPT_SLOTS);
+    if (n_losses < 1 || n_losses > 32 || main_index < 0 || main_index >= n_losses)
+        return fail(INSR_ERR_SHAPE, "iteration_update_peer: n_losses=%d main_index=%d", n_losses, main_index);
+    if (hist && (!hist_idx || hist_capacity < 1)) return fail(INSR_ERR_NULL, "iteration_update_peer: a loss log needs its index word and a capacity");
+    const unsigned char *own = ps.base[rank];
+    auto inside = [&](const float *p, int64_t count) {
+        const unsigned char *b = reinterpret_cast<const unsigned char *>(p);
+        return b >= own + INSR_PEER_HEADER_BYTES && b + 4 * count <= own + peer_bytes;
+    };
+    if (!inside(losses, n_losses)) return fail(INSR_ERR_SHAPE, "iteration_update_peer: the loss slots are not inside this rank's peer allocation");
+    insr_opt_slots sl{};
+    sl.n_slots = n_slots;
+    int64_t total = 0;
+    for (int k = 0; k < n_slots; ++k) {
+        if (!theta[k] || !grad[k] || !exp_avg[k] || !exp_avg_sq[k] || n[k] < 0)
+            return fail(INSR_ERR_NULL, "iteration_update_peer: slot %d has a NULL buffer or a negative size", k);
+        if (!inside(grad[k], n[k])) return fail(INSR_ERR_SHAPE, "iteration_update_peer: gradient slot %d is not inside this rank's peer allocation", k);
+        sl.theta[k] = theta[k]; sl.grad[k] = grad[k]; sl.m[k] = exp_avg[k]; sl.v[k] = exp_avg_sq[k]; sl.n[k] = n[k];
+        total += n[k];
+    }
+    if ((rc = check_device())) return rc;
+    int64_t blocks = (total + 511) / 512;
+    if (blocks < 1) blocks = 1;
+    if (blocks > INSR_PEER_MAX_CTAS) blocks = INSR_PEER_MAX_CTAS;
+    auto kfn = insr_peer::k_iteration_update_peer;
+    INSR_LAUNCH(kfn, dim3((unsigned)blocks), dim3(512), 0, stream, ps, sl, scale, sched, losses, n_losses, main_index, losses_red,
+                hist, hist_capacity, hist_idx, beta1, beta2, eps, factor, patience, threshold, min_lr, eps_lr, zero_grad, clear_losses);
+    ++g_launches;
+    return check_cuda("k_iteration_update_peer");
+}
+#endif
 
 int insr_svd_small(const float *F, int64_t n, int d, float *U, float *S, float *V, void *stream) {
     if (!F || !S) return fail(INSR_ERR_NULL, "svd_small: F and S must not be NULL");

@@ -70,7 +70,8 @@ __global__ void k_plateau_step(const float *__restrict__ loss, float *__restrict
 // ReduceLROnPlateau on the main loss, the step counter, and the iteration's loss values appended to a device ring.
 // Every thread reads lr / t at entry; the LAST CTA to finish (ticket) applies the scheduler and writes the log, so no
 // thread can see the updated schedule.  Replaces 2 memsets + 2 Adam launches + plateau + stack / index_copy / counter
-// nodes of the iteration graph.
+// nodes of the iteration graph.  clear_losses: the loss slots (accumulated into by the closures' kernels) are zeroed after
+// they have been consumed, so that the iteration graph needs no fill node for them either.
 #define INSR_MAX_OPT_SLOTS 8
 struct insr_opt_slots {
     int n_slots;
@@ -78,10 +79,10 @@ struct insr_opt_slots {
     int64_t n[INSR_MAX_OPT_SLOTS];
 };
 
-__global__ void k_iteration_update(insr_opt_slots sl, float *__restrict__ sched, const float *__restrict__ losses, int n_losses,
+__global__ void k_iteration_update(insr_opt_slots sl, float *__restrict__ sched, float *__restrict__ losses, int n_losses,
                                    int main_index, float *__restrict__ hist, int64_t hist_capacity, int64_t *hist_idx,
                                    unsigned int *ticket, float beta1, float beta2, float eps, float factor, int patience,
-                                   float threshold, float min_lr, float eps_lr, int zero_grad) {
+                                   float threshold, float min_lr, float eps_lr, int zero_grad, int clear_losses) {
     const float lr = sched[0];
     const float t = sched[3] + 1.f;
     const insr_adam_consts c = insr_adam_prepare(lr, t, beta1, beta2);
@@ -118,6 +119,9 @@ __global__ void k_iteration_update(insr_opt_slots sl, float *__restrict__ sched,
                     for (int q = 0; q < n_losses; ++q) hist[idx * n_losses + q] = losses[q];
                 *hist_idx = idx + 1;
             }
+            // the loss slots are accumulators of the closures' kernels: left zeroed for the next iteration, like the gradients
+            if (clear_losses)
+                for (int q = 0; q < n_losses; ++q) losses[q] = 0.f;
             *ticket = 0u;
         }
     }

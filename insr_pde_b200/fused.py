@@ -69,6 +69,18 @@ class Losses(dict):
         self.vector = vector
 
 
+_ACC_PROVIDER = []          # innermost first-class owner of the loss slots (GraphedLoop._iteration pushes itself)
+
+
+def _acc(n, device):
+    """the ``n`` loss slots one closure call accumulates into.  Eager callers get a fresh zero vector; under a
+    ``GraphedLoop`` the slots are a slice of the loop's persistent vector (with data parallelism: of the buffer the ranks
+    exchange), which the iteration's update kernel leaves zeroed -- no fill node, no copy into the exchange buffer."""
+    if _ACC_PROVIDER:
+        return _ACC_PROVIDER[-1](n, device)
+    return torch.zeros(n, dtype=torch.float32, device=device)
+
+
 def lsq(net, x, order, cy, cj=None, cl=None, target=None, scale=None, out=None):
     """loss = scale * sum_{n,c} (sum_o cy[c,o] y + cj[c,o,:].J + cl[c,o] lap - target[n,c])^2 ;
     d loss / d theta is ACCUMULATED into flat_grad(net); returns the loss (1-element tensor).
@@ -187,7 +199,9 @@ def parallel(ref, *fns):
 # advection (1-D, constant velocity)
 # ------------------------------------------------------------------------------------------------
 def advect_initialize(field, samples, init_values):
-    return {"main": lsq(field, samples, ORDER_VALUE, [[1.0]], target=init_values)}
+    acc = _acc(1, samples.device)
+    lsq(field, samples, ORDER_VALUE, [[1.0]], target=init_values, out=acc[0:1])
+    return Losses(acc, ("main",))
 
 
 def advect_step(field, field_prev, samples, boundary_samples, dt, vel):
@@ -199,7 +213,7 @@ def advect_step(field, field_prev, samples, boundary_samples, dt, vel):
             target = u_prev / dt - (0.5 * vel) * j_prev[:, :, 0]
         return lsq(field, samples, ORDER_JAC, [[1.0 / dt]], cj=[[[0.5 * vel]]], target=target, out=acc[0:1])
 
-    acc = torch.zeros(2, dtype=torch.float32, device=samples.device)
+    acc = _acc(2, samples.device)
     parallel(samples, interior, lambda: lsq(field, boundary_samples, ORDER_VALUE, [[1.0]], out=acc[1:2]))
     return Losses(acc, ("main", "bc"))
 
@@ -214,7 +228,9 @@ def _no_slip_terms(velocity, bc_x, bc_y, out):
 
 
 def fluid_initialize(velocity, samples, init_values):
-    return {"main": lsq(velocity, samples, ORDER_VALUE, _eye(2), target=init_values)}
+    acc = _acc(1, samples.device)
+    lsq(velocity, samples, ORDER_VALUE, _eye(2), target=init_values, out=acc[0:1])
+    return Losses(acc, ("main",))
 
 
 def fluid_advect_velocity(velocity, velocity_prev, samples, bc_x, bc_y, dt):
@@ -231,7 +247,7 @@ def fluid_advect_velocity(velocity, velocity_prev, samples, bc_x, bc_y, dt):
             (u_adv,) = evaluate(velocity_prev, back, ORDER_VALUE)
         return lsq(velocity, x, ORDER_VALUE, _eye(2), target=u_adv, out=acc[0:1])
 
-    acc = torch.zeros(2, dtype=torch.float32, device=x.device)
+    acc = _acc(2, x.device)
     parallel(x, interior, *_no_slip_terms(velocity, bc_x, bc_y, acc[1:2]))
     return Losses(acc, ("main", "bc"))
 
@@ -245,7 +261,7 @@ def fluid_solve_pressure(velocity, pressure, samples, bc_x, bc_y):
             div_u = jac_u[:, 0, 0] + jac_u[:, 1, 1]
         return lsq(pressure, samples, ORDER_LAP, [[0.0]], cl=[[1.0]], target=div_u, out=acc[0:1])
 
-    acc = torch.zeros(2, dtype=torch.float32, device=samples.device)
+    acc = _acc(2, samples.device)
     parallel(samples, interior,
              lambda: lsq(pressure, bc_x, ORDER_JAC, [[0.0]], cj=[[[1.0, 0.0]]], out=acc[1:2]),
              lambda: lsq(pressure, bc_y, ORDER_JAC, [[0.0]], cj=[[[0.0, 1.0]]], out=acc[1:2]))
@@ -263,7 +279,7 @@ def fluid_projection(velocity, velocity_prev, pressure, samples, bc_x, bc_y):
             target = u_prev - jac_p[:, 0, :]
         return lsq(velocity, samples, ORDER_VALUE, _eye(2), target=target, out=acc[0:1])
 
-    acc = torch.zeros(2, dtype=torch.float32, device=samples.device)
+    acc = _acc(2, samples.device)
     parallel(samples, interior, *_no_slip_terms(velocity, bc_x, bc_y, acc[1:2]))
     return Losses(acc, ("main", "bc"))
 
@@ -498,10 +514,10 @@ class DeviceOptimizer:
         _ops.plateau_step(main_loss.reshape(1), self.sched, self.factor, self.patience, self.threshold,
                           self.min_lr, 1e-8)
 
-    def update(self, losses, main_index, hist=None, hist_idx=None, zero_grad=True):
+    def update(self, losses, main_index, hist=None, hist_idx=None, zero_grad=True, clear_losses=False):
         """the whole tail of an iteration in ONE kernel (insr_iteration_update): Adam for every net, gradients zeroed for
         the next iteration, plateau schedule on ``losses[main_index]``, the loss values appended to ``hist[hist_idx++]``.
-        ``losses``: contiguous fp32 device vector of this iteration's loss terms."""
+        ``losses``: contiguous fp32 device vector of this iteration's loss terms (``clear_losses``: zeroed afterwards)."""
         if not hasattr(self, "_ticket"):
             self._ticket = torch.zeros(1, dtype=torch.int32, device=self.sched.device)
         lib = _ops._lib.get_lib()
@@ -512,7 +528,27 @@ class DeviceOptimizer:
                                  [t.numel() for _, t, _, _, _ in self.state], self.sched.data_ptr(), losses.data_ptr(),
                                  losses.numel(), main_index, _ops._ptr(hist), 0 if hist is None else hist.shape[0],
                                  _ops._ptr(hist_idx), self._ticket.data_ptr(), self.betas[0], self.betas[1], self.eps,
-                                 self.factor, self.patience, self.threshold, self.min_lr, 1e-8, zero_grad, _ops._stream(dev))
+                                 self.factor, self.patience, self.threshold, self.min_lr, 1e-8, zero_grad, _ops._stream(dev),
+                                 clear_losses=clear_losses)
+
+    def update_peer(self, peer, losses, main_index, hist=None, hist_idx=None, zero_grad=True, clear_losses=False, scale=None):
+        """``update`` with the data-parallel exchange folded in (insr_iteration_update_peer): the gradient buffers of the nets
+        and ``losses`` live in this rank's peer allocation (``peer``: a PeerBuffer); the kernel reads every rank's copy over
+        NVLink, averages (``scale`` = 1 / world) and applies Adam / schedule / log to the reduced values -- the iteration's
+        all-reduce and its optimiser step are ONE kernel, and the reduced gradient is never written."""
+        if not hasattr(self, "_losses_red"):
+            self._losses_red = torch.zeros(32, dtype=torch.float32, device=self.sched.device)
+        lib = _ops._lib.get_lib()
+        dev = self.sched.device
+        with _ops._DeviceGuard(dev):
+            lib.iteration_update_peer(peer.world, peer.rank, peer.bases, peer.bytes, (1.0 / peer.world) if scale is None else scale,
+                                      [t.data_ptr() for _, t, _, _, _ in self.state], [g.data_ptr() for _, _, g, _, _ in self.state],
+                                      [m.data_ptr() for _, _, _, m, _ in self.state], [v.data_ptr() for _, _, _, _, v in self.state],
+                                      [t.numel() for _, t, _, _, _ in self.state], self.sched.data_ptr(), losses.data_ptr(),
+                                      losses.numel(), main_index, self._losses_red.data_ptr(), _ops._ptr(hist),
+                                      0 if hist is None else hist.shape[0], _ops._ptr(hist_idx), self.betas[0], self.betas[1],
+                                      self.eps, self.factor, self.patience, self.threshold, self.min_lr, 1e-8, zero_grad,
+                                      clear_losses, _ops._stream(dev))
 
     def zero_grads(self):
         for _, _, grad, _, _ in self.state:
@@ -533,14 +569,20 @@ class DeviceOptimizer:
 class SharedGradBuffer:
     """[g_theta(net 0) | g_theta(net 1) | ... | loss slots] in ONE fp32 buffer: the nets' flat gradient
     buffers ARE slices of it, so the fused kernels write there directly and the data-parallel exchange of an iteration --
-    parameter gradients and the loss values every rank must agree on for the LR schedule -- is a single all-reduce with
-    no flatten copy.  Graph-capturable (NCCL collectives record into CUDA graphs)."""
+    parameter gradients and the loss values every rank must agree on for the LR schedule -- moves one buffer with no
+    flatten copy.  Where the ranks can map each other's memory the buffer is PEER memory (``peer.PeerBuffer``) and the
+    exchange is the library's own one-shot reduction over NVLink, fused into the iteration's update kernel
+    (``DeviceOptimizer.update_peer``); otherwise a single NCCL all-reduce.  Both record into CUDA graphs."""
 
     def __init__(self, nets, n_scalars=4, group=None):
+        from . import peer as _peer
         sizes = [n.flat_theta().numel() for n in nets]
         padded = [(sz + 3) // 4 * 4 for sz in sizes]            # every slice 16-byte aligned (C ABI requirement)
         dev = nets[0].flat_theta().device
-        self.buf = torch.zeros(sum(padded) + n_scalars, dtype=torch.float32, device=dev)
+        total = sum(padded) + n_scalars
+        self.peer = _peer.PeerBuffer.create(total, dev, group) if dev.type == "cuda" else None
+        self.buf = self.peer.data if self.peer is not None else torch.zeros(total, dtype=torch.float32, device=dev)
+        self.nets = list(nets)
         off = 0
         for n, sz, pd in zip(nets, sizes, padded):
             n._flat_grad = self.buf[off:off + sz]
@@ -550,17 +592,30 @@ class SharedGradBuffer:
         self.group = group
 
     def allreduce(self, values):
-        """values: list of 0-dim loss tensors of this rank -> list of their means over the ranks; the gradients are
-        averaged in place by the same collective"""
+        """values: this rank's loss terms (a vector, or a list of 0-dim tensors; may BE ``scalars``) -> their means over the
+        ranks as views of ``scalars``; the gradients are averaged in place by the same NCCL collective"""
         import torch.distributed as tdist
         k = len(values)
         if k > self.scalars.numel():
             raise ValueError(f"{k} loss terms, {self.scalars.numel()} slots")
-        self.scalars[:k].copy_(values if torch.is_tensor(values) else torch.stack([v.reshape(()) for v in values]))
+        if not (torch.is_tensor(values) and values.data_ptr() == self.scalars.data_ptr()):
+            self.scalars[:k].copy_(values if torch.is_tensor(values) else torch.stack([v.reshape(()) for v in values]))
         if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(self.group) > 1:
             tdist.all_reduce(self.buf, group=self.group)
             self.buf.div_(tdist.get_world_size(self.group))
         return [self.scalars[i] for i in range(k)]
+
+    def close(self):
+        """collective: release the peer allocation; the nets go back to private gradient buffers"""
+        if self.peer is None:
+            return
+        for n in self.nets:
+            n._flat_grad = None
+            for p in n.parameters():
+                p.grad = None
+        self.buf = self.scalars = None
+        self.peer.close()
+        self.peer = None
 
 
 class GraphedLoop:
@@ -571,29 +626,54 @@ class GraphedLoop:
 
     def __init__(self, nets, lr, closure, capacity=20000, data_parallel=False):
         self.nets, self.closure = list(nets), closure
-        # data_parallel: every rank runs the closure on its shard; ONE all-reduce per iteration inside the graph
+        # data_parallel: every rank runs the closure on its shard; ONE exchange per iteration inside the graph
         self.shared = SharedGradBuffer(self.nets) if data_parallel else None
         self.opt = DeviceOptimizer(self.nets, lr)
         self.capacity = capacity
         self.hist = None
         self.idx = torch.zeros(1, dtype=torch.long, device=self.opt.sched.device)
+        # the loss slots of an iteration: the closures' kernels accumulate into them (``_acc``), the update kernel consumes
+        # and re-zeroes them.  With data parallelism they are the tail of the exchanged buffer.
+        self.slots = self.shared.scalars if self.shared is not None else torch.zeros(4, dtype=torch.float32, device=self.opt.sched.device)
+        self._slot_off = 0
         self.graph = None
 
+    def _provide(self, n, device):
+        if device != self.slots.device or self._slot_off + n > self.slots.numel():
+            return torch.zeros(n, dtype=torch.float32, device=device)
+        out = self.slots[self._slot_off:self._slot_off + n]
+        self._slot_off += n
+        return out
+
     def _iteration(self):
-        # the gradient buffers are zero here: zeroed by run() before the first iteration, then by every update kernel
-        loss_dict = self.closure()
+        # the gradient buffers and the loss slots are zero here: zeroed by run() before the first iteration, then by every
+        # update kernel
+        self._slot_off = 0
+        _ACC_PROVIDER.append(self._provide)
+        try:
+            loss_dict = self.closure()
+        finally:
+            _ACC_PROVIDER.pop()
         _backward_if_needed(loss_dict)
         keys = list(loss_dict)
+        k = len(keys)
         vector = loss_dict.vector if isinstance(loss_dict, Losses) else None
-        if self.shared is not None:
-            self.shared.allreduce(vector if vector is not None else [loss_dict[k] for k in keys])
-            vals = self.shared.scalars[:len(keys)]             # averaged over the ranks, already contiguous
-        else:
-            vals = vector if vector is not None else torch.stack([loss_dict[k].reshape(()) for k in keys])
+        own = vector is not None and vector.data_ptr() == self.slots.data_ptr() and vector.numel() == k
         if self.hist is None:
-            self.hist = torch.zeros(self.capacity, len(keys), device=vals.device)
+            self.hist = torch.zeros(self.capacity, k, device=self.slots.device)
+        if self.shared is not None and self.shared.peer is not None:
+            # exchange + Adam (all nets) + zero_grad + plateau + loss log: ONE kernel over peer memory
+            if not own:
+                self.slots[:k].copy_(vector if vector is not None else torch.stack([loss_dict[q].reshape(()) for q in keys]))
+            self.opt.update_peer(self.shared.peer, self.slots[:k], keys.index("main"), self.hist, self.idx, clear_losses=own)
+            return keys
+        if self.shared is not None:
+            self.shared.allreduce(self.slots[:k] if own else (vector if vector is not None else [loss_dict[q] for q in keys]))
+            vals = self.shared.scalars[:k]                     # averaged over the ranks, already contiguous
+        else:
+            vals = vector if vector is not None else torch.stack([loss_dict[q].reshape(()) for q in keys])
         # Adam (all nets) + zero_grad + plateau + loss log: one kernel
-        self.opt.update(vals, keys.index("main"), self.hist, self.idx)
+        self.opt.update(vals, keys.index("main"), self.hist, self.idx, clear_losses=own)
         return keys
 
     def reset(self, lr):
@@ -602,14 +682,18 @@ class GraphedLoop:
         self.idx.zero_()
 
     def close(self):
-        """drop the captured graph NOW (it holds the kernels -- with data_parallel, the NCCL all-reduce -- of one iteration):
-        a process group must not be destroyed while a captured graph still references its communicator"""
+        """drop the captured graph NOW (it holds the kernels -- with data_parallel, the exchange -- of one iteration): a
+        process group must not be destroyed, and peer memory not released, while a captured graph still references it.
+        Collective when data_parallel (every rank closes its loops in the same order)."""
         if self.graph is not None:
             torch.cuda.synchronize()
             self.graph = None
+        if self.shared is not None:
+            self.shared.close()
 
     def run(self, n_iters, early_stop=False, check_every=100):
         self.opt.zero_grads()                          # whatever ran on these nets in between may have left gradients
+        self.slots.zero_()
         if self.graph is None:
             keys = self._iteration()                   # iteration 0 eagerly (also warms everything up)
             self.keys = keys

@@ -93,10 +93,26 @@ def test_auxiliary_entry_points_validate_before_touching_the_device(lib):
     arr = (ctypes.c_void_p * 1)(p)
     sizes = (ctypes.c_int64 * 1)(8)
     args = [ctypes.c_float(0.9), ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_float(0.1), 500,
-            ctypes.c_float(1e-4), ctypes.c_float(1e-8), ctypes.c_float(1e-8), 1, None]
+            ctypes.c_float(1e-4), ctypes.c_float(1e-8), ctypes.c_float(1e-8), 1, 0, None]
     assert c.insr_iteration_update(0, arr, arr, arr, arr, sizes, p, p, 1, 0, None, 0, None, p, *args) == -2    # no slots
     assert c.insr_iteration_update(1, arr, arr, arr, arr, sizes, p, p, 2, 2, None, 0, None, p, *args) == -2    # main index out of range
     assert c.insr_iteration_update(1, arr, arr, arr, arr, sizes, p, p, 1, 0, p, 0, None, p, *args) == -1       # log without index word
+    # peer memory: argument validation happens before any CUDA call
+    bases = (ctypes.c_void_p * 2)(p, p)
+    assert c.insr_peer_alloc(-1, ctypes.byref(ctypes.c_void_p()), ctypes.create_string_buffer(64)) == -2
+    assert c.insr_peer_alloc(16, None, None) == -1
+    assert c.insr_peer_open(None, None) == -1
+    assert c.insr_peer_allreduce(0, 0, bases, 1024, 8, 1.0, p, None) == -2          # world must be 1..16
+    assert c.insr_peer_allreduce(2, 2, bases, 1024, 8, 1.0, p, None) == -2          # rank outside the world
+    assert c.insr_peer_allreduce(2, 0, bases, 512, 8, 1.0, p, None) == -2           # data offset inside the header
+    assert c.insr_peer_allreduce(2, 0, bases, 1026, 8, 1.0, p, None) == -2          # data offset not 16-byte aligned
+    assert c.insr_peer_allreduce(2, 0, bases, 1024, 8, 1.0, None, None) == -1
+    assert c.insr_peer_allreduce(2, 0, (ctypes.c_void_p * 2)(p, None), 1024, 8, 1.0, p, None) == -1   # a peer mapping is missing
+    pargs = [ctypes.c_float(0.9), ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_float(0.1), 500,
+             ctypes.c_float(1e-4), ctypes.c_float(1e-8), ctypes.c_float(1e-8), 1, 1, None]
+    # gradient / loss slots must lie inside the own peer allocation (behind its header)
+    assert c.insr_iteration_update_peer(2, 0, bases, 8192, 0.5, 1, arr, arr, arr, arr, sizes, p, p, 1, 0, p, None, 0, None, *pargs) == -2
+    assert b"not inside this rank's peer allocation" in c.insr_last_error()
     # tape: offered for the tiled family on one workspace chunk only, never for the H <= 32 family or forced-generic
     assert lib.tape_supported(_lib.make_desc(2, 2, 68, 3), 20000, 1)
     assert not lib.tape_supported(_lib.make_desc(2, 1, 32, 3), 20000, 2)
