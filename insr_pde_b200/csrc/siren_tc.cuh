@@ -152,45 +152,85 @@ __host__ __device__ inline int pow2_cols(int c) {
     return r;
 }
 
-// stage the small operands shared by the forward and the backward kernel
-__device__ __forceinline__ void stage_small(const Params &p, float *biasS, float *w1S, float *woS, float *boS) {
+// Staging.  At the scripts' batch sizes (one wave of tiles) the prologue is a visible part of a launch: a loop of
+// "load theta -> dependent shared-memory stores" pays one L2 (first touch: HBM) round trip per trip.  So every staging loop
+// issues its loads together, through the read-only path, before the first store (theta is never written by these kernels).
+constexpr int STAGE_BATCH = 8;
+
+// stage the small operands shared by the forward and the backward kernel (NTH threads; single trip for L <= NTH / 32)
+template <int NTH>
+__device__ __forceinline__ void stage_small_t(const Params &p, float *biasS, float *w1S, float *woS, float *boS) {
     const SirenDims &dm = p.dm;
     const int L = dm.L, H = dm.H, D = dm.D, O = dm.O, tid = threadIdx.x;
     const float w = dm.omega;
-    for (int idx = tid; idx < L * HP; idx += THREADS) {
-        const int l = idx / HP, j = idx % HP;
-        biasS[idx] = (j < H) ? w * p.theta[insr_b_offset(dm, l + 1) + j] : 0.f;
-    }
-    for (int idx = tid; idx < HP * 4; idx += THREADS) {
-        const int j = idx >> 2, d = idx & 3;
-        float v = 0.f;
-        if (j < H) {
-            if (d < D) v = w * p.theta[insr_w_offset(dm, 0) + (int64_t)j * D + d];
-            else if (d == 3) v = w * p.theta[insr_b_offset(dm, 0) + j];
+    // first trip of every vector: loads, then stores
+    float vb = 0.f, v1 = 0.f, vo = 0.f, vbo = 0.f;
+    {
+        if (tid < L * HP) { const int l = tid / HP, j = tid % HP; if (j < H) vb = __ldg(p.theta + insr_b_offset(dm, l + 1) + j); }
+        if (tid < HP * 4) {
+            const int j = tid >> 2, d = tid & 3;
+            if (j < H) {
+                if (d < D) v1 = __ldg(p.theta + insr_w_offset(dm, 0) + (int64_t)j * D + d);
+                else if (d == 3) v1 = __ldg(p.theta + insr_b_offset(dm, 0) + j);
+            }
         }
-        w1S[idx] = v;
+        if (tid < 3 * HP) { const int o = tid / HP, j = tid % HP; if (o < O && j < H) vo = __ldg(p.theta + insr_w_offset(dm, L + 1) + (int64_t)o * H + j); }
+        if (tid < 4 && tid < O) vbo = __ldg(p.theta + insr_b_offset(dm, L + 1) + tid);
     }
-    for (int idx = tid; idx < 3 * HP; idx += THREADS) {
-        const int o = idx / HP, j = idx % HP;
-        woS[idx] = (o < O && j < H) ? p.theta[insr_w_offset(dm, L + 1) + (int64_t)o * H + j] : 0.f;
+    if (tid < L * HP) biasS[tid] = w * vb;
+    if (tid < HP * 4) w1S[tid] = w * v1;
+    if (tid < 3 * HP) woS[tid] = vo;
+    if (tid < 4) boS[tid] = vbo;
+    for (int idx = tid + NTH; idx < L * HP; idx += NTH) {          // deep nets with few threads only
+        const int l = idx / HP, j = idx % HP;
+        biasS[idx] = (j < H) ? w * __ldg(p.theta + insr_b_offset(dm, l + 1) + j) : 0.f;
     }
-    if (tid < 4) boS[tid] = (tid < O) ? p.theta[insr_b_offset(dm, L + 1) + tid] : 0.f;
+    static_assert(NTH >= HP * 4 && NTH >= 3 * HP, "w1 / wo are staged in one trip");
 }
-// hidden-layer weights split hi / lo in the UMMA K-major layout (omega folded in); transposed = B operand of
-// the data gradient (row = input neuron k, reduction index = output neuron j)
-__device__ __forceinline__ void stage_hidden(const Params &p, unsigned char *whi, unsigned char *wlo, bool transposed) {
+__device__ __forceinline__ void stage_small(const Params &p, float *biasS, float *w1S, float *woS, float *boS) {
+    stage_small_t<THREADS>(p, biasS, w1S, woS, boS);
+}
+// hidden-layer weights split hi / lo in the UMMA K-major layout (omega folded in); the transposed copy (wthi / wtlo, may be
+// NULL) is the B operand of the data gradient (row = input neuron k, reduction index = output neuron j)
+template <int NTH>
+__device__ __forceinline__ void stage_hidden_t(const Params &p, unsigned char *whi, unsigned char *wlo, unsigned char *wthi,
+                                               unsigned char *wtlo) {
     const SirenDims &dm = p.dm;
-    const int L = dm.L, H = dm.H;
+    const int L = dm.L, H = dm.H, total = L * HP * HP, tid = threadIdx.x;
     const float w = dm.omega;
-    for (int idx = threadIdx.x; idx < L * HP * HP; idx += THREADS) {
-        const int l = idx / (HP * HP), j = (idx / HP) % HP, k = idx % HP;
-        float v = 0.f;
-        if (j < H && k < H) v = w * p.theta[insr_w_offset(dm, l + 1) + (int64_t)j * H + k];
-        const float hi = tf32_hi(v);
-        const int off = l * W_BYTES + (transposed ? op_off(k, j) : op_off(j, k));
-        *reinterpret_cast<float *>(whi + off) = hi;
-        *reinterpret_cast<float *>(wlo + off) = v - hi;
+    for (int base = 0; base < total; base += STAGE_BATCH * NTH) {
+        float vv[STAGE_BATCH];
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < STAGE_BATCH; ++i) {
+            const int idx = base + i * NTH + tid;
+            vv[i] = 0.f;
+            if (idx < total) {
+                const int l = idx / (HP * HP), j = (idx / HP) % HP, k = idx % HP;
+                if (j < H && k < H) vv[i] = __ldg(p.theta + insr_w_offset(dm, l + 1) + (int64_t)j * H + k);
+            }
+        }
+        INSR_PRAGMA_UNROLL
+        for (int i = 0; i < STAGE_BATCH; ++i) {
+            const int idx = base + i * NTH + tid;
+            if (idx < total) {
+                const int l = idx / (HP * HP), j = (idx / HP) % HP, k = idx % HP;
+                const float v = w * vv[i];
+                const float hi = tf32_hi(v);
+                if (whi) {
+                    *reinterpret_cast<float *>(whi + l * W_BYTES + op_off(j, k)) = hi;
+                    *reinterpret_cast<float *>(wlo + l * W_BYTES + op_off(j, k)) = v - hi;
+                }
+                if (wthi) {
+                    *reinterpret_cast<float *>(wthi + l * W_BYTES + op_off(k, j)) = hi;
+                    *reinterpret_cast<float *>(wtlo + l * W_BYTES + op_off(k, j)) = v - hi;
+                }
+            }
+        }
     }
+}
+__device__ __forceinline__ void stage_hidden(const Params &p, unsigned char *whi, unsigned char *wlo, bool transposed) {
+    if (transposed) stage_hidden_t<THREADS>(p, nullptr, nullptr, whi, wlo);
+    else stage_hidden_t<THREADS>(p, whi, wlo, nullptr, nullptr);
 }
 
 // =============================================================================================
@@ -561,38 +601,9 @@ __global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__
     long long tprev = 0;
 #endif
 
-    // ---- stage the weights (BT threads)
-    {
-        const float w = dm.omega;
-        for (int idx = tid; idx < L * HP * HP; idx += BT) {
-            const int l = idx / (HP * HP), j = (idx / HP) % HP, k = idx % HP;
-            float v = 0.f;
-            if (j < H && k < H) v = w * p.theta[insr_w_offset(dm, l + 1) + (int64_t)j * H + k];
-            const float hi = tf32_hi(v);
-            *reinterpret_cast<float *>(smraw + M.w_hi + l * W_BYTES + op_off(j, k)) = hi;
-            *reinterpret_cast<float *>(smraw + M.w_lo + l * W_BYTES + op_off(j, k)) = v - hi;
-            *reinterpret_cast<float *>(smraw + M.wt_hi + l * W_BYTES + op_off(k, j)) = hi;
-            *reinterpret_cast<float *>(smraw + M.wt_lo + l * W_BYTES + op_off(k, j)) = v - hi;
-        }
-        for (int idx = tid; idx < L * HP; idx += BT) {
-            const int l = idx / HP, j = idx % HP;
-            biasS[idx] = (j < H) ? w * p.theta[insr_b_offset(dm, l + 1) + j] : 0.f;
-        }
-        for (int idx = tid; idx < HP * 4; idx += BT) {
-            const int j = idx >> 2, d = idx & 3;
-            float v = 0.f;
-            if (j < H) {
-                if (d < D) v = w * p.theta[insr_w_offset(dm, 0) + (int64_t)j * D + d];
-                else if (d == 3) v = w * p.theta[insr_b_offset(dm, 0) + j];
-            }
-            w1S[idx] = v;
-        }
-        for (int idx = tid; idx < 3 * HP; idx += BT) {
-            const int o = idx / HP, j = idx % HP;
-            woS[idx] = (o < O && j < H) ? p.theta[insr_w_offset(dm, L + 1) + (int64_t)o * H + j] : 0.f;
-        }
-        if (tid < 4) boS[tid] = (tid < O) ? p.theta[insr_b_offset(dm, L + 1) + tid] : 0.f;
-    }
+    // ---- stage the weights (BT threads): loads first, stores after (see stage_hidden_t)
+    stage_hidden_t<BT>(p, smraw + M.w_hi, smraw + M.w_lo, smraw + M.wt_hi, smraw + M.wt_lo);
+    stage_small_t<BT>(p, biasS, w1S, woS, boS);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(s32(smraw + M.tmem)), "r"(512) : "memory");
@@ -820,15 +831,15 @@ __global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__
                 }
             }
         }
-        // output-layer gradients (this thread's 8 neurons; a_L recomputed from the tape) and the cotangent of
-        // the last sine layer
+        // output-layer gradients (this thread's 8 neurons; a_L recomputed from the tape), the cotangent of the last sine
+        // layer and -- from the SAME tape values, one L2 round trip instead of two -- its activation adjoint zbar_L
         float ab[S][8];
         {
             const float4 *tl = tape + (size_t)L * NQ * BT;
             float v[O][8];
             INSR_PRAGMA_UNROLL
             for (int q = 0; q < 2; ++q) {
-                float tv[TV][4], a[S][4];
+                float tv[TV][4], a[S][4], abq[S][4];
                 INSR_PRAGMA_UNROLL
                 for (int t = 0; t < TV; ++t) {
                     const float4 u = tl[(size_t)(q * TV + t) * BT + tid];
@@ -844,6 +855,20 @@ __global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__
                         for (int s = 0; s < S; ++s) acc = fmaf(g[o][s], a[s][c], acc);
                         v[o][4 * q + c] = acc;
                     }
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s)
+                    INSR_PRAGMA_UNROLL
+                    for (int c = 0; c < 4; ++c) {
+                        float acc = 0.f;
+                        INSR_PRAGMA_UNROLL
+                        for (int o = 0; o < O; ++o) acc = fmaf(woS[o * HP + NPT * part + 4 * q + c], g[o][s], acc);
+                        abq[s][c] = acc;
+                    }
+                insr_fused::adj4<D, ORDER>(tv, abq);
+                INSR_PRAGMA_UNROLL
+                for (int s = 0; s < S; ++s)
+                    INSR_PRAGMA_UNROLL
+                    for (int c = 0; c < 4; ++c) ab[s][4 * q + c] = abq[s][c];
             }
             INSR_PRAGMA_UNROLL
             for (int o = 0; o < O; ++o) {
@@ -856,38 +881,30 @@ __global__ void __launch_bounds__(BT, 1) k_tc_bwd(Params p, float4 *__restrict__
                 }
             }
         }
-        INSR_PRAGMA_UNROLL
-        for (int s = 0; s < S; ++s)
-            INSR_PRAGMA_UNROLL
-            for (int i = 0; i < 8; ++i) {
-                float acc = 0.f;
-                INSR_PRAGMA_UNROLL
-                for (int o = 0; o < O; ++o) acc = fmaf(woS[o * HP + NPT * part + i], g[o][s], acc);
-                ab[s][i] = acc;
-            }
-
         TCP(4);
         // ================= reverse sweep =================
         for (int l = L; l >= 1; --l) {
-            // ---- activation adjoint of layer l: ab (cotangent of a_l) -> zbar_l (in place)
+            // ---- activation adjoint of layer l: ab (cotangent of a_l) -> zbar_l (in place); layer L's was taken above
             const float4 *tl = tape + (size_t)l * NQ * BT;
-            INSR_PRAGMA_UNROLL
-            for (int q = 0; q < 2; ++q) {
-                float tv[TV][4], abq[S][4];
+            if (l < L) {
                 INSR_PRAGMA_UNROLL
-                for (int t = 0; t < TV; ++t) {
-                    const float4 v = tl[(size_t)(q * TV + t) * BT + tid];
-                    tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
+                for (int q = 0; q < 2; ++q) {
+                    float tv[TV][4], abq[S][4];
+                    INSR_PRAGMA_UNROLL
+                    for (int t = 0; t < TV; ++t) {
+                        const float4 v = tl[(size_t)(q * TV + t) * BT + tid];
+                        tv[t][0] = v.x; tv[t][1] = v.y; tv[t][2] = v.z; tv[t][3] = v.w;
+                    }
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s)
+                        INSR_PRAGMA_UNROLL
+                        for (int c = 0; c < 4; ++c) abq[s][c] = ab[s][4 * q + c];
+                    insr_fused::adj4<D, ORDER>(tv, abq);
+                    INSR_PRAGMA_UNROLL
+                    for (int s = 0; s < S; ++s)
+                        INSR_PRAGMA_UNROLL
+                        for (int c = 0; c < 4; ++c) ab[s][4 * q + c] = abq[s][c];
                 }
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s)
-                    INSR_PRAGMA_UNROLL
-                    for (int c = 0; c < 4; ++c) abq[s][c] = ab[s][4 * q + c];
-                insr_fused::adj4<D, ORDER>(tv, abq);
-                INSR_PRAGMA_UNROLL
-                for (int s = 0; s < S; ++s)
-                    INSR_PRAGMA_UNROLL
-                    for (int c = 0; c < 4; ++c) ab[s][4 * q + c] = abq[s][c];
             }
             TCP(5);
             // bias gradient of layer l: sum over points of the value-stream zbar

@@ -637,6 +637,7 @@ class GraphedLoop:
         self.slots = self.shared.scalars if self.shared is not None else torch.zeros(4, dtype=torch.float32, device=self.opt.sched.device)
         self._slot_off = 0
         self.graph = None
+        self.graph_ready = False                   # True once the capture has completed
 
     def _provide(self, n, device):
         if device != self.slots.device or self._slot_off + n > self.slots.numel():
@@ -713,6 +714,7 @@ class GraphedLoop:
                 try:
                     with torch.cuda.graph(self.graph):
                         self._iteration()
+                    self.graph_ready = True
                 finally:
                     if gc_was_on:
                         gc.enable()

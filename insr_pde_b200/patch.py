@@ -303,7 +303,8 @@ def install_graphed_loops(data_parallel: bool = False):
 
         def loop(self):
             nets = list(self._trainable_networks.values())
-            if not widths_ok or not all(p.is_cuda for n in nets for p in n.parameters()):
+            off = self.__dict__.setdefault("_insr_graph_off", set())
+            if name in off or not widths_ok or not all(p.is_cuda for n in nets for p in n.parameters()):
                 return method(self)                              # CPU tensors: the reference's own loop
             loops = self.__dict__.setdefault("_insr_loops", {})
             if name not in loops:
@@ -311,7 +312,19 @@ def install_graphed_loops(data_parallel: bool = False):
                                                 data_parallel=data_parallel)
             else:
                 loops[name].reset(self.cfg.lr)
-            hist = loops[name].run(int(self.max_n_iters), early_stop=bool(self.cfg.early_stop))
+            try:
+                hist = loops[name].run(int(self.max_n_iters), early_stop=bool(self.cfg.early_stop))
+            except RuntimeError as e:
+                if loops[name].graph is not None and loops[name].graph_ready or "capture" not in str(e).lower() or data_parallel:
+                    raise
+                # the closure does something a CUDA graph cannot record (host-side sampling with a pageable copy, a
+                # synchronising call): this loop stays on the eager fused closures (one iteration has been taken already)
+                sys.stderr.write(f"insr_pde_b200: {type(self).__name__}.{name} cannot be captured as a CUDA graph ({str(e)[:120]}); "
+                                 "running it eagerly on the fused closures\n")
+                loops.pop(name).graph = None
+                off.add(name)
+                torch.cuda.synchronize()
+                return method(self)
             self.train_step = len(hist)
             for i, values in enumerate(hist):                   # the .item() logging of :116-118, in bulk
                 self.tb.add_scalars(name, values, global_step=i)
@@ -323,7 +336,24 @@ def install_graphed_loops(data_parallel: bool = False):
 
     adv = importlib.import_module("advection.model").Advection1DModel
     flu = importlib.import_module("fluid.model").Fluid2DModel
-    ela = importlib.import_module("elasticity.model").ElasticityModel
+    ela_mod = importlib.import_module("elasticity.model")
+    ela = ela_mod.ElasticityModel
+    # elasticity/sampling.py:4-9 draws the tetrahedron samples with numpy on the host and copies them (not capturable, and a
+    # host round trip per iteration): under the graphed loop the mesh is sampled by insr_sample_mesh on the device -- the
+    # same distribution from the library's Philox stream (keyed by torch's seed), one sampler per (V, F)
+    from .sampling import MeshSampler
+    samplers = {}
+
+    def sample_mesh(V, F, N, distrib=None):
+        if not V.is_cuda:
+            return ela_mod._insr_sample_mesh_ref(V, F, N, distrib)
+        key = (V.data_ptr(), F.data_ptr(), tuple(V.shape), tuple(F.shape))
+        if key not in samplers:
+            samplers[key] = MeshSampler(V, F, dim_out=3, seed=int(torch.initial_seed()) & 0x7FFFFFFF)
+        return samplers[key].sample(int(N))
+    if not hasattr(ela_mod, "_insr_sample_mesh_ref"):
+        ela_mod._insr_sample_mesh_ref = ela_mod.sample_mesh
+        ela_mod.sample_mesh = sample_mesh
     for cls, names in ((adv, ("_initialize", "_advect")), (flu, ("_initialize", "_advect_velocity", "_solve_pressure", "_projection")),
                        (ela, ("_solve_deformation",))):
         for name in names:

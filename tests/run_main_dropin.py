@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
 
-device, fused_closures, argv = sys.argv[1], sys.argv[2] == "1", sys.argv[3:]
+device, fused_closures, graphed, argv = sys.argv[1], sys.argv[2] in ("1", "2"), sys.argv[2] == "2", sys.argv[3:]
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -85,7 +85,7 @@ if reference_only:
         sys.argv = old_argv
         os.chdir(old_cwd)
 else:
-    patch.run_main(argv, root, fused_closures=fused_closures)
+    patch.run_main(argv, root, fused_closures=fused_closures, graphed=graphed)
 if torch.cuda.is_available():
     torch.cuda.synchronize()
 _elapsed = time.perf_counter() - _t0

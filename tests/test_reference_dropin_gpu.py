@@ -93,10 +93,12 @@ MAIN_CASES = {
 
 
 @pytest.mark.parametrize("case", sorted(MAIN_CASES))
-@pytest.mark.parametrize("closures", [0, 1])
+@pytest.mark.parametrize("closures", [0, 1, 2])
 def test_patched_main_py_runs_the_scripts(case, closures, tmp_path):
     """python main.py <script arguments> of the reference, unchanged, through patch.run_main on cuda:0 (closures=1: with
-    INSR_FUSED_CLOSURES): every frame's output and checkpoint is written and the losses are finite"""
+    INSR_FUSED_CLOSURES; closures=2: --insr-graphed, the CUDA-graphed iteration under @_training_loop -- for the bunny that
+    includes the device-side mesh sampler in place of the reference's host-side one): every frame's output and checkpoint is
+    written and the losses are finite"""
     argv = MAIN_CASES[case] + ["--proj_dir", str(tmp_path), "--tag", case]
     res = subprocess.run([sys.executable, "-W", "ignore", os.path.join(ROOT, "tests", "run_main_dropin.py"), "cuda", str(closures), *argv],
                          capture_output=True, text=True, timeout=900)
