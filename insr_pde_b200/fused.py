@@ -624,8 +624,12 @@ class GraphedLoop:
     cudaGraphLaunch.  Loss values are written to a device ring and read back in bulk; the early-stop test
     (lr <= 1.1e-8, base/baseModel.py:132-134) is evaluated every ``check_every`` iterations."""
 
-    def __init__(self, nets, lr, closure, capacity=20000, data_parallel=False):
+    def __init__(self, nets, lr, closure, capacity=20000, data_parallel=False, presample=None):
         self.nets, self.closure = list(nets), closure
+        # presample: draws the NEXT iteration's points into the persistent buffers the closure reads.  It runs on a parallel
+        # branch beside the update kernel (the closure's kernels have consumed the current points by then), so the sampling
+        # kernel leaves the critical path of the iteration; run() draws the first set.  Iteration i still sees draw i.
+        self.presample = presample
         # data_parallel: every rank runs the closure on its shard; ONE exchange per iteration inside the graph
         self.shared = SharedGradBuffer(self.nets) if data_parallel else None
         self.opt = DeviceOptimizer(self.nets, lr)
@@ -666,7 +670,8 @@ class GraphedLoop:
             # exchange + Adam (all nets) + zero_grad + plateau + loss log: ONE kernel over peer memory
             if not own:
                 self.slots[:k].copy_(vector if vector is not None else torch.stack([loss_dict[q].reshape(()) for q in keys]))
-            self.opt.update_peer(self.shared.peer, self.slots[:k], keys.index("main"), self.hist, self.idx, clear_losses=own)
+            self._tail(lambda: self.opt.update_peer(self.shared.peer, self.slots[:k], keys.index("main"), self.hist, self.idx,
+                                                    clear_losses=own))
             return keys
         if self.shared is not None:
             self.shared.allreduce(self.slots[:k] if own else (vector if vector is not None else [loss_dict[q] for q in keys]))
@@ -674,8 +679,14 @@ class GraphedLoop:
         else:
             vals = vector if vector is not None else torch.stack([loss_dict[q].reshape(()) for q in keys])
         # Adam (all nets) + zero_grad + plateau + loss log: one kernel
-        self.opt.update(vals, keys.index("main"), self.hist, self.idx, clear_losses=own)
+        self._tail(lambda: self.opt.update(vals, keys.index("main"), self.hist, self.idx, clear_losses=own))
         return keys
+
+    def _tail(self, update):
+        if self.presample is None:
+            update()
+        else:
+            parallel(self.slots, update, self.presample)
 
     def reset(self, lr):
         """reuse the captured graph for a new training loop: only the optimiser state and the log restart"""
@@ -695,6 +706,8 @@ class GraphedLoop:
     def run(self, n_iters, early_stop=False, check_every=100):
         self.opt.zero_grads()                          # whatever ran on these nets in between may have left gradients
         self.slots.zero_()
+        if self.presample is not None:
+            self.presample()                           # the first iteration's points
         if self.graph is None:
             keys = self._iteration()                   # iteration 0 eagerly (also warms everything up)
             self.keys = keys
@@ -748,7 +761,7 @@ class FluidStepper(_StepperBase):
         self.reducer_factory = reducer_factory
         self.graphed = graphed
         self.data_parallel = False                 # set by the caller for world > 1 with graphed=True
-        self.device_sampler, self.seed, self._samplers = device_sampler, seed, {}
+        self.device_sampler, self.seed, self._samplers, self._points = device_sampler, seed, {}, {}
         for p in self.prev.parameters():
             p.requires_grad_(False)
 
@@ -765,7 +778,11 @@ class FluidStepper(_StepperBase):
                 # every rank draws its own slice of ONE global Philox stream (point index offset by the rank)
                 self._samplers[n_shard_div] = sampling.BoxSampler(sets, 2, seed=self.seed, device=dev,
                                                                   point_offset=rank * per_rank)
-            return tuple(self._samplers[n_shard_div].sample())
+                self._points[n_shard_div] = torch.zeros(per_rank, 2, dtype=torch.float32, device=dev)
+            smp, buf = self._samplers[n_shard_div], self._points[n_shard_div]
+            if self.graphed:                 # drawn ahead by the loop (GraphedLoop.presample): the closure reads the buffer
+                return tuple(torch.split(buf, smp.sizes, dim=0))
+            return tuple(smp.sample(out=buf))
         x = sampling.sample_random(n // n_shard_div, 2, device=dev)
         bx = sampling.sample_boundary2D_separate(n // 100, "horizontal", device=dev)
         by = sampling.sample_boundary2D_separate(n // 100, "vertical", device=dev)
@@ -775,7 +792,12 @@ class FluidStepper(_StepperBase):
         if self.graphed:
             loops = self.__dict__.setdefault("_loops", {})
             if key not in loops:                       # capture once per closure kind, replay for every time step
-                loops[key] = GraphedLoop(nets, self.lr, lambda: closure(0), data_parallel=self.data_parallel)
+                pre = None
+                if self.device_sampler:
+                    div = world
+                    self._samples(div)                 # creates the sampler and its persistent point buffer
+                    pre = lambda: self._samplers[div].sample(out=self._points[div])
+                loops[key] = GraphedLoop(nets, self.lr, lambda: closure(0), data_parallel=self.data_parallel, presample=pre)
             else:
                 loops[key].reset(self.lr)
             return loops[key].run(n_iters)
@@ -789,19 +811,19 @@ class FluidStepper(_StepperBase):
         def c(i):
             x, _, _ = self._samples(world)
             return fluid_initialize(self.vel, x, init_fn(x))
-        return self._loop([self.vel], c, n_iters, key="initialize")
+        return self._loop([self.vel], c, n_iters, world=world, key="initialize")
 
     def step(self, n_iters, world=1):
         """advect -> pressure solve -> projection; returns the three loss histories"""
         nets = [self.vel, self.pres]
         self.prev.load_state_dict(self.vel.state_dict())
         h1 = self._loop(nets, lambda i: fluid_advect_velocity(self.vel, self.prev, *self._samples(world), self.dt), n_iters,
-                        key="advect")
+                        world=world, key="advect")
         h2 = self._loop(nets, lambda i: fluid_solve_pressure(self.vel, self.pres, *self._samples(world)), n_iters,
-                        key="pressure")
+                        world=world, key="pressure")
         self.prev.load_state_dict(self.vel.state_dict())
         h3 = self._loop(nets, lambda i: fluid_projection(self.vel, self.prev, self.pres, *self._samples(world)), n_iters,
-                        key="project")
+                        world=world, key="project")
         return h1, h2, h3
 
 
@@ -826,14 +848,18 @@ class AdvectionStepper(_StepperBase):
                 sets = [[(self.sr, (-half,), (half,))],
                         [(nb // 2, ((-1 - eps) * half,), ((-1 + eps) * half,)), (nb // 2, ((1 - eps) * half,), ((1 + eps) * half,))]]
                 self._sampler = sampling.BoxSampler(sets, 1, seed=self.seed, device=dev)
-            return tuple(self._sampler.sample())
+                self._points = torch.zeros(sum(self._sampler.sizes), 1, dtype=torch.float32, device=dev)
+            # drawn ahead by the loop (GraphedLoop.presample): the closure reads the persistent buffer
+            return tuple(torch.split(self._points, self._sampler.sizes, dim=0))
         return (sampling.sample_random(self.sr, 1, device=dev) * half, sampling.sample_boundary(nb, 1, device=dev) * half)
 
     def _loop(self, closure, n_iters, key):
         if self.graphed:
             loops = self.__dict__.setdefault("_loops", {})
             if key not in loops:
-                loops[key] = GraphedLoop([self.field], self.lr, lambda: closure(0))
+                self._samples()                        # creates the sampler and its persistent point buffer
+                loops[key] = GraphedLoop([self.field], self.lr, lambda: closure(0),
+                                         presample=lambda: self._sampler.sample(out=self._points))
             else:
                 loops[key].reset(self.lr)
             return loops[key].run(n_iters)
@@ -1036,11 +1062,11 @@ class ElasticityStepper(_StepperBase):
         return self._ebatch
 
     # --- the two training loops -----------------------------------------------------------------
-    def _loop(self, closure, n_iters, key):
+    def _loop(self, closure, n_iters, key, presample=None):
         if self.graphed:
             loops = self.__dict__.setdefault("_loops", {})
             if key not in loops:
-                loops[key] = GraphedLoop([self.defo], self.lr, lambda: closure(0))
+                loops[key] = GraphedLoop([self.defo], self.lr, lambda: closure(0), presample=presample)
             else:
                 loops[key].reset(self.lr)
             return loops[key].run(n_iters)
@@ -1067,15 +1093,14 @@ class ElasticityStepper(_StepperBase):
             batch.refresh(self.prev, self.pp)
 
         def c(i):
-            if batch is not None:
-                batch.draw()
+            if batch is not None:                      # its random rows are drawn ahead by the loop (presample = batch.draw)
                 return elasticity_solve_deformation(self.defo, self.prev, self.pp, None, None, None, dt=self.dt,
                                                     timestep=self.timestep, batch=batch, **self.kw)
             left, right = self._fixed(self.sr)
             return elasticity_solve_deformation(self.defo, self.prev, self.pp, self._interior(self.sr), left, right,
                                                 dt=self.dt, timestep=self.timestep, **self.kw)
         # the external-force term is a host-side branch on the time step: one captured graph per branch
-        return self._loop(c, n_iters, ("solve", forced))
+        return self._loop(c, n_iters, ("solve", forced), presample=batch.draw if batch is not None else None)
 
 
 def taylorgreen_velocity(samples):
