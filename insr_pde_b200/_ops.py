@@ -262,9 +262,10 @@ def elastic_energy(F, ratio_arap, ratio_volume, need_grad=True):
 
 def elastic_terms(y, J, x, y_prev, y_pp, n_left, n_right, *, dt, r_arap=0.0, r_volume=0.0, r_kinematics=0.0, r_left=0.0,
                   r_right=0.0, r_plane=0.0, plane_height=0.0, r_sphere=0.0, radius=0.0, external_force=None,
-                  offset_right=None, center=None):
+                  offset_right=None, center=None, loss_out=None):
     """every term of the elasticity closure and its cotangents in one kernel (include/insr_b200.h: insr_elastic_terms).
-    y (n + n_left + n_right, d), J (same rows, d, d) or None, x / y_prev / y_pp (n, d).  Returns (loss (1,), gy, gJ)."""
+    y (n + n_left + n_right, d), J (same rows, d, d) or None, x / y_prev / y_pp (n, d).  Returns (loss (1,), gy, gJ);
+    ``loss_out``: a 1-element fp32 view the loss is ACCUMULATED into instead of a fresh zero."""
     lib = _lib.get_lib()
     _require_cuda(y)
     d = y.shape[1]
@@ -284,7 +285,7 @@ def elastic_terms(y, J, x, y_prev, y_pp, n_left, n_right, *, dt, r_arap=0.0, r_v
         arr = getattr(t, name)
         for i in range(3):
             arr[i] = float(vals[i]) if vals is not None and i < len(vals) else 0.0
-    loss = torch.zeros(1, dtype=torch.float32, device=y.device)
+    loss = torch.zeros(1, dtype=torch.float32, device=y.device) if loss_out is None else loss_out
     gy = torch.empty_like(y)
     gJ = torch.empty_like(J) if J is not None else None
     if n_all:

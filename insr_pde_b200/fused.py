@@ -357,15 +357,16 @@ def elasticity_solve_deformation(deformation, prev, prev_prev, samples, fixed_le
             t.record_stream(torch.cuda.current_stream(samples.device))
     sign = -1.0 if "constraint_right_compress" in energy else 1.0
     forced = "external" in energy and timestep <= external_force_timesteps
+    acc = _acc(1, x_all.device)              # under a graphed loop: the loop's own loss slot (no fill, no copy into the log)
     loss, gy, gJ = _ops.elastic_terms(
         outs[0], outs[1] if order == ORDER_JAC else None, samples, y_prev, y_pp, n_left, n_right, dt=dt, r_arap=ra, r_volume=rv,
         r_kinematics=ratio_kinematics if "kinematics" in energy else 0.0, r_left=ratio_constraint if use_left else 0.0,
         r_right=ratio_constraint if use_right else 0.0, r_plane=ratio_collide if "collision" in energy else 0.0,
         plane_height=plane_height, r_sphere=ratio_collide if "collision_sphere" in energy else 0.0, radius=circle_radius,
         external_force=_host_vec(external_force) if forced else None,
-        offset_right=[sign * a for a in _host_vec(constraint_offset_right)], center=_host_vec(circle_center))
+        offset_right=[sign * a for a in _host_vec(constraint_offset_right)], center=_host_vec(circle_center), loss_out=acc[0:1])
     _ops.siren_backward(deformation.desc, theta, x_all, order, gy, gJ, None, gtheta=flat_grad(deformation), tape=tape)
-    return {"main": loss[0]}
+    return Losses(acc, ("main",))
 
 
 def elasticity_solve_deformation_autograd(deformation, prev, prev_prev, samples, fixed_left, fixed_right, *, dt, timestep, energy,
@@ -712,6 +713,15 @@ class GraphedLoop:
             keys = self._iteration()                   # iteration 0 eagerly (also warms everything up)
             self.keys = keys
             done = 1
+            if self.shared is not None and self.shared.peer is not None:
+                # the peer kernels give up (and say so) instead of hanging when a rank never shows up; find out now, on
+                # every rank together, rather than replaying a graph whose every iteration would wait for the time-out
+                import torch.distributed as tdist
+                ok = torch.tensor([1.0 if self.shared.peer.healthy() else 0.0], device=self.slots.device)
+                tdist.all_reduce(ok, op=tdist.ReduceOp.MIN, group=self.shared.group)
+                if float(ok.item()) < 0.5:
+                    raise RuntimeError("insr_pde_b200: the peer-memory exchange timed out on at least one rank "
+                                       "(set INSR_PEER_ALLREDUCE=0 for the NCCL exchange)")
         else:
             keys, done = self.keys, 0
         if n_iters > done:
