@@ -174,7 +174,7 @@ def siren_lsq_step(desc, theta, x, order, coef_y, coef_jac, coef_lap, target, sc
     return loss_out, gtheta
 
 
-def siren_target(x, n_res, a, b=None, mode=0, dt=0.0, lo=-1.0, hi=1.0):
+def siren_target(x, n_res, a, b=None, mode=0, dt=0.0, lo=-1.0, hi=1.0, out=None):
     """target (N, n_res) of a least-squares closure from one or two frozen fields in ONE kernel (include/insr_b200.h:
     insr_siren_target).  a, b: dicts with ``net`` (an MLP of the H <= 32 family), ``order`` and the coefficient lists
     ``cy`` (n_res x O), ``cj`` (n_res x O x D), ``cl`` (nested lists or None).  mode 0: a at x; 1: backtrace through a
@@ -195,7 +195,10 @@ def siren_target(x, n_res, a, b=None, mode=0, dt=0.0, lo=-1.0, hi=1.0):
         net = t["net"]
         return (net.desc, net.flat_theta().data_ptr(), t.get("order", 0), flat(t.get("cy")), flat(t.get("cj")), flat(t.get("cl")))
 
-    out = torch.empty(n, n_res, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(n, n_res, dtype=torch.float32, device=x.device)
+    elif tuple(out.shape) != (n, n_res) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+        raise ValueError("siren_target: out must be a contiguous fp32 (N, n_res) tensor on the points' device")
     if n:
         with _DeviceGuard(x.device):
             lib.target(pack(a), pack(b), mode, dt, lo, hi, x.data_ptr(), n, n_res, out.data_ptr(), _stream(x.device))

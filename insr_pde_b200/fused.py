@@ -141,7 +141,7 @@ def evaluate(net, x, order):
 _TARGET_OFF = set()          # (mode, shapes) for which insr_siren_target has no kernel: fall back to separate evaluations
 
 
-def _target(x, n_res, a, b=None, mode=0, dt=0.0):
+def _target(x, n_res, a, b=None, mode=0, dt=0.0, out=None):
     """the frozen-net side of a closure in one kernel where insr_siren_target serves the shapes; None otherwise"""
     def shape(t):
         n = t["net"]
@@ -150,7 +150,7 @@ def _target(x, n_res, a, b=None, mode=0, dt=0.0):
     if key in _TARGET_OFF or not x.is_cuda:
         return None
     try:
-        return _ops.siren_target(x, n_res, a, b, mode=mode, dt=dt)
+        return _ops.siren_target(x, n_res, a, b, mode=mode, dt=dt, out=out)
     except _ops._lib.InsrError as e:
         if e.code != -6:
             raise
@@ -204,14 +204,29 @@ def advect_initialize(field, samples, init_values):
     return Losses(acc, ("main",))
 
 
-def advect_step(field, field_prev, samples, boundary_samples, dt, vel):
-    """midpoint residual  (u - u_prev)/dt + vel (u_x + u_prev_x)/2  and Dirichlet band"""
+def _into(out, value):
+    """``value`` (N, R), in ``out`` where the caller provides a persistent buffer"""
+    if out is None:
+        return value
+    out.copy_(value.reshape(out.shape))
+    return out
+
+
+def advect_target(field_prev, samples, dt, vel, out=None):
+    """the frozen side of the midpoint residual: u_prev / dt - vel / 2 * d u_prev / dx  (advection/model.py:78-84)"""
+    target = _target(samples.detach().reshape(-1, 1), 1, dict(net=field_prev, order=ORDER_JAC, cy=[[1.0 / dt]], cj=[[[-0.5 * vel]]]), out=out)
+    if target is None:
+        u_prev, j_prev = evaluate(field_prev, samples, ORDER_JAC)
+        target = _into(out, u_prev / dt - (0.5 * vel) * j_prev[:, :, 0])
+    return target
+
+
+def advect_step(field, field_prev, samples, boundary_samples, dt, vel, target=None):
+    """midpoint residual  (u - u_prev)/dt + vel (u_x + u_prev_x)/2  and Dirichlet band; ``target``: the frozen side
+    (``advect_target``) where the caller has prepared it ahead"""
     def interior():
-        target = _target(samples.detach().reshape(-1, 1), 1, dict(net=field_prev, order=ORDER_JAC, cy=[[1.0 / dt]], cj=[[[-0.5 * vel]]]))
-        if target is None:
-            u_prev, j_prev = evaluate(field_prev, samples, ORDER_JAC)
-            target = u_prev / dt - (0.5 * vel) * j_prev[:, :, 0]
-        return lsq(field, samples, ORDER_JAC, [[1.0 / dt]], cj=[[[0.5 * vel]]], target=target, out=acc[0:1])
+        tgt = target if target is not None else advect_target(field_prev, samples, dt, vel)
+        return lsq(field, samples, ORDER_JAC, [[1.0 / dt]], cj=[[[0.5 * vel]]], target=tgt, out=acc[0:1])
 
     acc = _acc(2, samples.device)
     parallel(samples, interior, lambda: lsq(field, boundary_samples, ORDER_VALUE, [[1.0]], out=acc[1:2]))
@@ -233,18 +248,24 @@ def fluid_initialize(velocity, samples, init_values):
     return Losses(acc, ("main",))
 
 
-def fluid_advect_velocity(velocity, velocity_prev, samples, bc_x, bc_y, dt):
-    """semi-Lagrangian: u(x) = u_prev(clamp(x - u_prev(x) dt))"""
+def fluid_advect_target(velocity_prev, samples, dt, out=None):
+    """u_prev(clamp(x - u_prev(x) dt)): both evaluations, the clamp and nothing else in one kernel (fluid/model.py:78-87)"""
+    x = samples.detach().reshape(-1, 2)
+    u_adv = _target(x, 2, dict(net=velocity_prev, order=ORDER_VALUE), dict(net=velocity_prev, order=ORDER_VALUE, cy=_eye(2)),
+                    mode=1, dt=dt, out=out)
+    if u_adv is None:
+        (u_prev,) = evaluate(velocity_prev, x, ORDER_VALUE)
+        back = torch.clamp(x - u_prev * dt, min=-1.0, max=1.0)
+        u_adv = _into(out, evaluate(velocity_prev, back, ORDER_VALUE)[0])
+    return u_adv
+
+
+def fluid_advect_velocity(velocity, velocity_prev, samples, bc_x, bc_y, dt, target=None):
+    """semi-Lagrangian: u(x) = u_prev(clamp(x - u_prev(x) dt)); ``target``: the frozen side where prepared ahead"""
     x = samples.detach().reshape(-1, 2)
 
     def interior():
-        # u_prev(clamp(x - u_prev(x) dt)): both evaluations, the clamp and nothing else in one kernel
-        u_adv = _target(x, 2, dict(net=velocity_prev, order=ORDER_VALUE), dict(net=velocity_prev, order=ORDER_VALUE, cy=_eye(2)),
-                        mode=1, dt=dt)
-        if u_adv is None:
-            (u_prev,) = evaluate(velocity_prev, x, ORDER_VALUE)
-            back = torch.clamp(x - u_prev * dt, min=-1.0, max=1.0)
-            (u_adv,) = evaluate(velocity_prev, back, ORDER_VALUE)
+        u_adv = target if target is not None else fluid_advect_target(velocity_prev, x, dt)
         return lsq(velocity, x, ORDER_VALUE, _eye(2), target=u_adv, out=acc[0:1])
 
     acc = _acc(2, x.device)
@@ -252,13 +273,19 @@ def fluid_advect_velocity(velocity, velocity_prev, samples, bc_x, bc_y, dt):
     return Losses(acc, ("main", "bc"))
 
 
-def fluid_solve_pressure(velocity, pressure, samples, bc_x, bc_y):
-    """lap p = div u, Neumann band"""
+def fluid_pressure_target(velocity, samples, out=None):
+    """div u of the (detached) velocity (fluid/model.py:108-109)"""
+    div_u = _target(samples.detach().reshape(-1, 2), 1, dict(net=velocity, order=ORDER_JAC, cj=[[[1.0, 0.0], [0.0, 1.0]]]), out=out)
+    if div_u is None:
+        _, jac_u = evaluate(velocity, samples, ORDER_JAC)
+        div_u = _into(out, jac_u[:, 0, 0] + jac_u[:, 1, 1])
+    return div_u
+
+
+def fluid_solve_pressure(velocity, pressure, samples, bc_x, bc_y, target=None):
+    """lap p = div u, Neumann band; ``target``: div u where prepared ahead"""
     def interior():
-        div_u = _target(samples.detach().reshape(-1, 2), 1, dict(net=velocity, order=ORDER_JAC, cj=[[[1.0, 0.0], [0.0, 1.0]]]))
-        if div_u is None:
-            _, jac_u = evaluate(velocity, samples, ORDER_JAC)
-            div_u = jac_u[:, 0, 0] + jac_u[:, 1, 1]
+        div_u = target if target is not None else fluid_pressure_target(velocity, samples)
         return lsq(pressure, samples, ORDER_LAP, [[0.0]], cl=[[1.0]], target=div_u, out=acc[0:1])
 
     acc = _acc(2, samples.device)
@@ -268,16 +295,22 @@ def fluid_solve_pressure(velocity, pressure, samples, bc_x, bc_y):
     return Losses(acc, ("main", "bc"))
 
 
-def fluid_projection(velocity, velocity_prev, pressure, samples, bc_x, bc_y):
-    """u <- u_prev - grad p"""
+def fluid_projection_target(velocity_prev, pressure, samples, out=None):
+    """u_prev - grad p (fluid/model.py:131-137)"""
+    target = _target(samples.detach().reshape(-1, 2), 2, dict(net=velocity_prev, order=ORDER_VALUE, cy=_eye(2)),
+                     dict(net=pressure, order=ORDER_JAC, cj=[[[-1.0, 0.0]], [[0.0, -1.0]]]), mode=2, out=out)
+    if target is None:
+        (u_prev,) = evaluate(velocity_prev, samples, ORDER_VALUE)
+        _, jac_p = evaluate(pressure, samples, ORDER_JAC)
+        target = _into(out, u_prev - jac_p[:, 0, :])
+    return target
+
+
+def fluid_projection(velocity, velocity_prev, pressure, samples, bc_x, bc_y, target=None):
+    """u <- u_prev - grad p; ``target``: the frozen side where prepared ahead"""
     def interior():
-        target = _target(samples.detach().reshape(-1, 2), 2, dict(net=velocity_prev, order=ORDER_VALUE, cy=_eye(2)),
-                         dict(net=pressure, order=ORDER_JAC, cj=[[[-1.0, 0.0]], [[0.0, -1.0]]]), mode=2)
-        if target is None:
-            (u_prev,) = evaluate(velocity_prev, samples, ORDER_VALUE)
-            _, jac_p = evaluate(pressure, samples, ORDER_JAC)
-            target = u_prev - jac_p[:, 0, :]
-        return lsq(velocity, samples, ORDER_VALUE, _eye(2), target=target, out=acc[0:1])
+        tgt = target if target is not None else fluid_projection_target(velocity_prev, pressure, samples)
+        return lsq(velocity, samples, ORDER_VALUE, _eye(2), target=tgt, out=acc[0:1])
 
     acc = _acc(2, samples.device)
     parallel(samples, interior, *_no_slip_terms(velocity, bc_x, bc_y, acc[1:2]))
@@ -625,8 +658,22 @@ class GraphedLoop:
     cudaGraphLaunch.  Loss values are written to a device ring and read back in bulk; the early-stop test
     (lr <= 1.1e-8, base/baseModel.py:132-134) is evaluated every ``check_every`` iterations."""
 
-    def __init__(self, nets, lr, closure, capacity=20000, data_parallel=False, presample=None):
+    UNROLL = 4                                     # iterations per replayed graph (even: buffer sets alternate)
+
+    def __init__(self, nets, lr, closure, capacity=20000, data_parallel=False, presample=None, prepare=None):
         self.nets, self.closure = list(nets), closure
+        # prepare (a stronger form of presample): ``prepare(k)`` fills buffer set k in {0, 1} with an iteration's points AND
+        # everything that depends only on them and on FROZEN networks (the closures' targets); ``closure(k)`` then consumes
+        # set k.  An iteration runs closure(k) -> update on the main branch and prepare(1 - k) for the next iteration on a
+        # parallel branch from its very start, so sampling and the frozen-net kernels leave the critical path altogether:
+        # what remains is lsq -> update.  Two graphs (k = 0 / 1) are captured and replayed alternately.
+        self.prepare = prepare
+        self._k = 0
+        self.graph_b = None
+        self._prep_stream = None
+        # graph_u: UNROLL consecutive iterations as ONE graph (the gap between two graph launches is longer than a dependency
+        # edge inside a graph); the single-iteration graphs serve the remainders
+        self.graph_u = None
         # presample: draws the NEXT iteration's points into the persistent buffers the closure reads.  It runs on a parallel
         # branch beside the update kernel (the closure's kernels have consumed the current points by then), so the sampling
         # kernel leaves the critical path of the iteration; run() draws the first set.  Iteration i still sees draw i.
@@ -651,13 +698,32 @@ class GraphedLoop:
         self._slot_off += n
         return out
 
-    def _iteration(self):
+    def _iteration(self, k=0):
+        if self.prepare is None:
+            return self._iteration_body(self.closure)
+        # fork at the start of the iteration: the next iteration's buffer set is prepared beside this one's kernels
+        dev = self.slots.device
+        cur = torch.cuda.current_stream(dev)
+        if self._prep_stream is None:
+            self._prep_stream = torch.cuda.Stream(device=dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        self._prep_stream.wait_event(fork)
+        with torch.cuda.stream(self._prep_stream):
+            self.prepare(1 - k)
+        keys = self._iteration_body(lambda: self.closure(k))
+        done = torch.cuda.Event()
+        done.record(self._prep_stream)
+        cur.wait_event(done)
+        return keys
+
+    def _iteration_body(self, closure):
         # the gradient buffers and the loss slots are zero here: zeroed by run() before the first iteration, then by every
         # update kernel
         self._slot_off = 0
         _ACC_PROVIDER.append(self._provide)
         try:
-            loss_dict = self.closure()
+            loss_dict = closure()
         finally:
             _ACC_PROVIDER.pop()
         _backward_if_needed(loss_dict)
@@ -700,7 +766,7 @@ class GraphedLoop:
         Collective when data_parallel (every rank closes its loops in the same order)."""
         if self.graph is not None:
             torch.cuda.synchronize()
-            self.graph = None
+            self.graph = self.graph_b = self.graph_u = None
         if self.shared is not None:
             self.shared.close()
 
@@ -709,8 +775,12 @@ class GraphedLoop:
         self.slots.zero_()
         if self.presample is not None:
             self.presample()                           # the first iteration's points
+        if self.prepare is not None:
+            self.prepare(0)                            # the first iteration's buffer set
+            self._k = 0
         if self.graph is None:
-            keys = self._iteration()                   # iteration 0 eagerly (also warms everything up)
+            keys = self._iteration(0)                  # iteration 0 eagerly (also warms everything up)
+            self._k = 1
             self.keys = keys
             done = 1
             if self.shared is not None and self.shared.peer is not None:
@@ -736,15 +806,34 @@ class GraphedLoop:
                 gc.disable()
                 try:
                     with torch.cuda.graph(self.graph):
-                        self._iteration()
+                        self._iteration(0)
+                    if self.prepare is not None:       # the odd iterations: buffer set 1 consumed, set 0 prepared
+                        self.graph_b = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(self.graph_b):
+                            self._iteration(1)
+                    if self.UNROLL > 1 and n_iters - done >= 2 * self.UNROLL:
+                        self.graph_u = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(self.graph_u):
+                            for u in range(self.UNROLL):
+                                self._iteration(u & 1)
                     self.graph_ready = True
                 finally:
                     if gc_was_on:
                         gc.enable()
             while done < n_iters:
                 burst = min(check_every, n_iters - done)
-                for _ in range(burst):
-                    self.graph.replay()
+                i = 0
+                while i < burst:
+                    if self.graph_u is not None and self._k == 0 and burst - i >= self.UNROLL:
+                        self.graph_u.replay()
+                        i += self.UNROLL
+                    elif self.prepare is None:
+                        self.graph.replay()
+                        i += 1
+                    else:
+                        (self.graph_b if self._k else self.graph).replay()
+                        self._k ^= 1
+                        i += 1
                 done += burst
                 if early_stop and self.opt.lr <= 1.1e-8:
                     break
@@ -775,39 +864,58 @@ class FluidStepper(_StepperBase):
         for p in self.prev.parameters():
             p.requires_grad_(False)
 
+    def _sampler(self, n_shard_div):
+        """the one-kernel sampler of the three point sets (insr_sample_boxes) and its two persistent point buffers"""
+        from . import sampling
+        if n_shard_div not in self._samplers:
+            import torch.distributed as tdist
+            dev = next(self.vel.parameters()).device
+            n = self.sr ** 2
+            rank = tdist.get_rank() if (tdist.is_available() and tdist.is_initialized()) else 0
+            sets = sampling.fluid_sets(n // n_shard_div, n // 100)
+            per_rank = sum(int(bx[0]) for st in sets for bx in st)
+            # every rank draws its own slice of ONE global Philox stream (point index offset by the rank)
+            self._samplers[n_shard_div] = sampling.BoxSampler(sets, 2, seed=self.seed, device=dev, point_offset=rank * per_rank)
+            self._points[n_shard_div] = [torch.zeros(per_rank, 2, dtype=torch.float32, device=dev) for _ in range(2)]
+        return self._samplers[n_shard_div], self._points[n_shard_div]
+
     def _samples(self, n_shard_div=1):
         from . import sampling
         dev = next(self.vel.parameters()).device
         n = self.sr ** 2
-        if self.device_sampler:              # one kernel for the three sets (insr_sample_boxes)
-            if n_shard_div not in self._samplers:
-                import torch.distributed as tdist
-                rank = tdist.get_rank() if (tdist.is_available() and tdist.is_initialized()) else 0
-                sets = sampling.fluid_sets(n // n_shard_div, n // 100)
-                per_rank = sum(int(bx[0]) for st in sets for bx in st)
-                # every rank draws its own slice of ONE global Philox stream (point index offset by the rank)
-                self._samplers[n_shard_div] = sampling.BoxSampler(sets, 2, seed=self.seed, device=dev,
-                                                                  point_offset=rank * per_rank)
-                self._points[n_shard_div] = torch.zeros(per_rank, 2, dtype=torch.float32, device=dev)
-            smp, buf = self._samplers[n_shard_div], self._points[n_shard_div]
-            if self.graphed:                 # drawn ahead by the loop (GraphedLoop.presample): the closure reads the buffer
-                return tuple(torch.split(buf, smp.sizes, dim=0))
-            return tuple(smp.sample(out=buf))
+        if self.device_sampler:
+            smp, bufs = self._sampler(n_shard_div)
+            return tuple(smp.sample(out=bufs[0]))
         x = sampling.sample_random(n // n_shard_div, 2, device=dev)
         bx = sampling.sample_boundary2D_separate(n // 100, "horizontal", device=dev)
         by = sampling.sample_boundary2D_separate(n // 100, "vertical", device=dev)
         return x, bx, by                     # (same RNG stream order as the reference: not run in parallel)
 
-    def _loop(self, nets, closure, n_iters, world=1, key=None):
+    def _loop(self, nets, key, target, closure, n_iters, world=1):
+        """one training loop.  ``target(x, out)``: the frozen side of the closure at the interior points (into ``out`` where
+        given); ``closure(x, bx, by, tgt)``: the trainable side (``tgt`` None: compute the target inline)."""
+        def eager(i):
+            x, bx, by = self._samples(world)
+            return closure(x, bx, by, None)
         if self.graphed:
             loops = self.__dict__.setdefault("_loops", {})
             if key not in loops:                       # capture once per closure kind, replay for every time step
-                pre = None
                 if self.device_sampler:
-                    div = world
-                    self._samples(div)                 # creates the sampler and its persistent point buffer
-                    pre = lambda: self._samplers[div].sample(out=self._points[div])
-                loops[key] = GraphedLoop(nets, self.lr, lambda: closure(0), data_parallel=self.data_parallel, presample=pre)
+                    # buffer sets 0 / 1: an iteration consumes one while the next one's points AND frozen-net target are
+                    # prepared into the other on a parallel branch (GraphedLoop.prepare)
+                    smp, bufs = self._sampler(world)
+                    tgts = [None, None]
+
+                    def prepare(k):
+                        pts = smp.sample(out=bufs[k])
+                        tgts[k] = target(pts[0], tgts[k])
+
+                    def consume(k):
+                        x, bx, by = torch.split(bufs[k], smp.sizes, dim=0)
+                        return closure(x, bx, by, tgts[k])
+                    loops[key] = GraphedLoop(nets, self.lr, consume, data_parallel=self.data_parallel, prepare=prepare)
+                else:
+                    loops[key] = GraphedLoop(nets, self.lr, lambda: eager(0), data_parallel=self.data_parallel)
             else:
                 loops[key].reset(self.lr)
             return loops[key].run(n_iters)
@@ -815,25 +923,27 @@ class FluidStepper(_StepperBase):
             raise RuntimeError("FluidStepper: data_parallel needs graphed=True (all-reduce inside the iteration graph) or a "
                                "reducer_factory for the eager loop -- refusing to train unsynchronised replicas")
         red = self.reducer_factory(nets) if self.reducer_factory else None
-        return TrainingLoop(nets, self.lr, reducer=red).run(closure, n_iters)
+        return TrainingLoop(nets, self.lr, reducer=red).run(eager, n_iters)
 
     def initialize(self, init_fn, n_iters, world=1):
-        def c(i):
-            x, _, _ = self._samples(world)
-            return fluid_initialize(self.vel, x, init_fn(x))
-        return self._loop([self.vel], c, n_iters, world=world, key="initialize")
+        return self._loop([self.vel], "initialize", lambda x, out: _into(out, init_fn(x)) if out is not None else init_fn(x).contiguous(),
+                          lambda x, bx, by, tgt: fluid_initialize(self.vel, x, tgt if tgt is not None else init_fn(x)),
+                          n_iters, world=world)
 
     def step(self, n_iters, world=1):
         """advect -> pressure solve -> projection; returns the three loss histories"""
         nets = [self.vel, self.pres]
         self.prev.load_state_dict(self.vel.state_dict())
-        h1 = self._loop(nets, lambda i: fluid_advect_velocity(self.vel, self.prev, *self._samples(world), self.dt), n_iters,
-                        world=world, key="advect")
-        h2 = self._loop(nets, lambda i: fluid_solve_pressure(self.vel, self.pres, *self._samples(world)), n_iters,
-                        world=world, key="pressure")
+        h1 = self._loop(nets, "advect", lambda x, out: fluid_advect_target(self.prev, x, self.dt, out=out),
+                        lambda x, bx, by, tgt: fluid_advect_velocity(self.vel, self.prev, x, bx, by, self.dt, target=tgt),
+                        n_iters, world=world)
+        h2 = self._loop(nets, "pressure", lambda x, out: fluid_pressure_target(self.vel, x, out=out),
+                        lambda x, bx, by, tgt: fluid_solve_pressure(self.vel, self.pres, x, bx, by, target=tgt),
+                        n_iters, world=world)
         self.prev.load_state_dict(self.vel.state_dict())
-        h3 = self._loop(nets, lambda i: fluid_projection(self.vel, self.prev, self.pres, *self._samples(world)), n_iters,
-                        world=world, key="project")
+        h3 = self._loop(nets, "project", lambda x, out: fluid_projection_target(self.prev, self.pres, x, out=out),
+                        lambda x, bx, by, tgt: fluid_projection(self.vel, self.prev, self.pres, x, bx, by, target=tgt),
+                        n_iters, world=world)
         return h1, h2, h3
 
 
@@ -849,41 +959,63 @@ class AdvectionStepper(_StepperBase):
         for p in self.prev.parameters():
             p.requires_grad_(False)
 
+    def _device_sampler(self):
+        """base/sampling.py:21-37 scaled by length / 2 (bands around -half and +half) as ONE Philox kernel, and the two
+        persistent point buffers of the graphed loop"""
+        from . import sampling
+        if self._sampler is None:
+            dev = next(self.field.parameters()).device
+            nb, half, eps = max(self.sr // 100, 10), self.length / 2, 1e-4
+            sets = [[(self.sr, (-half,), (half,))],
+                    [(nb // 2, ((-1 - eps) * half,), ((-1 + eps) * half,)), (nb // 2, ((1 - eps) * half,), ((1 + eps) * half,))]]
+            self._sampler = sampling.BoxSampler(sets, 1, seed=self.seed, device=dev)
+            self._points = [torch.zeros(sum(self._sampler.sizes), 1, dtype=torch.float32, device=dev) for _ in range(2)]
+        return self._sampler, self._points
+
     def _samples(self):
         from . import sampling
         dev = next(self.field.parameters()).device
-        nb, half, eps = max(self.sr // 100, 10), self.length / 2, 1e-4
+        nb, half = max(self.sr // 100, 10), self.length / 2
         if self.graphed:
-            if self._sampler is None:       # base/sampling.py:21-37 scaled by length / 2: bands around -half and +half
-                sets = [[(self.sr, (-half,), (half,))],
-                        [(nb // 2, ((-1 - eps) * half,), ((-1 + eps) * half,)), (nb // 2, ((1 - eps) * half,), ((1 + eps) * half,))]]
-                self._sampler = sampling.BoxSampler(sets, 1, seed=self.seed, device=dev)
-                self._points = torch.zeros(sum(self._sampler.sizes), 1, dtype=torch.float32, device=dev)
-            # drawn ahead by the loop (GraphedLoop.presample): the closure reads the persistent buffer
-            return tuple(torch.split(self._points, self._sampler.sizes, dim=0))
+            smp, bufs = self._device_sampler()
+            return tuple(smp.sample(out=bufs[0]))
         return (sampling.sample_random(self.sr, 1, device=dev) * half, sampling.sample_boundary(nb, 1, device=dev) * half)
 
-    def _loop(self, closure, n_iters, key):
+    def _loop(self, key, target, closure, n_iters):
+        """``target(x, out)``: the frozen side of the closure; ``closure(x, xb, tgt)``: the trainable side"""
         if self.graphed:
             loops = self.__dict__.setdefault("_loops", {})
             if key not in loops:
-                self._samples()                        # creates the sampler and its persistent point buffer
-                loops[key] = GraphedLoop([self.field], self.lr, lambda: closure(0),
-                                         presample=lambda: self._sampler.sample(out=self._points))
+                # buffer sets 0 / 1: an iteration consumes one while the next one's points and frozen-field target are prepared
+                # into the other on a parallel branch (GraphedLoop.prepare)
+                smp, bufs = self._device_sampler()
+                tgts = [None, None]
+
+                def prepare(k):
+                    pts = smp.sample(out=bufs[k])
+                    tgts[k] = target(pts[0], tgts[k])
+
+                def consume(k):
+                    x, xb = torch.split(bufs[k], smp.sizes, dim=0)
+                    return closure(x, xb, tgts[k])
+                loops[key] = GraphedLoop([self.field], self.lr, consume, prepare=prepare)
             else:
                 loops[key].reset(self.lr)
             return loops[key].run(n_iters)
-        return TrainingLoop([self.field], self.lr).run(closure, n_iters)
+
+        def eager(i):
+            x, xb = self._samples()
+            return closure(x, xb, None)
+        return TrainingLoop([self.field], self.lr).run(eager, n_iters)
 
     def initialize(self, init_fn, n_iters):
-        def c(i):
-            x, _ = self._samples()
-            return advect_initialize(self.field, x, init_fn(x))
-        return self._loop(c, n_iters, "initialize")
+        return self._loop("initialize", lambda x, out: _into(out, init_fn(x)) if out is not None else init_fn(x).contiguous(),
+                          lambda x, xb, tgt: advect_initialize(self.field, x, tgt if tgt is not None else init_fn(x)), n_iters)
 
     def step(self, n_iters):
         self.prev.load_state_dict(self.field.state_dict())
-        return self._loop(lambda i: advect_step(self.field, self.prev, *self._samples(), self.dt, self.vel), n_iters, "advect")
+        return self._loop("advect", lambda x, out: advect_target(self.prev, x, self.dt, self.vel, out=out),
+                          lambda x, xb, tgt: advect_step(self.field, self.prev, x, xb, self.dt, self.vel, target=tgt), n_iters)
 
 
 def gaussian_like(x, mu=-1.5, sigma=0.1):

@@ -320,6 +320,49 @@ def test_graphed_loop_equals_eager_loop_on_fixed_samples():
     assert h_graph[-1]["main"] < h_graph[0]["main"]
 
 
+def test_prepared_ahead_graph_follows_the_eager_stepper_on_the_same_philox_stream():
+    """FluidStepper / AdvectionStepper with the device sampler: the graphed loops prepare the NEXT iteration's points and
+    frozen-net target on a parallel branch into the other of two buffer sets (GraphedLoop.prepare, two alternating graphs);
+    iteration i must still see draw i of the Philox stream.  Checked against the eager stepper (same sampler, same seed,
+    targets computed inline, torch Adam) over the first loop of each, plus one full fluid step for sanity."""
+    from insr_pde_b200 import fused
+
+    def fluid(graphed):
+        torch.manual_seed(4)
+        vel, prev, pres = (ib.MLP(2, o, 3, 32, nonlinearity="sine").cuda() for o in (2, 2, 1))
+        st = fused.FluidStepper(vel, prev, pres, dt=0.05, sample_resolution=64, lr=1e-3, graphed=graphed, device_sampler=True, seed=3)
+        h0 = st.initialize(fused.taylorgreen_velocity, 25)
+        theta0 = vel.flat_theta().detach().clone()
+        h1, h2, h3 = st.step(7)
+        st.close()
+        return h0, theta0, (h1, h2, h3)
+
+    (e0, te, es), (g0, tg, gs) = fluid(False), fluid(True)
+    assert len(g0) == 25 and all(abs(a["main"] - b["main"]) < 2e-4 * abs(a["main"]) for a, b in zip(e0, g0)), (e0[-1], g0[-1])
+    assert rel(tg, te) < 1e-4
+    assert all(len(h) == 7 and all(np.isfinite(list(d.values())).all() for d in h) for h in gs)
+    # the first iteration of the next loop starts from (nearly) the same weights on fresh points: same loss level
+    assert abs(gs[0][0]["main"] - es[0][0]["main"]) < 0.2 * abs(es[0][0]["main"])
+
+    def advect(graphed):
+        torch.manual_seed(5)
+        field, prev = ib.MLP(1, 1, 2, 20, nonlinearity="sine").cuda(), ib.MLP(1, 1, 2, 20, nonlinearity="sine").cuda()
+        st = fused.AdvectionStepper(field, prev, sample_resolution=2000, lr=1e-3, graphed=graphed, seed=9)
+        if not graphed:                              # the eager stepper draws with torch: give it the same device sampler
+            smp, bufs = st._device_sampler()
+            st._samples = lambda: tuple(smp.sample(out=bufs[0]))
+        h0 = st.initialize(fused.gaussian_like, 25)
+        theta0 = field.flat_theta().detach().clone()
+        h1 = st.step(6)
+        st.close()
+        return h0, theta0, h1
+
+    (e0, te, e1), (g0, tg, g1) = advect(False), advect(True)
+    assert all(abs(a["main"] - b["main"]) < 2e-4 * abs(a["main"]) + 1e-9 for a, b in zip(e0, g0)), (e0[-1], g0[-1])
+    assert rel(tg, te) < 1e-4
+    assert len(g1) == 6 and all(np.isfinite(list(d.values())).all() for d in g1)
+
+
 @pytest.mark.parametrize("case", [(2, 1, 32, 3, 127, 2), (2, 1, 32, 3, 129, 2), (2, 2, 32, 2, 40001, 1), (1, 1, 20, 1, 19000, 1),
                                   (2, 1, 5, 3, 300, 2), (2, 2, 32, 3, 148 * 128 * 2 + 5, 2), (2, 1, 32, 1, 256, 0)])
 def test_tcgen05_tile_boundaries_and_persistent_loop(case):

@@ -17,8 +17,8 @@ for key, lp in st._loops.items():
     if g is None:
         continue
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for _ in range(R):
-            g.replay()
+        for i in range(R):                      # loops that prepare ahead alternate two graphs (buffer sets 0 / 1)
+            (lp.graph_b if (lp.graph_b is not None and i % 2) else g).replay()
         torch.cuda.synchronize()
     ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     agg = collections.defaultdict(lambda: [0, 0.0])
