@@ -217,7 +217,7 @@ def advect_target(field_prev, samples, dt, vel, out=None):
     target = _target(samples.detach().reshape(-1, 1), 1, dict(net=field_prev, order=ORDER_JAC, cy=[[1.0 / dt]], cj=[[[-0.5 * vel]]]), out=out)
     if target is None:
         u_prev, j_prev = evaluate(field_prev, samples, ORDER_JAC)
-        target = _into(out, u_prev / dt - (0.5 * vel) * j_prev[:, :, 0])
+        target = _into(out, (u_prev / dt - (0.5 * vel) * j_prev[:, :, 0]).reshape(-1, 1))
     return target
 
 
@@ -278,7 +278,7 @@ def fluid_pressure_target(velocity, samples, out=None):
     div_u = _target(samples.detach().reshape(-1, 2), 1, dict(net=velocity, order=ORDER_JAC, cj=[[[1.0, 0.0], [0.0, 1.0]]]), out=out)
     if div_u is None:
         _, jac_u = evaluate(velocity, samples, ORDER_JAC)
-        div_u = _into(out, jac_u[:, 0, 0] + jac_u[:, 1, 1])
+        div_u = _into(out, (jac_u[:, 0, 0] + jac_u[:, 1, 1]).reshape(-1, 1))
     return div_u
 
 

@@ -246,6 +246,62 @@ def test_fused_closures_match_reference_goldens_emulated(emu_backend):
     check_fused_closures_against_goldens("cpu")
 
 
+def test_split_closures_and_loss_slots_emulated(emu_backend):
+    """the closures split into a frozen side (``*_target``, what a graphed loop prepares one iteration ahead into a persistent
+    buffer) and a trainable side (``target=`` override), and the loss slots handed out by a provider (``fused._acc``, what
+    GraphedLoop does): same losses and gradients as the one-call closure; slots are accumulated into, not overwritten"""
+    from insr_pde_b200 import fused
+    torch.manual_seed(3)
+    vel, prev = ib.MLP(2, 2, 3, 32, nonlinearity="sine"), ib.MLP(2, 2, 3, 32, nonlinearity="sine")
+    pres = ib.MLP(2, 1, 3, 32, nonlinearity="sine")
+    x = torch.rand(192, 2) * 2 - 1
+    bx, by = ib.sample_boundary2D_separate(20, "horizontal"), ib.sample_boundary2D_separate(20, "vertical")
+
+    def grads():
+        return torch.cat([fused.flat_grad(n).clone() for n in (vel, pres)])
+
+    cases = [
+        (lambda out: fused.fluid_advect_target(prev, x, 0.05, out=out), 2,
+         lambda t: fused.fluid_advect_velocity(vel, prev, x, bx, by, 0.05, target=t)),
+        (lambda out: fused.fluid_pressure_target(vel, x, out=out), 1,
+         lambda t: fused.fluid_solve_pressure(vel, pres, x, bx, by, target=t)),
+        (lambda out: fused.fluid_projection_target(prev, pres, x, out=out), 2,
+         lambda t: fused.fluid_projection(vel, prev, pres, x, bx, by, target=t)),
+    ]
+    for target, n_res, closure in cases:
+        fused.zero_grads(vel, pres)
+        ref = closure(None)
+        g_ref, l_ref = grads(), {k: float(v) for k, v in ref.items()}
+        buf = torch.full((x.shape[0], n_res), 7.0)                   # persistent buffer, stale content
+        got = target(buf)
+        assert got.data_ptr() == buf.data_ptr() and tuple(target(None).shape) == (x.shape[0], n_res)
+        slots = torch.zeros(4)
+        fused._ACC_PROVIDER.append(lambda n, device: slots[:n])
+        try:
+            fused.zero_grads(vel, pres)
+            ld = closure(buf)
+        finally:
+            fused._ACC_PROVIDER.pop()
+        assert isinstance(ld, fused.Losses) and ld.vector.data_ptr() == slots.data_ptr()
+        assert torch.equal(grads(), g_ref) and {k: float(v) for k, v in ld.items()} == l_ref
+        assert float(slots[0]) == l_ref["main"] and float(slots[1]) == l_ref["bc"] and float(slots[2:].abs().max()) == 0.0
+        fused._ACC_PROVIDER.append(lambda n, device: slots[:n])      # a second call ACCUMULATES (the update kernel zeroes)
+        try:
+            closure(buf)
+        finally:
+            fused._ACC_PROVIDER.pop()
+        assert abs(float(slots[0]) - 2 * l_ref["main"]) <= 1e-6 * abs(l_ref["main"])
+    # advection (1-D): the same split
+    field, fprev = ib.MLP(1, 1, 2, 20, nonlinearity="sine"), ib.MLP(1, 1, 2, 20, nonlinearity="sine")
+    xa, xb = torch.rand(150, 1) * 4 - 2, torch.tensor([[-2.0], [2.0]])
+    fused.zero_grads(field)
+    ref = fused.advect_step(field, fprev, xa, xb, 0.05, 0.25)
+    g_ref = fused.flat_grad(field).clone()
+    fused.zero_grads(field)
+    ld = fused.advect_step(field, fprev, xa, xb, 0.05, 0.25, target=fused.advect_target(fprev, xa, 0.05, 0.25, out=torch.empty(150, 1)))
+    assert torch.equal(fused.flat_grad(field), g_ref) and float(ld["main"]) == float(ref["main"])
+
+
 def test_fused_training_loop_and_stepper_emulated(emu_backend):
     from insr_pde_b200 import fused
     torch.manual_seed(0)
