@@ -307,21 +307,34 @@ def install_graphed_loops(data_parallel: bool = False):
             if name in off or not widths_ok or not all(p.is_cuda for n in nets for p in n.parameters()):
                 return method(self)                              # CPU tensors: the reference's own loop
             loops = self.__dict__.setdefault("_insr_loops", {})
-            if name not in loops:
-                loops[name] = fused.GraphedLoop(nets, self.cfg.lr, lambda: body(self), capacity=max(int(self.max_n_iters), 1),
-                                                data_parallel=data_parallel)
+            # host-side branches of a closure are frozen into its captured graph: one graph per branch.  The elasticity
+            # closure applies the external force only while timestep <= external_force_timesteps (elasticity/model.py:151-155)
+            forced = bool("external" in getattr(self, "energy", ()) and getattr(self, "timestep", 0) <= getattr(self, "external_force_timesteps", -1))
+            key = (name, forced) if hasattr(self, "external_force_timesteps") else name
+            closure, presample = (lambda: body(self)), None
+            batch = _elastic_batch(self) if (name == "_solve_deformation" and not data_parallel) else None
+            if batch is not None:
+                # the stepper's persistent batch (fused.ElasticityBatch) under the reference's own model: the constant rows
+                # (uniform grid / mesh vertices) are written once, the random rows drawn in place by the Philox samplers one
+                # iteration ahead, the previous-frame fields evaluated on the constant rows once per time step -- instead of
+                # the model's ~40 torch sampling kernels and two full frozen-field evaluations per iteration
+                batch.refresh(self.deformation_field_prev, self.deformation_field_prev_prev)
+                closure, presample = (lambda: _elastic_closure(self, batch)), batch.draw
+            if key not in loops:
+                loops[key] = fused.GraphedLoop(nets, self.cfg.lr, closure, capacity=max(int(self.max_n_iters), 1),
+                                               data_parallel=data_parallel, presample=presample)
             else:
-                loops[name].reset(self.cfg.lr)
+                loops[key].reset(self.cfg.lr)
             try:
-                hist = loops[name].run(int(self.max_n_iters), early_stop=bool(self.cfg.early_stop))
+                hist = loops[key].run(int(self.max_n_iters), early_stop=bool(self.cfg.early_stop))
             except RuntimeError as e:
-                if loops[name].graph is not None and loops[name].graph_ready or "capture" not in str(e).lower() or data_parallel:
+                if loops[key].graph is not None and loops[key].graph_ready or "capture" not in str(e).lower() or data_parallel:
                     raise
                 # the closure does something a CUDA graph cannot record (host-side sampling with a pageable copy, a
                 # synchronising call): this loop stays on the eager fused closures (one iteration has been taken already)
                 sys.stderr.write(f"insr_pde_b200: {type(self).__name__}.{name} cannot be captured as a CUDA graph ({str(e)[:120]}); "
                                  "running it eagerly on the fused closures\n")
-                loops.pop(name).graph = None
+                loops.pop(key).graph = None
                 off.add(name)
                 torch.cuda.synchronize()
                 return method(self)
@@ -333,6 +346,39 @@ def install_graphed_loops(data_parallel: bool = False):
             self._insr_last_hist = hist
         loop.__name__ = name
         setattr(cls, name, loop)
+
+    class _StepperView:
+        """what fused.ElasticityBatch / ElasticityStepper._batch read from a stepper, taken from the reference's model"""
+
+        def __init__(self, m):
+            self.dim, self.sr, self.pattern = m.dim, m.sample_resolution, tuple(m.sample_pattern)
+            self.mesh = (m.mesh_V, m.mesh_F) if m.use_mesh else None
+            self.seed = int(torch.initial_seed()) & 0x7FFFFFFF
+            self.kw = {"energy": list(m.energy)}
+            self._dev = next(m.deformation_field.parameters()).device
+
+        def _device(self):
+            return self._dev
+
+    def _elastic_batch(m):
+        if "_insr_view" not in m.__dict__:
+            try:
+                m._insr_view = _StepperView(m)
+            except Exception:                                    # an attribute this view does not know: the model's own sampling
+                m._insr_view = None
+        view = m._insr_view
+        if view is None or not all(k in ("random", "uniform") for k in view.pattern):
+            return None
+        return fused.ElasticityStepper._batch(view)
+
+    def _elastic_closure(m, batch):
+        return fused.elasticity_solve_deformation(
+            m.deformation_field, m.deformation_field_prev, m.deformation_field_prev_prev, None, None, None,
+            dt=m.dt, timestep=m.timestep, energy=m.energy, ratio_arap=m.ratio_arap, ratio_volume=m.ratio_volume,
+            ratio_kinematics=m.ratio_kinematics, ratio_constraint=m.ratio_constraint, ratio_collide=m.ratio_collide,
+            external_force=m.external_force, external_force_timesteps=m.external_force_timesteps,
+            constraint_offset_right=m.constraint_offset_right, plane_height=m.plane_height,
+            circle_center=m.circle_center, circle_radius=m.circle_radius, batch=batch)
 
     adv = importlib.import_module("advection.model").Advection1DModel
     flu = importlib.import_module("fluid.model").Fluid2DModel
