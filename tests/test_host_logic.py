@@ -302,6 +302,90 @@ def test_split_closures_and_loss_slots_emulated(emu_backend):
     assert torch.equal(fused.flat_grad(field), g_ref) and float(ld["main"]) == float(ref["main"])
 
 
+def test_graphed_loop_replay_schedule(monkeypatch):
+    """GraphedLoop.run's bookkeeping without a GPU: CUDA graphs replaced by recorders that re-run the captured iteration
+    indices.  With ``prepare`` the buffer sets must alternate 0, 1, 0, 1, ... across the eager first iteration, the unrolled
+    graph (UNROLL iterations per replay) and the single-iteration remainders; every run() primes set 0 and starts there;
+    exactly n_iters iterations happen, and iteration i consumes what prepare wrote i calls ago."""
+    from insr_pde_b200 import fused
+
+    state = {"capturing": None}
+
+    class FakeGraph:
+        def __init__(self):
+            self.iters = []
+
+        def replay(self):
+            for k in self.iters:
+                probe._execute(k)
+
+    class FakeCapture:
+        def __init__(self, g):
+            self.g = g
+
+        def __enter__(self):
+            state["capturing"] = self.g
+
+        def __exit__(self, *a):
+            state["capturing"] = None
+
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", FakeCapture)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+
+    class Probe(fused.GraphedLoop):
+        def __init__(self, with_prepare):
+            self.draws = 0                      # counter of the "sampler"
+            self.buf = [None, None]
+            self.log = []                       # (buffer set, draw consumed) per executed iteration
+            net = ib.MLP(1, 1, 1, 4, nonlinearity="sine")
+            super().__init__([net], 1e-3, closure=None, prepare=self._prep if with_prepare else None)
+            self.keys = ["main"]
+            self.hist = torch.zeros(self.capacity, 1)
+
+        def _prep(self, k):
+            if state["capturing"] is None:
+                self.buf[k] = self.draws
+                self.draws += 1
+
+        def _execute(self, k):
+            if self.prepare is not None:
+                self.log.append((k, self.buf[k]))
+                self.buf[1 - k] = self.draws    # prepare(1 - k) of this iteration
+                self.draws += 1
+            else:
+                self.log.append((0, None))
+            self.hist[int(self.idx)] = float(len(self.log))
+            self.idx += 1
+
+        def _iteration(self, k=0):
+            if state["capturing"] is not None:
+                state["capturing"].iters.append(k)
+            else:
+                self._execute(k)
+            return self.keys
+
+    for with_prepare in (True, False):
+        for n in (1, 2, 3, 8, 9, 10, 101):
+            probe = Probe(with_prepare)
+            h = probe.run(n, check_every=7)
+            assert len(h) == n and len(probe.log) == n, (with_prepare, n, len(probe.log))
+            if with_prepare:
+                assert [k for k, _ in probe.log] == [i % 2 for i in range(n)]
+                assert [d for _, d in probe.log] == list(range(n))             # iteration i consumes draw i
+            # a second training loop on the same captured graphs: fresh prime, starts at set 0 again
+            probe.reset(1e-3)
+            probe.log.clear()
+            first = probe.draws
+            h = probe.run(n + 1, check_every=100)
+            assert len(h) == n + 1 and len(probe.log) == n + 1
+            if with_prepare:
+                assert [k for k, _ in probe.log] == [i % 2 for i in range(n + 1)]
+                assert [d for _, d in probe.log] == list(range(first, first + n + 1))
+            if n >= 2 * fused.GraphedLoop.UNROLL + 1:
+                assert probe.graph_u is not None and len(probe.graph_u.iters) == fused.GraphedLoop.UNROLL
+
+
 def test_fused_training_loop_and_stepper_emulated(emu_backend):
     from insr_pde_b200 import fused
     torch.manual_seed(0)
