@@ -512,3 +512,12 @@ def test_one_kernel_iteration_update_matches_torch(emu_backend):
     assert opt.param_groups[0]["lr"] < 1e-2 and int(idx) == len(losses) and float(dev_opt.sched[3]) == len(losses)
     assert torch.equal(hist[:len(losses), 1], torch.tensor(losses)) and torch.equal(hist[:len(losses), 0], 7.0 + torch.arange(len(losses)))
     assert bool((hist[len(losses):] == -1).all()) and int(dev_opt._ticket) == 0
+    # clear_losses: the loss slots are accumulators of the closures' kernels -- logged, then left zeroed for the next iteration
+    slots = torch.tensor([3.0, 0.25, 9.0])
+    dev_opt.update(slots[:2], 1, hist, idx, clear_losses=True)
+    assert float(hist[len(losses), 0]) == 3.0 and float(hist[len(losses), 1]) == 0.25
+    assert slots.tolist() == [0.0, 0.0, 9.0]                                 # only the n_losses consumed slots
+    dev_opt.update(slots[:2], 1, hist, idx, clear_losses=False)
+    slots[:2] = torch.tensor([1.0, 2.0])
+    dev_opt.update(slots[:2], 1, hist, idx)
+    assert slots.tolist() == [1.0, 2.0, 9.0]
