@@ -502,7 +502,11 @@ class OperatorCase:
         self.peer, self.collective = None, None
         if world > 1:
             from insr_pde_b200 import peer as _peer
-            self.peer = _peer.PeerBuffer.create(self.P, dev)
+            # one-shot means every rank reads all W copies: right for the latency-bound payloads of the script networks
+            # (3.6-56 KB), wrong for megabytes (measured at 8 GPUs: H = 512, 3-5 MB per exchange, 5 % slower per step than
+            # NCCL's ring) -- above PEER_MAX_FLOATS the flat gradient goes through NCCL
+            if self.P <= PEER_MAX_FLOATS:
+                self.peer = _peer.PeerBuffer.create(self.P, dev)
             self.collective = "nccl all-reduce of the flat gradient"
         self.gtheta = self.peer.data if self.peer is not None else torch.zeros(self.P, device=dev)
         self.gsum = torch.empty(self.P, device=dev) if self.peer is not None else self.gtheta
@@ -577,6 +581,8 @@ class OperatorCase:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+
+PEER_MAX_FLOATS = 1 << 18        # 1 MB: largest flat gradient exchanged by the one-shot peer-memory kernel in this bench
 
 # the other BASELINE.json shapes, each on its own fixed GLOBAL batch (split over the ranks like the headline)
 SWEEP = [("advect1D", 1 << 22), ("fluid2Dtlgn.velocity", 1 << 22), ("elasticity2Dstretch", 1 << 20), ("elasticity3Dbunny", 1 << 20),
@@ -841,6 +847,8 @@ def run_ours(args):
                 sweep[wl] = {"global_points": n_loc * world, "ms_per_step": round(sms / k_s, 4), "points_per_s": round(v, 1),
                              "frac_fp32_step": round(3 * sc.f_fwd * v / 1e12 / (peak * world), 4),
                              "family": lib.kernel_family(sc.desc, sc.order, True), "params": sc.P}
+                if world > 1:
+                    sweep[wl]["exchange"] = "peer" if sc.peer is not None else "nccl"
                 sc.close()
                 del sc
             except Exception as e:                      # a secondary measurement must not take the headline line down
