@@ -464,21 +464,6 @@ int insr_iteration_update(int n_slots, float *const *theta, float *const *grad, 
 }
 
 // ---------------------------------------------------------------- peer memory (one box, one process per GPU)
-#ifdef INSR_CPU_EMU
-int insr_peer_alloc(int64_t, void **, unsigned char *) { return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build"); }
-int insr_peer_open(const unsigned char *, void **) { return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build"); }
-int insr_peer_close(void *) { return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build"); }
-int insr_peer_free(void *) { return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build"); }
-int insr_peer_status(void *, int) { return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build"); }
-int insr_peer_allreduce(int, int, void *const *, int64_t, int64_t, float, float *, void *) {
-    return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build");
-}
-int insr_iteration_update_peer(int, int, void *const *, int64_t, float, int, float *const *, float *const *, float *const *,
-                               float *const *, const int64_t *, float *, float *, int, int, float *, float *, int64_t, int64_t *,
-                               float, float, float, float, int, float, float, float, int, int, void *) {
-    return fail(INSR_ERR_UNSUPPORTED, "peer memory needs the CUDA build");
-}
-#else
 namespace {
 int peer_set(int world, int rank, void *const *bases, insr_peer_set *ps) {
     if (!bases) return fail(INSR_ERR_NULL, "peer: bases is NULL");
@@ -495,6 +480,7 @@ int peer_set(int world, int rank, void *const *bases, insr_peer_set *ps) {
 }
 }  // namespace
 
+#ifndef INSR_CPU_EMU
 int insr_peer_alloc(int64_t data_bytes, void **base, unsigned char *handle64) {
     if (!base || !handle64) return fail(INSR_ERR_NULL, "peer_alloc: NULL argument");
     if (data_bytes < 0) return fail(INSR_ERR_SHAPE, "peer_alloc: data_bytes=%lld", (long long)data_bytes);
@@ -550,6 +536,38 @@ int insr_peer_status(void *base, int reset) {
     if (e != cudaSuccess) { cudaGetLastError(); return fail((int)e, "peer_status: %s", cudaGetErrorString(e)); }
     return (int)v;                                      // 0 healthy, 1 a barrier timed out since the last reset
 }
+
+#else
+// emulation build (tests/emu): "peer memory" is host memory of one process whose ranks are host threads; the handle is the address
+int insr_peer_alloc(int64_t data_bytes, void **base, unsigned char *handle64) {
+    if (!base || !handle64) return fail(INSR_ERR_NULL, "peer_alloc: NULL argument");
+    if (data_bytes < 0) return fail(INSR_ERR_SHAPE, "peer_alloc: data_bytes=%lld", (long long)data_bytes);
+    const size_t bytes = (size_t)INSR_PEER_HEADER_BYTES + (((size_t)data_bytes + 255) & ~(size_t)255);
+    void *p = aligned_alloc(256, bytes);
+    if (!p) return fail(INSR_ERR_WORKSPACE, "peer_alloc: out of memory");
+    memset(p, 0, bytes);
+    static_cast<uint32_t *>(p)[INSR_PEER_EPOCH_WORD] = 1u;
+    memset(handle64, 0, 64);
+    memcpy(handle64, &p, sizeof(p));
+    *base = p;
+    return 0;
+}
+int insr_peer_open(const unsigned char *handle64, void **base) {
+    if (!handle64 || !base) return fail(INSR_ERR_NULL, "peer_open: NULL argument");
+    memcpy(base, handle64, sizeof(void *));
+    return 0;
+}
+int insr_peer_close(void *) { return 0; }
+int insr_peer_free(void *base) { free(base); return 0; }
+int insr_peer_status(void *base, int reset) {
+    if (!base) return fail(INSR_ERR_NULL, "peer_status: NULL argument");
+    uint32_t *w = static_cast<uint32_t *>(base) + INSR_PEER_STATUS_WORD;
+    const uint32_t v = *w;
+    if (reset) *w = 0;
+    return (int)v;
+}
+
+#endif
 
 int insr_peer_allreduce(int world, int rank, void *const *bases, int64_t offset_floats, int64_t n, float scale, float *out,
                         void *stream) {
@@ -612,7 +630,6 @@ int insr_iteration_update_peer(int world, int rank, void *const *bases, int64_t 
     ++g_launches;
     return check_cuda("k_iteration_update_peer");
 }
-#endif
 
 int insr_svd_small(const float *F, int64_t n, int d, float *U, float *S, float *V, void *stream) {
     if (!F || !S) return fail(INSR_ERR_NULL, "svd_small: F and S must not be NULL");

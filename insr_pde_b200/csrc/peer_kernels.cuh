@@ -20,6 +20,10 @@
 #pragma once
 #include "insr_platform.h"
 #include "optim_kernels.cuh"
+#ifdef INSR_CPU_EMU
+#include <atomic>
+#include <chrono>
+#endif
 
 #define INSR_PEER_MAX_WORLD 16
 #define INSR_PEER_MAX_CTAS 32
@@ -34,9 +38,20 @@ struct insr_peer_set {
     unsigned char *base[INSR_PEER_MAX_WORLD];  // this process's mappings of every rank's allocation (base[rank] = own)
 };
 
-#ifndef INSR_CPU_EMU
 namespace insr_peer {
 
+#ifdef INSR_CPU_EMU
+// host emulation (tests/emu): the ranks are host threads of one process that launch concurrently, "peer memory" is ordinary memory
+inline void st_release_sys(uint32_t *p, uint32_t v) { reinterpret_cast<std::atomic<uint32_t> *>(p)->store(v, std::memory_order_release); }
+inline uint32_t ld_acquire_sys(const uint32_t *p) {
+    return reinterpret_cast<const std::atomic<uint32_t> *>(p)->load(std::memory_order_acquire);
+}
+inline float ld_peer(const float *p) { return *reinterpret_cast<const volatile float *>(p); }
+inline float4 ld_peer4(const float *p) { return make_float4(ld_peer(p), ld_peer(p + 1), ld_peer(p + 2), ld_peer(p + 3)); }
+inline unsigned long long now_ns() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#else
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
@@ -60,6 +75,7 @@ __device__ __forceinline__ unsigned long long now_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#endif
 __device__ __forceinline__ uint32_t *header(const insr_peer_set &ps, int r) { return reinterpret_cast<uint32_t *>(ps.base[r]); }
 
 // CTA blockIdx.x of this rank meets CTA blockIdx.x of every other rank at epoch value e
@@ -191,4 +207,3 @@ __global__ void __launch_bounds__(512) k_iteration_update_peer(insr_peer_set ps,
 }
 
 }  // namespace insr_peer
-#endif  // !INSR_CPU_EMU

@@ -56,7 +56,9 @@ struct BlockCtx {
     std::vector<std::vector<uint32_t>> warp_xchg;   // [warp][lane]
     std::vector<unsigned char> dyn_smem;
 };
-inline BlockCtx *&ctx() { static BlockCtx *c = nullptr; return c; }
+// per OS thread (set by launch() in the launching thread and in every kernel thread): launches issued concurrently from several
+// host threads -- the ranks of the peer-memory exchange test -- do not see each other's block context
+inline BlockCtx *&ctx() { static thread_local BlockCtx *c = nullptr; return c; }
 struct ThreadCtx { uint3 tid, bid; };
 inline ThreadCtx &tctx() { static thread_local ThreadCtx t; return t; }
 
@@ -80,6 +82,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
                 ts.reserve(nthreads);
                 for (unsigned t = 0; t < nthreads; ++t) {
                     ts.emplace_back([&, t]() {
+                        ctx() = &c;
                         ThreadCtx &tc = tctx();
                         tc.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
                         tc.bid = uint3{bx, by, bz};
@@ -141,6 +144,10 @@ static inline unsigned int atomicAdd(unsigned int *addr, unsigned int v) {
     return reinterpret_cast<std::atomic<unsigned int> *>(addr)->fetch_add(v, std::memory_order_acq_rel);
 }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline unsigned int atomicExch(unsigned int *addr, unsigned int v) {
+    return reinterpret_cast<std::atomic<unsigned int> *>(addr)->exchange(v, std::memory_order_acq_rel);
+}
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 #define __sinf(x) sinf(x)   /* glibc declares __sinf/__cosf itself: use macros */
 #define __cosf(x) cosf(x)
