@@ -6,6 +6,7 @@ sum (bit-identical on every rank), tails and unaligned outputs of the stand-alon
 iteration update against torch.optim.Adam + ReduceLROnPlateau on the averaged gradient."""
 import ctypes
 import threading
+import time
 
 import numpy as np
 import pytest
@@ -51,6 +52,8 @@ def test_one_shot_allreduce_between_emulated_ranks(emu_library, world):
 
         def rank(r):
             for it in range(rounds):
+                if (it + r) % 3 == 0:
+                    time.sleep(0.03 * (r + 1))                  # skewed arrivals: a rank may be a whole call behind the others
                 data[r].copy_(value(r, it))                     # this rank's "gradient" of the round
                 out = outs[r][1:] if it % 2 else outs[r][:n]    # odd rounds: an output that is not 16-byte aligned
                 lib.peer_allreduce(world, r, bases, HEADER // 4, n, scale, out.data_ptr(), None)
